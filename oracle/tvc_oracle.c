@@ -1,0 +1,845 @@
+/*
+ * tvc_oracle.c -- CPU ORACLE (test infrastructure, NOT product code).  See tvc_oracle.h.
+ *
+ * Every function cites the reference lines (relative to /root/reference/) or the SURVEY.md
+ * section-8(a) row it restates.  "ref:" = env/enhanced_rocket_tvc_env.py.
+ *
+ * Arithmetic: IEEE double, evaluated in the reference's operation order so that the env
+ * layer reproduces the reference's own Python code bit-for-bit wherever that code works in
+ * float64.  Where NumPy 2 keeps float32 intermediates (np.linalg.norm of the float32
+ * action, ref:152,173,203) the same float32 roundings are emulated.
+ * Build with -ffp-contract=off (no FMA contraction).
+ */
+#include "tvc_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define PI_D 3.14159265358979323846
+
+/* ------------------------------------------------------------------ */
+/* small vector helpers                                                */
+/* ------------------------------------------------------------------ */
+static inline void cross3(const double a[3], const double b[3], double o[3]) {
+    double x = a[1] * b[2] - a[2] * b[1];
+    double y = a[2] * b[0] - a[0] * b[2];
+    double z = a[0] * b[1] - a[1] * b[0];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+static inline double dot3(const double a[3], const double b[3]) {
+    return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+}
+/* row-major 3x3 times vector */
+static inline void matvec(const double m[9], const double v[3], double o[3]) {
+    double x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2];
+    double y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2];
+    double z = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+static inline void matTvec(const double m[9], const double v[3], double o[3]) {
+    double x = m[0] * v[0] + m[3] * v[1] + m[6] * v[2];
+    double y = m[1] * v[0] + m[4] * v[1] + m[7] * v[2];
+    double z = m[2] * v[0] + m[5] * v[1] + m[8] * v[2];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+static inline double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+/* ------------------------------------------------------------------ */
+/* Bullet helper functions (row B8, B7)                                */
+/* ------------------------------------------------------------------ */
+
+/* btMatrix3x3::setRotation, as used by pybullet getMatrixFromQuaternion (ref:546). Row B8. */
+void orc_matrix_from_quat(const double q[4], double m[9]) {
+    double d = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    double s = 2.0 / d;
+    double xs = q[0] * s, ys = q[1] * s, zs = q[2] * s;
+    double wx = q[3] * xs, wy = q[3] * ys, wz = q[3] * zs;
+    double xx = q[0] * xs, xy = q[0] * ys, xz = q[0] * zs;
+    double yy = q[1] * ys, yz = q[1] * zs, zz = q[2] * zs;
+    m[0] = 1.0 - (yy + zz); m[1] = xy - wz;         m[2] = xz + wy;
+    m[3] = xy + wz;         m[4] = 1.0 - (xx + zz); m[5] = yz - wx;
+    m[6] = xz - wy;         m[7] = yz + wx;         m[8] = 1.0 - (xx + yy);
+}
+
+/* btMatrix3x3::getRotation (matrix -> quaternion). */
+static void quat_from_matrix(const double m[9], double q[4]) {
+    double trace = m[0] + m[4] + m[8];
+    double t[4];
+    if (trace > 0.0) {
+        double s = sqrt(trace + 1.0);
+        t[3] = s * 0.5;
+        s = 0.5 / s;
+        t[0] = (m[7] - m[5]) * s;
+        t[1] = (m[2] - m[6]) * s;
+        t[2] = (m[3] - m[1]) * s;
+    } else {
+        int i = m[0] < m[4] ? (m[4] < m[8] ? 2 : 1) : (m[0] < m[8] ? 2 : 0);
+        int j = (i + 1) % 3, k = (i + 2) % 3;
+        double s = sqrt(m[i * 3 + i] - m[j * 3 + j] - m[k * 3 + k] + 1.0);
+        t[i] = s * 0.5;
+        s = 0.5 / s;
+        t[3] = (m[k * 3 + j] - m[j * 3 + k]) * s;
+        t[j] = (m[j * 3 + i] + m[i * 3 + j]) * s;
+        t[k] = (m[k * 3 + i] + m[i * 3 + k]) * s;
+    }
+    q[0] = t[0]; q[1] = t[1]; q[2] = t[2]; q[3] = t[3];
+}
+
+/* Row B7: getBasePositionAndOrientation reports btTransform(setRotation(q)).getRotation():
+ * quaternion -> matrix -> quaternion, which canonicalises the sign. */
+void orc_reported_quat(const double q[4], double out[4]) {
+    double m[9];
+    orc_matrix_from_quat(q, m);
+    quat_from_matrix(m, out);
+}
+
+/* pybullet.c getEulerFromQuaternion (ref:614, ref:728). Row B8. */
+void orc_euler_from_quat(const double q[4], double rpy[3]) {
+    double sqx = q[0] * q[0], sqy = q[1] * q[1], sqz = q[2] * q[2], squ = q[3] * q[3];
+    double sarg = -2 * (q[0] * q[2] - q[3] * q[1]);
+    if (sarg <= -0.99999) {
+        rpy[0] = 0; rpy[1] = -0.5 * PI_D; rpy[2] = 2 * atan2(q[0], -q[1]);
+    } else if (sarg >= 0.99999) {
+        rpy[0] = 0; rpy[1] = 0.5 * PI_D; rpy[2] = 2 * atan2(-q[0], q[1]);
+    } else {
+        rpy[0] = atan2(2 * (q[1] * q[2] + q[3] * q[0]), squ - sqx - sqy + sqz);
+        rpy[1] = asin(sarg);
+        rpy[2] = atan2(2 * (q[0] * q[1] + q[3] * q[2]), squ + sqx - sqy - sqz);
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* Physics layer                                                       */
+/* ------------------------------------------------------------------ */
+
+void orc_body_params_default(orc_body_params *p) {
+    /* ref:412-432 mass/inertia; ref:451-458 damping + contact material; ref:338-345 world */
+    double mass = 2.0, length = 1.0, radius = 0.05;
+    memset(p, 0, sizeof(*p));
+    p->mass = mass;
+    p->inertia[0] = p->inertia[1] = (1.0 / 12.0) * mass * (3 * radius * radius + length * length);
+    p->inertia[2] = (1.0 / 2.0) * mass * radius * radius;
+    p->lin_damp = 0.01; p->ang_damp = 0.02;
+    p->use_gyro = 0;
+    p->substeps = 4;
+    p->gravity[0] = 0; p->gravity[1] = 0; p->gravity[2] = -9.81;
+    p->dt_step = 0.02;
+    p->max_vel = 100.0;
+    p->ground = 1;
+    p->contact_iters = 8;
+    p->radius = radius; p->half_len = 0.5 * length; p->cg = 0.0;
+    p->mu = 0.3 * 0.8;                       /* ref:456 x ref:350, Bullet combines by product */
+    p->mu_spin = 0.1 * 0.8 + 0.1 * 0.3;      /* ref:351,457: Bullet combined torsional friction */
+    p->mu_roll = 0.05 * 0.8 + 0.05 * 0.3;    /* ref:352,458 */
+    p->restitution = 0.1 * 0.0 + 0.1;        /* ref:455; plane restitution 0 -> we keep the body's */
+    p->rest_threshold = 0.2;                 /* Bullet restitutionVelocityThreshold default */
+    p->erp = 0.2;                            /* Bullet m_erp2 default */
+    p->margin = 0.02;
+}
+
+void orc_body_init(orc_body *b, const double pos[3], const double quat[4]) {
+    memset(b, 0, sizeof(*b));
+    memcpy(b->pos, pos, sizeof(double) * 3);
+    memcpy(b->quat, quat, sizeof(double) * 4);
+}
+
+/* Row B3: applyExternalForce(..., pos, WORLD_FRAME) on the base: addBaseForce(F);
+ * addBaseTorque((pos - base_origin) x F), evaluated once at call time. */
+void orc_apply_external_force(orc_body *b, const double f[3], const double pos_world[3]) {
+    double rel[3] = {pos_world[0] - b->pos[0], pos_world[1] - b->pos[1], pos_world[2] - b->pos[2]};
+    double t[3];
+    cross3(rel, f, t);
+    for (int i = 0; i < 3; i++) { b->force[i] += f[i]; b->torque[i] += t[i]; }
+}
+void orc_apply_external_torque(orc_body *b, const double t[3]) {
+    for (int i = 0; i < 3; i++) b->torque[i] += t[i];
+}
+
+/*
+ * Ground contact -- OUR documented model (option (a)); Bullet's
+ * GJK manifold + btMultiBodyConstraintSolver cannot be restated without its source
+ * (row B9).  Same model, same constants, same iteration order in the CUDA kernel.
+ *
+ *  - plane z = 0, normal +z;  cylinder caps at local z = +-half_len - cg
+ *  - stateless 5-point manifold per substep: the lowest rim point of the lower cap (c0),
+ *    the two rim points at +-90 deg (c1,c2), the opposite rim point (c3), and the lowest rim
+ *    point of the other cap (c4)
+ *  - a candidate is active while gap < margin; speculative rows: vn >= -gap/dt (gap>=0),
+ *    Baumgarte vn >= -erp*gap/dt (gap<0), restitution when approaching faster than threshold
+ *  - projected Gauss-Seidel on velocities, contact_iters sweeps, no warm start; per contact:
+ *    normal row (lambda>=0), then the two world-axis tangent rows projected on the friction
+ *    disc mu*lambda_n; then spinning/rolling rows on the first active contact
+ */
+static void solve_contacts(const orc_body_params *p, orc_body *b, double dt, const double R[9]) {
+    const double r = p->radius, h = p->half_len;
+    const double R31 = R[6], R32 = R[7], R33 = R[8];
+    double rho = sqrt(R31 * R31 + R32 * R32);
+    double ux, uy;
+    if (rho > 1e-3) { ux = -R31 / rho; uy = -R32 / rho; } else { ux = 1.0; uy = 0.0; }
+    double zn = (R33 >= 0 ? -h : h) - p->cg;
+    double zf = (R33 >= 0 ? h : -h) - p->cg;
+    double gap0 = b->pos[2] + R33 * zn + r * (R31 * ux + R32 * uy);
+    if (!(gap0 < p->margin)) return;
+
+    double c[5][3] = {
+        { r * ux,  r * uy, zn},
+        {-r * uy,  r * ux, zn},
+        { r * uy, -r * ux, zn},
+        {-r * ux, -r * uy, zn},
+        { r * ux,  r * uy, zf},
+    };
+    /* world inverse inertia  R diag(1/I) R^T */
+    double ii[3] = {1.0 / p->inertia[0], 1.0 / p->inertia[1], 1.0 / p->inertia[2]};
+    double W[9];
+    for (int a = 0; a < 3; a++)
+        for (int d = 0; d < 3; d++)
+            W[a * 3 + d] = R[a * 3 + 0] * ii[0] * R[d * 3 + 0] + R[a * 3 + 1] * ii[1] * R[d * 3 + 1] +
+                           R[a * 3 + 2] * ii[2] * R[d * 3 + 2];
+    const double inv_m = 1.0 / p->mass;
+
+    int active[5];
+    double arm[5][3], jn[5][3], j1[5][3], j2[5][3];   /* r x n, r x t1, r x t2 */
+    double kn[5][3], k1[5][3], k2[5][3];              /* W * (r x d) */
+    double mn[5], m1[5], m2[5], target[5];
+    double ln[5] = {0}, l1[5] = {0}, l2[5] = {0};
+    int first = -1;
+    for (int i = 0; i < 5; i++) {
+        matvec(R, c[i], arm[i]);
+        double gap = b->pos[2] + arm[i][2];
+        active[i] = gap < p->margin;
+        if (!active[i]) continue;
+        if (first < 0) first = i;
+        jn[i][0] = arm[i][1];  jn[i][1] = -arm[i][0]; jn[i][2] = 0.0;        /* r x z */
+        j1[i][0] = 0.0;        j1[i][1] = arm[i][2];  j1[i][2] = -arm[i][1]; /* r x x */
+        j2[i][0] = -arm[i][2]; j2[i][1] = 0.0;        j2[i][2] = arm[i][0];  /* r x y */
+        matvec(W, jn[i], kn[i]); matvec(W, j1[i], k1[i]); matvec(W, j2[i], k2[i]);
+        mn[i] = inv_m + dot3(jn[i], kn[i]);
+        m1[i] = inv_m + dot3(j1[i], k1[i]);
+        m2[i] = inv_m + dot3(j2[i], k2[i]);
+        double vn0 = b->vel[2] + dot3(b->omega, jn[i]);
+        double rest = (vn0 < -p->rest_threshold) ? -p->restitution * vn0 : 0.0;
+        target[i] = rest + (gap > 0 ? -gap / dt : -p->erp * gap / dt);
+    }
+    if (first < 0) return;
+    double lsp = 0, lr1 = 0, lr2 = 0;
+    for (int it = 0; it < p->contact_iters; it++) {
+        for (int i = 0; i < 5; i++) {
+            if (!active[i]) continue;
+            /* normal */
+            double vn = b->vel[2] + dot3(b->omega, jn[i]);
+            double nl = ln[i] + (target[i] - vn) / mn[i];
+            if (nl < 0) nl = 0;
+            double d = nl - ln[i];
+            ln[i] = nl;
+            b->vel[2] += d * inv_m;
+            for (int a = 0; a < 3; a++) b->omega[a] += kn[i][a] * d;
+            /* friction disc */
+            double vt1 = b->vel[0] + dot3(b->omega, j1[i]);
+            double vt2 = b->vel[1] + dot3(b->omega, j2[i]);
+            double a1 = l1[i] - vt1 / m1[i];
+            double a2 = l2[i] - vt2 / m2[i];
+            double lim = p->mu * ln[i];
+            double mag = sqrt(a1 * a1 + a2 * a2);
+            if (mag > lim) { double sc = (mag > 0) ? lim / mag : 0.0; a1 *= sc; a2 *= sc; }
+            double d1 = a1 - l1[i], d2 = a2 - l2[i];
+            l1[i] = a1; l2[i] = a2;
+            b->vel[0] += d1 * inv_m;
+            b->vel[1] += d2 * inv_m;
+            for (int a = 0; a < 3; a++) b->omega[a] += k1[i][a] * d1 + k2[i][a] * d2;
+        }
+        /* torsional rows on the first active contact (Bullet adds them for one point per manifold) */
+        {
+            double lim = p->mu_spin * ln[first];
+            double nl = clampd(lsp - b->omega[2] / W[8], -lim, lim);
+            double d = nl - lsp; lsp = nl;
+            b->omega[0] += W[2] * d; b->omega[1] += W[5] * d; b->omega[2] += W[8] * d;
+            lim = p->mu_roll * ln[first];
+            nl = clampd(lr1 - b->omega[0] / W[0], -lim, lim);
+            d = nl - lr1; lr1 = nl;
+            b->omega[0] += W[0] * d; b->omega[1] += W[3] * d; b->omega[2] += W[6] * d;
+            nl = clampd(lr2 - b->omega[1] / W[4], -lim, lim);
+            d = nl - lr2; lr2 = nl;
+            b->omega[0] += W[1] * d; b->omega[1] += W[4] * d; b->omega[2] += W[7] * d;
+        }
+    }
+}
+
+/* Rows B2, B4, B5, B6: one p.stepSimulation() (ref:477). */
+void orc_step_simulation(const orc_body_params *p, orc_body *b, double *trace) {
+    const int K = p->substeps;
+    const double dt = p->dt_step / K;                 /* B2: 0.02/4 = 0.005 exactly */
+    /* B4: applyGravity() once before the substep loop; forces constant over the K substeps */
+    double F[3], T[3];
+    for (int i = 0; i < 3; i++) { F[i] = b->force[i] + p->gravity[i] * p->mass; T[i] = b->torque[i]; }
+
+    for (int k = 0; k < K; k++) {
+        double R[9];
+        orc_matrix_from_quat(b->quat, R);
+        /* B5: ABA for a lone floating base, in base-local coordinates */
+        double wl[3], tl[3], wdl[3], wd[3];
+        matTvec(R, b->omega, wl);
+        matTvec(R, T, tl);
+        double wn2 = dot3(wl, wl);
+        double wn = wn2 > 2.220446049250313e-16 ? sqrt(wn2) : 0.0;  /* btVector3::safeNorm */
+        double kd = p->ang_damp + p->ang_damp * wn;
+        double zacc[3];
+        for (int i = 0; i < 3; i++) zacc[i] = -tl[i] + p->inertia[i] * wl[i] * kd;
+        if (p->use_gyro) {
+            double Iw[3] = {p->inertia[0] * wl[0], p->inertia[1] * wl[1], p->inertia[2] * wl[2]}, g[3];
+            cross3(wl, Iw, g);
+            for (int i = 0; i < 3; i++) zacc[i] += g[i];
+        }
+        for (int i = 0; i < 3; i++) wdl[i] = -(zacc[i] / p->inertia[i]);
+        matvec(R, wdl, wd);
+        double vn2 = dot3(b->vel, b->vel);
+        double vn = vn2 > 2.220446049250313e-16 ? sqrt(vn2) : 0.0;
+        double kl = p->lin_damp + p->lin_damp * vn;
+        for (int i = 0; i < 3; i++) {   /* applyDeltaVeeMultiDof with the +-100 clamp */
+            b->omega[i] = clampd(b->omega[i] + wd[i] * dt, -p->max_vel, p->max_vel);
+        }
+        for (int i = 0; i < 3; i++) {
+            double vd = F[i] / p->mass - b->vel[i] * kl;
+            b->vel[i] = clampd(b->vel[i] + vd * dt, -p->max_vel, p->max_vel);
+        }
+        /* B9 (our model): contacts detected at the pre-integration pose, solved on velocities */
+        if (p->ground) solve_contacts(p, b, dt, R);
+
+        /* B6: stepPositionsMultiDof -- semi-implicit Euler, exponential map */
+        for (int i = 0; i < 3; i++) b->pos[i] += dt * b->vel[i];
+        double ang = sqrt(dot3(b->omega, b->omega));
+        if (ang * dt > 0.25 * PI_D) ang = 0.5 * (0.5 * PI_D) / dt;       /* ANGULAR_MOTION_THRESHOLD */
+        double ax[3], sc;
+        if (ang < 0.001) sc = 0.5 * dt - (dt * dt * dt) * 0.020833333333 * ang * ang;
+        else sc = sin(0.5 * ang * dt) / ang;
+        for (int i = 0; i < 3; i++) ax[i] = b->omega[i] * sc;
+        double cw = cos(ang * dt * 0.5);
+        /* q <- dq (x) q  with dq = (ax, cw) */
+        double *q = b->quat;
+        double nx = cw * q[0] + ax[0] * q[3] + ax[1] * q[2] - ax[2] * q[1];
+        double ny = cw * q[1] + ax[1] * q[3] + ax[2] * q[0] - ax[0] * q[2];
+        double nz = cw * q[2] + ax[2] * q[3] + ax[0] * q[1] - ax[1] * q[0];
+        double nw = cw * q[3] - ax[0] * q[0] - ax[1] * q[1] - ax[2] * q[2];
+        double inv = 1.0 / sqrt(nx * nx + ny * ny + nz * nz + nw * nw);
+        q[0] = nx * inv; q[1] = ny * inv; q[2] = nz * inv; q[3] = nw * inv;
+
+        if (trace) {
+            double *t = trace + 13 * k;
+            memcpy(t, b->pos, 24); memcpy(t + 3, b->quat, 32); memcpy(t + 7, b->vel, 24); memcpy(t + 10, b->omega, 24);
+        }
+    }
+    /* B4: clearForces() after the loop */
+    for (int i = 0; i < 3; i++) { b->force[i] = 0; b->torque[i] = 0; }
+}
+
+/* ------------------------------------------------------------------ */
+/* Philox4x32-10 (Salmon et al., Random123) -- counter-based RNG       */
+/* ------------------------------------------------------------------ */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+enum { ST_DR_A = 1, ST_DR_B = 2, ST_NOISE_A = 3, ST_NOISE_B = 4, ST_ACTION = 5, ST_ACTOR = 6, ST_DR_C = 7 };
+
+static void draw4(uint64_t seed, int64_t gid, uint32_t stream, uint32_t a, uint32_t b, uint32_t out[4]) {
+    uint32_t ctr[4] = {(uint32_t)gid, (uint32_t)(((uint64_t)gid >> 32) & 0xFFFFu) | (stream << 16), a, b};
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    orc_philox4x32_10(ctr, key, out);
+}
+/* 24-bit uniform in (0,1): exact in float32 and float64 */
+static inline double u01(uint32_t x) { return ((double)(x >> 8) + 0.5) * (1.0 / 16777216.0); }
+static inline void box_muller(uint32_t x0, uint32_t x1, double *n0, double *n1) {
+    double r = sqrt(-2.0 * log(u01(x0)));
+    double th = 2.0 * PI_D * u01(x1);
+    *n0 = r * cos(th); *n1 = r * sin(th);
+}
+
+/* ------------------------------------------------------------------ */
+/* Env layer                                                           */
+/* ------------------------------------------------------------------ */
+struct orc_sim {
+    orc_config cfg;
+    int64_t n;
+    orc_env *envs;
+    double stats[ORC_NSTATS];
+    double *trace;  /* K x 13, env 0 */
+    double fuel_tab[1002];
+};
+
+/* Row S4 (ref:530-533): fuel after n decrements, by repeated fp64 subtraction. */
+static void build_fuel_table(double *t) {
+    double f = 1.0;
+    t[0] = f;
+    for (int n = 1; n <= 1001; n++) { f = f - 0.001; if (f < 0) f = 0; t[n] = f; }
+}
+double orc_fuel_table(int n) {
+    static double tab[1002]; static int init = 0;
+    if (!init) { build_fuel_table(tab); init = 1; }
+    if (n < 0) n = 0;
+    if (n > 1001) n = 1001;
+    return tab[n];
+}
+
+/* Contract X thrust curve (our definition; the reference's thrust is the constant ref:463).
+ * Multiplier as a function of burn fraction u = burn/1000: ignition spike to 1.3 at 5 %,
+ * settling to 1.0 at 15 %, flat, linear tail-off to 0.5 over the last 10 %. */
+double orc_thrust_curve(int mode, int burn) {
+    if (mode == 0) return 1.0;
+    double u = burn * 0.001;
+    if (u < 0.05) return 1.0 + 6.0 * u;
+    if (u < 0.15) return 1.3 - 3.0 * (u - 0.05);
+    if (u < 0.9) return 1.0;
+    return 1.0 - 5.0 * (u - 0.9);
+}
+
+void orc_config_default(orc_config *c, int contract) {
+    memset(c, 0, sizeof(*c));
+    c->contract = contract;
+    c->substeps = contract == ORC_CONTRACT_R ? 4 : 10;
+    c->max_episode_steps = 1000;
+    c->autoreset = 0;
+    c->quirks = contract == ORC_CONTRACT_R ? ORC_Q_ALL_REFERENCE : (ORC_Q_DOUBLE_GRAVITY | ORC_Q_LAGGED_PHASE);
+    c->diversity_mode = contract == ORC_CONTRACT_R ? ORC_DIV_EXACT : ORC_DIV_FAST;
+    c->contact_iters = 8;
+    c->ground = 1;
+    c->dt_step = 0.02;
+    c->gradient_penalty = 0.1; c->diversity_bonus = 0.05;      /* ref:83-84 defaults */
+    c->mass = 2.0; c->radius = 0.05; c->length = 1.0; c->thrust = 35.0;   /* ref:412-414, 463 */
+    c->gimbal_max_rad = 18.0 * (PI_D / 180.0);                 /* ref:471 np.radians(18.0) */
+    c->lin_damp = 0.01; c->ang_damp = 0.02;                    /* ref:453-454 */
+    if (contract == ORC_CONTRACT_X) {
+        /* config/config.yaml:340-349 */
+        c->mass_variation = 0.3;
+        c->thrust_std = 0.2; c->thrust_lo = 0.4; c->thrust_hi = 1.6;
+        c->cg_offset_max = 0.1;
+        c->wind_std = 3.0;
+        c->sensor_noise_std = 0.02;
+        c->init_tilt_max = 0.0; c->init_omega_max = 0.0;
+        c->propellant_fraction = 0.0; c->cg_burn_shift = 0.0;
+        c->delay_steps = 0; c->thrust_curve = 0;
+    }
+    c->thrust_lo = c->thrust_lo ? c->thrust_lo : 0.4;
+    c->thrust_hi = c->thrust_hi ? c->thrust_hi : 1.6;
+    c->seed = 42;
+    c->env_id_base = 0;
+}
+
+static void env_params(const orc_config *c, const orc_env *e, orc_body_params *p) {
+    orc_body_params_default(p);
+    double ms = (c->contract == ORC_CONTRACT_X) ? e->mass_scale : 1.0;
+    double burnt = 1.0 - e->fuel;
+    double m = c->mass * ms * (1.0 - c->propellant_fraction * burnt);
+    double cg = (c->contract == ORC_CONTRACT_X) ? e->cg_offset + c->cg_burn_shift * burnt : 0.0;
+    p->mass = m;
+    p->radius = c->radius; p->half_len = 0.5 * c->length;
+    p->inertia[0] = p->inertia[1] = (1.0 / 12.0) * m * (3 * c->radius * c->radius + c->length * c->length) + m * cg * cg;
+    p->inertia[2] = (1.0 / 2.0) * m * c->radius * c->radius;
+    p->cg = cg;
+    p->lin_damp = c->lin_damp; p->ang_damp = c->ang_damp;
+    p->substeps = c->substeps; p->dt_step = c->dt_step;
+    p->ground = c->ground; p->contact_iters = c->contact_iters;
+}
+
+/* ref:587-606 _get_enhanced_observation */
+static void build_obs(const orc_config *c, const orc_env *e, int64_t gid, int phase_for_obs, float obs[10]) {
+    double orn[4];
+    orc_reported_quat(e->body.quat, orn);
+    double o[10] = {orn[0], orn[1], orn[2], orn[3], e->body.omega[0], e->body.omega[1], e->body.omega[2],
+                    e->fuel, (double)phase_for_obs / 7.0,
+                    fmin(1.0, (double)e->step / (double)c->max_episode_steps)};
+    if (c->contract == ORC_CONTRACT_X && c->sensor_noise_std > 0) {
+        uint32_t a[4], b[4]; double n[8];
+        draw4(c->seed, gid, ST_NOISE_A, (uint32_t)e->episode, (uint32_t)e->step, a);
+        draw4(c->seed, gid, ST_NOISE_B, (uint32_t)e->episode, (uint32_t)e->step, b);
+        box_muller(a[0], a[1], &n[0], &n[1]); box_muller(a[2], a[3], &n[2], &n[3]);
+        box_muller(b[0], b[1], &n[4], &n[5]); box_muller(b[2], b[3], &n[6], &n[7]);
+        for (int i = 0; i < 7; i++) o[i] += c->sensor_noise_std * n[i];
+    }
+    for (int i = 0; i < 10; i++) obs[i] = (float)o[i];
+}
+
+/* ref:381-407 reset + ref:409-464 _create_enhanced_rocket (row S13, quirks Q10, Q11, Q15) */
+static void env_reset(const orc_config *c, orc_env *e, int64_t gid, int first_time) {
+    double pos[3] = {0, 0, 1.0}, quat[4] = {0, 0, 0, 1};
+    e->episode += 1;
+    orc_body_init(&e->body, pos, quat);
+    e->fuel = 1.0; e->burn = 0;
+    e->step = 0; e->phase = 0; e->success = 0;
+    e->ep_return = 0;
+    if (first_time || !(c->quirks & ORC_Q_KEEP_CRITERIA)) { e->consec = 0; e->crit_pushes = 0; }
+    if (first_time || !(c->quirks & ORC_Q_KEEP_REWARD_HIST)) {
+        e->has_prev = 0; e->prev_action[0] = e->prev_action[1] = 0;
+        e->hist_count = 0; e->n_clip = 0; e->n_run = 0;
+        memset(e->clip_bits, 0, sizeof(e->clip_bits)); memset(e->run_bits, 0, sizeof(e->run_bits));
+    }
+    e->mass_scale = 1; e->thrust_scale = 1; e->cg_offset = 0; e->wind[0] = e->wind[1] = 0;
+    memset(e->delay_ring, 0, sizeof(e->delay_ring));
+    if (c->contract == ORC_CONTRACT_X) {
+        uint32_t a[4], b[4], d[4]; double n0, n1, n2, n3;
+        draw4(c->seed, gid, ST_DR_A, (uint32_t)e->episode, 0, a);
+        draw4(c->seed, gid, ST_DR_B, (uint32_t)e->episode, 0, b);
+        draw4(c->seed, gid, ST_DR_C, (uint32_t)e->episode, 0, d);
+        box_muller(a[1], a[2], &n0, &n1);
+        box_muller(b[0], b[1], &n2, &n3);
+        e->mass_scale = 1.0 + c->mass_variation * (2.0 * u01(a[0]) - 1.0);
+        e->thrust_scale = clampd(1.0 + c->thrust_std * n0, c->thrust_lo, c->thrust_hi);
+        e->wind[0] = c->wind_std * n1;
+        e->wind[1] = c->wind_std * n2;
+        e->cg_offset = c->cg_offset_max * (2.0 * u01(a[3]) - 1.0);
+        double tx = c->init_tilt_max * (2.0 * u01(b[2]) - 1.0);
+        double ty = c->init_tilt_max * (2.0 * u01(b[3]) - 1.0);
+        double ang = sqrt(tx * tx + ty * ty);
+        double sc = ang < 1e-6 ? 0.5 - ang * ang / 48.0 : sin(0.5 * ang) / ang;
+        e->body.quat[0] = tx * sc; e->body.quat[1] = ty * sc; e->body.quat[2] = 0; e->body.quat[3] = cos(0.5 * ang);
+        for (int i = 0; i < 3; i++) e->body.omega[i] = c->init_omega_max * (2.0 * u01(d[i]) - 1.0);
+    }
+}
+
+/* numpy pairwise sum of exactly 10 doubles (np.add.reduce, n=10: 8-lane block + 2 tail) */
+static double np_sum10(const double *a) {
+    double r = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+    r += a[8]; r += a[9];
+    return r;
+}
+
+static inline float clipf1(float x) { return x < -1.0f ? -1.0f : (x > 1.0f ? 1.0f : x); }
+
+/* number of distinct values among the stored reward history (ref:221 len(set(history))) */
+static int distinct_exact(const orc_env *e) {
+    int len = e->hist_count < ORC_HIST ? (int)e->hist_count : ORC_HIST;
+    int distinct = 0;
+    for (int i = 0; i < len; i++) {
+        int dup = 0;
+        for (int j = 0; j < i; j++) if (e->hist[j] == e->hist[i]) { dup = 1; break; }
+        distinct += !dup;
+    }
+    return distinct;
+}
+
+static inline int bit_get(const uint32_t *w, int pos) { return (w[pos >> 5] >> (pos & 31)) & 1u; }
+static inline void bit_set(uint32_t *w, int pos, int v) {
+    if (v) w[pos >> 5] |= (1u << (pos & 31)); else w[pos >> 5] &= ~(1u << (pos & 31));
+}
+
+/* push into reward_history (ref:123) with the fast duplicate bookkeeping:
+ *   clip bit : value == -1000 (the only clip value that occurs; +200 is unreachable)
+ *   run bit  : value == immediately preceding value (and not a clip value)
+ * distinct = len - n_run - n_clip + (n_clip > 0).  Exact for clip duplicates and runs;
+ * differs from len(set()) only for non-adjacent coincidences. */
+static void hist_push(orc_env *e, double v) {
+    int slot = (int)(e->hist_count % ORC_HIST);
+    if (e->hist_count >= ORC_HIST) {
+        /* the entry in `slot` leaves the window */
+        if (bit_get(e->clip_bits, slot)) e->n_clip--;
+        if (bit_get(e->run_bits, slot)) e->n_run--;
+        /* the new oldest entry can no longer be a run-duplicate of its predecessor */
+        int nxt = (slot + 1) % ORC_HIST;
+        if (bit_get(e->run_bits, nxt)) { bit_set(e->run_bits, nxt, 0); e->n_run--; }
+    }
+    int is_clip = (v == -1000.0);
+    int is_run = 0;
+    if (!is_clip && e->hist_count > 0) {
+        int prev = (int)((e->hist_count - 1) % ORC_HIST);
+        is_run = (e->hist[prev] == v);
+    }
+    /* a window of length 1 about to be overwritten has no predecessor inside the window */
+    bit_set(e->clip_bits, slot, is_clip); bit_set(e->run_bits, slot, is_run);
+    e->n_clip += is_clip; e->n_run += is_run;
+    e->hist[slot] = v;
+    e->hist_count++;
+}
+
+static void env_step(orc_sim *s, orc_env *e, int64_t gid, const float *act, orc_step_out *o, double *trace,
+                     double *stats) {
+    const orc_config *c = &s->cfg;
+    const int X = c->contract == ORC_CONTRACT_X;
+    orc_step_out local;
+    if (!o) o = &local;
+    memset(o, 0, sizeof(*o));
+
+    /* ---- S2 (ref:470-471): clip, scale to gimbal angle ---- */
+    float a[2] = {clipf1(act[0]), clipf1(act[1])};
+    float ap[2] = {a[0], a[1]};
+    if (X && c->delay_steps > 0) {               /* actuator delay ring (Contract X) */
+        int D = c->delay_steps;
+        ap[0] = e->delay_ring[0][0]; ap[1] = e->delay_ring[0][1];
+        for (int i = 0; i + 1 < D; i++) { e->delay_ring[i][0] = e->delay_ring[i + 1][0]; e->delay_ring[i][1] = e->delay_ring[i + 1][1]; }
+        e->delay_ring[D - 1][0] = a[0]; e->delay_ring[D - 1][1] = a[1];
+    }
+    double pitch = (double)ap[0] * c->gimbal_max_rad;
+    double yaw = (double)ap[1] * c->gimbal_max_rad;
+
+    /* ---- S3 (ref:520-559) _apply_enhanced_control ---- */
+    orc_body_params P;
+    env_params(c, e, &P);            /* mass/inertia/cg from the pre-step fuel */
+    orc_body *b = &e->body;
+    double orn[4], R[9];
+    orc_reported_quat(b->quat, orn);
+    if (c->quirks & ORC_Q_DOUBLE_GRAVITY) {       /* Q1 (ref:525-527) */
+        double g[3] = {0, 0, -9.81 * P.mass};
+        orc_apply_external_force(b, g, b->pos);
+    }
+    if (e->fuel > 0) {                            /* Q4 (ref:530-533) */
+        int burn_before = e->burn;
+        e->burn += 1;
+        e->fuel = s->fuel_tab[e->burn > 1001 ? 1001 : e->burn];
+        double T = c->thrust;
+        if (X) T = T * e->thrust_scale * orc_thrust_curve(c->thrust_curve, burn_before);
+        double fl[3] = {T * sin(yaw), T * sin(pitch), T * cos(pitch) * cos(yaw)};   /* Q2 (ref:539-543) */
+        orc_matrix_from_quat(orn, R);
+        double fw[3], off[3] = {0, 0, -(P.half_len + P.cg)}, rel[3], tp[3];
+        matvec(R, fl, fw);
+        matvec(R, off, rel);
+        for (int i = 0; i < 3; i++) tp[i] = b->pos[i] + rel[i];                     /* ref:550 */
+        orc_apply_external_force(b, fw, tp);
+    }
+    /* ---- S5 (ref:561-585) _apply_aerodynamics ---- */
+    {
+        double rho = 1.225 * exp(-b->pos[2] / 8400);
+        double vmag = sqrt(b->vel[0] * b->vel[0] + b->vel[1] * b->vel[1] + b->vel[2] * b->vel[2]);
+        if (vmag > 0.1) {                          /* Q5 */
+            double area = PI_D * (0.05 * 0.05);
+            double dm = 0.5 * rho * (vmag * vmag) * 0.47 * area;
+            double df[3];
+            for (int i = 0; i < 3; i++) df[i] = dm * (-b->vel[i] / vmag);
+            orc_apply_external_force(b, df, b->pos);
+        }
+        double ad = 0.02 * rho;
+        double dt3[3] = {-ad * b->omega[0], -ad * b->omega[1], -ad * b->omega[2]};
+        orc_apply_external_torque(b, dt3);
+    }
+    if (X) {                                       /* wind: constant world-frame force per episode */
+        double w[3] = {e->wind[0], e->wind[1], 0};
+        orc_apply_external_force(b, w, b->pos);
+    }
+
+    /* ---- S6 (ref:477) ---- */
+    orc_step_simulation(&P, b, trace);
+    e->step += 1;                                  /* ref:478 */
+
+    /* ---- S7 (ref:608-633) _get_state_dict ---- */
+    double rpy[3];
+    orc_reported_quat(b->quat, orn);
+    orc_euler_from_quat(orn, rpy);
+    double tilt = sqrt(rpy[1] * rpy[1] + rpy[2] * rpy[2]);                 /* Q7 */
+    double wmag = sqrt(b->omega[0] * b->omega[0] + b->omega[1] * b->omega[1] + b->omega[2] * b->omega[2]);
+    double vh = sqrt(b->vel[0] * b->vel[0] + b->vel[1] * b->vel[1]);
+    double vv = fabs(b->vel[2]);
+    double alt = b->pos[2];
+    int crashed = alt < 0.1;                                               /* Q17 */
+    int phase_pre = e->phase, success_pre = e->success;                    /* Q8, Q9 */
+
+    /* ---- S9 (ref:635-657) _update_mission_phase ---- */
+    if (e->phase == 0 && e->fuel < 0.8) e->phase = 1;
+    else if (e->phase == 1 && alt < 5.0) e->phase = 2;
+    else if (e->phase == 2 && alt < 1.0) e->phase = 3;
+    else if (e->phase == 3 && alt < 0.5) {
+        if (tilt < 0.087 && wmag < 0.1) { e->phase = 5; e->success = 1; }
+    }
+    /* ---- S10 (ref:659-695) _check_mission_success ---- */
+    if (!e->success) {
+        int all_met = (tilt < 0.087) && (vv < 2.0 && vh < 0.5) && (0.2 <= alt && alt <= 2.0) && (wmag < 0.1);
+        e->consec = all_met ? (e->consec < 1000000 ? e->consec + 1 : e->consec) : 0;
+        e->crit_pushes += e->crit_pushes < 1000000;
+        if (e->consec >= 100) e->success = 1;      /* deque(maxlen=100) full and all true */
+    }
+    int phase_r = (c->quirks & ORC_Q_LAGGED_PHASE) ? phase_pre : e->phase;
+    int success_r = (c->quirks & ORC_Q_LAGGED_PHASE) ? success_pre : e->success;
+
+    /* ---- S8 (ref:587-606): obs uses the lagged phase (Q8) ---- */
+    build_obs(c, e, gid, phase_r, o->obs);
+
+    /* ---- R1-R10 (ref:86-224) MultiObjectiveReward.compute_reward ---- */
+    double comp[ORC_NCOMP] = {0};
+    comp[0] = (success_r ? 1.0 : (phase_r == 2 ? 0.1 : 0.0)) * 100.0;                        /* R1 */
+    {
+        double tp = exp(-10 * fmax(0.0, tilt - 0.087));
+        double apn = exp(-5 * fmax(0.0, wmag - 0.1));
+        double alp = (0.2 <= alt && alt <= 20.0) ? 1.0 : 0.5;
+        comp[1] = ((tp + apn + alp) / 3.0) * 50.0;                                           /* R2 */
+    }
+    float ce = sqrtf(a[0] * a[0] + a[1] * a[1]);            /* np.linalg.norm(float32[2]) -> float32 */
+    if (e->fuel > 0.1 && ce < 0.5f) {
+        float fe = (float)e->fuel * (1.0f - ce);             /* NumPy 2 weak-scalar promotion: float32 */
+        comp[2] = (double)(fe * 20.0f);                                                      /* R3 */
+    } else comp[2] = 0.0 * 20.0;
+    comp[3] = ((tilt < 0.05 && wmag < 0.1) ? 1.0 : ((tilt < 0.1 && wmag < 0.2) ? 0.5 : 0.0)) * 10.0;   /* R4 */
+    if (e->has_prev) {                                                                        /* R5, Q11 */
+        float d0 = a[0] - e->prev_action[0], d1 = a[1] - e->prev_action[1];
+        float ad = sqrtf(d0 * d0 + d1 * d1);
+        float sm = expf(-5.0f * ad);
+        comp[4] = (double)(sm * 5.0f);
+    } else comp[4] = 1.0 * 5.0;
+    e->prev_action[0] = a[0]; e->prev_action[1] = a[1]; e->has_prev = 1;
+    comp[5] = exp(-2 * fabs(alt - 3.0)) * 5.0;                                                /* R6 */
+    int has_crash = crashed, has_tilt = tilt > 0.52, has_sat = ce > 0.9f;                     /* R7 */
+    if (has_crash) comp[6] = -1000.0;
+    if (has_tilt) comp[7] = -500.0 * (tilt - 0.52);
+    if (has_sat) comp[8] = (double)(-50.0f * (ce - 0.9f));
+    /* R8, R9 (ref:209-224) */
+    double adj = 0.0;
+    int64_t hc = e->hist_count;
+    int len = hc < ORC_HIST ? (int)hc : ORC_HIST;
+    if (len > 10) {
+        double r10[10], d10[10];
+        for (int i = 0; i < 10; i++) r10[i] = e->hist[(hc - 10 + i) % ORC_HIST];
+        double mean = np_sum10(r10) / 10.0;
+        for (int i = 0; i < 10; i++) { double d = r10[i] - mean; d10[i] = d * d; }
+        double var = np_sum10(d10) / 10.0;
+        if (var > 10000) adj -= c->gradient_penalty * var;
+    }
+    int div_flag = 0;
+    if (c->diversity_mode == ORC_DIV_EXACT) div_flag = (double)distinct_exact(e) > len * 0.8;
+    else if (c->diversity_mode == ORC_DIV_FAST) {
+        int distinct = len - e->n_run - e->n_clip + (e->n_clip > 0);
+        div_flag = (double)distinct > len * 0.8;
+    }
+    if (div_flag) adj += c->diversity_bonus;
+    /* R10: Python sum() over the dict in insertion order, then + adjustment, clip, append */
+    double total = 0;
+    total = total + comp[0]; total = total + comp[1]; total = total + comp[2];
+    total = total + comp[3]; total = total + comp[4]; total = total + comp[5];
+    if (has_crash) total = total + comp[6];
+    if (has_tilt) total = total + comp[7];
+    if (has_sat) total = total + comp[8];
+    total = total + adj;
+    comp[9] = adj; comp[10] = total; comp[11] = div_flag;
+    double reward = clampd(total, -1000.0, 200.0);
+    hist_push(e, reward);
+    memcpy(o->comp, comp, sizeof(comp));
+    o->reward = reward;
+    e->ep_return += reward;
+
+    /* ---- S11 (ref:697-721) _check_termination ---- */
+    int terminated = 0, truncated = 0, reason = 0;
+    if (e->success) { terminated = 1; reason = 1; }                       /* Q16 */
+    else {
+        if (crashed) { terminated = 1; reason = 2; }
+        else if (tilt > 0.52) { terminated = 1; reason = 3; }
+        else if (alt > 20.0) { terminated = 1; reason = 4; }
+        else if (sqrt(b->pos[0] * b->pos[0] + b->pos[1] * b->pos[1]) > 50.0) { terminated = 1; reason = 5; }
+        if (e->step >= c->max_episode_steps) truncated = 1;
+    }
+    o->terminated = terminated; o->truncated = truncated; o->term_reason = reason;
+
+    /* ---- S12 (ref:723-742) info ---- */
+    o->altitude = alt; o->tilt = tilt; o->omega_mag = wmag; o->fuel = e->fuel; o->vh = vh; o->vv = vv;
+    memcpy(o->position, b->pos, 24);
+    o->phase = e->phase; o->success = e->success; o->step = e->step;
+    o->criteria_met = (e->crit_pushes >= 10) && (e->consec >= 10);        /* Q18 */
+
+    /* ---- episode statistics ---- */
+    stats[14] += 1;
+    {
+        double tilt_deg = tilt * (180.0 / PI_D);
+        int viol = (tilt_deg > 0.52 * (180.0 / PI_D)) || (wmag > 5.0) || (alt < 0.1) || (alt > 20.0);
+        stats[10] += viol;
+    }
+    if (terminated || truncated) {
+        stats[0] += 1; stats[1] += e->ep_return; stats[2] += e->ep_return * e->ep_return; stats[3] += e->step;
+        stats[4] += e->success;
+        stats[5] += reason == 2; stats[6] += reason == 3; stats[7] += reason == 4; stats[8] += reason == 5;
+        stats[9] += truncated;
+        stats[11] += alt; stats[12] += tilt; stats[13] += e->fuel;
+        if (c->autoreset) {
+            memcpy(o->final_obs, o->obs, sizeof(o->obs));
+            env_reset(c, e, gid, 0);
+            build_obs(c, e, gid, 0, o->obs);
+        }
+    }
+}
+
+orc_sim *orc_create(const orc_config *c, int64_t n) {
+    orc_sim *s = (orc_sim *)calloc(1, sizeof(orc_sim));
+    s->cfg = *c; s->n = n;
+    s->envs = (orc_env *)calloc((size_t)n, sizeof(orc_env));
+    s->trace = (double *)calloc((size_t)(c->substeps > 0 ? c->substeps : 1) * 13, sizeof(double));
+    build_fuel_table(s->fuel_tab);
+    for (int64_t i = 0; i < n; i++) { s->envs[i].episode = -1; env_reset(&s->cfg, &s->envs[i], c->env_id_base + i, 1); }
+    return s;
+}
+void orc_destroy(orc_sim *s) { if (!s) return; free(s->envs); free(s->trace); free(s); }
+int64_t orc_num_envs(const orc_sim *s) { return s->n; }
+orc_env *orc_env_ptr(orc_sim *s, int64_t i) { return &s->envs[i]; }
+orc_config *orc_config_ptr(orc_sim *s) { return &s->cfg; }
+const double *orc_last_trace(const orc_sim *s) { return s->trace; }
+
+void orc_reset(orc_sim *s, const uint8_t *mask, float *obs_out) {
+    for (int64_t i = 0; i < s->n; i++) {
+        if (mask && !mask[i]) continue;
+        int64_t gid = s->cfg.env_id_base + i;
+        env_reset(&s->cfg, &s->envs[i], gid, 0);
+        if (obs_out) build_obs(&s->cfg, &s->envs[i], gid, 0, obs_out + 10 * i);
+    }
+}
+
+void orc_step(orc_sim *s, const float *actions, orc_step_out *outs, int threads) {
+    const int64_t n = s->n;
+    if (threads <= 1 || n < 2) {
+        for (int64_t i = 0; i < n; i++)
+            env_step(s, &s->envs[i], s->cfg.env_id_base + i, actions + 2 * i, outs ? outs + i : NULL,
+                     i == 0 ? s->trace : NULL, s->stats);
+        return;
+    }
+#ifdef _OPENMP
+    double acc[ORC_NSTATS] = {0};
+#pragma omp parallel num_threads(threads)
+    {
+        double loc[ORC_NSTATS] = {0};
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < n; i++)
+            env_step(s, &s->envs[i], s->cfg.env_id_base + i, actions + 2 * i, outs ? outs + i : NULL,
+                     i == 0 ? s->trace : NULL, loc);
+#pragma omp critical
+        for (int k = 0; k < ORC_NSTATS; k++) acc[k] += loc[k];
+    }
+    for (int k = 0; k < ORC_NSTATS; k++) s->stats[k] += acc[k];
+#else
+    for (int64_t i = 0; i < n; i++)
+        env_step(s, &s->envs[i], s->cfg.env_id_base + i, actions + 2 * i, outs ? outs + i : NULL,
+                 i == 0 ? s->trace : NULL, s->stats);
+#endif
+}
+
+void orc_step_arrays(orc_sim *s, const float *actions, float *obs, double *reward, uint8_t *terminated,
+                     uint8_t *truncated, float *final_obs, int threads) {
+    const int64_t n = s->n;
+    orc_step_out *outs = (orc_step_out *)malloc(sizeof(orc_step_out) * (size_t)n);
+    orc_step(s, actions, outs, threads);
+    for (int64_t i = 0; i < n; i++) {
+        if (obs) memcpy(obs + 10 * i, outs[i].obs, 40);
+        if (reward) reward[i] = outs[i].reward;
+        if (terminated) terminated[i] = (uint8_t)outs[i].terminated;
+        if (truncated) truncated[i] = (uint8_t)outs[i].truncated;
+        if (final_obs && (outs[i].terminated || outs[i].truncated)) memcpy(final_obs + 10 * i, outs[i].final_obs, 40);
+    }
+    free(outs);
+}
+
+void orc_random_actions(const orc_sim *s, int64_t t, float *out) {
+    for (int64_t i = 0; i < s->n; i++) {
+        uint32_t r[4];
+        draw4(s->cfg.seed, s->cfg.env_id_base + i, ST_ACTION, (uint32_t)t, (uint32_t)((uint64_t)t >> 32), r);
+        out[2 * i + 0] = (float)(2.0 * u01(r[0]) - 1.0);
+        out[2 * i + 1] = (float)(2.0 * u01(r[1]) - 1.0);
+    }
+}
+
+void orc_stats(orc_sim *s, double out[ORC_NSTATS], int reset_after) {
+    memcpy(out, s->stats, sizeof(s->stats));
+    if (reset_after) memset(s->stats, 0, sizeof(s->stats));
+}
