@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the batched TVC step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[2]'s per-GPU slab -- 262,144 envs per GPU (weak
+scaling), Contract X with full domain randomisation, sensor noise, K=10 substeps per step, same-step
+autoreset, pre-generated U(-1,1) actions resident in HBM -- because the metric is quoted "at 1/2/4/8
+B200".  configs[1] (4,096 envs on one GPU, latency-bound) is reported beside it under "small_batch".
+One "step" = one launch of the step kernel over the rank's env slab.
+
+Timing: W warm-up steps, then K steps each bracketed by CUDA events on the launching stream; L2 is
+flushed between timed steps by zeroing a 256 MiB buffer (not timed); ms_per_step is the MAX over
+ranks of the mean per-step device time.  `value` = envs over all ranks / that time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 262144
+ALGO_BYTES_PER_ENV_STEP_X = 366   # Contract X state r/w + DR params + delay ring + I/O
+ALGO_BYTES_PER_ENV_STEP_R = 294
+HBM_FALLBACK_GBS = 6650.0
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:  # noqa: BLE001
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def _traffic():
+    """dram bytes per launch of the step kernel from the committed ncu --set full capture, or None."""
+    p = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])), mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _workload_cfg(A, env_id_base=0, contract=None):
+    contract = A.CONTRACT_X if contract is None else contract
+    return A.default_config(contract, autoreset=1, env_id_base=env_id_base)
+
+
+def _oracle_cfg(O):
+    return O.default_config(O.CONTRACT_X, autoreset=1)
+
+
+def cpu_baseline(budget_s: float = 12.0):
+    """The fp64 oracle port on the host cores (OpenMP over envs), same workload, bounded sample."""
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    n = 4096
+    sim = O.OracleSim(_oracle_cfg(O), n)
+    sim.reset()
+    acts = sim.random_actions(0)
+    for w in range(2):
+        sim.step_arrays(acts, threads=cores)
+    t0 = time.perf_counter()
+    sim.step_arrays(acts, threads=cores)
+    one = max(time.perf_counter() - t0, 1e-6)
+    steps = int(max(5, min(400, budget_s / one)))
+    t0 = time.perf_counter()
+    for t in range(steps):
+        sim.step_arrays(sim.random_actions(t + 3), threads=cores)
+    dt = time.perf_counter() - t0
+    sim.close()
+    return {"value": n * steps / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{n} envs x {steps} steps, Contract X K=10, fp64 C oracle (oracle/tvc_oracle.c), OpenMP {cores} threads; "
+                      "PyBullet reference not installable (SURVEY.md F2)"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The reference itself
+    (Python + PyBullet) cannot run in this image, so this is the oracle port with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    n = 16384   # bounded sample of the 262144-env slab per "step"
+    sim = O.OracleSim(_oracle_cfg(O), n)
+    sim.reset()
+    for w in range(args.warmup):
+        sim.step_arrays(sim.random_actions(w), threads=cores)
+    t0 = time.perf_counter()
+    for t in range(args.steps):
+        sim.step_arrays(sim.random_actions(args.warmup + t), threads=cores)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    line = {"impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"bounded sample: {n} of the {ENVS_PER_GPU}-env slab per step, Contract X full DR, K=10, "
+                                   "autoreset, Philox actions", "substeps": 10},
+            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                             "sample": f"{n} envs x {args.steps} steps; fp64 C oracle, OpenMP {cores} threads "
+                                       "(PyBullet reference not installable here)"},
+            "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from tvc_ai_b200 import _abi as A
+    from tvc_ai_b200 import dist as D
+    from tvc_ai_b200.engine import BatchedEngine
+    from tvc_ai_b200.vector_env import RocketTVCVectorEnv
+
+    rank, world, local = D.init_from_env("nccl")
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    n = args.envs_per_gpu
+    eng = BatchedEngine(n, _workload_cfg(A, env_id_base=rank * n), device=local)
+    eng.reset()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    pool = [torch.rand((n, 2), generator=gen, device=dev) * 2 - 1 for _ in range(16)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    side = torch.cuda.Stream(device=dev)
+    K, W = args.steps, max(args.warmup, 3)
+    launches = 0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for w in range(W):
+        eng.step(pool[w % 16], want_final=False)
+    if world > 1:   # warm the NCCL communicator outside the timed region
+        D.allreduce_stats(eng.stats_device(False))
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    wall0 = time.perf_counter()
+    for k in range(K):
+        flush.zero_()
+        starts[k].record()
+        eng.step(pool[k % 16], want_final=False)
+        launches += 1
+        ends[k].record()
+        if (k + 1) % 64 == 0:   # episode-statistics reduction (+ NCCL all-reduce over NVLink when N>1), side stream
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                D.allreduce_stats(eng.stats_device(False))
+            launches += 1
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    per = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    ms = sum(per) / K
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    total_envs = n * world
+    value = total_envs / (ms_max * 1e-3)
+
+    # warm-L2 number (no flush, back to back) -- reported beside the headline, not instead of it
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(K):
+        eng.step(pool[k % 16], want_final=False)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    warm_ms = e0.elapsed_time(e1) / K
+
+    stats = D.stats_dict(D.allreduce_stats(eng.stats_device(False)))
+    torch.cuda.synchronize(dev)
+    eng.close()
+
+    extra = {}
+    if rank == 0:
+        # configs[1]: 4,096 envs on one GPU (latency-bound), same Contract X settings
+        small = BatchedEngine(4096, _workload_cfg(A), device=local)
+        small.reset()
+        acts = [torch.rand((4096, 2), device=dev) * 2 - 1 for _ in range(4)]
+        for w in range(20):
+            small.step(acts[w % 4], want_final=False)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for k in range(200):
+            small.step(acts[k % 4], want_final=False)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        us = 1e3 * e0.elapsed_time(e1) / 200
+        extra["small_batch"] = {"workload": "configs[1]: 4096 envs, 1 GPU, full DR, K=10, L2-resident by size",
+                                "us_per_step": us, "env_steps_per_sec": 4096 / (us * 1e-6)}
+        small.close()
+
+        # end-to-end through the public VectorEnv API with HOST (numpy) actions and results
+        venv = RocketTVCVectorEnv(n, config={}, contract="X", device=local, final_info=False)
+        venv.reset(seed=42)
+        import numpy as np
+        host_actions = [np.random.default_rng(i).uniform(-1, 1, (n, 2)).astype(np.float32) for i in range(4)]
+        for w in range(3):
+            venv.step(host_actions[w % 4])
+        ke = max(5, min(K, 30))
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for k in range(ke):
+            venv.step(host_actions[k % 4])
+        torch.cuda.synchronize(dev)
+        e2e_dt = (time.perf_counter() - t0) / ke
+        venv.close()
+        extra["e2e"] = {"value": n / e2e_dt, "unit": "env-steps/s", "h2d_bytes_per_step": n * 8,
+                        "d2h_bytes_per_step": n * (40 + 4 + 1 + 1 + 40), "ms_per_step": 1e3 * e2e_dt,
+                        "n_gpus_measured": 1,
+                        "api": "RocketTVCVectorEnv.step(numpy) -> tvc_step_host (pinned host buffers, sync inside)"}
+        launches += ke
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        per_launch_bytes = ALGO_BYTES_PER_ENV_STEP_X * n
+        achieved = per_launch_bytes / (ms * 1e-3) / 1e9      # this rank's kernel, GB/s
+        line = {
+            "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"configs[2] per-GPU slab: {n} envs/GPU x {world} GPU, Contract X (mass/thrust/cg/wind DR, "
+                                   "sensor noise), K=10 substeps/step, same-step autoreset, U(-1,1) actions resident in HBM, "
+                                   "episode-stat reduction every 64 steps (NCCL all-reduce when N>1)",
+                       "envs_per_gpu": n, "substeps": 10, "contact_iters": 8, "parallelism": f"env-slab x{world}",
+                       "l2": "flushed between timed steps (256 MiB zero-fill, not timed)"},
+            "env_substeps_per_sec": value * 10,
+            "warm_l2": {"ms_per_step": warm_ms, "env_steps_per_sec_per_gpu": n / (warm_ms * 1e-3),
+                        "note": "back-to-back launches, state L2-resident (62 MB < 126 MB)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": _traffic(), "peak_source": peak_src,
+                         "kernel": "step_kernel<X=true,DIV=fast>", "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP_X,
+                         "note": "compute-bound kernel (contact PGS + transcendental mix); see DESIGN.md and profiles/"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "region_wall_ms": 1e3 * wall,
+            "episode_stats": {k: stats[k] for k in ("episodes", "successes", "steps", "term_crash", "term_tilt")},
+        }
+        line.update(extra)
+        if "e2e" not in line:
+            line["e2e"] = None
+        if world == 1 or True:
+            line["cpu_baseline"] = cpu_baseline() if world == 1 else None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

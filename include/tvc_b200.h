@@ -1,0 +1,221 @@
+/*
+ * tvc_b200.h -- C ABI of libtvc_b200.so: the batched, B200-native (sm_100a) replacement for the
+ * EnhancedRocketTVCEnv step/reset hot path of NIKHILSAI71/TVC-AI.
+ *
+ * The reference is pure Python; its "FFI" for this path is the set of PyBullet calls made from
+ * env/enhanced_rocket_tvc_env.py.  Each entry point below names the reference interface it
+ * replaces (file:line relative to the reference root).  The reference-side binding is a ctypes
+ * stub, shown in INTEGRATION.md and implemented in tvc_ai_b200/_abi.py.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative TVC_E_* code; tvc_last_error() gives the
+ *    message (thread-local).  No exceptions, no exit(), no allocation on the step path.
+ *  - *_dev pointers are raw CUDA device pointers owned by the caller (e.g. tensor.data_ptr());
+ *    the library owns only the persistent per-env state inside the handle.
+ *  - launches are enqueued on the caller's stream and do not synchronise, except where noted.
+ *  - a handle is bound to one device; one process per GPU.  Not thread-safe.
+ *  - there is NO CPU fallback: tvc_create fails with TVC_E_DEVICE on a non-sm_100 device.
+ */
+#ifndef TVC_B200_H
+#define TVC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TVC_ABI_VERSION 3
+
+#define TVC_OBS_DIM 10
+#define TVC_ACT_DIM 2
+#define TVC_NUM_COMPONENTS 12 /* mission, safety, fuel, stability, smoothness, altitude, crash, tilt,
+                                 saturation, adjustment, total_unclipped, diversity_flag */
+#define TVC_NUM_STATS 16      /* episodes, sum_return, sum_return_sq, sum_length, successes, term_crash,
+                                 term_tilt, term_altitude, term_range, truncations, safety_violations,
+                                 sum_final_altitude, sum_final_tilt, sum_fuel_left, steps, reserved */
+#define TVC_MAX_DELAY 4
+
+enum {
+    TVC_OK = 0,
+    TVC_E_BADARG = -1,
+    TVC_E_CUDA = -2,
+    TVC_E_DEVICE = -3, /* not an sm_100 device */
+    TVC_E_ABI = -4,
+    TVC_E_NOMEM = -5,
+    TVC_E_STATE = -6
+};
+
+enum { TVC_CONTRACT_R = 0 /* reference-faithful */, TVC_CONTRACT_X = 1 /* extension */ };
+enum { TVC_DIV_OFF = 0, TVC_DIV_FAST = 1, TVC_DIV_EXACT = 2 };
+
+/* quirk switches, SURVEY.md section 8(a) quirk index */
+#define TVC_Q_DOUBLE_GRAVITY   (1u << 0) /* Q1  enhanced_rocket_tvc_env.py:338 + :525-527 */
+#define TVC_Q_KEEP_CRITERIA    (1u << 1) /* Q10 :300, :399-401 */
+#define TVC_Q_KEEP_REWARD_HIST (1u << 2) /* Q11 :301, :82, :172-178 */
+#define TVC_Q_LAGGED_PHASE     (1u << 3) /* Q8/Q9 :481-482 vs :485-493 */
+#define TVC_Q_ALL_REFERENCE    0xFu
+
+typedef struct tvc_handle tvc_handle;
+typedef void *tvc_stream; /* cudaStream_t */
+
+/* Everything the reference hard-codes (enhanced_rocket_tvc_env.py:409-464) or, for Contract X,
+ * leaves in YAML nobody reads (config/config.yaml:335-349). */
+typedef struct tvc_config {
+    int32_t abi_version; /* must be TVC_ABI_VERSION */
+    int32_t contract;
+    int32_t substeps;          /* R: 4 (:341) */
+    int32_t max_episode_steps; /* :282 */
+    int32_t autoreset;         /* 0: gym.Env semantics; 1: same-step autoreset (VectorEnv) */
+    uint32_t quirks;
+    int32_t diversity_mode;
+    int32_t contact_iters;
+    int32_t ground;
+    int32_t delay_steps;  /* X: actuator delay, control steps */
+    int32_t thrust_curve; /* X: 0 constant, 1 model-rocket curve */
+    int32_t reserved0;
+    double dt_step;       /* :340 */
+    float gradient_penalty, diversity_bonus; /* :83-84 */
+    float mass, radius, length, thrust;      /* :412-414, :463 */
+    float gimbal_max_rad;                    /* :471 */
+    float lin_damp, ang_damp;                /* :453-454 */
+    /* Contract X domain randomisation (config/config.yaml:344-349) */
+    float mass_variation;
+    float thrust_std, thrust_lo, thrust_hi;
+    float cg_offset_max;
+    float wind_std;
+    float sensor_noise_std;
+    float init_tilt_max, init_omega_max;
+    float propellant_fraction, cg_burn_shift;
+    float reserved1;
+    uint64_t seed;
+    int64_t env_id_base; /* global id of env 0 of this handle: Philox counters use global ids, so
+                            results do not depend on how envs are sharded over GPUs */
+} tvc_config;
+
+/* scripts/curriculum_manager.py:76-94 `conditions` dict */
+typedef struct tvc_stage_conditions {
+    float max_initial_tilt;
+    float max_initial_angular_vel;
+    int32_t domain_randomization;
+    int32_t sensor_noise;
+    float max_gimbal_angle_deg; /* <= 0: keep the env's 18 deg */
+    int32_t wind_enabled;
+    float wind_force;
+    float mass_variation;
+} tvc_stage_conditions;
+
+/* Optional per-env info written by tvc_step_ex / tvc_read_info (enhanced_rocket_tvc_env.py:723-742).
+ * Any member may be NULL. */
+typedef struct tvc_info_soa {
+    float *altitude;
+    float *tilt_deg;
+    float *omega_mag;
+    float *fuel;
+    float *position; /* [N,3] */
+    int32_t *phase;  /* MissionPhase index, :21-29 */
+    int32_t *step;
+    uint8_t *success;
+    uint8_t *criteria_met;
+    float *reward_components; /* [N, TVC_NUM_COMPONENTS] (step_ex only) */
+} tvc_info_soa;
+
+typedef struct tvc_step_io {
+    const float *actions;   /* [N,2]; NULL => Philox actions U(-1,1), stream 5, counter = lifetime step */
+    float *obs;             /* [N,10] post-autoreset observation */
+    float *reward;          /* [N] */
+    uint8_t *terminated;    /* [N] */
+    uint8_t *truncated;     /* [N] */
+    float *final_obs;       /* [N,10] nullable; written only where terminated|truncated */
+    float *actions_out;     /* [N,2] nullable; the actions actually applied (Philox mode) */
+    tvc_info_soa info;      /* terminal (pre-autoreset) info */
+} tvc_step_io;
+
+/* Portable per-env state blob for tvc_get_state / tvc_set_state (parity tests, checkpoints). */
+typedef struct tvc_env_state {
+    float pos[3];
+    float quat[4];
+    float vel[3];
+    float omega[3];
+    float prev_action[2];
+    float ep_return;
+    int32_t step, burn, phase, success, has_prev, consec;
+    int32_t hist_count, episode;
+    int32_t n_clip, n_run;
+    float ring10[10]; /* slot = push_index % 10 */
+    float mass_scale, thrust_scale, cg_offset, wind[2];
+    float delay_ring[TVC_MAX_DELAY][2];
+} tvc_env_state;
+
+/* SAC actor for the fused rollout (config 4): Linear(10,256)-ReLU-Linear(256,256)-ReLU-Linear(256,4).
+ * Row-major [out,in] float32 device arrays (torch nn.Linear layout); converted to bf16 inside. */
+typedef struct tvc_actor_weights {
+    const float *w1, *b1; /* [256,10], [256] */
+    const float *w2, *b2; /* [256,256], [256] */
+    const float *w3, *b3; /* [4,256], [4] : mean(2), log_std(2) */
+} tvc_actor_weights;
+
+typedef struct tvc_rollout_io {
+    float *obs;          /* [N,10] nullable: observation after the last step */
+    float *reward_sum;   /* [N] nullable: sum of rewards over the T steps */
+    float *actions_last; /* [N,2] nullable */
+    float *actions_all;  /* [T,N,2] nullable (parity tests) */
+    float *reward_all;   /* [T,N] nullable */
+    int32_t deterministic; /* 1: a = tanh(mean) */
+} tvc_rollout_io;
+
+int tvc_abi_version(void);
+const char *tvc_last_error(void);
+
+/* defaults == what enhanced_rocket_tvc_env.py hard-codes (R) / config.yaml:335-349 (X) */
+int tvc_config_default(tvc_config *cfg, int contract);
+
+/* replaces EnhancedRocketTVCEnv.__init__ + _setup_physics (:279-352) for N envs */
+int tvc_create(const tvc_config *cfg, int device, int64_t num_envs, tvc_handle **out);
+/* replaces close() (:749-753) */
+int tvc_destroy(tvc_handle *h);
+
+/* replaces reset() (:381-407).  mask_dev NULL = all envs.  seed != 0 re-keys the Philox streams
+ * (Contract X); in Contract R it has no effect on dynamics (quirk Q15). */
+int tvc_reset(tvc_handle *h, const uint8_t *mask_dev, uint64_t seed, float *obs_out_dev, tvc_stream stream);
+
+/* replaces step() (:466-518) for N envs: clip -> control -> K substeps -> obs/phase/success/
+ * reward/termination (+ same-step autoreset when cfg.autoreset). */
+int tvc_step(tvc_handle *h, const float *actions_dev, float *obs_dev, float *reward_dev,
+             uint8_t *terminated_dev, uint8_t *truncated_dev, float *final_obs_dev, tvc_stream stream);
+int tvc_step_ex(tvc_handle *h, const tvc_step_io *io, tvc_stream stream);
+
+/* Same step through HOST buffers: H2D of actions, launch, D2H of results, stream sync.
+ * This is the end-to-end call the Python VectorEnv facade makes for numpy inputs. */
+int tvc_step_host(tvc_handle *h, const float *actions_host, float *obs_host, float *reward_host,
+                  uint8_t *terminated_host, uint8_t *truncated_host, float *final_obs_host);
+
+/* Fused rollout: T env steps per launch with the SAC actor MLP evaluated inside the loop
+ * (replaces train.py:546-603's get_action -> step loop for the legacy 2x256 actor). */
+int tvc_rollout(tvc_handle *h, const tvc_actor_weights *w, int32_t T, const tvc_rollout_io *io, tvc_stream stream);
+
+/* state exchange; dev_blob = N x tvc_env_state on the device */
+size_t tvc_state_bytes(const tvc_handle *h);
+int tvc_get_state(tvc_handle *h, void *dev_blob, size_t bytes, tvc_stream stream);
+int tvc_set_state(tvc_handle *h, const void *dev_blob, size_t bytes, tvc_stream stream);
+
+/* _get_enhanced_info (:723-742) for the current state */
+int tvc_read_info(tvc_handle *h, const tvc_info_soa *dev, tvc_stream stream);
+
+/* episode statistics (what train.py:608-618 consumes).  Synchronises `stream`. */
+int tvc_episode_stats(tvc_handle *h, double *host_out, int reset_after, tvc_stream stream);
+/* device-side reduction into a caller buffer of TVC_NUM_STATS doubles (feed to ncclAllReduce) */
+int tvc_episode_stats_dev(tvc_handle *h, double *dev_out, int reset_after, tvc_stream stream);
+
+/* curriculum_manager.py:191-246 decides the stage on the host; this applies its conditions */
+int tvc_set_curriculum(tvc_handle *h, const tvc_stage_conditions *c);
+
+int tvc_get_config(const tvc_handle *h, tvc_config *out);
+int64_t tvc_num_envs(const tvc_handle *h);
+int64_t tvc_lifetime_steps(const tvc_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TVC_B200_H */

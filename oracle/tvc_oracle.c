@@ -360,8 +360,8 @@ static void draw4(uint64_t seed, int64_t gid, uint32_t stream, uint32_t a, uint3
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     orc_philox4x32_10(ctr, key, out);
 }
-/* 24-bit uniform in (0,1): exact in float32 and float64 */
-static inline double u01(uint32_t x) { return ((double)(x >> 8) + 0.5) * (1.0 / 16777216.0); }
+/* 23-bit uniform in (0,1), (k + 0.5) / 2^23: exact in float32 and float64 */
+static inline double u01(uint32_t x) { return ((double)(x >> 9) + 0.5) * (1.0 / 8388608.0); }
 static inline void box_muller(uint32_t x0, uint32_t x1, double *n0, double *n1) {
     double r = sqrt(-2.0 * log(u01(x0)));
     double th = 2.0 * PI_D * u01(x1);

@@ -1,0 +1,196 @@
+"""CPU tests of the oracle: golden trajectories produced by the reference's own Python class
+(tests/golden/make_golden.py), known-answer vectors and analytic checks.  No GPU."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+SCENARIOS = ["zero_120", "random_raw", "random_autoreset", "two_episodes", "burnout_1100", "crash_leak"]
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, f"{name}.npz"))
+
+
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_env_layer_matches_reference_python(oracle_mod, golden_dir, name):
+    """The C env layer must reproduce the reference class (run over the same physics layer):
+    every flag, phase and counter exactly; floats to fp64 round-off (float32 intermediates of
+    NumPy 2 in three reward terms allow 1e-6)."""
+    O = oracle_mod
+    g = _load(golden_dir, name)
+    sim = O.OracleSim(O.default_config(O.CONTRACT_R), 1)
+    T = len(g["reward"])
+    for t in range(T):
+        obs, r, term, trunc, outs = sim.step(g["actions"][t:t + 1])
+        o = outs[0]
+        assert bool(o.terminated) == bool(g["terminated"][t]), (name, t)
+        assert bool(o.truncated) == bool(g["truncated"][t]), (name, t)
+        assert o.phase == g["phase"][t] and bool(o.success) == bool(g["success"][t]), (name, t)
+        assert o.step == g["step"][t] and bool(o.criteria_met) == bool(g["criteria_met"][t]), (name, t)
+        assert o.fuel == g["fuel"][t]
+        np.testing.assert_allclose(obs[0], g["obs"][t], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(r[0], g["reward"][t], rtol=0, atol=2e-6)
+        np.testing.assert_allclose(list(o.comp)[:9], g["comp"][t], rtol=0, atol=2e-6)
+        e = sim.env(0)
+        st = list(e.body.pos) + list(e.body.quat) + list(e.body.vel) + list(e.body.omega)
+        np.testing.assert_allclose(st, g["state"][t], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(np.degrees(o.tilt), g["tilt_deg"][t], rtol=0, atol=1e-9)
+        if g["was_reset"][t]:
+            np.testing.assert_array_equal(sim.reset()[0], g["next_obs"][t])
+
+
+def test_golden_expected_events(golden_dir):
+    """Facts SURVEY.md section 8(a) predicts from reading the reference."""
+    z = _load(golden_dir, "zero_120")
+    assert np.flatnonzero(z["terminated"])[0] == 99            # success after 100 criteria pushes (S10)
+    assert z["success"][99] and not z["success"][98]
+    two = _load(golden_dir, "two_episodes")
+    assert two["terminated"][100] and two["step"][100] == 1    # Q10: episode 2 succeeds on its first step
+    b = _load(golden_dir, "burnout_1100")
+    assert b["fuel"][198] >= 0.8 > b["fuel"][199]              # S4: first fuel < 0.8 after decrement 200
+    assert b["fuel"][898] > 0.1 and not b["fuel"][899] > 0.1   # first not > 0.1 at 900
+    assert b["fuel"][998] > 0 and b["fuel"][999] == 0          # reaches 0 at 1000
+    assert b["truncated"][999] == False and b["terminated"][999]  # Q16: success masks truncation  # noqa: E712
+    c = _load(golden_dir, "crash_leak")
+    crash = np.flatnonzero(c["altitude"] < 0.1)
+    assert len(crash) and np.all(c["reward"][crash[0]:crash[0] + 10] == -1000.0)  # Q13
+
+
+def test_philox_known_answers(oracle_mod):
+    """Random123 kat_vectors for philox4x32-10."""
+    O = oracle_mod
+    assert O.philox4x32_10((0, 0, 0, 0), (0, 0)) == (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)
+    assert O.philox4x32_10((0xffffffff,) * 4, (0xffffffff,) * 2) == (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)
+    assert O.philox4x32_10((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == \
+        (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)
+
+
+def test_fuel_table_thresholds_and_float32_formula(oracle_mod):
+    """Row S4: iterated fp64 subtraction decides steps 200/900/1000, and the kernel's
+    (float)(1.0 - n*0.001) equals its float32 rounding for every n."""
+    L = oracle_mod.lib()
+    tab = [L.orc_fuel_table(n) for n in range(1002)]
+    f = 1.0
+    for n in range(1, 1002):
+        f = max(0, f - 0.001)
+        assert tab[n] == f
+    assert next(n for n in range(1002) if tab[n] < 0.8) == 200
+    assert next(n for n in range(1002) if not tab[n] > 0.1) == 900
+    assert next(n for n in range(1002) if tab[n] == 0) == 1000
+    for n in range(1000):
+        assert np.float32(tab[n]) == np.float32(1.0 - n * 0.001)
+
+
+def test_diversity_threshold_is_integer_compare():
+    for L in range(0, 1001):
+        for d in range(0, L + 1):
+            assert (d > L * 0.8) == (5 * d > 4 * L)
+
+
+def test_euler_axis_aligned(oracle_mod):
+    """Row B8 on known quaternions."""
+    O = oracle_mod
+    assert O.euler_from_quat((0, 0, 0, 1)) == (0.0, 0.0, 0.0)
+    s = math.sin(0.25)
+    r, p, y = O.euler_from_quat((s, 0, 0, math.cos(0.25)))
+    assert abs(r - 0.5) < 1e-15 and p == 0 and y == 0
+    r, p, y = O.euler_from_quat((0, s, 0, math.cos(0.25)))
+    assert abs(p - 0.5) < 1e-15 and r == 0 and y == 0
+    r, p, y = O.euler_from_quat((0, 0, s, math.cos(0.25)))
+    assert abs(y - 0.5) < 1e-15 and r == 0 and p == 0
+    h = math.sqrt(0.5)
+    r, p, y = O.euler_from_quat((0, h, 0, h))            # gimbal lock branch
+    assert r == 0 and abs(p - math.pi / 2) < 1e-12
+    # B7: sign canonicalisation
+    q = O.reported_quat((0.1, -0.2, 0.3, -math.sqrt(1 - 0.14)))
+    assert q[3] > 0 and abs(q[0] + 0.1) < 1e-15
+
+
+def _free_body(O, **kw):
+    import ctypes as C
+    p = O.BodyParams()
+    O.lib().orc_body_params_default(C.byref(p))
+    p.ground = 0
+    for k, v in kw.items():
+        setattr(p, k, v)
+    b = O.Body()
+    O.lib().orc_body_init(C.byref(b), O._d((0, 0, 100.0)), O._d((0, 0, 0, 1)))
+    return p, b
+
+
+def test_free_fall_matches_damped_recurrence(oracle_mod):
+    """Rows B4/B5: zero torque, gravity only: v_{k+1} = v_k + dt (g - v_k k_L (1 + |v_k|)),
+    z_{k+1} = z_k + dt v_{k+1} (semi-implicit); first step from rest gives dv = g*dt exactly."""
+    import ctypes as C
+    O = oracle_mod
+    p, b = _free_body(O)
+    v, z, dt = 0.0, 100.0, 0.005
+    for step in range(50):
+        O.lib().orc_step_simulation(C.byref(p), C.byref(b), None)
+        for _ in range(4):
+            v = v + (-9.81 - v * (0.01 + 0.01 * abs(v))) * dt
+            z = z + dt * v
+        assert abs(b.vel[2] - v) < 1e-12 and abs(b.pos[2] - z) < 1e-10
+    assert b.quat[3] == 1.0 and b.omega[0] == 0.0
+
+
+def test_torque_free_rotation(oracle_mod):
+    """Row B6: constant omega about z with damping off keeps |q| = 1 and advances the angle by w*t."""
+    import ctypes as C
+    O = oracle_mod
+    p, b = _free_body(O, ang_damp=0.0, lin_damp=0.0)
+    p.gravity[2] = 0.0
+    b.omega[2] = 1.5
+    for _ in range(100):
+        O.lib().orc_step_simulation(C.byref(p), C.byref(b), None)
+    ang = 2 * math.atan2(b.quat[2], b.quat[3])
+    assert abs(ang - 1.5 * 2.0) < 1e-9
+    assert abs(sum(x * x for x in b.quat) - 1.0) < 1e-14
+
+
+def test_resting_contact_is_stable(oracle_mod):
+    """Our contact model: zero action -> touches down near step 35, rests upright at z ~ 0.5."""
+    O = oracle_mod
+    sim = O.OracleSim(O.default_config(O.CONTRACT_R), 1)
+    z = []
+    for t in range(99):
+        _, _, term, _, outs = sim.step(np.zeros((1, 2), np.float32))
+        z.append(outs[0].altitude)
+        assert not term[0]
+    assert 0.499 < z[-1] < 0.502 and abs(z[-1] - z[-20]) < 1e-6
+    assert min(z) > 0.49
+
+
+def test_contract_x_draws_are_reproducible_and_bounded(oracle_mod):
+    O = oracle_mod
+    a = O.OracleSim(O.default_config(O.CONTRACT_X, init_tilt_max=0.2, init_omega_max=0.1), 256)
+    b = O.OracleSim(O.default_config(O.CONTRACT_X, init_tilt_max=0.2, init_omega_max=0.1, env_id_base=128), 128)
+    ms = np.array([a.env(i).mass_scale for i in range(256)])
+    ts = np.array([a.env(i).thrust_scale for i in range(256)])
+    assert ms.min() >= 0.7 and ms.max() <= 1.3 and ms.std() > 0.1
+    assert ts.min() >= 0.4 and ts.max() <= 1.6
+    for i in range(128):   # global env ids make draws independent of sharding
+        assert a.env(128 + i).mass_scale == b.env(i).mass_scale and a.env(128 + i).wind[0] == b.env(i).wind[0]
+    acts = a.random_actions(3)
+    assert acts.min() >= -1 and acts.max() <= 1 and abs(acts.mean()) < 0.1
+    np.testing.assert_array_equal(acts[128:], b.random_actions(3))
+
+
+def test_fast_diversity_matches_exact_on_goldens(oracle_mod, golden_dir):
+    """The fast duplicate bookkeeping (clip + run bits) gives the same bonus decision as len(set())
+    on every golden step except where non-adjacent repeats occur (deterministic replays)."""
+    O = oracle_mod
+    for name, allowed in (("random_raw", 0), ("random_autoreset", 0), ("crash_leak", 0), ("zero_120", 0)):
+        g = _load(golden_dir, name)
+        ex = O.OracleSim(O.default_config(O.CONTRACT_R, diversity_mode=O.DIV_EXACT), 1)
+        fa = O.OracleSim(O.default_config(O.CONTRACT_R, diversity_mode=O.DIV_FAST), 1)
+        diff = 0
+        for t in range(len(g["reward"])):
+            _, r1, _, _, o1 = ex.step(g["actions"][t:t + 1])
+            _, r2, _, _, o2 = fa.step(g["actions"][t:t + 1])
+            diff += o1[0].comp[11] != o2[0].comp[11]
+            if g["was_reset"][t]:
+                ex.reset(), fa.reset()
+        assert diff <= allowed, (name, diff)

@@ -1,0 +1,549 @@
+// tvc_abi.cu -- kernels + the C ABI declared in include/tvc_b200.h (libtvc_b200.so).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include "../../include/tvc_b200.h"
+#include "tvc_device.cuh"
+#include "tvc_internal.h"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+using namespace tvc;
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+
+// Coalesced [rows,10] fp32 store of one warp's observations through shared memory.
+__device__ __forceinline__ void warp_store_obs(float *dst, const float *s_warp, long long base, long long n, int lane) {
+    long long cnt = n - base;
+    if (cnt <= 0) return;
+    if (cnt > 32) cnt = 32;
+    const int n2 = (int)cnt * 5;   // float2 elements; base*10 floats is 8-byte aligned
+    float2 *d2 = reinterpret_cast<float2 *>(dst + base * 10);
+    const float2 *s2 = reinterpret_cast<const float2 *>(s_warp);
+    for (int k = lane; k < n2; k += 32) d2[k] = s2[k];
+}
+
+template <bool X, int DIV>
+__global__ void __launch_bounds__(TVC_BLOCK)
+step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState st, const __grid_constant__ DevIO io) {
+    __shared__ __align__(16) float s_obs[TVC_BLOCK * 10];
+    __shared__ double s_stat[TVC_WARPS][TVC_NSTAT];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long i = (long long)blockIdx.x * TVC_BLOCK + threadIdx.x;
+    const bool live = i < st.n;
+    const long long gid = c.env_base + i;
+
+    int done = 0, viol = 0;
+    int ev_len = 0, ev_succ = 0, ev_reason = 0, ev_trunc = 0;
+    float ev_ret = 0.0f, ev_alt = 0.0f, ev_tilt = 0.0f, ev_fuel = 0.0f;
+
+    if (live) {
+        Env e;
+        load_env(st, X, i, e);
+        float2 a;
+        if (io.actions) a = io.actions[i];
+        else {
+            uint4 rr = philox(c.seed_lo, c.seed_hi, gid, ST_ACTION, (unsigned)io.t, (unsigned)(io.t >> 32));
+            a = make_float2(2.0f * u01(rr.x) - 1.0f, 2.0f * u01(rr.y) - 1.0f);
+        }
+        if (io.actions_out) io.actions_out[i] = a;
+        StepResult r;
+        env_step<X, DIV>(c, st, i, gid, e, a.x, a.y, r);
+
+        io.reward[i] = r.reward;
+        io.term[i] = (uint8_t)r.terminated;
+        io.trunc[i] = (uint8_t)r.truncated;
+        if (io.altitude) io.altitude[i] = r.alt;
+        if (io.tilt_deg) io.tilt_deg[i] = r.tilt * 57.29577951308232f;
+        if (io.omega_mag) io.omega_mag[i] = r.wmag;
+        if (io.fuel) io.fuel[i] = r.fuel;
+        if (io.position) { io.position[3 * i] = e.px; io.position[3 * i + 1] = e.py; io.position[3 * i + 2] = e.pz; }
+        if (io.phase) io.phase[i] = e.phase;
+        if (io.step) io.step[i] = e.step;
+        if (io.success) io.success[i] = (uint8_t)e.success;
+        if (io.criteria_met) io.criteria_met[i] = (uint8_t)(e.consec >= 10);   // Q18
+        if (io.comp) {
+#pragma unroll
+            for (int k = 0; k < 12; k++) io.comp[12 * i + k] = r.comp[k];
+        }
+        viol = r.viol;
+        done = r.terminated | r.truncated;
+        if (done) {
+            ev_len = e.step; ev_succ = e.success; ev_reason = r.reason; ev_trunc = r.truncated;
+            ev_ret = e.ep_ret; ev_alt = r.alt; ev_tilt = r.tilt; ev_fuel = r.fuel;
+            if (io.final_obs) {
+                float2 *f2 = reinterpret_cast<float2 *>(io.final_obs + 10 * i);
+#pragma unroll
+                for (int k = 0; k < 5; k++) f2[k] = make_float2(r.obs[2 * k], r.obs[2 * k + 1]);
+            }
+            if (c.autoreset) {
+                reset_env(c, X, gid, e, false);
+                build_obs(c, X, gid, e, 0, r.obs);
+            }
+        }
+        store_env(st, X, i, e);
+#pragma unroll
+        for (int k = 0; k < 10; k++) s_obs[threadIdx.x * 10 + k] = r.obs[k];
+    }
+    __syncwarp();
+    warp_store_obs(io.obs, s_obs + warp * 320, (long long)blockIdx.x * TVC_BLOCK + warp * 32, st.n, lane);
+
+    // ---- episode statistics: warp shuffle -> shared -> one owner row per CTA (no atomics) ----
+    const int any_ev = __syncthreads_or(done | viol);
+    if (!any_ev) return;
+    {
+        const unsigned full = 0xffffffffu;
+        int n_ep = __reduce_add_sync(full, done);
+        int n_len = __reduce_add_sync(full, ev_len);
+        int n_succ = __reduce_add_sync(full, done ? ev_succ : 0);
+        int n_cr = __reduce_add_sync(full, ev_reason == 2);
+        int n_ti = __reduce_add_sync(full, ev_reason == 3);
+        int n_al = __reduce_add_sync(full, ev_reason == 4);
+        int n_ra = __reduce_add_sync(full, ev_reason == 5);
+        int n_tr = __reduce_add_sync(full, ev_trunc);
+        int n_vi = __reduce_add_sync(full, viol);
+        double d_ret = ev_ret, d_ret2 = (double)ev_ret * (double)ev_ret, d_alt = ev_alt, d_tilt = ev_tilt, d_fuel = ev_fuel;
+        if (n_ep) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                d_ret += __shfl_xor_sync(full, d_ret, o);
+                d_ret2 += __shfl_xor_sync(full, d_ret2, o);
+                d_alt += __shfl_xor_sync(full, d_alt, o);
+                d_tilt += __shfl_xor_sync(full, d_tilt, o);
+                d_fuel += __shfl_xor_sync(full, d_fuel, o);
+            }
+        }
+        if (lane == 0) {
+            double *s = s_stat[warp];
+            s[0] = n_ep; s[1] = d_ret; s[2] = d_ret2; s[3] = n_len; s[4] = n_succ; s[5] = n_cr; s[6] = n_ti;
+            s[7] = n_al; s[8] = n_ra; s[9] = n_tr; s[10] = n_vi; s[11] = d_alt; s[12] = d_tilt; s[13] = d_fuel;
+            s[14] = 0.0; s[15] = 0.0;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < TVC_NSTAT) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < TVC_WARPS; w++) s += s_stat[w][threadIdx.x];
+        if (s != 0.0) st.partial[(long long)blockIdx.x * TVC_NSTAT + threadIdx.x] += s;
+    }
+}
+
+template <bool X>
+__global__ void __launch_bounds__(TVC_BLOCK)
+reset_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState st, const uint8_t *mask, float *obs,
+             int first_time) {
+    const long long i = (long long)blockIdx.x * TVC_BLOCK + threadIdx.x;
+    if (i >= st.n) return;
+    if (mask && !mask[i]) return;
+    const long long gid = c.env_base + i;
+    Env e;
+    if (first_time) { memset(&e, 0, sizeof(e)); e.episode = -1; }
+    else load_env(st, X, i, e);
+    reset_env(c, X, gid, e, first_time != 0);
+    store_env(st, X, i, e);
+    if (obs) {
+        float o[10];
+        build_obs(c, X, gid, e, 0, o);
+#pragma unroll
+        for (int k = 0; k < 10; k++) obs[10 * i + k] = o[k];
+    }
+}
+
+template <bool X>
+__global__ void get_state_kernel(const __grid_constant__ DevState st, tvc_env_state *out, int delay) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st.n) return;
+    Env e;
+    load_env(st, X, i, e);
+    tvc_env_state s;
+    memset(&s, 0, sizeof(s));
+    s.pos[0] = e.px; s.pos[1] = e.py; s.pos[2] = e.pz;
+    s.quat[0] = e.qx; s.quat[1] = e.qy; s.quat[2] = e.qz; s.quat[3] = e.qw;
+    s.vel[0] = e.vx; s.vel[1] = e.vy; s.vel[2] = e.vz;
+    s.omega[0] = e.wx; s.omega[1] = e.wy; s.omega[2] = e.wz;
+    s.prev_action[0] = e.ap0; s.prev_action[1] = e.ap1;
+    s.ep_return = e.ep_ret;
+    s.step = e.step; s.burn = e.burn; s.phase = e.phase; s.success = e.success; s.has_prev = e.has_prev;
+    s.consec = e.consec; s.hist_count = e.hist_count; s.episode = e.episode; s.n_clip = e.n_clip; s.n_run = e.n_run;
+    for (int k = 0; k < 10; k++) s.ring10[k] = st.ring[(long long)k * st.n + i];
+    s.mass_scale = e.mass_scale; s.thrust_scale = e.thrust_scale; s.cg_offset = e.cg_off;
+    s.wind[0] = e.wind_x; s.wind[1] = e.wind_y;
+    if (X) for (int k = 0; k < delay; k++) { float2 d = st.delay[(long long)k * st.n + i]; s.delay_ring[k][0] = d.x; s.delay_ring[k][1] = d.y; }
+    out[i] = s;
+}
+
+template <bool X>
+__global__ void set_state_kernel(const __grid_constant__ DevState st, const tvc_env_state *in, int delay) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st.n) return;
+    const tvc_env_state s = in[i];
+    Env e;
+    e.px = s.pos[0]; e.py = s.pos[1]; e.pz = s.pos[2]; e.ep_ret = s.ep_return;
+    e.qx = s.quat[0]; e.qy = s.quat[1]; e.qz = s.quat[2]; e.qw = s.quat[3];
+    e.vx = s.vel[0]; e.vy = s.vel[1]; e.vz = s.vel[2]; e.step = s.step;
+    e.wx = s.omega[0]; e.wy = s.omega[1]; e.wz = s.omega[2];
+    e.burn = s.burn; e.phase = s.phase; e.success = s.success; e.has_prev = s.has_prev; e.consec = s.consec;
+    e.ap0 = s.prev_action[0]; e.ap1 = s.prev_action[1];
+    e.hist_count = s.hist_count; e.n_clip = s.n_clip; e.n_run = s.n_run;
+    e.mass_scale = s.mass_scale; e.thrust_scale = s.thrust_scale; e.cg_off = s.cg_offset;
+    e.wind_x = s.wind[0]; e.wind_y = s.wind[1]; e.episode = s.episode;
+    store_env(st, X, i, e);
+    for (int k = 0; k < 10; k++) st.ring[(long long)k * st.n + i] = s.ring10[k];
+    if (X) for (int k = 0; k < delay; k++) st.delay[(long long)k * st.n + i] = make_float2(s.delay_ring[k][0], s.delay_ring[k][1]);
+}
+
+template <bool X>
+__global__ void info_kernel(const __grid_constant__ DevState st, const __grid_constant__ DevIO io) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st.n) return;
+    Env e;
+    load_env(st, X, i, e);
+    float ox, oy, oz, ow, pitch, yaw;
+    reported_quat(e.qx, e.qy, e.qz, e.qw, ox, oy, oz, ow);
+    euler_pitch_yaw(ox, oy, oz, ow, pitch, yaw);
+    if (io.altitude) io.altitude[i] = e.pz;
+    if (io.tilt_deg) io.tilt_deg[i] = sqrtf(pitch * pitch + yaw * yaw) * 57.29577951308232f;
+    if (io.omega_mag) io.omega_mag[i] = sqrtf(e.wx * e.wx + e.wy * e.wy + e.wz * e.wz);
+    if (io.fuel) io.fuel[i] = fuel_of(e.burn);
+    if (io.position) { io.position[3 * i] = e.px; io.position[3 * i + 1] = e.py; io.position[3 * i + 2] = e.pz; }
+    if (io.phase) io.phase[i] = e.phase;
+    if (io.step) io.step[i] = e.step;
+    if (io.success) io.success[i] = (uint8_t)e.success;
+    if (io.criteria_met) io.criteria_met[i] = (uint8_t)(e.consec >= 10);
+}
+
+// deterministic reduction of the per-CTA partial rows: one thread per statistic, fixed order
+__global__ void stats_reduce_kernel(double *partial, int nblocks, double *out, double steps, int reset_after) {
+    const int k = threadIdx.x;
+    if (k >= TVC_NSTAT) return;
+    double s = 0.0;
+    for (int b = 0; b < nblocks; b++) {
+        s += partial[(long long)b * TVC_NSTAT + k];
+        if (reset_after) partial[(long long)b * TVC_NSTAT + k] = 0.0;
+    }
+    out[k] = (k == 14) ? steps : s;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+const char *tvc_set_err(const std::string &m) { g_err = m; return g_err.c_str(); }
+
+#define CUDA_OK(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            tvc_set_err(std::string(#expr) + ": " + cudaGetErrorString(_e));                       \
+            return TVC_E_CUDA;                                                                     \
+        }                                                                                          \
+    } while (0)
+
+static void make_devcfg(const tvc_config &c, DevCfg &d) {
+    memset(&d, 0, sizeof(d));
+    d.contract = c.contract; d.K = c.substeps; d.max_steps = c.max_episode_steps; d.autoreset = c.autoreset;
+    d.quirks = c.quirks; d.div_mode = c.diversity_mode; d.contact_iters = c.contact_iters; d.ground = c.ground;
+    d.delay = c.delay_steps; d.thrust_curve = c.thrust_curve;
+    const double dt = c.dt_step / (double)c.substeps;
+    d.dt = (float)dt; d.inv_dt = (float)(1.0 / dt);
+    d.gp = c.gradient_penalty; d.db = c.diversity_bonus;
+    d.mass = c.mass; d.radius = c.radius; d.half_len = 0.5f * c.length; d.thrust = c.thrust; d.gimbal_max = c.gimbal_max_rad;
+    d.lin_damp = c.lin_damp; d.ang_damp = c.ang_damp;
+    d.mass_var = c.mass_variation; d.thrust_std = c.thrust_std; d.thrust_lo = c.thrust_lo; d.thrust_hi = c.thrust_hi;
+    d.cg_max = c.cg_offset_max; d.wind_std = c.wind_std; d.noise_std = c.sensor_noise_std;
+    d.tilt_max = c.init_tilt_max; d.omega_max = c.init_omega_max; d.prop_frac = c.propellant_fraction; d.cg_burn = c.cg_burn_shift;
+    // contact material: enhanced_rocket_tvc_env.py:349-352 (plane) x :455-458 (rocket); Bullet combination rules
+    d.mu = 0.3f * 0.8f; d.mu_spin = 0.1f * 0.8f + 0.1f * 0.3f; d.mu_roll = 0.05f * 0.8f + 0.05f * 0.3f;
+    d.restitution = 0.1f; d.rest_thr = 0.2f; d.erp = 0.2f; d.margin = 0.02f;
+    d.seed_lo = (unsigned)c.seed; d.seed_hi = (unsigned)(c.seed >> 32);
+    d.env_base = c.env_id_base;
+}
+
+extern "C" {
+
+int tvc_abi_version(void) { return TVC_ABI_VERSION; }
+const char *tvc_last_error(void) { return g_err.c_str(); }
+
+int tvc_config_default(tvc_config *c, int contract) {
+    if (!c || (contract != TVC_CONTRACT_R && contract != TVC_CONTRACT_X)) { tvc_set_err("tvc_config_default: bad argument"); return TVC_E_BADARG; }
+    memset(c, 0, sizeof(*c));
+    c->abi_version = TVC_ABI_VERSION;
+    c->contract = contract;
+    c->substeps = contract == TVC_CONTRACT_R ? 4 : 10;
+    c->max_episode_steps = 1000;
+    c->autoreset = 0;
+    c->quirks = contract == TVC_CONTRACT_R ? TVC_Q_ALL_REFERENCE : (TVC_Q_DOUBLE_GRAVITY | TVC_Q_LAGGED_PHASE);
+    c->diversity_mode = contract == TVC_CONTRACT_R ? TVC_DIV_EXACT : TVC_DIV_FAST;
+    c->contact_iters = 8;
+    c->ground = 1;
+    c->dt_step = 0.02;
+    c->gradient_penalty = 0.1f; c->diversity_bonus = 0.05f;
+    c->mass = 2.0f; c->radius = 0.05f; c->length = 1.0f; c->thrust = 35.0f;
+    c->gimbal_max_rad = (float)(18.0 * (3.14159265358979323846 / 180.0));
+    c->lin_damp = 0.01f; c->ang_damp = 0.02f;
+    c->thrust_lo = 0.4f; c->thrust_hi = 1.6f;
+    if (contract == TVC_CONTRACT_X) {
+        c->mass_variation = 0.3f; c->thrust_std = 0.2f; c->cg_offset_max = 0.1f; c->wind_std = 3.0f;
+        c->sensor_noise_std = 0.02f;
+    }
+    c->seed = 42;
+    return TVC_OK;
+}
+
+}  // extern "C"
+
+static int validate(const tvc_config *c, int64_t n) {
+    if (!c) { tvc_set_err("config is NULL"); return TVC_E_BADARG; }
+    if (c->abi_version != TVC_ABI_VERSION) { tvc_set_err("tvc_config.abi_version mismatch"); return TVC_E_ABI; }
+    if (n <= 0 || n > (1ll << 31)) { tvc_set_err("num_envs out of range"); return TVC_E_BADARG; }
+    if (c->contract != TVC_CONTRACT_R && c->contract != TVC_CONTRACT_X) { tvc_set_err("bad contract"); return TVC_E_BADARG; }
+    if (c->substeps < 1 || c->substeps > 64) { tvc_set_err("substeps out of range [1,64]"); return TVC_E_BADARG; }
+    if (c->max_episode_steps < 1) { tvc_set_err("max_episode_steps < 1"); return TVC_E_BADARG; }
+    if (c->diversity_mode < 0 || c->diversity_mode > 2) { tvc_set_err("bad diversity_mode"); return TVC_E_BADARG; }
+    if (c->delay_steps < 0 || c->delay_steps > TVC_MAX_DELAY) { tvc_set_err("delay_steps out of range"); return TVC_E_BADARG; }
+    if (c->contact_iters < 0 || c->contact_iters > 256) { tvc_set_err("contact_iters out of range"); return TVC_E_BADARG; }
+    if (!(c->dt_step > 0) || !(c->mass > 0) || !(c->radius > 0) || !(c->length > 0)) { tvc_set_err("non-positive physical parameter"); return TVC_E_BADARG; }
+    return TVC_OK;
+}
+
+template <typename T>
+static int dalloc(T **p, size_t count) {
+    CUDA_OK(cudaMalloc((void **)p, count * sizeof(T)));
+    CUDA_OK(cudaMemset(*p, 0, count * sizeof(T)));
+    return TVC_OK;
+}
+
+extern "C" {
+
+int tvc_create(const tvc_config *cfg, int device, int64_t num_envs, tvc_handle **out) {
+    if (!out) { tvc_set_err("out is NULL"); return TVC_E_BADARG; }
+    *out = nullptr;
+    int rc = validate(cfg, num_envs);
+    if (rc) return rc;
+    int ndev = 0;
+    CUDA_OK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { tvc_set_err("device index out of range"); return TVC_E_BADARG; }
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        tvc_set_err(std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                    "; libtvc_b200 is built for sm_100a only (no fallback path)");
+        return TVC_E_DEVICE;
+    }
+    CUDA_OK(cudaSetDevice(device));
+    tvc_handle *h = new (std::nothrow) tvc_handle();
+    if (!h) { tvc_set_err("out of host memory"); return TVC_E_NOMEM; }
+    h->device = device; h->n = num_envs; h->base = *cfg; h->cur = *cfg; h->num_sms = prop.multiProcessorCount;
+    make_devcfg(h->cur, h->dc);
+    const size_t n = (size_t)num_envs;
+    h->grid = (int)((num_envs + TVC_BLOCK - 1) / TVC_BLOCK);
+    DevState &s = h->st;
+    memset(&s, 0, sizeof(s));
+    s.n = num_envs;
+#define TRY(x) do { rc = (x); if (rc) { tvc_destroy(h); return rc; } } while (0)
+    TRY(dalloc(&s.s0, n)); TRY(dalloc(&s.s1, n)); TRY(dalloc(&s.s2, n)); TRY(dalloc(&s.s3, n)); TRY(dalloc(&s.s4, n));
+    TRY(dalloc(&s.ring, 10 * n));
+    if (cfg->contract == TVC_CONTRACT_X) {
+        TRY(dalloc(&s.d0, n)); TRY(dalloc(&s.d1, n));
+        TRY(dalloc(&s.delay, (size_t)TVC_MAX_DELAY * n));
+    }
+    if (cfg->diversity_mode == TVC_DIV_FAST) { TRY(dalloc(&s.clipb, 32 * n)); TRY(dalloc(&s.runb, 32 * n)); }
+    if (cfg->diversity_mode == TVC_DIV_EXACT) TRY(dalloc(&s.hist, (size_t)TVC_HIST * n));
+    TRY(dalloc(&s.partial, (size_t)h->grid * TVC_NSTAT));
+    TRY(dalloc(&h->stats_dev, (size_t)TVC_NSTAT));
+    {
+        cudaError_t e = cudaMallocHost((void **)&h->stats_host, sizeof(double) * TVC_NSTAT);
+        if (e != cudaSuccess) { tvc_set_err(cudaGetErrorString(e)); tvc_destroy(h); return TVC_E_CUDA; }
+        e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { tvc_set_err(cudaGetErrorString(e)); tvc_destroy(h); return TVC_E_CUDA; }
+    }
+#undef TRY
+    // first-time initialisation == reset with cleared histories
+    if (cfg->contract == TVC_CONTRACT_X) reset_kernel<true><<<h->grid, TVC_BLOCK>>>(h->dc, h->st, nullptr, nullptr, 1);
+    else reset_kernel<false><<<h->grid, TVC_BLOCK>>>(h->dc, h->st, nullptr, nullptr, 1);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { tvc_set_err(std::string("init kernel: ") + cudaGetErrorString(e)); tvc_destroy(h); return TVC_E_CUDA; }
+    *out = h;
+    return TVC_OK;
+}
+
+int tvc_destroy(tvc_handle *h) {
+    if (!h) return TVC_OK;
+    cudaSetDevice(h->device);
+    DevState &s = h->st;
+    cudaFree(s.s0); cudaFree(s.s1); cudaFree(s.s2); cudaFree(s.s3); cudaFree(s.s4);
+    cudaFree(s.d0); cudaFree(s.d1); cudaFree(s.ring); cudaFree(s.clipb); cudaFree(s.runb); cudaFree(s.hist);
+    cudaFree(s.delay); cudaFree(s.partial); cudaFree(h->stats_dev);
+    cudaFree(h->io_act); cudaFree(h->io_obs); cudaFree(h->io_rew); cudaFree(h->io_term); cudaFree(h->io_trunc); cudaFree(h->io_final);
+    tvc_rollout_free(h);
+    if (h->stats_host) cudaFreeHost(h->stats_host);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return TVC_OK;
+}
+
+#define CHECK_H(h) do { if (!(h)) { tvc_set_err("handle is NULL"); return TVC_E_BADARG; } } while (0)
+#define LAUNCH_OK(what) do { cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { tvc_set_err(std::string(what) + ": " + cudaGetErrorString(_e)); return TVC_E_CUDA; } } while (0)
+
+int tvc_reset(tvc_handle *h, const uint8_t *mask_dev, uint64_t seed, float *obs_out_dev, tvc_stream stream) {
+    CHECK_H(h);
+    if (seed != 0) { h->cur.seed = seed; h->base.seed = seed; h->dc.seed_lo = (unsigned)seed; h->dc.seed_hi = (unsigned)(seed >> 32); }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (h->cur.contract == TVC_CONTRACT_X) reset_kernel<true><<<h->grid, TVC_BLOCK, 0, s>>>(h->dc, h->st, mask_dev, obs_out_dev, 0);
+    else reset_kernel<false><<<h->grid, TVC_BLOCK, 0, s>>>(h->dc, h->st, mask_dev, obs_out_dev, 0);
+    LAUNCH_OK("reset_kernel");
+    return TVC_OK;
+}
+
+static int launch_step(tvc_handle *h, const DevIO &io, cudaStream_t s) {
+    const bool X = h->cur.contract == TVC_CONTRACT_X;
+    const int dv = h->cur.diversity_mode;
+#define GO(XX, DD) step_kernel<XX, DD><<<h->grid, TVC_BLOCK, 0, s>>>(h->dc, h->st, io)
+    if (X) { if (dv == 0) GO(true, 0); else if (dv == 1) GO(true, 1); else GO(true, 2); }
+    else   { if (dv == 0) GO(false, 0); else if (dv == 1) GO(false, 1); else GO(false, 2); }
+#undef GO
+    LAUNCH_OK("step_kernel");
+    h->lifetime_steps += 1;
+    h->stat_steps += 1;
+    return TVC_OK;
+}
+
+int tvc_step_ex(tvc_handle *h, const tvc_step_io *u, tvc_stream stream) {
+    CHECK_H(h);
+    if (!u || !u->obs || !u->reward || !u->terminated || !u->truncated) { tvc_set_err("tvc_step: obs/reward/terminated/truncated must be non-NULL"); return TVC_E_BADARG; }
+    DevIO io;
+    memset(&io, 0, sizeof(io));
+    io.actions = (const float2 *)u->actions; io.obs = u->obs; io.reward = u->reward; io.term = u->terminated; io.trunc = u->truncated;
+    io.final_obs = u->final_obs; io.actions_out = (float2 *)u->actions_out;
+    io.altitude = u->info.altitude; io.tilt_deg = u->info.tilt_deg; io.omega_mag = u->info.omega_mag; io.fuel = u->info.fuel;
+    io.position = u->info.position; io.phase = u->info.phase; io.step = u->info.step; io.success = u->info.success;
+    io.criteria_met = u->info.criteria_met; io.comp = u->info.reward_components;
+    io.t = (unsigned long long)h->lifetime_steps;
+    return launch_step(h, io, (cudaStream_t)stream);
+}
+
+int tvc_step(tvc_handle *h, const float *actions_dev, float *obs_dev, float *reward_dev, uint8_t *terminated_dev,
+             uint8_t *truncated_dev, float *final_obs_dev, tvc_stream stream) {
+    tvc_step_io u;
+    memset(&u, 0, sizeof(u));
+    u.actions = actions_dev; u.obs = obs_dev; u.reward = reward_dev; u.terminated = terminated_dev; u.truncated = truncated_dev;
+    u.final_obs = final_obs_dev;
+    return tvc_step_ex(h, &u, stream);
+}
+
+int tvc_step_host(tvc_handle *h, const float *actions_host, float *obs_host, float *reward_host, uint8_t *terminated_host,
+                  uint8_t *truncated_host, float *final_obs_host) {
+    CHECK_H(h);
+    if (!obs_host || !reward_host || !terminated_host || !truncated_host) { tvc_set_err("tvc_step_host: NULL output"); return TVC_E_BADARG; }
+    const size_t n = (size_t)h->n;
+    if (!h->io_obs) {   // one-time staging buffers (not on the steady-state step path)
+        int rc;
+        if ((rc = dalloc(&h->io_act, 2 * n))) return rc;
+        if ((rc = dalloc(&h->io_obs, 10 * n))) return rc;
+        if ((rc = dalloc(&h->io_rew, n))) return rc;
+        if ((rc = dalloc(&h->io_term, n))) return rc;
+        if ((rc = dalloc(&h->io_trunc, n))) return rc;
+        if ((rc = dalloc(&h->io_final, 10 * n))) return rc;
+    }
+    cudaStream_t s = h->own_stream;
+    if (actions_host) CUDA_OK(cudaMemcpyAsync(h->io_act, actions_host, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, s));
+    int rc = tvc_step(h, actions_host ? h->io_act : nullptr, h->io_obs, h->io_rew, h->io_term, h->io_trunc,
+                      final_obs_host ? h->io_final : nullptr, (tvc_stream)s);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(obs_host, h->io_obs, sizeof(float) * 10 * n, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(reward_host, h->io_rew, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(terminated_host, h->io_term, n, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(truncated_host, h->io_trunc, n, cudaMemcpyDeviceToHost, s));
+    if (final_obs_host) CUDA_OK(cudaMemcpyAsync(final_obs_host, h->io_final, sizeof(float) * 10 * n, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    return TVC_OK;
+}
+
+size_t tvc_state_bytes(const tvc_handle *h) { return h ? (size_t)h->n * sizeof(tvc_env_state) : 0; }
+
+int tvc_get_state(tvc_handle *h, void *dev_blob, size_t bytes, tvc_stream stream) {
+    CHECK_H(h);
+    if (!dev_blob || bytes < tvc_state_bytes(h)) { tvc_set_err("tvc_get_state: blob too small"); return TVC_E_BADARG; }
+    const int g = (int)((h->n + 127) / 128);
+    if (h->cur.contract == TVC_CONTRACT_X) get_state_kernel<true><<<g, 128, 0, (cudaStream_t)stream>>>(h->st, (tvc_env_state *)dev_blob, TVC_MAX_DELAY);
+    else get_state_kernel<false><<<g, 128, 0, (cudaStream_t)stream>>>(h->st, (tvc_env_state *)dev_blob, 0);
+    LAUNCH_OK("get_state_kernel");
+    return TVC_OK;
+}
+
+int tvc_set_state(tvc_handle *h, const void *dev_blob, size_t bytes, tvc_stream stream) {
+    CHECK_H(h);
+    if (!dev_blob || bytes < tvc_state_bytes(h)) { tvc_set_err("tvc_set_state: blob too small"); return TVC_E_BADARG; }
+    const int g = (int)((h->n + 127) / 128);
+    if (h->cur.contract == TVC_CONTRACT_X) set_state_kernel<true><<<g, 128, 0, (cudaStream_t)stream>>>(h->st, (const tvc_env_state *)dev_blob, TVC_MAX_DELAY);
+    else set_state_kernel<false><<<g, 128, 0, (cudaStream_t)stream>>>(h->st, (const tvc_env_state *)dev_blob, 0);
+    LAUNCH_OK("set_state_kernel");
+    return TVC_OK;
+}
+
+int tvc_read_info(tvc_handle *h, const tvc_info_soa *u, tvc_stream stream) {
+    CHECK_H(h);
+    if (!u) { tvc_set_err("info is NULL"); return TVC_E_BADARG; }
+    DevIO io;
+    memset(&io, 0, sizeof(io));
+    io.altitude = u->altitude; io.tilt_deg = u->tilt_deg; io.omega_mag = u->omega_mag; io.fuel = u->fuel; io.position = u->position;
+    io.phase = u->phase; io.step = u->step; io.success = u->success; io.criteria_met = u->criteria_met;
+    const int g = (int)((h->n + 127) / 128);
+    if (h->cur.contract == TVC_CONTRACT_X) info_kernel<true><<<g, 128, 0, (cudaStream_t)stream>>>(h->st, io);
+    else info_kernel<false><<<g, 128, 0, (cudaStream_t)stream>>>(h->st, io);
+    LAUNCH_OK("info_kernel");
+    return TVC_OK;
+}
+
+int tvc_episode_stats_dev(tvc_handle *h, double *dev_out, int reset_after, tvc_stream stream) {
+    CHECK_H(h);
+    if (!dev_out) { tvc_set_err("dev_out is NULL"); return TVC_E_BADARG; }
+    const double steps = (double)h->stat_steps * (double)h->n;
+    stats_reduce_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->st.partial, h->grid, dev_out, steps, reset_after);
+    LAUNCH_OK("stats_reduce_kernel");
+    if (reset_after) h->stat_steps = 0;
+    return TVC_OK;
+}
+
+int tvc_episode_stats(tvc_handle *h, double *host_out, int reset_after, tvc_stream stream) {
+    CHECK_H(h);
+    if (!host_out) { tvc_set_err("host_out is NULL"); return TVC_E_BADARG; }
+    int rc = tvc_episode_stats_dev(h, h->stats_dev, reset_after, stream);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(h->stats_host, h->stats_dev, sizeof(double) * TVC_NSTAT, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    memcpy(host_out, h->stats_host, sizeof(double) * TVC_NSTAT);
+    return TVC_OK;
+}
+
+int tvc_set_curriculum(tvc_handle *h, const tvc_stage_conditions *c) {
+    CHECK_H(h);
+    if (!c) { tvc_set_err("conditions is NULL"); return TVC_E_BADARG; }
+    if (h->cur.contract != TVC_CONTRACT_X) { tvc_set_err("tvc_set_curriculum: the reference env has no curriculum coupling; use Contract X"); return TVC_E_STATE; }
+    tvc_config n = h->base;
+    n.init_tilt_max = c->max_initial_tilt;
+    n.init_omega_max = c->max_initial_angular_vel;
+    if (!c->domain_randomization) { n.mass_variation = 0.0f; n.thrust_std = 0.0f; n.cg_offset_max = 0.0f; }
+    else n.mass_variation = c->mass_variation;
+    if (!c->sensor_noise) n.sensor_noise_std = 0.0f;
+    n.wind_std = c->wind_enabled ? c->wind_force : 0.0f;
+    if (c->max_gimbal_angle_deg > 0.0f) n.gimbal_max_rad = c->max_gimbal_angle_deg * (float)(3.14159265358979323846 / 180.0);
+    n.seed = h->cur.seed;
+    h->cur = n;
+    make_devcfg(h->cur, h->dc);
+    return TVC_OK;
+}
+
+int tvc_get_config(const tvc_handle *h, tvc_config *out) {
+    CHECK_H(h);
+    if (!out) { tvc_set_err("out is NULL"); return TVC_E_BADARG; }
+    *out = h->cur;
+    return TVC_OK;
+}
+int64_t tvc_num_envs(const tvc_handle *h) { return h ? h->n : -1; }
+int64_t tvc_lifetime_steps(const tvc_handle *h) { return h ? h->lifetime_steps : -1; }
+
+}  // extern "C"

@@ -1,0 +1,658 @@
+// tvc_device.cuh -- device-side model of the TVC env step (fp32, one thread per env).
+//
+// Restates, for sm_100a, the reference hot path env/enhanced_rocket_tvc_env.py (step :466-518,
+// reward :86-224, phases :635-657, success :659-695, termination :697-721, reset :381-464) and
+// the slice of Bullet it drives.  "ref:" below means that
+// file.  The fp64 CPU oracle (oracle/tvc_oracle.c) restates the same rows independently; the
+// two are compared by tests/ -- this file never includes or calls the oracle.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define TVC_BLOCK 128
+#define TVC_WARPS (TVC_BLOCK / 32)
+#define TVC_HIST 1000
+#define TVC_NSTAT 16
+
+namespace tvc {
+
+struct DevCfg {
+    int contract, K, max_steps, autoreset;
+    unsigned quirks;
+    int div_mode, contact_iters, ground, delay, thrust_curve;
+    float dt, inv_dt;  // substep
+    float gp, db;
+    float mass, radius, half_len, thrust, gimbal_max;
+    float lin_damp, ang_damp;
+    float mass_var, thrust_std, thrust_lo, thrust_hi, cg_max, wind_std, noise_std, tilt_max, omega_max;
+    float prop_frac, cg_burn;
+    float mu, mu_spin, mu_roll, restitution, rest_thr, erp, margin;
+    unsigned seed_lo, seed_hi;
+    long long env_base;
+};
+
+// Persistent per-env state, SoA planes of 16-byte groups (coalesced LDG.128/STG.128).
+struct DevState {
+    float4 *s0;  // px py pz ep_return
+    float4 *s1;  // qx qy qz qw            (body->world, internal sign)
+    float4 *s2;  // vx vy vz step(int)
+    float4 *s3;  // wx wy wz flags(int): burn[0:11) phase[11:14) success[14] has_prev[15] consec[16:27)
+    float4 *s4;  // a_prev0 a_prev1 hist_count(int) div(int): n_clip[0:10) n_run[10:20) | n_distinct
+    float4 *d0;  // X: mass_scale thrust_scale cg_offset wind_x
+    float4 *d1;  // X: wind_y episode(int) - -
+    float *ring;      // [10][N] last ten clipped totals, slot = push % 10
+    unsigned *clipb;  // [32][N] fast diversity: value == -1000
+    unsigned *runb;   // [32][N] fast diversity: value == predecessor
+    float *hist;      // [1000][N] exact diversity only
+    float2 *delay;    // [TVC_MAX_DELAY][N] X: actuator delay ring, slot = step % delay
+    double *partial;  // [grid][16] per-CTA episode statistics
+    long long n;
+};
+
+struct DevIO {
+    const float2 *actions;
+    float *obs, *reward;
+    uint8_t *term, *trunc;
+    float *final_obs;
+    float2 *actions_out;
+    float *altitude, *tilt_deg, *omega_mag, *fuel, *position;
+    int *phase, *step;
+    uint8_t *success, *criteria_met;
+    float *comp;
+    unsigned long long t;  // lifetime step index (Philox action stream counter)
+};
+
+struct Env {
+    float px, py, pz, ep_ret;
+    float qx, qy, qz, qw;
+    float vx, vy, vz;
+    int step;
+    float wx, wy, wz;
+    int burn, phase, success, has_prev, consec;
+    float ap0, ap1;
+    int hist_count, n_clip, n_run;
+    float mass_scale, thrust_scale, cg_off, wind_x, wind_y;
+    int episode;
+};
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (counter-based; Salmon et al. 2011).  Counter = (env_lo, env_hi16 | stream<<16,
+// a, b), key = seed.  Same layout as the oracle so both sides draw identical bits.
+// ------------------------------------------------------------------------------------------
+enum { ST_DR_A = 1, ST_DR_B = 2, ST_NOISE_A = 3, ST_NOISE_B = 4, ST_ACTION = 5, ST_ACTOR = 6, ST_DR_C = 7 };
+
+__device__ __forceinline__ uint4 philox(unsigned seed_lo, unsigned seed_hi, long long gid, unsigned stream,
+                                        unsigned a, unsigned b) {
+    unsigned c0 = (unsigned)gid, c1 = (unsigned)(((unsigned long long)gid >> 32) & 0xFFFFu) | (stream << 16);
+    unsigned c2 = a, c3 = b, k0 = seed_lo, k1 = seed_hi;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        unsigned h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        unsigned h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        unsigned n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+// (k + 0.5) / 2^23 : exact in fp32
+__device__ __forceinline__ float u01(unsigned x) { return ((float)(x >> 9) + 0.5f) * (1.0f / 8388608.0f); }
+__device__ __forceinline__ void box_muller(unsigned x0, unsigned x1, float &n0, float &n1) {
+    float r = sqrtf(-2.0f * logf(u01(x0)));
+    float s, c;
+    sincosf(6.283185307179586f * u01(x1), &s, &c);
+    n0 = r * c; n1 = r * s;
+}
+
+// ------------------------------------------------------------------------------------------
+// Bullet helpers (rows B7, B8)
+// ------------------------------------------------------------------------------------------
+// btMatrix3x3::setRotation (ref:546 getMatrixFromQuaternion), row-major
+__device__ __forceinline__ void quat_to_mat(float x, float y, float z, float w, float R[9]) {
+    float d = x * x + y * y + z * z + w * w;
+    float s = 2.0f / d;
+    float xs = x * s, ys = y * s, zs = z * s;
+    float wx = w * xs, wy = w * ys, wz = w * zs;
+    float xx = x * xs, xy = x * ys, xz = x * zs;
+    float yy = y * ys, yz = y * zs, zz = z * zs;
+    R[0] = 1.0f - (yy + zz); R[1] = xy - wz;          R[2] = xz + wy;
+    R[3] = xy + wz;          R[4] = 1.0f - (xx + zz); R[5] = yz - wx;
+    R[6] = xz - wy;          R[7] = yz + wx;          R[8] = 1.0f - (xx + yy);
+}
+
+// Row B7: the reported orientation is quat -> btMatrix3x3 -> quat, which normalises and fixes the
+// sign (w > 0 when trace > 0, else the component of the largest diagonal is positive).
+__device__ __forceinline__ void reported_quat(float x, float y, float z, float w, float &ox, float &oy, float &oz,
+                                              float &ow) {
+    float d = x * x + y * y + z * z + w * w;
+    float s = 2.0f / d;
+    float xx = x * x * s, yy = y * y * s, zz = z * z * s;
+    float m00 = 1.0f - (yy + zz), m11 = 1.0f - (xx + zz), m22 = 1.0f - (xx + yy);
+    float trace = m00 + m11 + m22;
+    float lead;
+    if (trace > 0.0f) lead = w;
+    else {
+        int i = m00 < m11 ? (m11 < m22 ? 2 : 1) : (m00 < m22 ? 2 : 0);
+        lead = i == 0 ? x : (i == 1 ? y : z);
+    }
+    float sc = rsqrtf(d);
+    if (lead < 0.0f) sc = -sc;
+    ox = x * sc; oy = y * sc; oz = z * sc; ow = w * sc;
+}
+
+// pybullet.c getEulerFromQuaternion (ref:614); only pitch and yaw feed the env (quirk Q7)
+__device__ __forceinline__ void euler_pitch_yaw(float x, float y, float z, float w, float &pitch, float &yaw) {
+    float sarg = -2.0f * (x * z - w * y);
+    if (sarg <= -0.99999f) { pitch = -1.5707963267948966f; yaw = 2.0f * atan2f(x, -y); }
+    else if (sarg >= 0.99999f) { pitch = 1.5707963267948966f; yaw = 2.0f * atan2f(-x, y); }
+    else {
+        pitch = asinf(sarg);
+        yaw = atan2f(2.0f * (x * y + w * z), w * w + x * x - y * y - z * z);
+    }
+}
+
+// Row S4 (ref:530-533): fuel after n decrements.  (float)(1.0 - n*0.001) evaluated in fp64 equals
+// the float32 rounding of the reference's iterated fp64 subtraction for every n in [0,1000]
+// (checked exhaustively in tests/test_oracle.py); thresholds are integer compares on n.
+__device__ __forceinline__ float fuel_of(int n) {
+    return n >= 1000 ? 0.0f : __double2float_rn(__dsub_rn(1.0, __dmul_rn((double)n, 0.001)));
+}
+
+__device__ __forceinline__ float thrust_curve(int mode, int burn) {
+    if (mode == 0) return 1.0f;
+    float u = burn * 0.001f;
+    if (u < 0.05f) return 1.0f + 6.0f * u;
+    if (u < 0.15f) return 1.3f - 3.0f * (u - 0.05f);
+    if (u < 0.9f) return 1.0f;
+    return 1.0f - 5.0f * (u - 0.9f);
+}
+
+struct BodyP {
+    float mass, inv_mass, Ixy, Iz, inv_Ixy, inv_Iz, cg;
+};
+
+__device__ __forceinline__ BodyP body_params(const DevCfg &c, bool X, float mass_scale, float cg_off, float fuel) {
+    BodyP P;
+    float burnt = 1.0f - fuel;
+    float m = X ? c.mass * mass_scale * (1.0f - c.prop_frac * burnt) : c.mass;
+    float cg = X ? cg_off + c.cg_burn * burnt : 0.0f;
+    float len = 2.0f * c.half_len;
+    P.mass = m; P.inv_mass = 1.0f / m; P.cg = cg;
+    P.Ixy = (1.0f / 12.0f) * m * (3.0f * c.radius * c.radius + len * len) + m * cg * cg;   // ref:431
+    P.Iz = 0.5f * m * c.radius * c.radius;                                                  // ref:432
+    P.inv_Ixy = 1.0f / P.Ixy; P.inv_Iz = 1.0f / P.Iz;
+    return P;
+}
+
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+// ------------------------------------------------------------------------------------------
+// Ground contact: our documented model (DESIGN.md "Contact model"; oracle solve_contacts()).
+// Stateless 5-point manifold, speculative/Baumgarte normal rows, friction disc, torsional rows
+// on the first active point, projected Gauss-Seidel on velocities.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, const float R[9], float pz, float &vx,
+                                               float &vy, float &vz, float &wx, float &wy, float &wz) {
+    const float r = c.radius, h = c.half_len;
+    const float R31 = R[6], R32 = R[7], R33 = R[8];
+    float rho = sqrtf(R31 * R31 + R32 * R32);
+    float ux, uy;
+    if (rho > 1e-3f) { ux = -R31 / rho; uy = -R32 / rho; } else { ux = 1.0f; uy = 0.0f; }
+    float zn = (R33 >= 0.0f ? -h : h) - P.cg;
+    float zf = (R33 >= 0.0f ? h : -h) - P.cg;
+    float gap0 = pz + R33 * zn + r * (R31 * ux + R32 * uy);
+    if (!(gap0 < c.margin)) return;
+
+    // world inverse inertia W = R diag(1/I) R^T (symmetric)
+    const float ia = P.inv_Ixy, ib = P.inv_Iz;
+    const float W00 = ia * (R[0] * R[0] + R[1] * R[1]) + ib * R[2] * R[2];
+    const float W01 = ia * (R[0] * R[3] + R[1] * R[4]) + ib * R[2] * R[5];
+    const float W02 = ia * (R[0] * R[6] + R[1] * R[7]) + ib * R[2] * R[8];
+    const float W11 = ia * (R[3] * R[3] + R[4] * R[4]) + ib * R[5] * R[5];
+    const float W12 = ia * (R[3] * R[6] + R[4] * R[7]) + ib * R[5] * R[8];
+    const float W22 = ia * (R[6] * R[6] + R[7] * R[7]) + ib * R[8] * R[8];
+    const float im = P.inv_mass;
+
+    const float clx[5] = {r * ux, -r * uy, r * uy, -r * ux, r * ux};
+    const float cly[5] = {r * uy, r * ux, -r * ux, -r * uy, r * uy};
+    float ax[5], ay[5], az[5], tgt[5], imn[5], im1[5], im2[5];
+    float ln[5], l1[5], l2[5];
+    bool act[5];
+    int first = -1;
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        float cz = i == 4 ? zf : zn;
+        ax[i] = R[0] * clx[i] + R[1] * cly[i] + R[2] * cz;
+        ay[i] = R[3] * clx[i] + R[4] * cly[i] + R[5] * cz;
+        az[i] = R[6] * clx[i] + R[7] * cly[i] + R[8] * cz;
+        float gap = pz + az[i];
+        act[i] = gap < c.margin;
+        if (act[i] && first < 0) first = i;
+        // effective masses for n = z, t1 = x, t2 = y at arm (ax,ay,az)
+        float mn = im + (W00 * ay[i] * ay[i] - 2.0f * W01 * ax[i] * ay[i] + W11 * ax[i] * ax[i]);
+        float m1 = im + (W11 * az[i] * az[i] - 2.0f * W12 * az[i] * ay[i] + W22 * ay[i] * ay[i]);
+        float m2 = im + (W00 * az[i] * az[i] - 2.0f * W02 * az[i] * ax[i] + W22 * ax[i] * ax[i]);
+        imn[i] = 1.0f / mn; im1[i] = 1.0f / m1; im2[i] = 1.0f / m2;
+        float vn0 = vz + wx * ay[i] - wy * ax[i];
+        float rest = (vn0 < -c.rest_thr) ? -c.restitution * vn0 : 0.0f;
+        tgt[i] = rest + (gap > 0.0f ? -gap * c.inv_dt : -c.erp * gap * c.inv_dt);
+        ln[i] = 0.0f; l1[i] = 0.0f; l2[i] = 0.0f;
+    }
+    float lsp = 0.0f, lr1 = 0.0f, lr2 = 0.0f;
+    const float iW22 = 1.0f / W22, iW00 = 1.0f / W00, iW11 = 1.0f / W11;
+    for (int it = 0; it < c.contact_iters; it++) {
+        float lnf = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+            if (act[i]) {
+                // normal row
+                float vn = vz + wx * ay[i] - wy * ax[i];
+                float nl = fmaxf(ln[i] + (tgt[i] - vn) * imn[i], 0.0f);
+                float d = nl - ln[i];
+                ln[i] = nl;
+                vz += d * im;
+                wx += (W00 * ay[i] - W01 * ax[i]) * d;
+                wy += (W01 * ay[i] - W11 * ax[i]) * d;
+                wz += (W02 * ay[i] - W12 * ax[i]) * d;
+                // friction disc
+                float vt1 = vx + wy * az[i] - wz * ay[i];
+                float vt2 = vy + wz * ax[i] - wx * az[i];
+                float a1 = l1[i] - vt1 * im1[i];
+                float a2 = l2[i] - vt2 * im2[i];
+                float lim = c.mu * nl;
+                float mag = sqrtf(a1 * a1 + a2 * a2);
+                if (mag > lim) { float sc = mag > 0.0f ? lim / mag : 0.0f; a1 *= sc; a2 *= sc; }
+                float d1 = a1 - l1[i], d2 = a2 - l2[i];
+                l1[i] = a1; l2[i] = a2;
+                vx += d1 * im; vy += d2 * im;
+                float tx = -az[i] * d2, ty = az[i] * d1, tz = ax[i] * d2 - ay[i] * d1;
+                wx += W00 * tx + W01 * ty + W02 * tz;
+                wy += W01 * tx + W11 * ty + W12 * tz;
+                wz += W02 * tx + W12 * ty + W22 * tz;
+                if (i == first) lnf = nl;
+            }
+        }
+        {   // spinning / rolling friction rows on the first active contact
+            float lim = c.mu_spin * lnf;
+            float nl = clampf(lsp - wz * iW22, -lim, lim);
+            float d = nl - lsp; lsp = nl;
+            wx += W02 * d; wy += W12 * d; wz += W22 * d;
+            lim = c.mu_roll * lnf;
+            nl = clampf(lr1 - wx * iW00, -lim, lim);
+            d = nl - lr1; lr1 = nl;
+            wx += W00 * d; wy += W01 * d; wz += W02 * d;
+            nl = clampf(lr2 - wy * iW11, -lim, lim);
+            d = nl - lr2; lr2 = nl;
+            wx += W01 * d; wy += W11 * d; wz += W12 * d;
+        }
+    }
+}
+
+// Rows B2, B4, B5, B6: K substeps with the world-frame force F and torque T held constant (Q3).
+__device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &e, float Fx, float Fy, float Fz,
+                                          float Tx, float Ty, float Tz) {
+    const float dt = c.dt;
+    const float ax_ = Fx * P.inv_mass, ay_ = Fy * P.inv_mass, az_ = Fz * P.inv_mass;
+    for (int k = 0; k < c.K; k++) {
+        float R[9];
+        quat_to_mat(e.qx, e.qy, e.qz, e.qw, R);
+        // B5: base-local angular acceleration, damping k(1 + |w|), no gyroscopic term
+        float wl0 = R[0] * e.wx + R[3] * e.wy + R[6] * e.wz;
+        float wl1 = R[1] * e.wx + R[4] * e.wy + R[7] * e.wz;
+        float wl2 = R[2] * e.wx + R[5] * e.wy + R[8] * e.wz;
+        float tl0 = R[0] * Tx + R[3] * Ty + R[6] * Tz;
+        float tl1 = R[1] * Tx + R[4] * Ty + R[7] * Tz;
+        float tl2 = R[2] * Tx + R[5] * Ty + R[8] * Tz;
+        float wn2 = wl0 * wl0 + wl1 * wl1 + wl2 * wl2;
+        float wn = wn2 > 2.220446049250313e-16f ? sqrtf(wn2) : 0.0f;
+        float kd = c.ang_damp + c.ang_damp * wn;
+        float wd0 = tl0 * P.inv_Ixy - wl0 * kd;
+        float wd1 = tl1 * P.inv_Ixy - wl1 * kd;
+        float wd2 = tl2 * P.inv_Iz - wl2 * kd;
+        float dwx = R[0] * wd0 + R[1] * wd1 + R[2] * wd2;
+        float dwy = R[3] * wd0 + R[4] * wd1 + R[5] * wd2;
+        float dwz = R[6] * wd0 + R[7] * wd1 + R[8] * wd2;
+        float vn2 = e.vx * e.vx + e.vy * e.vy + e.vz * e.vz;
+        float vn = vn2 > 2.220446049250313e-16f ? sqrtf(vn2) : 0.0f;
+        float kl = c.lin_damp + c.lin_damp * vn;
+        e.wx = clampf(e.wx + dwx * dt, -100.0f, 100.0f);
+        e.wy = clampf(e.wy + dwy * dt, -100.0f, 100.0f);
+        e.wz = clampf(e.wz + dwz * dt, -100.0f, 100.0f);
+        e.vx = clampf(e.vx + (ax_ - e.vx * kl) * dt, -100.0f, 100.0f);
+        e.vy = clampf(e.vy + (ay_ - e.vy * kl) * dt, -100.0f, 100.0f);
+        e.vz = clampf(e.vz + (az_ - e.vz * kl) * dt, -100.0f, 100.0f);
+
+        if (c.ground) solve_contacts(c, P, R, e.pz, e.vx, e.vy, e.vz, e.wx, e.wy, e.wz);
+
+        // B6: semi-implicit Euler + exponential map, q <- dq (x) q, normalise
+        e.px += dt * e.vx; e.py += dt * e.vy; e.pz += dt * e.vz;
+        float ang = sqrtf(e.wx * e.wx + e.wy * e.wy + e.wz * e.wz);
+        if (ang * dt > 0.7853981633974483f) ang = 0.7853981633974483f / dt;
+        float sc;
+        if (ang < 0.001f) sc = 0.5f * dt - (dt * dt * dt) * 0.020833333333f * ang * ang;
+        else sc = sinf(0.5f * ang * dt) / ang;
+        float bx = e.wx * sc, by = e.wy * sc, bz = e.wz * sc, cw = cosf(ang * dt * 0.5f);
+        float nx = cw * e.qx + bx * e.qw + by * e.qz - bz * e.qy;
+        float ny = cw * e.qy + by * e.qw + bz * e.qx - bx * e.qz;
+        float nz = cw * e.qz + bz * e.qw + bx * e.qy - by * e.qx;
+        float nw = cw * e.qw - bx * e.qx - by * e.qy - bz * e.qz;
+        float inv = rsqrtf(nx * nx + ny * ny + nz * nz + nw * nw);
+        e.qx = nx * inv; e.qy = ny * inv; e.qz = nz * inv; e.qw = nw * inv;
+    }
+}
+
+// ref:381-464 reset (rows S13, Q10, Q11, Q15) + Contract X per-episode draws
+__device__ __forceinline__ void reset_env(const DevCfg &c, bool X, long long gid, Env &e, bool first_time) {
+    e.episode += 1;
+    e.px = 0.0f; e.py = 0.0f; e.pz = 1.0f; e.ep_ret = 0.0f;
+    e.qx = 0.0f; e.qy = 0.0f; e.qz = 0.0f; e.qw = 1.0f;
+    e.vx = e.vy = e.vz = 0.0f; e.step = 0;
+    e.wx = e.wy = e.wz = 0.0f;
+    e.burn = 0; e.phase = 0; e.success = 0;
+    if (first_time || !(c.quirks & 2u)) e.consec = 0;
+    if (first_time || !(c.quirks & 4u)) { e.has_prev = 0; e.ap0 = 0.0f; e.ap1 = 0.0f; e.hist_count = 0; e.n_clip = 0; e.n_run = 0; }
+    e.mass_scale = 1.0f; e.thrust_scale = 1.0f; e.cg_off = 0.0f; e.wind_x = 0.0f; e.wind_y = 0.0f;
+    if (X) {
+        uint4 a = philox(c.seed_lo, c.seed_hi, gid, ST_DR_A, (unsigned)e.episode, 0u);
+        uint4 b = philox(c.seed_lo, c.seed_hi, gid, ST_DR_B, (unsigned)e.episode, 0u);
+        uint4 d = philox(c.seed_lo, c.seed_hi, gid, ST_DR_C, (unsigned)e.episode, 0u);
+        float n0, n1, n2, n3;
+        box_muller(a.y, a.z, n0, n1);
+        box_muller(b.x, b.y, n2, n3);
+        e.mass_scale = 1.0f + c.mass_var * (2.0f * u01(a.x) - 1.0f);
+        e.thrust_scale = clampf(1.0f + c.thrust_std * n0, c.thrust_lo, c.thrust_hi);
+        e.wind_x = c.wind_std * n1;
+        e.wind_y = c.wind_std * n2;
+        e.cg_off = c.cg_max * (2.0f * u01(a.w) - 1.0f);
+        float tx = c.tilt_max * (2.0f * u01(b.z) - 1.0f);
+        float ty = c.tilt_max * (2.0f * u01(b.w) - 1.0f);
+        float ang = sqrtf(tx * tx + ty * ty);
+        float sc = ang < 1e-6f ? 0.5f - ang * ang * (1.0f / 48.0f) : sinf(0.5f * ang) / ang;
+        e.qx = tx * sc; e.qy = ty * sc; e.qz = 0.0f; e.qw = cosf(0.5f * ang);
+        e.wx = c.omega_max * (2.0f * u01(d.x) - 1.0f);
+        e.wy = c.omega_max * (2.0f * u01(d.y) - 1.0f);
+        e.wz = c.omega_max * (2.0f * u01(d.z) - 1.0f);
+    }
+}
+
+// ref:587-606 _get_enhanced_observation (+ Contract X sensor noise on obs[0:7])
+__device__ __forceinline__ void build_obs(const DevCfg &c, bool X, long long gid, const Env &e, int phase_for_obs,
+                                          float o[10]) {
+    reported_quat(e.qx, e.qy, e.qz, e.qw, o[0], o[1], o[2], o[3]);
+    o[4] = e.wx; o[5] = e.wy; o[6] = e.wz;
+    o[7] = fuel_of(e.burn);
+    o[8] = (float)((double)phase_for_obs / 7.0);
+    o[9] = fminf(1.0f, (float)e.step / (float)c.max_steps);
+    if (X && c.noise_std > 0.0f) {
+        uint4 a = philox(c.seed_lo, c.seed_hi, gid, ST_NOISE_A, (unsigned)e.episode, (unsigned)e.step);
+        uint4 b = philox(c.seed_lo, c.seed_hi, gid, ST_NOISE_B, (unsigned)e.episode, (unsigned)e.step);
+        float n[8];
+        box_muller(a.x, a.y, n[0], n[1]); box_muller(a.z, a.w, n[2], n[3]);
+        box_muller(b.x, b.y, n[4], n[5]); box_muller(b.z, b.w, n[6], n[7]);
+#pragma unroll
+        for (int i = 0; i < 7; i++) o[i] += c.noise_std * n[i];
+    }
+}
+
+__device__ __forceinline__ void load_env(const DevState &st, bool X, long long i, Env &e) {
+    float4 a = st.s0[i], b = st.s1[i], c = st.s2[i], d = st.s3[i], f = st.s4[i];
+    e.px = a.x; e.py = a.y; e.pz = a.z; e.ep_ret = a.w;
+    e.qx = b.x; e.qy = b.y; e.qz = b.z; e.qw = b.w;
+    e.vx = c.x; e.vy = c.y; e.vz = c.z; e.step = __float_as_int(c.w);
+    e.wx = d.x; e.wy = d.y; e.wz = d.z;
+    int fl = __float_as_int(d.w);
+    e.burn = fl & 0x7FF; e.phase = (fl >> 11) & 7; e.success = (fl >> 14) & 1; e.has_prev = (fl >> 15) & 1;
+    e.consec = (fl >> 16) & 0x7FF;
+    e.ap0 = f.x; e.ap1 = f.y; e.hist_count = __float_as_int(f.z);
+    int dv = __float_as_int(f.w);
+    e.n_clip = dv & 0x3FF; e.n_run = (dv >> 10) & 0x3FF;
+    if (X) {
+        float4 g = st.d0[i], h = st.d1[i];
+        e.mass_scale = g.x; e.thrust_scale = g.y; e.cg_off = g.z; e.wind_x = g.w;
+        e.wind_y = h.x; e.episode = __float_as_int(h.y);
+    } else {
+        e.mass_scale = 1.0f; e.thrust_scale = 1.0f; e.cg_off = 0.0f; e.wind_x = 0.0f; e.wind_y = 0.0f; e.episode = 0;
+    }
+}
+
+__device__ __forceinline__ void store_env(const DevState &st, bool X, long long i, const Env &e) {
+    st.s0[i] = make_float4(e.px, e.py, e.pz, e.ep_ret);
+    st.s1[i] = make_float4(e.qx, e.qy, e.qz, e.qw);
+    st.s2[i] = make_float4(e.vx, e.vy, e.vz, __int_as_float(e.step));
+    int cs = e.consec > 0x7FF ? 0x7FF : e.consec;
+    int fl = (e.burn & 0x7FF) | ((e.phase & 7) << 11) | ((e.success & 1) << 14) | ((e.has_prev & 1) << 15) | (cs << 16);
+    st.s3[i] = make_float4(e.wx, e.wy, e.wz, __int_as_float(fl));
+    int dv = (e.n_clip & 0x3FF) | ((e.n_run & 0x3FF) << 10);
+    st.s4[i] = make_float4(e.ap0, e.ap1, __int_as_float(e.hist_count), __int_as_float(dv));
+    if (X) {
+        st.d0[i] = make_float4(e.mass_scale, e.thrust_scale, e.cg_off, e.wind_x);
+        st.d1[i] = make_float4(e.wind_y, __int_as_float(e.episode), 0.0f, 0.0f);
+    }
+}
+
+struct StepResult {
+    float obs[10];
+    float reward;
+    int terminated, truncated, reason;
+    float alt, tilt, wmag, fuel;
+    float comp[12];
+    int viol;
+};
+
+// One env step on register-resident state (ref:466-518).  `a0,a1` is the raw policy action.
+template <bool X, int DIV>
+__device__ __forceinline__ void env_step(const DevCfg &c, const DevState &st, long long i, long long gid, Env &e,
+                                         float a0, float a1, StepResult &r) {
+    // ---- S2 (ref:470-471) ----
+    a0 = clampf(a0, -1.0f, 1.0f); a1 = clampf(a1, -1.0f, 1.0f);
+    float p0 = a0, p1 = a1;
+    if (X && c.delay > 0) {   // actuator delay: the command issued `delay` control steps ago
+        int slot = e.step % c.delay;
+        float2 old = st.delay[(long long)slot * st.n + i];
+        st.delay[(long long)slot * st.n + i] = make_float2(a0, a1);
+        if (e.step >= c.delay) { p0 = old.x; p1 = old.y; } else { p0 = 0.0f; p1 = 0.0f; }
+    }
+    const float pitch = p0 * c.gimbal_max, yaw = p1 * c.gimbal_max;
+
+    // ---- S3 (ref:520-559) control forces from the pre-step state ----
+    float fuel_pre = fuel_of(e.burn);
+    BodyP P = body_params(c, X, e.mass_scale, e.cg_off, fuel_pre);
+    float Fx = 0.0f, Fy = 0.0f, Fz = 0.0f, Tx = 0.0f, Ty = 0.0f, Tz = 0.0f;
+    if (c.quirks & 1u) Fz += -9.81f * P.mass;                         // Q1: explicit gravity force
+    if (e.burn < 1000) {                                               // Q4: fuel > 0 on entry
+        int burn_before = e.burn;
+        e.burn += 1;
+        float T = c.thrust;
+        if (X) T = T * e.thrust_scale * thrust_curve(c.thrust_curve, burn_before);
+        float sp, cp, sy, cy;
+        sincosf(pitch, &sp, &cp); sincosf(yaw, &sy, &cy);
+        float fl0 = T * sy, fl1 = T * sp, fl2 = T * cp * cy;           // Q2 (ref:539-543)
+        float R[9];
+        quat_to_mat(e.qx, e.qy, e.qz, e.qw, R);
+        float fwx = R[0] * fl0 + R[1] * fl1 + R[2] * fl2;
+        float fwy = R[3] * fl0 + R[4] * fl1 + R[5] * fl2;
+        float fwz = R[6] * fl0 + R[7] * fl1 + R[8] * fl2;
+        float arm = -(c.half_len + P.cg);                              // thrust acts at the base (ref:550)
+        float rx = R[2] * arm, ry = R[5] * arm, rz = R[8] * arm;
+        Fx += fwx; Fy += fwy; Fz += fwz;
+        Tx += ry * fwz - rz * fwy; Ty += rz * fwx - rx * fwz; Tz += rx * fwy - ry * fwx;
+    }
+    {   // ---- S5 (ref:561-585) aerodynamics ----
+        float rho = 1.225f * expf(-e.pz / 8400.0f);
+        float vmag = sqrtf(e.vx * e.vx + e.vy * e.vy + e.vz * e.vz);
+        if (vmag > 0.1f) {                                             // Q5
+            float dm = 0.5f * rho * (vmag * vmag) * 0.47f * (3.14159265358979f * 0.0025f);
+            float k = -dm / vmag;
+            Fx += k * e.vx; Fy += k * e.vy; Fz += k * e.vz;
+        }
+        float ad = 0.02f * rho;
+        Tx -= ad * e.wx; Ty -= ad * e.wy; Tz -= ad * e.wz;
+    }
+    if (X) { Fx += e.wind_x; Fy += e.wind_y; }
+    Fz += -9.81f * P.mass;                                             // B4: world gravity (ref:338)
+
+    // ---- S6 (ref:477) ----
+    integrate(c, P, e, Fx, Fy, Fz, Tx, Ty, Tz);
+    e.step += 1;
+
+    // ---- S7 (ref:608-633) ----
+    float ox, oy, oz, ow, epitch, eyaw;
+    reported_quat(e.qx, e.qy, e.qz, e.qw, ox, oy, oz, ow);
+    euler_pitch_yaw(ox, oy, oz, ow, epitch, eyaw);
+    const float tilt = sqrtf(epitch * epitch + eyaw * eyaw);           // Q7
+    const float wmag = sqrtf(e.wx * e.wx + e.wy * e.wy + e.wz * e.wz);
+    const float vh = sqrtf(e.vx * e.vx + e.vy * e.vy), vv = fabsf(e.vz);
+    const float alt = e.pz;
+    const bool crashed = alt < 0.1f;                                   // Q17
+    const int phase_pre = e.phase, success_pre = e.success;
+    const int burn = e.burn;   // fuel thresholds as integer compares (row S4): <0.8 <=> n>=200, >0.1 <=> n<=899
+
+    // ---- S9 (ref:635-657) ----
+    if (e.phase == 0 && burn >= 200) e.phase = 1;
+    else if (e.phase == 1 && alt < 5.0f) e.phase = 2;
+    else if (e.phase == 2 && alt < 1.0f) e.phase = 3;
+    else if (e.phase == 3 && alt < 0.5f) {
+        if (tilt < 0.087f && wmag < 0.1f) { e.phase = 5; e.success = 1; }
+    }
+    // ---- S10 (ref:659-695): deque(100) all-true == 100 consecutive all-met pushes ----
+    if (!e.success) {
+        bool all_met = (tilt < 0.087f) && (vv < 2.0f && vh < 0.5f) && (0.2f <= alt && alt <= 2.0f) && (wmag < 0.1f);
+        e.consec = all_met ? min(e.consec + 1, 0x7FF) : 0;
+        if (e.consec >= 100) e.success = 1;
+    }
+    const bool lag = (c.quirks & 8u) != 0;
+    const int phase_r = lag ? phase_pre : e.phase;
+    const int success_r = lag ? success_pre : e.success;
+
+    // ---- S8 (ref:587-606) ----
+    build_obs(c, X, gid, e, phase_r, r.obs);
+    const float fuel = r.obs[7] = fuel_of(e.burn);
+
+    // ---- R1-R10 (ref:86-224) ----
+    float comp[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) comp[k] = 0.0f;
+    comp[0] = success_r ? 100.0f : (phase_r == 2 ? 10.0f : 0.0f);
+    {
+        float tp = expf(-10.0f * fmaxf(0.0f, tilt - 0.087f));
+        float apn = expf(-5.0f * fmaxf(0.0f, wmag - 0.1f));
+        float alp = (0.2f <= alt && alt <= 20.0f) ? 1.0f : 0.5f;
+        comp[1] = ((tp + apn + alp) / 3.0f) * 50.0f;
+    }
+    const float ce = sqrtf(a0 * a0 + a1 * a1);
+    if (burn <= 899 && ce < 0.5f) comp[2] = (fuel * (1.0f - ce)) * 20.0f;
+    comp[3] = (tilt < 0.05f && wmag < 0.1f) ? 10.0f : ((tilt < 0.1f && wmag < 0.2f) ? 5.0f : 0.0f);
+    if (e.has_prev) {                                                   // Q11
+        float d0 = a0 - e.ap0, d1 = a1 - e.ap1;
+        comp[4] = expf(-5.0f * sqrtf(d0 * d0 + d1 * d1)) * 5.0f;
+    } else comp[4] = 5.0f;
+    e.ap0 = a0; e.ap1 = a1; e.has_prev = 1;
+    comp[5] = expf(-2.0f * fabsf(alt - 3.0f)) * 5.0f;
+    if (crashed) comp[6] = -1000.0f;
+    if (tilt > 0.52f) comp[7] = -500.0f * (tilt - 0.52f);
+    if (ce > 0.9f) comp[8] = -50.0f * (ce - 0.9f);
+
+    // R8 (ref:213-218): population variance of the last ten stored totals
+    float adj = 0.0f;
+    const int hc = e.hist_count;
+    const int len = min(hc, TVC_HIST);
+    float last_pushed = 0.0f;
+    {
+        float rv[10];
+#pragma unroll
+        for (int k = 0; k < 10; k++) rv[k] = st.ring[(long long)k * st.n + i];
+        int ls = (hc + 9) % 10;   // slot of push hc-1
+#pragma unroll
+        for (int k = 0; k < 10; k++) if (k == ls) last_pushed = rv[k];
+        if (len > 10) {
+            float s = ((rv[0] + rv[1]) + (rv[2] + rv[3])) + ((rv[4] + rv[5]) + (rv[6] + rv[7])) + rv[8] + rv[9];
+            float mean = s / 10.0f, q = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 10; k++) { float d = rv[k] - mean; q += d * d; }
+            float var = q / 10.0f;
+            if (var > 10000.0f) adj -= c.gp * var;
+        }
+    }
+    // R9 (ref:220-224): diversity bonus, len(set(history)) > 0.8 len  <=>  5 distinct > 4 len
+    int distinct = 0;
+    if (DIV == 1) distinct = len - e.n_run - e.n_clip + (e.n_clip > 0 ? 1 : 0);
+    if (DIV == 2) distinct = e.n_clip;   // exact mode keeps the distinct count in the n_clip field
+    const bool div_flag = (DIV != 0) && (5 * distinct > 4 * len);
+    if (div_flag) adj += c.db;
+    float total = comp[0] + comp[1];
+    total += comp[2]; total += comp[3]; total += comp[4]; total += comp[5];
+    if (crashed) total += comp[6];
+    if (tilt > 0.52f) total += comp[7];
+    if (ce > 0.9f) total += comp[8];
+    total += adj;
+    comp[9] = adj; comp[10] = total; comp[11] = div_flag ? 1.0f : 0.0f;
+    const float reward = clampf(total, -1000.0f, 200.0f);
+
+    // ---- push into reward_history (ref:123) ----
+    {
+        const int slot = hc % TVC_HIST;
+        if (DIV == 1) {
+            const int wi = slot >> 5;
+            const unsigned bit = 1u << (slot & 31);
+            unsigned cw = st.clipb[(long long)wi * st.n + i], rw = st.runb[(long long)wi * st.n + i];
+            if (hc >= TVC_HIST) {
+                if (cw & bit) e.n_clip--;
+                if (rw & bit) e.n_run--;
+                const int nxt = (slot + 1) % TVC_HIST, wj = nxt >> 5;
+                const unsigned nb = 1u << (nxt & 31);
+                if (wj == wi) { if (rw & nb) { rw &= ~nb; e.n_run--; } }
+                else {
+                    unsigned r2 = st.runb[(long long)wj * st.n + i];
+                    if (r2 & nb) { st.runb[(long long)wj * st.n + i] = r2 & ~nb; e.n_run--; }
+                }
+            }
+            const bool is_clip = reward == -1000.0f;
+            const bool is_run = !is_clip && hc > 0 && last_pushed == reward;
+            cw = is_clip ? (cw | bit) : (cw & ~bit);
+            rw = is_run ? (rw | bit) : (rw & ~bit);
+            e.n_clip += is_clip; e.n_run += is_run;
+            st.clipb[(long long)wi * st.n + i] = cw;
+            st.runb[(long long)wi * st.n + i] = rw;
+        }
+        if (DIV == 2) {
+            // exact: one pass over the window counting copies of the leaving and the entering value
+            const bool full = hc >= TVC_HIST;
+            const float leaving = full ? st.hist[(long long)slot * st.n + i] : 0.0f;
+            int cx = 0, cy = 0;
+            for (int k = 0; k < len; k++) {
+                float v = st.hist[(long long)k * st.n + i];
+                cx += (v == reward); cy += (v == leaving);
+            }
+            if (full) {
+                if (cy == 1) e.n_clip--;             // the leaving value had no other copy
+                if (leaving == reward) cx -= 1;      // do not count the slot being overwritten
+            }
+            if (cx == 0) e.n_clip++;
+            st.hist[(long long)slot * st.n + i] = reward;
+        }
+        st.ring[(long long)(hc % 10) * st.n + i] = reward;
+        e.hist_count = hc + 1;
+        if (e.hist_count >= 2000000000) e.hist_count -= 1000000000;   // keeps % 10, % 1000 and len
+    }
+    e.ep_ret += reward;
+
+    // ---- S11 (ref:697-721) ----
+    int terminated = 0, truncated = 0, reason = 0;
+    if (e.success) { terminated = 1; reason = 1; }                     // Q16
+    else {
+        if (crashed) { terminated = 1; reason = 2; }
+        else if (tilt > 0.52f) { terminated = 1; reason = 3; }
+        else if (alt > 20.0f) { terminated = 1; reason = 4; }
+        else if (sqrtf(e.px * e.px + e.py * e.py) > 50.0f) { terminated = 1; reason = 5; }
+        if (e.step >= c.max_steps) truncated = 1;
+    }
+    r.reward = reward; r.terminated = terminated; r.truncated = truncated; r.reason = reason;
+    r.alt = alt; r.tilt = tilt; r.wmag = wmag; r.fuel = fuel;
+#pragma unroll
+    for (int k = 0; k < 12; k++) r.comp[k] = comp[k];
+    // scripts/train.py:620-641 _check_safety_violation
+    r.viol = (tilt * 57.29577951308232f > 0.52f * 57.29577951308232f) || (wmag > 5.0f) || (alt < 0.1f) || (alt > 20.0f);
+}
+
+}  // namespace tvc

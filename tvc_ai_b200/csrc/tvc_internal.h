@@ -1,0 +1,30 @@
+// tvc_internal.h -- host-side handle shared by the translation units of libtvc_b200.so
+#pragma once
+#include "../../include/tvc_b200.h"
+#include "tvc_device.cuh"
+
+#include <string>
+
+struct tvc_handle {
+    int device = 0;
+    int num_sms = 0;
+    int64_t n = 0;
+    int grid = 0;
+    tvc_config base;   // as created
+    tvc_config cur;    // after tvc_set_curriculum
+    tvc::DevCfg dc;
+    tvc::DevState st;
+    int64_t lifetime_steps = 0;  // env steps taken by every env of this handle (Philox action counter)
+    int64_t stat_steps = 0;      // steps since the statistics were last reset
+    double *stats_dev = nullptr;
+    double *stats_host = nullptr;  // pinned
+    cudaStream_t own_stream = nullptr;
+    // staging for tvc_step_host
+    float *io_act = nullptr, *io_obs = nullptr, *io_rew = nullptr, *io_final = nullptr;
+    uint8_t *io_term = nullptr, *io_trunc = nullptr;
+    // fused-rollout workspace (tvc_rollout.cu)
+    void *rollout_ws = nullptr;
+};
+
+const char *tvc_set_err(const std::string &m);
+void tvc_rollout_free(tvc_handle *h);

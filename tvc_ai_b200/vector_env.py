@@ -1,0 +1,126 @@
+"""RocketTVCVectorEnv: Gymnasium-VectorEnv-shaped batched env over the CUDA engine.
+
+The reference has no vectorised env (training.num_envs is never read); this
+is the drop-in boundary SURVEY.md section 8(b) specifies: `num_envs`, single/batched spaces,
+`reset(seed=, options=) -> (obs[N,10], infos)`, `step(actions[N,2]) -> (obs, rewards, terminations,
+truncations, infos)` with Gymnasium 0.26-0.29 same-step autoreset (`final_observation` /
+`final_info` plus `_key` masks).  numpy in -> numpy out (through tvc_step_host: host buffers, one C
+call); torch CUDA in -> torch CUDA out, zero-copy views of the engine's buffers.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _abi as A
+from . import spaces
+from .engine import BatchedEngine
+from .env import PHASES, engine_config_from_yaml
+
+
+class RocketTVCVectorEnv:
+    metadata = {"render_modes": [], "autoreset_mode": "same_step"}
+
+    def __init__(self, num_envs: int, config: Optional[dict] = None, max_episode_steps: int = 1000,
+                 contract: str | int = "R", device: Optional[int] = None, env_id_base: int = 0,
+                 final_info: bool = True, **engine_over):
+        if isinstance(contract, str):
+            contract = {"R": A.CONTRACT_R, "X": A.CONTRACT_X}[contract.upper()]
+        self.num_envs = int(num_envs)
+        self.contract = contract
+        self.max_episode_steps = int(max_episode_steps)
+        cfg = engine_config_from_yaml(config, contract, max_episode_steps, autoreset=1, env_id_base=int(env_id_base),
+                                      **engine_over)
+        self.engine = BatchedEngine(self.num_envs, cfg, device=device)
+        self.single_observation_space = spaces.observation_space()
+        self.single_action_space = spaces.action_space()
+        self.observation_space = spaces.batch_space(self.single_observation_space, self.num_envs)
+        self.action_space = spaces.batch_space(self.single_action_space, self.num_envs)
+        self.render_mode = None
+        self.closed = False
+        self._want_final_info = bool(final_info)
+
+    # ------------------------------------------------------------------
+    def reset(self, *, seed: Optional[int] = None, options: Optional[dict] = None):
+        """Resets every env.  `seed` re-keys the Philox streams in Contract X; in Contract R the
+        reference's reset is deterministic and ignores it (quirk Q15)."""
+        as_torch = bool(options and options.get("return_torch"))
+        obs = self.engine.reset(seed=int(seed) if seed is not None else 0)
+        return (obs if as_torch else obs.cpu().numpy().copy()), {}
+
+    def step(self, actions):
+        if isinstance(actions, torch.Tensor):
+            return self._step_torch(actions)
+        return self._step_numpy(np.asarray(actions, np.float32))
+
+    def step_random(self):
+        """Step with in-kernel Philox U(-1,1) actions (synthetic-workload path used by bench.py)."""
+        return self._step_torch(None)
+
+    def _step_torch(self, actions):
+        if actions is not None and actions.dtype != torch.float32:
+            actions = actions.float()
+        if self._want_final_info:
+            obs, rew, term, trunc, info = self.engine.step_ex(actions)
+        else:
+            obs, rew, term, trunc = self.engine.step(actions)
+            info = None
+        term_b, trunc_b = term.bool(), trunc.bool()
+        done = term_b | trunc_b
+        infos = {"final_observation": self.engine.final_obs, "_final_observation": done}
+        if info is not None:
+            infos["final_info"] = {k: info[k] for k in ("altitude", "tilt_deg", "omega_mag", "fuel", "phase", "step",
+                                                        "success", "criteria_met", "reward_components")}
+            infos["_final_info"] = done
+        return obs, rew, term_b, trunc_b, infos
+
+    def _step_numpy(self, actions):
+        if actions.shape != (self.num_envs, 2):
+            raise ValueError(f"actions must have shape {(self.num_envs, 2)}, got {actions.shape}")
+        obs, rew, term, trunc, final = self.engine.step_host(actions, want_final=True)
+        obs, rew, term, trunc = obs.copy(), rew.astype(np.float64), term.copy(), trunc.copy()
+        done = term | trunc
+        infos = {}
+        if done.any():
+            idx = np.flatnonzero(done)
+            fo = np.full(self.num_envs, None, dtype=object)
+            for i in idx:
+                fo[i] = final[i].copy()
+            infos["final_observation"] = fo
+            infos["_final_observation"] = done
+            # terminal info is not available through the host fast path; episode-level numbers come
+            # from episode_stats().  mission_successful is recoverable: success <=> terminated with
+            # a non-penalised reward is not reliable, so it is omitted rather than guessed.
+        return obs, rew, term, trunc, infos
+
+    # ------------------------------------------------------------------
+    def episode_stats(self, reset_after: bool = False) -> dict:
+        s = self.engine.stats(reset_after)
+        return dict(zip(A.STAT_NAMES, s.tolist()))
+
+    def set_curriculum(self, conditions: dict):
+        self.engine.set_curriculum(conditions)
+
+    def call_info(self) -> dict:
+        """Current (post-autoreset) per-env info as numpy arrays, keys as in the reference's info dict."""
+        t = self.engine.read_info()
+        phase = t["phase"].cpu().numpy()
+        return {"altitude": t["altitude"].cpu().numpy(), "tilt_angle_deg": t["tilt_deg"].cpu().numpy(),
+                "angular_velocity_mag": t["omega_mag"].cpu().numpy(), "fuel_remaining": t["fuel"].cpu().numpy(),
+                "mission_phase": np.array([PHASES[p].value for p in phase]),
+                "mission_successful": t["success"].cpu().numpy().astype(bool), "step": t["step"].cpu().numpy(),
+                "success_criteria_met": t["criteria_met"].cpu().numpy().astype(bool),
+                "position": t["position"].cpu().numpy()}
+
+    def close(self, **kwargs):
+        if not self.closed:
+            self.engine.close()
+            self.closed = True
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
