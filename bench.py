@@ -194,6 +194,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # burn-in: every env starts at z = 1 m in lock-step; run until episodes have desynchronised so the
+    # timed region sees the steady-state mix of free flight, ground contact and resets
+    for b in range(args.burn_in):
+        eng.step(pool[b % 16], want_final=False)
+    eng.stats(reset_after=True)
     for w in range(W):
         eng.step(pool[w % 16], want_final=False)
     if world > 1:   # warm the NCCL communicator outside the timed region
@@ -247,7 +252,7 @@ def run_ours(args):
         small = BatchedEngine(4096, _workload_cfg(A), device=local)
         small.reset()
         acts = [torch.rand((4096, 2), device=dev) * 2 - 1 for _ in range(4)]
-        for w in range(20):
+        for w in range(args.burn_in):
             small.step(acts[w % 4], want_final=False)
         torch.cuda.synchronize(dev)
         e0.record()
@@ -293,7 +298,8 @@ def run_ours(args):
                                    "sensor noise), K=10 substeps/step, same-step autoreset, U(-1,1) actions resident in HBM, "
                                    "episode-stat reduction every 64 steps (NCCL all-reduce when N>1)",
                        "envs_per_gpu": n, "substeps": 10, "contact_iters": 8, "parallelism": f"env-slab x{world}",
-                       "l2": "flushed between timed steps (256 MiB zero-fill, not timed)"},
+                       "l2": "flushed between timed steps (256 MiB zero-fill, not timed)",
+                       "burn_in_steps": args.burn_in},
             "env_substeps_per_sec": value * 10,
             "warm_l2": {"ms_per_step": warm_ms, "env_steps_per_sec_per_gpu": n / (warm_ms * 1e-3),
                         "note": "back-to-back launches, state L2-resident (62 MB < 126 MB)"},
@@ -325,6 +331,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--burn-in", type=int, default=400, help="untimed steps before warm-up (episode desynchronisation)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

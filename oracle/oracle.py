@@ -15,6 +15,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libtvc_oracle.so")
+_LIB_F32_PATH = os.path.join(_HERE, "libtvc_oracle_f32.so")   # physics layer in float32 (sensitivity probe)
 
 MAX_DELAY = 4
 HIST = 1000
@@ -86,34 +87,46 @@ class StepOut(C.Structure):
                 ("step", C.c_int32), ("criteria_met", C.c_int32), ("term_reason", C.c_int32)]
 
 
-def build(force: bool = False) -> str:
-    """Compile oracle/libtvc_oracle.so (building the checker is not using it)."""
+def build(force: bool = False, f32: bool = False) -> str:
+    """Compile oracle/libtvc_oracle.so (building the checker is not using it).  f32=True builds the
+    variant whose physics layer evaluates in float32 (-DORC_PHYS_FLOAT)."""
     src = os.path.join(_HERE, "tvc_oracle.c")
     hdr = os.path.join(_HERE, "tvc_oracle.h")
-    if (not force and os.path.exists(_LIB_PATH)
-            and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
-        return _LIB_PATH
-    base = ["-O2", "-fPIC", "-std=c11", "-ffp-contract=off", "-fno-fast-math", "-shared", "-o", _LIB_PATH, src, "-lm"]
+    out = _LIB_F32_PATH if f32 else _LIB_PATH
+    if (not force and os.path.exists(out)
+            and os.path.getmtime(out) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+        return out
+    base = ["-O2", "-fPIC", "-std=c11", "-ffp-contract=off", "-fno-fast-math", "-shared", "-o", out, src, "-lm"]
+    if f32:
+        base = ["-DORC_PHYS_FLOAT"] + base
     last = None
     for cc in ("/usr/bin/gcc", "gcc", "cc"):
         for omp in (["-fopenmp"], []):
             try:
                 subprocess.run([cc] + omp + base, check=True, capture_output=True)
-                return _LIB_PATH
+                return out
             except (OSError, subprocess.CalledProcessError) as exc:  # try the next compiler / no OpenMP
                 last = exc
     raise RuntimeError(f"could not build the oracle: {last}")
 
 
 _lib = None
+_lib_f32 = None
 
 
-def lib():
-    global _lib
+def lib(f32: bool = False):
+    global _lib, _lib_f32
+    if f32:
+        if _lib_f32 is None:
+            _lib_f32 = _declare(C.CDLL(build(f32=True)))
+        return _lib_f32
     if _lib is not None:
         return _lib
-    build()
-    L = C.CDLL(_LIB_PATH)
+    _lib = _declare(C.CDLL(build()))
+    return _lib
+
+
+def _declare(L):
     dp = C.POINTER(C.c_double)
     L.orc_body_params_default.argtypes = [C.POINTER(BodyParams)]
     L.orc_body_init.argtypes = [C.POINTER(Body), dp, dp]
@@ -145,7 +158,6 @@ def lib():
     L.orc_fuel_table.restype = C.c_double
     L.orc_thrust_curve.argtypes = [C.c_int, C.c_int]
     L.orc_thrust_curve.restype = C.c_double
-    _lib = L
     return L
 
 
@@ -192,8 +204,8 @@ def matrix_from_quat(q):
 class OracleSim:
     """Batch of oracle envs (fp64).  Mirrors the device engine's reset/step surface."""
 
-    def __init__(self, cfg: Config | None = None, num_envs: int = 1, **over):
-        self.L = lib()
+    def __init__(self, cfg: Config | None = None, num_envs: int = 1, f32_physics: bool = False, **over):
+        self.L = lib(f32_physics)
         self.cfg = cfg if cfg is not None else default_config(**over)
         self.n = int(num_envs)
         self.h = self.L.orc_create(C.byref(self.cfg), self.n)

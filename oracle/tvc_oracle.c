@@ -138,7 +138,7 @@ void orc_body_params_default(orc_body_params *p) {
     p->restitution = 0.1 * 0.0 + 0.1;        /* ref:455; plane restitution 0 -> we keep the body's */
     p->rest_threshold = 0.2;                 /* Bullet restitutionVelocityThreshold default */
     p->erp = 0.2;                            /* Bullet m_erp2 default */
-    p->margin = 0.02;
+    p->margin = 0.05;
 }
 
 void orc_body_init(orc_body *b, const double pos[3], const double quat[4]) {
@@ -160,110 +160,148 @@ void orc_apply_external_torque(orc_body *b, const double t[3]) {
 }
 
 /*
- * Ground contact -- OUR documented model (SURVEY.md section 7.3 item 1, option (a)); Bullet's
- * GJK manifold + btMultiBodyConstraintSolver cannot be restated without its source
- * (row B9).  Same model, same constants, same iteration order in the CUDA kernel.
- *
- *  - plane z = 0, normal +z;  cylinder caps at local z = +-half_len - cg
- *  - stateless 5-point manifold per substep: the lowest rim point of the lower cap (c0),
- *    the two rim points at +-90 deg (c1,c2), the opposite rim point (c3), and the lowest rim
- *    point of the other cap (c4)
- *  - a candidate is active while gap < margin; speculative rows: vn >= -gap/dt (gap>=0),
- *    Baumgarte vn >= -erp*gap/dt (gap<0), restitution when approaching faster than threshold
- *  - projected Gauss-Seidel on velocities, contact_iters sweeps, no warm start; per contact:
- *    normal row (lambda>=0), then the two world-axis tangent rows projected on the friction
- *    disc mu*lambda_n; then spinning/rolling rows on the first active contact
+ * `real` is double for the oracle proper.  Compiling with -DORC_PHYS_FLOAT makes the physics
+ * layer (contact + integrator) evaluate in float32, which emulates the device arithmetic on the
+ * CPU; tests use that second build only to *measure* fp32 sensitivity, never as the reference.
  */
-static void solve_contacts(const orc_body_params *p, orc_body *b, double dt, const double R[9]) {
-    const double r = p->radius, h = p->half_len;
-    const double R31 = R[6], R32 = R[7], R33 = R[8];
-    double rho = sqrt(R31 * R31 + R32 * R32);
-    double ux, uy;
-    if (rho > 1e-3) { ux = -R31 / rho; uy = -R32 / rho; } else { ux = 1.0; uy = 0.0; }
-    double zn = (R33 >= 0 ? -h : h) - p->cg;
-    double zf = (R33 >= 0 ? h : -h) - p->cg;
-    double gap0 = b->pos[2] + R33 * zn + r * (R31 * ux + R32 * uy);
-    if (!(gap0 < p->margin)) return;
+#ifdef ORC_PHYS_FLOAT
+typedef float real;
+#define R_SQRT sqrtf
+#define R_SIN sinf
+#define R_COS cosf
+#define R_EPS2 2.220446049250313e-16f
+#else
+typedef double real;
+#define R_SQRT sqrt
+#define R_SIN sin
+#define R_COS cos
+#define R_EPS2 2.220446049250313e-16
+#endif
 
-    double c[5][3] = {
-        { r * ux,  r * uy, zn},
-        {-r * uy,  r * ux, zn},
-        { r * uy, -r * ux, zn},
-        {-r * ux, -r * uy, zn},
-        { r * ux,  r * uy, zf},
+static inline real r_clamp(real x, real lo, real hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+static void r_matrix_from_quat(const real q[4], real m[9]) {
+    real d = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    real s = (real)2.0 / d;
+    real xs = q[0] * s, ys = q[1] * s, zs = q[2] * s;
+    real wx = q[3] * xs, wy = q[3] * ys, wz = q[3] * zs;
+    real xx = q[0] * xs, xy = q[0] * ys, xz = q[0] * zs;
+    real yy = q[1] * ys, yz = q[1] * zs, zz = q[2] * zs;
+    m[0] = (real)1.0 - (yy + zz); m[1] = xy - wz;                 m[2] = xz + wy;
+    m[3] = xy + wz;               m[4] = (real)1.0 - (xx + zz);   m[5] = yz - wx;
+    m[6] = xz - wy;               m[7] = yz + wx;                 m[8] = (real)1.0 - (xx + yy);
+}
+
+/*
+ * Ground contact -- OUR documented model (SURVEY.md section 7.3 item 1, option (a)); Bullet's
+ * GJK manifold + btMultiBodyConstraintSolver cannot be restated without its source (row B9).
+ * Same model, constants and row order in the CUDA kernel (tvc_device.cuh solve_contacts).
+ * Designed to be CONTINUOUS in the state so that fp32 and fp64 evaluations stay close:
+ *
+ *  - plane z = 0, normal +z; cylinder caps at local z = -+half_len - cg
+ *  - stateless 5-point manifold per substep, always in this order:
+ *      p0  lowest rim point of the bottom cap,  p1  lowest rim point of the top cap
+ *          (direction -(R31,R32)/max(rho, 1e-3): slides to the cap centre as the axis becomes vertical)
+ *      f0,f1,f2  three body-fixed rim points of the bottom cap at 0, 120, 240 degrees
+ *  - entered only when the lowest candidate is closer than `margin`; then ALL five normal rows are
+ *    processed: vn >= -gap/dt (gap >= 0, speculative) or vn >= -erp*gap/dt (gap < 0, Baumgarte),
+ *    plus restitution e when approaching faster than the threshold; distant rows never bind
+ *  - per row: normal impulse (lambda >= 0), then the two world-axis tangent rows projected on the
+ *    friction disc mu*lambda_n; after the five points, spinning and rolling friction rows limited by
+ *    mu_spin / mu_roll times the total normal impulse
+ *  - projected Gauss-Seidel on velocities, contact_iters sweeps, no warm start
+ */
+static void solve_contacts(const orc_body_params *p, real dt, const real R[9], real pz, real v[3], real w[3]) {
+    const real r = (real)p->radius, h = (real)p->half_len, cg = (real)p->cg, margin = (real)p->margin;
+    const real R31 = R[6], R32 = R[7], R33 = R[8];
+    const real rho = R_SQRT(R31 * R31 + R32 * R32);
+    const real inv = (real)1.0 / (rho > (real)1e-3 ? rho : (real)1e-3);
+    const real ux = -R31 * inv, uy = -R32 * inv;
+    const real zb = -h - cg, zt = h - cg;
+    const real low = r * (R31 * ux + R32 * uy);          /* = -r*rho outside the regularised zone */
+    const real gb = pz + R33 * zb + low, gt = pz + R33 * zt + low;
+    if (!((gb < gt ? gb : gt) < margin)) return;
+
+    const real c[5][3] = {
+        {r * ux, r * uy, zb},
+        {r * ux, r * uy, zt},
+        {r, (real)0.0, zb},
+        {(real)-0.5 * r, (real)0.8660254037844386 * r, zb},
+        {(real)-0.5 * r, (real)-0.8660254037844386 * r, zb},
     };
-    /* world inverse inertia  R diag(1/I) R^T */
-    double ii[3] = {1.0 / p->inertia[0], 1.0 / p->inertia[1], 1.0 / p->inertia[2]};
-    double W[9];
-    for (int a = 0; a < 3; a++)
-        for (int d = 0; d < 3; d++)
-            W[a * 3 + d] = R[a * 3 + 0] * ii[0] * R[d * 3 + 0] + R[a * 3 + 1] * ii[1] * R[d * 3 + 1] +
-                           R[a * 3 + 2] * ii[2] * R[d * 3 + 2];
-    const double inv_m = 1.0 / p->mass;
+    /* world inverse inertia W = R diag(1/I) R^T (symmetric) */
+    const real ia = (real)(1.0 / p->inertia[0]), ib = (real)(1.0 / p->inertia[2]);
+    const real W00 = ia * (R[0] * R[0] + R[1] * R[1]) + ib * R[2] * R[2];
+    const real W01 = ia * (R[0] * R[3] + R[1] * R[4]) + ib * R[2] * R[5];
+    const real W02 = ia * (R[0] * R[6] + R[1] * R[7]) + ib * R[2] * R[8];
+    const real W11 = ia * (R[3] * R[3] + R[4] * R[4]) + ib * R[5] * R[5];
+    const real W12 = ia * (R[3] * R[6] + R[4] * R[7]) + ib * R[5] * R[8];
+    const real W22 = ia * (R[6] * R[6] + R[7] * R[7]) + ib * R[8] * R[8];
+    const real im = (real)(1.0 / p->mass);
+    const real mu = (real)p->mu, mus = (real)p->mu_spin, mur = (real)p->mu_roll;
+    const real inv_dt = (real)1.0 / dt;
 
-    int active[5];
-    double arm[5][3], jn[5][3], j1[5][3], j2[5][3];   /* r x n, r x t1, r x t2 */
-    double kn[5][3], k1[5][3], k2[5][3];              /* W * (r x d) */
-    double mn[5], m1[5], m2[5], target[5];
-    double ln[5] = {0}, l1[5] = {0}, l2[5] = {0};
-    int first = -1;
+    real ax[5], ay[5], az[5], tgt[5], imn[5], im1[5], im2[5];
+    real ln[5], l1[5], l2[5];
     for (int i = 0; i < 5; i++) {
-        matvec(R, c[i], arm[i]);
-        double gap = b->pos[2] + arm[i][2];
-        active[i] = gap < p->margin;
-        if (!active[i]) continue;
-        if (first < 0) first = i;
-        jn[i][0] = arm[i][1];  jn[i][1] = -arm[i][0]; jn[i][2] = 0.0;        /* r x z */
-        j1[i][0] = 0.0;        j1[i][1] = arm[i][2];  j1[i][2] = -arm[i][1]; /* r x x */
-        j2[i][0] = -arm[i][2]; j2[i][1] = 0.0;        j2[i][2] = arm[i][0];  /* r x y */
-        matvec(W, jn[i], kn[i]); matvec(W, j1[i], k1[i]); matvec(W, j2[i], k2[i]);
-        mn[i] = inv_m + dot3(jn[i], kn[i]);
-        m1[i] = inv_m + dot3(j1[i], k1[i]);
-        m2[i] = inv_m + dot3(j2[i], k2[i]);
-        double vn0 = b->vel[2] + dot3(b->omega, jn[i]);
-        double rest = (vn0 < -p->rest_threshold) ? -p->restitution * vn0 : 0.0;
-        target[i] = rest + (gap > 0 ? -gap / dt : -p->erp * gap / dt);
+        ax[i] = R[0] * c[i][0] + R[1] * c[i][1] + R[2] * c[i][2];
+        ay[i] = R[3] * c[i][0] + R[4] * c[i][1] + R[5] * c[i][2];
+        az[i] = R[6] * c[i][0] + R[7] * c[i][1] + R[8] * c[i][2];
+        real gap = pz + az[i];
+        /* effective masses for n = z, t1 = x, t2 = y at arm (ax, ay, az) */
+        real mn = im + (W00 * ay[i] * ay[i] - (real)2.0 * W01 * ax[i] * ay[i] + W11 * ax[i] * ax[i]);
+        real m1 = im + (W11 * az[i] * az[i] - (real)2.0 * W12 * az[i] * ay[i] + W22 * ay[i] * ay[i]);
+        real m2 = im + (W00 * az[i] * az[i] - (real)2.0 * W02 * az[i] * ax[i] + W22 * ax[i] * ax[i]);
+        imn[i] = (real)1.0 / mn; im1[i] = (real)1.0 / m1; im2[i] = (real)1.0 / m2;
+        real vn0 = v[2] + w[0] * ay[i] - w[1] * ax[i];
+        real rest = (vn0 < -(real)p->rest_threshold) ? -(real)p->restitution * vn0 : (real)0.0;
+        tgt[i] = rest + (gap > 0 ? -gap * inv_dt : -(real)p->erp * gap * inv_dt);
+        ln[i] = 0; l1[i] = 0; l2[i] = 0;
     }
-    if (first < 0) return;
-    double lsp = 0, lr1 = 0, lr2 = 0;
+    real lsp = 0, lr1 = 0, lr2 = 0;
+    const real iW22 = (real)1.0 / W22, iW00 = (real)1.0 / W00, iW11 = (real)1.0 / W11;
     for (int it = 0; it < p->contact_iters; it++) {
+        real lsum = 0;
         for (int i = 0; i < 5; i++) {
-            if (!active[i]) continue;
-            /* normal */
-            double vn = b->vel[2] + dot3(b->omega, jn[i]);
-            double nl = ln[i] + (target[i] - vn) / mn[i];
+            /* normal row */
+            real vn = v[2] + w[0] * ay[i] - w[1] * ax[i];
+            real nl = ln[i] + (tgt[i] - vn) * imn[i];
             if (nl < 0) nl = 0;
-            double d = nl - ln[i];
+            real d = nl - ln[i];
             ln[i] = nl;
-            b->vel[2] += d * inv_m;
-            for (int a = 0; a < 3; a++) b->omega[a] += kn[i][a] * d;
+            lsum += nl;
+            v[2] += d * im;
+            w[0] += (W00 * ay[i] - W01 * ax[i]) * d;
+            w[1] += (W01 * ay[i] - W11 * ax[i]) * d;
+            w[2] += (W02 * ay[i] - W12 * ax[i]) * d;
             /* friction disc */
-            double vt1 = b->vel[0] + dot3(b->omega, j1[i]);
-            double vt2 = b->vel[1] + dot3(b->omega, j2[i]);
-            double a1 = l1[i] - vt1 / m1[i];
-            double a2 = l2[i] - vt2 / m2[i];
-            double lim = p->mu * ln[i];
-            double mag = sqrt(a1 * a1 + a2 * a2);
-            if (mag > lim) { double sc = (mag > 0) ? lim / mag : 0.0; a1 *= sc; a2 *= sc; }
-            double d1 = a1 - l1[i], d2 = a2 - l2[i];
+            real vt1 = v[0] + w[1] * az[i] - w[2] * ay[i];
+            real vt2 = v[1] + w[2] * ax[i] - w[0] * az[i];
+            real a1 = l1[i] - vt1 * im1[i];
+            real a2 = l2[i] - vt2 * im2[i];
+            real lim = mu * nl;
+            real mag2 = a1 * a1 + a2 * a2;
+            if (mag2 > lim * lim) { real sc = lim / R_SQRT(mag2); a1 *= sc; a2 *= sc; }
+            real d1 = a1 - l1[i], d2 = a2 - l2[i];
             l1[i] = a1; l2[i] = a2;
-            b->vel[0] += d1 * inv_m;
-            b->vel[1] += d2 * inv_m;
-            for (int a = 0; a < 3; a++) b->omega[a] += k1[i][a] * d1 + k2[i][a] * d2;
+            v[0] += d1 * im; v[1] += d2 * im;
+            real tx = -az[i] * d2, ty = az[i] * d1, tz = ax[i] * d2 - ay[i] * d1;
+            w[0] += W00 * tx + W01 * ty + W02 * tz;
+            w[1] += W01 * tx + W11 * ty + W12 * tz;
+            w[2] += W02 * tx + W12 * ty + W22 * tz;
         }
-        /* torsional rows on the first active contact (Bullet adds them for one point per manifold) */
-        {
-            double lim = p->mu_spin * ln[first];
-            double nl = clampd(lsp - b->omega[2] / W[8], -lim, lim);
-            double d = nl - lsp; lsp = nl;
-            b->omega[0] += W[2] * d; b->omega[1] += W[5] * d; b->omega[2] += W[8] * d;
-            lim = p->mu_roll * ln[first];
-            nl = clampd(lr1 - b->omega[0] / W[0], -lim, lim);
+        {   /* spinning / rolling friction, limited by the total normal impulse */
+            real lim = mus * lsum;
+            real nl = r_clamp(lsp - w[2] * iW22, -lim, lim);
+            real d = nl - lsp; lsp = nl;
+            w[0] += W02 * d; w[1] += W12 * d; w[2] += W22 * d;
+            lim = mur * lsum;
+            nl = r_clamp(lr1 - w[0] * iW00, -lim, lim);
             d = nl - lr1; lr1 = nl;
-            b->omega[0] += W[0] * d; b->omega[1] += W[3] * d; b->omega[2] += W[6] * d;
-            nl = clampd(lr2 - b->omega[1] / W[4], -lim, lim);
+            w[0] += W00 * d; w[1] += W01 * d; w[2] += W02 * d;
+            nl = r_clamp(lr2 - w[1] * iW11, -lim, lim);
             d = nl - lr2; lr2 = nl;
-            b->omega[0] += W[1] * d; b->omega[1] += W[4] * d; b->omega[2] += W[7] * d;
+            w[0] += W01 * d; w[1] += W11 * d; w[2] += W12 * d;
         }
     }
 }
@@ -271,66 +309,81 @@ static void solve_contacts(const orc_body_params *p, orc_body *b, double dt, con
 /* Rows B2, B4, B5, B6: one p.stepSimulation() (ref:477). */
 void orc_step_simulation(const orc_body_params *p, orc_body *b, double *trace) {
     const int K = p->substeps;
-    const double dt = p->dt_step / K;                 /* B2: 0.02/4 = 0.005 exactly */
+    const real dt = (real)(p->dt_step / K);           /* B2: 0.02/4 = 0.005 exactly */
+    const real maxv = (real)p->max_vel;
+    const real Ia = (real)p->inertia[0], Ib = (real)p->inertia[1], Ic = (real)p->inertia[2];
     /* B4: applyGravity() once before the substep loop; forces constant over the K substeps */
-    double F[3], T[3];
-    for (int i = 0; i < 3; i++) { F[i] = b->force[i] + p->gravity[i] * p->mass; T[i] = b->torque[i]; }
+    real F[3], T[3], pos[3], q[4], v[3], w[3];
+    for (int i = 0; i < 3; i++) {
+        F[i] = (real)(b->force[i] + p->gravity[i] * p->mass); T[i] = (real)b->torque[i];
+        pos[i] = (real)b->pos[i]; v[i] = (real)b->vel[i]; w[i] = (real)b->omega[i];
+    }
+    for (int i = 0; i < 4; i++) q[i] = (real)b->quat[i];
+    const real inv_m = (real)(1.0 / p->mass);
+    (void)inv_m;
 
     for (int k = 0; k < K; k++) {
-        double R[9];
-        orc_matrix_from_quat(b->quat, R);
+        real R[9];
+        r_matrix_from_quat(q, R);
         /* B5: ABA for a lone floating base, in base-local coordinates */
-        double wl[3], tl[3], wdl[3], wd[3];
-        matTvec(R, b->omega, wl);
-        matTvec(R, T, tl);
-        double wn2 = dot3(wl, wl);
-        double wn = wn2 > 2.220446049250313e-16 ? sqrt(wn2) : 0.0;  /* btVector3::safeNorm */
-        double kd = p->ang_damp + p->ang_damp * wn;
-        double zacc[3];
-        for (int i = 0; i < 3; i++) zacc[i] = -tl[i] + p->inertia[i] * wl[i] * kd;
+        real wl[3], tl[3], wdl[3], wd[3];
+        wl[0] = R[0] * w[0] + R[3] * w[1] + R[6] * w[2];
+        wl[1] = R[1] * w[0] + R[4] * w[1] + R[7] * w[2];
+        wl[2] = R[2] * w[0] + R[5] * w[1] + R[8] * w[2];
+        tl[0] = R[0] * T[0] + R[3] * T[1] + R[6] * T[2];
+        tl[1] = R[1] * T[0] + R[4] * T[1] + R[7] * T[2];
+        tl[2] = R[2] * T[0] + R[5] * T[1] + R[8] * T[2];
+        real wn2 = wl[0] * wl[0] + wl[1] * wl[1] + wl[2] * wl[2];
+        real wn = wn2 > R_EPS2 ? R_SQRT(wn2) : (real)0.0;      /* btVector3::safeNorm */
+        real kd = (real)p->ang_damp + (real)p->ang_damp * wn;
+        real zacc[3] = {-tl[0] + Ia * wl[0] * kd, -tl[1] + Ib * wl[1] * kd, -tl[2] + Ic * wl[2] * kd};
         if (p->use_gyro) {
-            double Iw[3] = {p->inertia[0] * wl[0], p->inertia[1] * wl[1], p->inertia[2] * wl[2]}, g[3];
-            cross3(wl, Iw, g);
-            for (int i = 0; i < 3; i++) zacc[i] += g[i];
+            real Iw[3] = {Ia * wl[0], Ib * wl[1], Ic * wl[2]};
+            zacc[0] += wl[1] * Iw[2] - wl[2] * Iw[1];
+            zacc[1] += wl[2] * Iw[0] - wl[0] * Iw[2];
+            zacc[2] += wl[0] * Iw[1] - wl[1] * Iw[0];
         }
-        for (int i = 0; i < 3; i++) wdl[i] = -(zacc[i] / p->inertia[i]);
-        matvec(R, wdl, wd);
-        double vn2 = dot3(b->vel, b->vel);
-        double vn = vn2 > 2.220446049250313e-16 ? sqrt(vn2) : 0.0;
-        double kl = p->lin_damp + p->lin_damp * vn;
-        for (int i = 0; i < 3; i++) {   /* applyDeltaVeeMultiDof with the +-100 clamp */
-            b->omega[i] = clampd(b->omega[i] + wd[i] * dt, -p->max_vel, p->max_vel);
-        }
+        wdl[0] = -(zacc[0] / Ia); wdl[1] = -(zacc[1] / Ib); wdl[2] = -(zacc[2] / Ic);
+        wd[0] = R[0] * wdl[0] + R[1] * wdl[1] + R[2] * wdl[2];
+        wd[1] = R[3] * wdl[0] + R[4] * wdl[1] + R[5] * wdl[2];
+        wd[2] = R[6] * wdl[0] + R[7] * wdl[1] + R[8] * wdl[2];
+        real vn2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+        real vn = vn2 > R_EPS2 ? R_SQRT(vn2) : (real)0.0;
+        real kl = (real)p->lin_damp + (real)p->lin_damp * vn;
+        for (int i = 0; i < 3; i++)      /* applyDeltaVeeMultiDof with the +-100 clamp */
+            w[i] = r_clamp(w[i] + wd[i] * dt, -maxv, maxv);
         for (int i = 0; i < 3; i++) {
-            double vd = F[i] / p->mass - b->vel[i] * kl;
-            b->vel[i] = clampd(b->vel[i] + vd * dt, -p->max_vel, p->max_vel);
+            real vd = F[i] / (real)p->mass - v[i] * kl;
+            v[i] = r_clamp(v[i] + vd * dt, -maxv, maxv);
         }
         /* B9 (our model): contacts detected at the pre-integration pose, solved on velocities */
-        if (p->ground) solve_contacts(p, b, dt, R);
+        if (p->ground) solve_contacts(p, dt, R, pos[2], v, w);
 
         /* B6: stepPositionsMultiDof -- semi-implicit Euler, exponential map */
-        for (int i = 0; i < 3; i++) b->pos[i] += dt * b->vel[i];
-        double ang = sqrt(dot3(b->omega, b->omega));
-        if (ang * dt > 0.25 * PI_D) ang = 0.5 * (0.5 * PI_D) / dt;       /* ANGULAR_MOTION_THRESHOLD */
-        double ax[3], sc;
-        if (ang < 0.001) sc = 0.5 * dt - (dt * dt * dt) * 0.020833333333 * ang * ang;
-        else sc = sin(0.5 * ang * dt) / ang;
-        for (int i = 0; i < 3; i++) ax[i] = b->omega[i] * sc;
-        double cw = cos(ang * dt * 0.5);
+        for (int i = 0; i < 3; i++) pos[i] += dt * v[i];
+        real ang = R_SQRT(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+        if (ang * dt > (real)(0.25 * PI_D)) ang = (real)(0.5 * (0.5 * PI_D)) / dt;   /* ANGULAR_MOTION_THRESHOLD */
+        real sc;
+        if (ang < (real)0.001) sc = (real)0.5 * dt - (dt * dt * dt) * (real)0.020833333333 * ang * ang;
+        else sc = R_SIN((real)0.5 * ang * dt) / ang;
+        real ax0 = w[0] * sc, ax1 = w[1] * sc, ax2 = w[2] * sc;
+        real cw = R_COS(ang * dt * (real)0.5);
         /* q <- dq (x) q  with dq = (ax, cw) */
-        double *q = b->quat;
-        double nx = cw * q[0] + ax[0] * q[3] + ax[1] * q[2] - ax[2] * q[1];
-        double ny = cw * q[1] + ax[1] * q[3] + ax[2] * q[0] - ax[0] * q[2];
-        double nz = cw * q[2] + ax[2] * q[3] + ax[0] * q[1] - ax[1] * q[0];
-        double nw = cw * q[3] - ax[0] * q[0] - ax[1] * q[1] - ax[2] * q[2];
-        double inv = 1.0 / sqrt(nx * nx + ny * ny + nz * nz + nw * nw);
+        real nx = cw * q[0] + ax0 * q[3] + ax1 * q[2] - ax2 * q[1];
+        real ny = cw * q[1] + ax1 * q[3] + ax2 * q[0] - ax0 * q[2];
+        real nz = cw * q[2] + ax2 * q[3] + ax0 * q[1] - ax1 * q[0];
+        real nw = cw * q[3] - ax0 * q[0] - ax1 * q[1] - ax2 * q[2];
+        real inv = (real)1.0 / R_SQRT(nx * nx + ny * ny + nz * nz + nw * nw);
         q[0] = nx * inv; q[1] = ny * inv; q[2] = nz * inv; q[3] = nw * inv;
 
         if (trace) {
             double *t = trace + 13 * k;
-            memcpy(t, b->pos, 24); memcpy(t + 3, b->quat, 32); memcpy(t + 7, b->vel, 24); memcpy(t + 10, b->omega, 24);
+            for (int i = 0; i < 3; i++) { t[i] = pos[i]; t[7 + i] = v[i]; t[10 + i] = w[i]; }
+            for (int i = 0; i < 4; i++) t[3 + i] = q[i];
         }
     }
+    for (int i = 0; i < 3; i++) { b->pos[i] = pos[i]; b->vel[i] = v[i]; b->omega[i] = w[i]; }
+    for (int i = 0; i < 4; i++) b->quat[i] = q[i];
     /* B4: clearForces() after the loop */
     for (int i = 0; i < 3; i++) { b->force[i] = 0; b->torque[i] = 0; }
 }

@@ -194,3 +194,34 @@ def test_fast_diversity_matches_exact_on_goldens(oracle_mod, golden_dir):
             if g["was_reset"][t]:
                 ex.reset(), fa.reset()
         assert diff <= allowed, (name, diff)
+
+
+def test_fp32_sensitivity_of_the_model(oracle_mod, golden_dir):
+    """How much does evaluating the physics layer in float32 (the device's arithmetic) move one
+    teacher-forced step away from fp64?  Uses the -DORC_PHYS_FLOAT build of the same C source.  This
+    bounds what the GPU parity tests can demand: free-flight steps stay within K*1e-5; steps in ground
+    contact are amplified by the PGS rows (1/I_zz = 400) up to a few 1e-4."""
+    import ctypes as C
+    O = oracle_mod
+    g = _load(golden_dir, "random_raw")
+    a = O.OracleSim(O.default_config(O.CONTRACT_R), 1)
+    b = O.OracleSim(O.default_config(O.CONTRACT_R), 1, f32_physics=True)
+    free, contact = [], []
+    for t in range(400):
+        C.memmove(C.byref(b.env(0)), C.byref(a.env(0)), C.sizeof(O.Env))
+        eb = b.env(0)
+        for f in ("pos", "quat", "vel", "omega"):
+            arr = getattr(eb.body, f)
+            for i in range(len(arr)):
+                arr[i] = float(np.float32(arr[i]))
+        z_pre = a.env(0).body.pos[2]
+        a.step(g["actions"][t:t + 1])
+        b.step(g["actions"][t:t + 1])
+        ea = a.env(0)
+        sa = np.array(list(ea.body.pos) + list(ea.body.quat) + list(ea.body.vel) + list(ea.body.omega))
+        sb = np.array(list(eb.body.pos) + list(eb.body.quat) + list(eb.body.vel) + list(eb.body.omega))
+        err = float((np.abs(sa - sb) / np.maximum(1, np.abs(sa))).max())
+        (free if min(z_pre, ea.body.pos[2]) > 0.62 else contact).append(err)
+    assert len(free) >= 10 and len(contact) > 100
+    assert max(free) <= 4e-5
+    assert max(contact) <= 1e-3 and np.median(contact) < 2e-5

@@ -257,7 +257,7 @@ static void make_devcfg(const tvc_config &c, DevCfg &d) {
     d.tilt_max = c.init_tilt_max; d.omega_max = c.init_omega_max; d.prop_frac = c.propellant_fraction; d.cg_burn = c.cg_burn_shift;
     // contact material: enhanced_rocket_tvc_env.py:349-352 (plane) x :455-458 (rocket); Bullet combination rules
     d.mu = 0.3f * 0.8f; d.mu_spin = 0.1f * 0.8f + 0.1f * 0.3f; d.mu_roll = 0.05f * 0.8f + 0.05f * 0.3f;
-    d.restitution = 0.1f; d.rest_thr = 0.2f; d.erp = 0.2f; d.margin = 0.02f;
+    d.restitution = 0.1f; d.rest_thr = 0.2f; d.erp = 0.2f; d.margin = 0.05f;
     d.seed_lo = (unsigned)c.seed; d.seed_hi = (unsigned)(c.seed >> 32);
     d.env_base = c.env_id_base;
 }

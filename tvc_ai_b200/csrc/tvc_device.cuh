@@ -188,21 +188,26 @@ __device__ __forceinline__ BodyP body_params(const DevCfg &c, bool X, float mass
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 
 // ------------------------------------------------------------------------------------------
-// Ground contact: our documented model (DESIGN.md "Contact model"; oracle solve_contacts()).
-// Stateless 5-point manifold, speculative/Baumgarte normal rows, friction disc, torsional rows
-// on the first active point, projected Gauss-Seidel on velocities.
+// Ground contact: our documented model (DESIGN.md "Contact model"), continuous in the state.
+//   p0 / p1 : lowest rim point of the bottom / top cap, direction -(R31,R32)/max(rho,1e-3)
+//   f0..f2  : body-fixed rim points of the bottom cap at 0, 120, 240 degrees
+// Entered when the lowest candidate is within `margin`; then all five rows are processed
+// (speculative vn >= -gap/dt, Baumgarte for gap < 0, restitution), friction disc per point,
+// spinning / rolling rows limited by the total normal impulse; projected Gauss-Seidel on
+// velocities, contact_iters sweeps, no warm start.  Bullet's own manifold/solver (row B9) is not
+// reproducible without its source; this model is shared with the oracle by specification only.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, const float R[9], float pz, float &vx,
                                                float &vy, float &vz, float &wx, float &wy, float &wz) {
     const float r = c.radius, h = c.half_len;
     const float R31 = R[6], R32 = R[7], R33 = R[8];
-    float rho = sqrtf(R31 * R31 + R32 * R32);
-    float ux, uy;
-    if (rho > 1e-3f) { ux = -R31 / rho; uy = -R32 / rho; } else { ux = 1.0f; uy = 0.0f; }
-    float zn = (R33 >= 0.0f ? -h : h) - P.cg;
-    float zf = (R33 >= 0.0f ? h : -h) - P.cg;
-    float gap0 = pz + R33 * zn + r * (R31 * ux + R32 * uy);
-    if (!(gap0 < c.margin)) return;
+    const float rho = sqrtf(R31 * R31 + R32 * R32);
+    const float inv = 1.0f / fmaxf(rho, 1e-3f);
+    const float ux = -R31 * inv, uy = -R32 * inv;
+    const float zb = -h - P.cg, zt = h - P.cg;
+    const float low = r * (R31 * ux + R32 * uy);
+    const float gb = pz + R33 * zb + low, gt = pz + R33 * zt + low;
+    if (!(fminf(gb, gt) < c.margin)) return;
 
     // world inverse inertia W = R diag(1/I) R^T (symmetric)
     const float ia = P.inv_Ixy, ib = P.inv_Iz;
@@ -214,71 +219,65 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
     const float W22 = ia * (R[6] * R[6] + R[7] * R[7]) + ib * R[8] * R[8];
     const float im = P.inv_mass;
 
-    const float clx[5] = {r * ux, -r * uy, r * uy, -r * ux, r * ux};
-    const float cly[5] = {r * uy, r * ux, -r * ux, -r * uy, r * uy};
+    const float clx[5] = {r * ux, r * ux, r, -0.5f * r, -0.5f * r};
+    const float cly[5] = {r * uy, r * uy, 0.0f, 0.8660254037844386f * r, -0.8660254037844386f * r};
     float ax[5], ay[5], az[5], tgt[5], imn[5], im1[5], im2[5];
     float ln[5], l1[5], l2[5];
-    bool act[5];
-    int first = -1;
 #pragma unroll
     for (int i = 0; i < 5; i++) {
-        float cz = i == 4 ? zf : zn;
+        const float cz = i == 1 ? zt : zb;
         ax[i] = R[0] * clx[i] + R[1] * cly[i] + R[2] * cz;
         ay[i] = R[3] * clx[i] + R[4] * cly[i] + R[5] * cz;
         az[i] = R[6] * clx[i] + R[7] * cly[i] + R[8] * cz;
-        float gap = pz + az[i];
-        act[i] = gap < c.margin;
-        if (act[i] && first < 0) first = i;
+        const float gap = pz + az[i];
         // effective masses for n = z, t1 = x, t2 = y at arm (ax,ay,az)
-        float mn = im + (W00 * ay[i] * ay[i] - 2.0f * W01 * ax[i] * ay[i] + W11 * ax[i] * ax[i]);
-        float m1 = im + (W11 * az[i] * az[i] - 2.0f * W12 * az[i] * ay[i] + W22 * ay[i] * ay[i]);
-        float m2 = im + (W00 * az[i] * az[i] - 2.0f * W02 * az[i] * ax[i] + W22 * ax[i] * ax[i]);
+        const float mn = im + (W00 * ay[i] * ay[i] - 2.0f * W01 * ax[i] * ay[i] + W11 * ax[i] * ax[i]);
+        const float m1 = im + (W11 * az[i] * az[i] - 2.0f * W12 * az[i] * ay[i] + W22 * ay[i] * ay[i]);
+        const float m2 = im + (W00 * az[i] * az[i] - 2.0f * W02 * az[i] * ax[i] + W22 * ax[i] * ax[i]);
         imn[i] = 1.0f / mn; im1[i] = 1.0f / m1; im2[i] = 1.0f / m2;
-        float vn0 = vz + wx * ay[i] - wy * ax[i];
-        float rest = (vn0 < -c.rest_thr) ? -c.restitution * vn0 : 0.0f;
+        const float vn0 = vz + wx * ay[i] - wy * ax[i];
+        const float rest = (vn0 < -c.rest_thr) ? -c.restitution * vn0 : 0.0f;
         tgt[i] = rest + (gap > 0.0f ? -gap * c.inv_dt : -c.erp * gap * c.inv_dt);
         ln[i] = 0.0f; l1[i] = 0.0f; l2[i] = 0.0f;
     }
     float lsp = 0.0f, lr1 = 0.0f, lr2 = 0.0f;
     const float iW22 = 1.0f / W22, iW00 = 1.0f / W00, iW11 = 1.0f / W11;
     for (int it = 0; it < c.contact_iters; it++) {
-        float lnf = 0.0f;
+        float lsum = 0.0f;
 #pragma unroll
         for (int i = 0; i < 5; i++) {
-            if (act[i]) {
-                // normal row
-                float vn = vz + wx * ay[i] - wy * ax[i];
-                float nl = fmaxf(ln[i] + (tgt[i] - vn) * imn[i], 0.0f);
-                float d = nl - ln[i];
-                ln[i] = nl;
-                vz += d * im;
-                wx += (W00 * ay[i] - W01 * ax[i]) * d;
-                wy += (W01 * ay[i] - W11 * ax[i]) * d;
-                wz += (W02 * ay[i] - W12 * ax[i]) * d;
-                // friction disc
-                float vt1 = vx + wy * az[i] - wz * ay[i];
-                float vt2 = vy + wz * ax[i] - wx * az[i];
-                float a1 = l1[i] - vt1 * im1[i];
-                float a2 = l2[i] - vt2 * im2[i];
-                float lim = c.mu * nl;
-                float mag = sqrtf(a1 * a1 + a2 * a2);
-                if (mag > lim) { float sc = mag > 0.0f ? lim / mag : 0.0f; a1 *= sc; a2 *= sc; }
-                float d1 = a1 - l1[i], d2 = a2 - l2[i];
-                l1[i] = a1; l2[i] = a2;
-                vx += d1 * im; vy += d2 * im;
-                float tx = -az[i] * d2, ty = az[i] * d1, tz = ax[i] * d2 - ay[i] * d1;
-                wx += W00 * tx + W01 * ty + W02 * tz;
-                wy += W01 * tx + W11 * ty + W12 * tz;
-                wz += W02 * tx + W12 * ty + W22 * tz;
-                if (i == first) lnf = nl;
-            }
+            // normal row
+            const float vn = vz + wx * ay[i] - wy * ax[i];
+            const float nl = fmaxf(ln[i] + (tgt[i] - vn) * imn[i], 0.0f);
+            const float d = nl - ln[i];
+            ln[i] = nl;
+            lsum += nl;
+            vz += d * im;
+            wx += (W00 * ay[i] - W01 * ax[i]) * d;
+            wy += (W01 * ay[i] - W11 * ax[i]) * d;
+            wz += (W02 * ay[i] - W12 * ax[i]) * d;
+            // friction disc
+            const float vt1 = vx + wy * az[i] - wz * ay[i];
+            const float vt2 = vy + wz * ax[i] - wx * az[i];
+            float a1 = l1[i] - vt1 * im1[i];
+            float a2 = l2[i] - vt2 * im2[i];
+            const float lim = c.mu * nl;
+            const float mag2 = a1 * a1 + a2 * a2;
+            if (mag2 > lim * lim) { const float sc = lim * rsqrtf(mag2); a1 *= sc; a2 *= sc; }
+            const float d1 = a1 - l1[i], d2 = a2 - l2[i];
+            l1[i] = a1; l2[i] = a2;
+            vx += d1 * im; vy += d2 * im;
+            const float tx = -az[i] * d2, ty = az[i] * d1, tz = ax[i] * d2 - ay[i] * d1;
+            wx += W00 * tx + W01 * ty + W02 * tz;
+            wy += W01 * tx + W11 * ty + W12 * tz;
+            wz += W02 * tx + W12 * ty + W22 * tz;
         }
-        {   // spinning / rolling friction rows on the first active contact
-            float lim = c.mu_spin * lnf;
+        {   // spinning / rolling friction rows, limited by the total normal impulse
+            float lim = c.mu_spin * lsum;
             float nl = clampf(lsp - wz * iW22, -lim, lim);
             float d = nl - lsp; lsp = nl;
             wx += W02 * d; wy += W12 * d; wz += W22 * d;
-            lim = c.mu_roll * lnf;
+            lim = c.mu_roll * lsum;
             nl = clampf(lr1 - wx * iW00, -lim, lim);
             d = nl - lr1; lr1 = nl;
             wx += W00 * d; wy += W01 * d; wz += W02 * d;
