@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(TVC_BLOCK)
 step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState st, const __grid_constant__ DevIO io) {
     __shared__ __align__(16) float s_obs[TVC_BLOCK * 10];
     __shared__ double s_stat[TVC_WARPS][TVC_NSTAT];
+    __shared__ ContactSmem s_contact;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long i = (long long)blockIdx.x * TVC_BLOCK + threadIdx.x;
     const bool live = i < st.n;
@@ -39,8 +40,10 @@ step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState s
     int ev_len = 0, ev_succ = 0, ev_reason = 0, ev_trunc = 0;
     float ev_ret = 0.0f, ev_alt = 0.0f, ev_tilt = 0.0f, ev_fuel = 0.0f;
 
+    Env e;
+    BodyP P;
+    Forces f;
     if (live) {
-        Env e;
         load_env(st, X, i, e);
         float2 a;
         if (io.actions) a = io.actions[i];
@@ -49,8 +52,17 @@ step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState s
             a = make_float2(2.0f * u01(rr.x) - 1.0f, 2.0f * u01(rr.y) - 1.0f);
         }
         if (io.actions_out) io.actions_out[i] = a;
+        env_pre<X>(c, st, i, e, a.x, a.y, P, f);
+    } else {   // threads past the end still take part in the CTA-wide contact exchange
+        memset(&e, 0, sizeof(e));
+        e.qw = 1.0f; e.pz = 1.0f;
+        P = body_params(c, false, 1.0f, 0.0f, 1.0f);
+        f.Fx = f.Fy = f.Fz = f.Tx = f.Ty = f.Tz = f.a0 = f.a1 = 0.0f;
+    }
+    integrate(c, P, e, f.Fx, f.Fy, f.Fz, f.Tx, f.Ty, f.Tz, live, s_contact);
+    if (live) {
         StepResult r;
-        env_step<X, DIV>(c, st, i, gid, e, a.x, a.y, r);
+        env_post<X, DIV>(c, st, i, gid, e, f.a0, f.a1, r);
 
         io.reward[i] = r.reward;
         io.term[i] = (uint8_t)r.terminated;
@@ -215,16 +227,19 @@ __global__ void info_kernel(const __grid_constant__ DevState st, const __grid_co
     if (io.criteria_met) io.criteria_met[i] = (uint8_t)(e.consec >= 10);
 }
 
-// deterministic reduction of the per-CTA partial rows: one thread per statistic, fixed order
+// deterministic reduction of the per-CTA partial rows: one warp per statistic, lane-strided partial sums in
+// a fixed order, then a fixed shuffle tree
 __global__ void stats_reduce_kernel(double *partial, int nblocks, double *out, double steps, int reset_after) {
-    const int k = threadIdx.x;
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (k >= TVC_NSTAT) return;
     double s = 0.0;
-    for (int b = 0; b < nblocks; b++) {
+    for (int b = lane; b < nblocks; b += 32) {
         s += partial[(long long)b * TVC_NSTAT + k];
         if (reset_after) partial[(long long)b * TVC_NSTAT + k] = 0.0;
     }
-    out[k] = (k == 14) ? steps : s;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[k] = (k == 14) ? steps : s;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -502,7 +517,7 @@ int tvc_episode_stats_dev(tvc_handle *h, double *dev_out, int reset_after, tvc_s
     CHECK_H(h);
     if (!dev_out) { tvc_set_err("dev_out is NULL"); return TVC_E_BADARG; }
     const double steps = (double)h->stat_steps * (double)h->n;
-    stats_reduce_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->st.partial, h->grid, dev_out, steps, reset_after);
+    stats_reduce_kernel<<<1, 32 * TVC_NSTAT, 0, (cudaStream_t)stream>>>(h->st.partial, h->grid, dev_out, steps, reset_after);
     LAUNCH_OK("stats_reduce_kernel");
     if (reset_after) h->stat_steps = 0;
     return TVC_OK;

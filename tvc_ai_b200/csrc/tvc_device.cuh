@@ -197,17 +197,34 @@ __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fm
 // velocities, contact_iters sweeps, no warm start.  Bullet's own manifold/solver (row B9) is not
 // reproducible without its source; this model is shared with the oracle by specification only.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, const float R[9], float pz, float &vx,
-                                               float &vy, float &vz, float &wx, float &wy, float &wz) {
+// Broadphase, evaluated per substep by the env's own thread.  The solve is entered when the lowest
+// candidate is within `margin` (the model's rule, as in the oracle) AND some row can bind at all:
+// a row binds only if (1+e) * approach speed * dt exceeds its gap, and the approach speed of any
+// point is bounded by |vz| + |w| * reach -- when that fails the solve is exactly a no-op, so
+// skipping it does not change the result.
+__device__ __forceinline__ bool contact_needed(const DevCfg &c, const BodyP &P, const float R[9], float pz, float vz,
+                                               float wx, float wy, float wz) {
     const float r = c.radius, h = c.half_len;
     const float R31 = R[6], R32 = R[7], R33 = R[8];
     const float rho = sqrtf(R31 * R31 + R32 * R32);
     const float inv = 1.0f / fmaxf(rho, 1e-3f);
+    const float low = -r * (R31 * R31 + R32 * R32) * inv;
+    const float gmin = pz + fminf(R33 * (-h - P.cg), R33 * (h - P.cg)) + low;
+    if (!(gmin < c.margin)) return false;
+    const float hh = h + fabsf(P.cg);
+    const float reach = sqrtf(hh * hh + r * r);
+    const float vmax = fabsf(vz) + sqrtf(wx * wx + wy * wy + wz * wz) * reach;
+    return gmin - 1e-4f < (1.0f + c.restitution) * vmax * c.dt;
+}
+
+__device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, const float R[9], float pz, float &vx,
+                                               float &vy, float &vz, float &wx, float &wy, float &wz) {
+    const float r = c.radius, h = c.half_len;
+    const float R31 = R[6], R32 = R[7];
+    const float rho = sqrtf(R31 * R31 + R32 * R32);
+    const float inv = 1.0f / fmaxf(rho, 1e-3f);
     const float ux = -R31 * inv, uy = -R32 * inv;
     const float zb = -h - P.cg, zt = h - P.cg;
-    const float low = r * (R31 * ux + R32 * uy);
-    const float gb = pz + R33 * zb + low, gt = pz + R33 * zt + low;
-    if (!(fminf(gb, gt) < c.margin)) return;
 
     // world inverse inertia W = R diag(1/I) R^T (symmetric)
     const float ia = P.inv_Ixy, ib = P.inv_Iz;
@@ -288,11 +305,22 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
     }
 }
 
+// Shared-memory exchange used to compact ground-contact problems across the CTA: each env that needs
+// the solver this substep posts its problem to a slot; the first ceil(M/32) (rotated) warps solve the
+// M problems with (nearly) full lanes instead of every warp running the solver for a few lanes.
+#define TVC_PROB_FIELDS 15
+struct ContactSmem {
+    float f[TVC_PROB_FIELDS][TVC_BLOCK];   // qx qy qz qw pz vx vy vz wx wy wz inv_mass inv_Ixy inv_Iz cg
+    int cnt[TVC_WARPS];
+};
+
 // Rows B2, B4, B5, B6: K substeps with the world-frame force F and torque T held constant (Q3).
+// Block-cooperative: EVERY thread of the CTA must call this (threads without an env pass live=false).
 __device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &e, float Fx, float Fy, float Fz,
-                                          float Tx, float Ty, float Tz) {
+                                          float Tx, float Ty, float Tz, bool live, ContactSmem &sm) {
     const float dt = c.dt;
     const float ax_ = Fx * P.inv_mass, ay_ = Fy * P.inv_mass, az_ = Fz * P.inv_mass;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int k = 0; k < c.K; k++) {
         float R[9];
         quat_to_mat(e.qx, e.qy, e.qz, e.qw, R);
@@ -322,7 +350,45 @@ __device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &
         e.vy = clampf(e.vy + (ay_ - e.vy * kl) * dt, -100.0f, 100.0f);
         e.vz = clampf(e.vz + (az_ - e.vz * kl) * dt, -100.0f, 100.0f);
 
-        if (c.ground) solve_contacts(c, P, R, e.pz, e.vx, e.vy, e.vz, e.wx, e.wy, e.wz);
+        if (c.ground) {
+            // B9 (our model): contacts detected at the pre-integration pose, solved on velocities
+            const bool need = live && contact_needed(c, P, R, e.pz, e.vz, e.wx, e.wy, e.wz);
+            const unsigned bal = __ballot_sync(0xffffffffu, need);
+            if (lane == 0) sm.cnt[warp] = __popc(bal);
+            __syncthreads();
+            int total = 0, base = 0;
+#pragma unroll
+            for (int w = 0; w < TVC_WARPS; w++) { const int n = sm.cnt[w]; if (w < warp) base += n; total += n; }
+            if (total > 0) {                                   // CTA-uniform
+                const int slot = base + __popc(bal & ((1u << lane) - 1u));
+                if (need) {
+                    sm.f[0][slot] = e.qx; sm.f[1][slot] = e.qy; sm.f[2][slot] = e.qz; sm.f[3][slot] = e.qw;
+                    sm.f[4][slot] = e.pz;
+                    sm.f[5][slot] = e.vx; sm.f[6][slot] = e.vy; sm.f[7][slot] = e.vz;
+                    sm.f[8][slot] = e.wx; sm.f[9][slot] = e.wy; sm.f[10][slot] = e.wz;
+                    sm.f[11][slot] = P.inv_mass; sm.f[12][slot] = P.inv_Ixy; sm.f[13][slot] = P.inv_Iz; sm.f[14][slot] = P.cg;
+                }
+                __syncthreads();
+                // rotate the solver warps over the SMSPs (warp w of every CTA sits on SMSP w % 4)
+                const int t = (threadIdx.x + 32 * ((blockIdx.x + k) & (TVC_WARPS - 1))) & (TVC_BLOCK - 1);
+                if (t < total) {
+                    float Rs[9];
+                    quat_to_mat(sm.f[0][t], sm.f[1][t], sm.f[2][t], sm.f[3][t], Rs);
+                    BodyP Q;
+                    Q.inv_mass = sm.f[11][t]; Q.inv_Ixy = sm.f[12][t]; Q.inv_Iz = sm.f[13][t]; Q.cg = sm.f[14][t];
+                    float vx = sm.f[5][t], vy = sm.f[6][t], vz = sm.f[7][t];
+                    float wx = sm.f[8][t], wy = sm.f[9][t], wz = sm.f[10][t];
+                    solve_contacts(c, Q, Rs, sm.f[4][t], vx, vy, vz, wx, wy, wz);
+                    sm.f[5][t] = vx; sm.f[6][t] = vy; sm.f[7][t] = vz;
+                    sm.f[8][t] = wx; sm.f[9][t] = wy; sm.f[10][t] = wz;
+                }
+                __syncthreads();
+                if (need) {
+                    e.vx = sm.f[5][slot]; e.vy = sm.f[6][slot]; e.vz = sm.f[7][slot];
+                    e.wx = sm.f[8][slot]; e.wy = sm.f[9][slot]; e.wz = sm.f[10][slot];
+                }
+            }
+        }
 
         // B6: semi-implicit Euler + exponential map, q <- dq (x) q, normalise
         e.px += dt * e.vx; e.py += dt * e.vy; e.pz += dt * e.vz;
@@ -439,10 +505,15 @@ struct StepResult {
     int viol;
 };
 
-// One env step on register-resident state (ref:466-518).  `a0,a1` is the raw policy action.
-template <bool X, int DIV>
-__device__ __forceinline__ void env_step(const DevCfg &c, const DevState &st, long long i, long long gid, Env &e,
-                                         float a0, float a1, StepResult &r) {
+struct Forces {
+    float Fx, Fy, Fz, Tx, Ty, Tz;
+    float a0, a1;   // clipped policy action
+};
+
+// First half of one env step (ref:466-476): S2 action processing, S3 control forces, S5 aerodynamics.
+template <bool X>
+__device__ __forceinline__ void env_pre(const DevCfg &c, const DevState &st, long long i, Env &e, float a0, float a1,
+                                        BodyP &P, Forces &f) {
     // ---- S2 (ref:470-471) ----
     a0 = clampf(a0, -1.0f, 1.0f); a1 = clampf(a1, -1.0f, 1.0f);
     float p0 = a0, p1 = a1;
@@ -456,7 +527,7 @@ __device__ __forceinline__ void env_step(const DevCfg &c, const DevState &st, lo
 
     // ---- S3 (ref:520-559) control forces from the pre-step state ----
     float fuel_pre = fuel_of(e.burn);
-    BodyP P = body_params(c, X, e.mass_scale, e.cg_off, fuel_pre);
+    P = body_params(c, X, e.mass_scale, e.cg_off, fuel_pre);
     float Fx = 0.0f, Fy = 0.0f, Fz = 0.0f, Tx = 0.0f, Ty = 0.0f, Tz = 0.0f;
     if (c.quirks & 1u) Fz += -9.81f * P.mass;                         // Q1: explicit gravity force
     if (e.burn < 1000) {                                               // Q4: fuel > 0 on entry
@@ -490,9 +561,13 @@ __device__ __forceinline__ void env_step(const DevCfg &c, const DevState &st, lo
     }
     if (X) { Fx += e.wind_x; Fy += e.wind_y; }
     Fz += -9.81f * P.mass;                                             // B4: world gravity (ref:338)
+    f.Fx = Fx; f.Fy = Fy; f.Fz = Fz; f.Tx = Tx; f.Ty = Ty; f.Tz = Tz; f.a0 = a0; f.a1 = a1;
+}
 
-    // ---- S6 (ref:477) ----
-    integrate(c, P, e, Fx, Fy, Fz, Tx, Ty, Tz);
+// Second half (ref:478-518), after the K substeps: S7-S12 and the reward R1-R10.
+template <bool X, int DIV>
+__device__ __forceinline__ void env_post(const DevCfg &c, const DevState &st, long long i, long long gid, Env &e,
+                                         float a0, float a1, StepResult &r) {
     e.step += 1;
 
     // ---- S7 (ref:608-633) ----

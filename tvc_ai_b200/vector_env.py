@@ -22,6 +22,7 @@ from .env import PHASES, engine_config_from_yaml
 
 class RocketTVCVectorEnv:
     metadata = {"render_modes": [], "autoreset_mode": "same_step"}
+    OBJECT_INFO_MAX = 4096   # above this, final_observation is a dense array + mask instead of an object array
 
     def __init__(self, num_envs: int, config: Optional[dict] = None, max_episode_steps: int = 1000,
                  contract: str | int = "R", device: Optional[int] = None, env_id_base: int = 0,
@@ -84,15 +85,16 @@ class RocketTVCVectorEnv:
         done = term | trunc
         infos = {}
         if done.any():
-            idx = np.flatnonzero(done)
-            fo = np.full(self.num_envs, None, dtype=object)
-            for i in idx:
-                fo[i] = final[i].copy()
+            if self.num_envs <= self.OBJECT_INFO_MAX:
+                # Gymnasium 0.26-0.29 layout: object array holding the terminal observation of finished envs
+                fo = np.full(self.num_envs, None, dtype=object)
+                for i in np.flatnonzero(done):
+                    fo[i] = final[i].copy()
+            else:
+                # large batches: dense [N,10] array, valid where the mask is set (no per-env Python loop)
+                fo = final.copy()
             infos["final_observation"] = fo
             infos["_final_observation"] = done
-            # terminal info is not available through the host fast path; episode-level numbers come
-            # from episode_stats().  mission_successful is recoverable: success <=> terminated with
-            # a non-penalised reward is not reliable, so it is omitted rather than guessed.
         return obs, rew, term, trunc, infos
 
     # ------------------------------------------------------------------
