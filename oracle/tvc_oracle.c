@@ -211,8 +211,12 @@ static void r_matrix_from_quat(const real q[4], real m[9]) {
  *    mu_spin / mu_roll times the total normal impulse
  *  - projected Gauss-Seidel on velocities, contact_iters sweeps, no warm start
  */
+/* diagnostic counters (not thread-safe; meaningful for serial runs only) */
+long long orc_dbg_substeps = 0, orc_dbg_entered = 0, orc_dbg_canbind = 0;
+
 static void solve_contacts(const orc_body_params *p, real dt, const real R[9], real pz, real v[3], real w[3]) {
     const real r = (real)p->radius, h = (real)p->half_len, cg = (real)p->cg, margin = (real)p->margin;
+    orc_dbg_substeps++;
     const real R31 = R[6], R32 = R[7], R33 = R[8];
     const real rho = R_SQRT(R31 * R31 + R32 * R32);
     const real inv = (real)1.0 / (rho > (real)1e-3 ? rho : (real)1e-3);
@@ -221,6 +225,12 @@ static void solve_contacts(const orc_body_params *p, real dt, const real R[9], r
     const real low = r * (R31 * ux + R32 * uy);          /* = -r*rho outside the regularised zone */
     const real gb = pz + R33 * zb + low, gt = pz + R33 * zt + low;
     if (!((gb < gt ? gb : gt) < margin)) return;
+    orc_dbg_entered++;
+    {
+        real hh = h + (cg < 0 ? -cg : cg), reach = R_SQRT(hh * hh + r * r);
+        real vmax = (v[2] < 0 ? -v[2] : v[2]) + R_SQRT(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]) * reach;
+        if ((gb < gt ? gb : gt) - (real)1e-4 < ((real)1.0 + (real)p->restitution) * vmax * dt) orc_dbg_canbind++;
+    }
 
     const real c[5][3] = {
         {r * ux, r * uy, zb},

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtvc_b200.so")
+LIB_PATH = os.environ.get("TVC_B200_LIB") or os.path.join(_HERE, "libtvc_b200.so")
 
 ABI_VERSION = 3
 OBS_DIM, ACT_DIM, NUM_COMPONENTS, NUM_STATS, MAX_DELAY = 10, 2, 12, 16, 4

@@ -25,8 +25,11 @@ __device__ __forceinline__ void warp_store_obs(float *dst, const float *s_warp, 
     for (int k = lane; k < n2; k += 32) d2[k] = s2[k];
 }
 
+#ifndef TVC_MIN_BLOCKS
+#define TVC_MIN_BLOCKS 4
+#endif
 template <bool X, int DIV>
-__global__ void __launch_bounds__(TVC_BLOCK)
+__global__ void __launch_bounds__(TVC_BLOCK, TVC_MIN_BLOCKS)
 step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState st, const __grid_constant__ DevIO io) {
     __shared__ __align__(16) float s_obs[TVC_BLOCK * 10];
     __shared__ double s_stat[TVC_WARPS][TVC_NSTAT];
