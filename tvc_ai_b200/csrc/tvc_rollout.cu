@@ -1,10 +1,417 @@
-// tvc_rollout.cu -- fused actor-MLP rollout (config 4).  Placeholder until the tcgen05 kernel lands.
+// tvc_rollout.cu -- fused SAC-actor rollout (BASELINE config 4): T env steps per launch, the actor
+// MLP Linear(10,256)-ReLU-Linear(256,256)-ReLU-Linear(256,4) evaluated inside the step loop.
+//
+// Replaces the get_action -> env.step loop of scripts/train.py:546-603 for the legacy 2x256 SAC actor
+// (shape from scripts/export_tflm.py:85-156, tests/test_agent.py:46-56).
+//
+// sm_100a design: CTA = 128 threads = 128 envs = 128 TMEM lanes (thread i owns env i and accumulator
+// row i).  bf16 weights are packed once into UMMA "K-major, no swizzle" core-matrix images and copied
+// into shared memory with one TMA bulk copy (cp.async.bulk) for the whole rollout.  Per step:
+//   obs tile -> smem (bf16)          -> tcgen05.mma M128 N256 K16   (layer 1, accumulators in TMEM)
+//   tcgen05.ld -> bias+ReLU -> smem  -> 16 x tcgen05.mma M128 N256 K16 (layer 2)
+//   tcgen05.ld -> bias+ReLU -> 256->4 head accumulated in registers (0.8 % of the FLOPs, CUDA cores)
+//   Philox eps, tanh -> action -> env_pre / integrate / env_post (same device code as step_kernel).
+// One elected thread issues the MMAs; completion is signalled through tcgen05.commit -> mbarrier.
 #include "tvc_internal.h"
 
-void tvc_rollout_free(tvc_handle *h) { (void)h; }
+#include <cuda_bf16.h>
+#include <cstring>
+#include <string>
 
-extern "C" int tvc_rollout(tvc_handle *h, const tvc_actor_weights *w, int32_t T, const tvc_rollout_io *io, tvc_stream stream) {
-    (void)h; (void)w; (void)T; (void)io; (void)stream;
-    tvc_set_err("tvc_rollout: not implemented in this build");
-    return TVC_E_STATE;
+using namespace tvc;
+
+namespace {
+
+constexpr int HID = 256;
+constexpr int K1 = 16;               // layer-1 K (10 obs padded to one UMMA K step)
+constexpr uint32_t W1_BYTES = HID * K1 * 2;        // 8 KB   image [K1/8][256][8] bf16
+constexpr uint32_t W2_BYTES = HID * HID * 2;       // 128 KB image [256/8][256][8] bf16
+constexpr uint32_t A1_BYTES = TVC_BLOCK * K1 * 2;  // 4 KB   obs tile [K1/8][128][8] bf16
+constexpr uint32_t H1_BYTES = TVC_BLOCK * HID * 2; // 64 KB  hidden tile [256/8][128][8] bf16
+constexpr uint32_t VEC_FLOATS = HID + HID + 4 * HID + 4;   // b1, b2, W3[4][256], b3
+constexpr uint32_t VEC_BYTES = ((VEC_FLOATS * 4 + 15) / 16) * 16;
+
+// shared-memory map (dynamic smem, 1024-byte aligned base)
+constexpr uint32_t OFF_W2 = 0;
+constexpr uint32_t OFF_W1 = OFF_W2 + W2_BYTES;
+constexpr uint32_t OFF_A1 = OFF_W1 + W1_BYTES;
+constexpr uint32_t OFF_H1 = OFF_A1 + A1_BYTES;          // also the contact-exchange area during physics
+constexpr uint32_t OFF_VEC = OFF_H1 + H1_BYTES;
+constexpr uint32_t OFF_BAR = OFF_VEC + VEC_BYTES;       // 2 mbarriers + tmem base
+constexpr uint32_t SMEM_TOTAL = OFF_BAR + 64;
+static_assert(sizeof(ContactSmem) <= H1_BYTES, "contact exchange must fit in the hidden-tile area");
+static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
+
+// UMMA instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=128 (cute::UMMA::InstrDescriptor)
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+
+struct RolloutWs {
+    uint8_t *img = nullptr;   // [W2 image][W1 image][vec] in the shared-memory layout
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// core matrix = 8 rows x 16 bytes; SBO = stride between 8-row groups, LBO = stride between the two
+// 16-byte K chunks of one K=16 step.  Images are laid out [K/8][rows/8][8 rows][8 elems].
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t lo = (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16);
+    uint64_t hi = (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) | (1ull << 14);   // version = 1 (Blackwell)
+    return lo | (hi << 32);
+}
+
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}\n"
+        :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 32 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+// fp32 [out,in] torch weights -> bf16 UMMA images + fp32 vectors, in the shared-memory layout
+__global__ void pack_actor_kernel(tvc_actor_weights w, uint8_t *img) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nthreads = gridDim.x * blockDim.x;
+    // W2 image: element (n, k) at (k/8)*4096 + n*16 + (k%8)*2
+    for (int idx = tid; idx < HID * (HID / 8); idx += nthreads) {
+        const int n = idx % HID, c = idx / HID;
+        uint32_t p[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) p[j] = pack_bf16(w.w2[n * HID + 8 * c + 2 * j], w.w2[n * HID + 8 * c + 2 * j + 1]);
+        *reinterpret_cast<uint4 *>(img + OFF_W2 + c * (HID * 16) + n * 16) = make_uint4(p[0], p[1], p[2], p[3]);
+    }
+    // W1 image (K padded 10 -> 16)
+    for (int idx = tid; idx < HID * (K1 / 8); idx += nthreads) {
+        const int n = idx % HID, c = idx / HID;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) { const int k = 8 * c + j; v[j] = k < 10 ? w.w1[n * 10 + k] : 0.0f; }
+        *reinterpret_cast<uint4 *>(img + OFF_W1 + c * (HID * 16) + n * 16) =
+            make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    }
+    float *vec = reinterpret_cast<float *>(img + W2_BYTES + W1_BYTES);
+    for (int idx = tid; idx < (int)VEC_FLOATS; idx += nthreads) {
+        float x;
+        if (idx < HID) x = w.b1[idx];
+        else if (idx < 2 * HID) x = w.b2[idx - HID];
+        else if (idx < 6 * HID) x = w.w3[idx - 2 * HID];
+        else x = w.b3[idx - 6 * HID];
+        vec[idx] = x;
+    }
+}
+
+struct RolloutIO {
+    float *obs;          // [N,10] in: current observation; out: observation after the last step
+    float *reward_sum, *actions_last, *actions_all, *reward_all;
+    int T, deterministic;
+    unsigned long long t0;   // lifetime step of the first rollout step (Philox counters)
+};
+
+template <bool X, int DIV>
+__global__ void __launch_bounds__(TVC_BLOCK, 1)
+rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState st, const uint8_t *__restrict__ img,
+               const __grid_constant__ RolloutIO io) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long i = (long long)blockIdx.x * TVC_BLOCK + tid;
+    const bool live = i < st.n;
+    const long long gid = c.env_base + i;
+
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t bar_w = s_base + OFF_BAR, bar_mma = s_base + OFF_BAR + 8;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 16);
+    const float *b1 = reinterpret_cast<const float *>(smem + OFF_VEC);
+    const float *b2 = b1 + HID;
+    const float *w3 = b2 + HID;
+    const float *b3 = w3 + 4 * HID;
+    ContactSmem &s_contact = *reinterpret_cast<ContactSmem *>(smem + OFF_H1);
+
+    // ---- one-time setup: barriers, TMEM (256 columns), weights via TMA bulk copy ----
+    if (tid == 0) {
+        mbar_init(bar_w, 1);
+        mbar_init(bar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" :: "r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (tid == 0) {
+        mbar_expect_tx(bar_w, W2_BYTES + W1_BYTES + VEC_BYTES);
+#pragma unroll
+        for (uint32_t off = 0; off < W2_BYTES; off += 32768) bulk_g2s(s_base + OFF_W2 + off, img + off, 32768, bar_w);
+        bulk_g2s(s_base + OFF_W1, img + W2_BYTES, W1_BYTES, bar_w);
+        bulk_g2s(s_base + OFF_VEC, img + W2_BYTES + W1_BYTES, VEC_BYTES, bar_w);
+    }
+
+    Env e;
+    float obs[10];
+    if (live) {
+        load_env(st, X, i, e);
+#pragma unroll
+        for (int k = 0; k < 10; k++) obs[k] = io.obs[10 * i + k];
+    } else {
+        memset(&e, 0, sizeof(e));
+        e.qw = 1.0f; e.pz = 1.0f;
+#pragma unroll
+        for (int k = 0; k < 10; k++) obs[k] = 0.0f;
+    }
+    mbar_wait(bar_w, 0);
+
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);   // this warp's 32 TMEM lanes
+    uint32_t mma_phase = 0;
+    float rsum = 0.0f, a0 = 0.0f, a1 = 0.0f;
+    int done = 0, viol = 0;   // statistics are accumulated per CTA at the end of every step
+
+    for (int t = 0; t < io.T; t++) {
+        // ---- layer 1 operand: obs row -> bf16 tile [2][128][8] ----
+        {
+            uint4 c0 = make_uint4(pack_bf16(obs[0], obs[1]), pack_bf16(obs[2], obs[3]), pack_bf16(obs[4], obs[5]), pack_bf16(obs[6], obs[7]));
+            uint4 c1 = make_uint4(pack_bf16(obs[8], obs[9]), 0u, 0u, 0u);
+            *reinterpret_cast<uint4 *>(smem + OFF_A1 + tid * 16) = c0;
+            *reinterpret_cast<uint4 *>(smem + OFF_A1 + TVC_BLOCK * 16 + tid * 16) = c1;
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            mma_bf16(tmem_base, umma_desc(s_base + OFF_A1, TVC_BLOCK * 16, 128), umma_desc(s_base + OFF_W1, HID * 16, 128), 0u);
+            mma_commit(bar_mma);
+        }
+        mbar_wait(bar_mma, mma_phase);
+        mma_phase ^= 1u;
+        tc_fence_after();
+        // ---- epilogue 1: bias + ReLU -> bf16 hidden tile [32][128][8] (thread-contiguous 16-byte stores) ----
+#pragma unroll 1
+        for (int ch = 0; ch < 8; ch++) {
+            uint32_t v[32];
+            tmem_ld32(taddr + ch * 32, v);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                float h[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) h[j] = fmaxf(__uint_as_float(v[8 * q + j]) + b1[ch * 32 + 8 * q + j], 0.0f);
+                *reinterpret_cast<uint4 *>(smem + OFF_H1 + (ch * 4 + q) * (TVC_BLOCK * 16) + tid * 16) =
+                    make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- layer 2: 16 K-steps of M128 N256 K16 ----
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < HID / 16; kk++)
+                mma_bf16(tmem_base, umma_desc(s_base + OFF_H1 + kk * 2 * (TVC_BLOCK * 16), TVC_BLOCK * 16, 128),
+                         umma_desc(s_base + OFF_W2 + kk * 2 * (HID * 16), HID * 16, 128), kk > 0 ? 1u : 0u);
+            mma_commit(bar_mma);
+        }
+        mbar_wait(bar_mma, mma_phase);
+        mma_phase ^= 1u;
+        tc_fence_after();
+        // ---- epilogue 2 + head: h2 = ReLU(d + b2); out[k] += h2 * W3[k][:] ----
+        float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f, o3 = 0.0f;
+#pragma unroll 1
+        for (int ch = 0; ch < 8; ch++) {
+            uint32_t v[32];
+            tmem_ld32(taddr + ch * 32, v);
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const int col = ch * 32 + j;
+                const float h = fmaxf(__uint_as_float(v[j]) + b2[col], 0.0f);
+                o0 = fmaf(h, w3[col], o0); o1 = fmaf(h, w3[HID + col], o1);
+                o2 = fmaf(h, w3[2 * HID + col], o2); o3 = fmaf(h, w3[3 * HID + col], o3);
+            }
+        }
+        tc_fence_before();
+        __syncthreads();   // all TMEM reads retired and the hidden tile is free: the area now serves the contact exchange
+        // ---- action: tanh(mean + exp(clamp(log_std)) * eps), eps from Philox stream 6 ----
+        const float mean0 = o0 + b3[0], mean1 = o1 + b3[1];
+        const float ls0 = clampf(o2 + b3[2], -20.0f, 2.0f), ls1 = clampf(o3 + b3[3], -20.0f, 2.0f);
+        float e0 = 0.0f, e1 = 0.0f;
+        if (!io.deterministic) {
+            const unsigned long long tt = io.t0 + (unsigned long long)t;
+            const uint4 rr = philox(c.seed_lo, c.seed_hi, gid, ST_ACTOR, (unsigned)tt, (unsigned)(tt >> 32));
+            box_muller(rr.x, rr.y, e0, e1);
+        }
+        a0 = tanhf(mean0 + expf(ls0) * e0);
+        a1 = tanhf(mean1 + expf(ls1) * e1);
+
+        // ---- env step (same device code as step_kernel) ----
+        BodyP P;
+        Forces f;
+        if (live) env_pre<X>(c, st, i, e, a0, a1, P, f);
+        else {
+            P = body_params(c, false, 1.0f, 0.0f, 1.0f);
+            f.Fx = f.Fy = f.Fz = f.Tx = f.Ty = f.Tz = f.a0 = f.a1 = 0.0f;
+        }
+        integrate(c, P, e, f.Fx, f.Fy, f.Fz, f.Tx, f.Ty, f.Tz, live, s_contact);
+        done = 0; viol = 0;
+        int ev_len = 0, ev_succ = 0, ev_reason = 0, ev_trunc = 0;
+        float ev_ret = 0.0f, ev_alt = 0.0f, ev_tilt = 0.0f, ev_fuel = 0.0f;
+        if (live) {
+            StepResult r;
+            env_post<X, DIV>(c, st, i, gid, e, f.a0, f.a1, r);
+            rsum += r.reward;
+            if (io.actions_all) reinterpret_cast<float2 *>(io.actions_all)[(long long)t * st.n + i] = make_float2(a0, a1);
+            if (io.reward_all) io.reward_all[(long long)t * st.n + i] = r.reward;
+            viol = r.viol;
+            done = r.terminated | r.truncated;
+            if (done) {
+                ev_len = e.step; ev_succ = e.success; ev_reason = r.reason; ev_trunc = r.truncated;
+                ev_ret = e.ep_ret; ev_alt = r.alt; ev_tilt = r.tilt; ev_fuel = r.fuel;
+                if (c.autoreset) {
+                    reset_env(c, X, gid, e, false);
+                    build_obs(c, X, gid, e, 0, r.obs);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 10; k++) obs[k] = r.obs[k];
+        }
+        // ---- episode statistics (same scheme as step_kernel; the contact area is idle now) ----
+        __syncthreads();
+        const int any_ev = __syncthreads_or(done | viol);
+        if (any_ev) {
+            double *s_stat = reinterpret_cast<double *>(smem + OFF_H1);   // [4][16] doubles
+            const unsigned full = 0xffffffffu;
+            int n_ep = __reduce_add_sync(full, done), n_len = __reduce_add_sync(full, ev_len);
+            int n_succ = __reduce_add_sync(full, done ? ev_succ : 0);
+            int n_cr = __reduce_add_sync(full, ev_reason == 2), n_ti = __reduce_add_sync(full, ev_reason == 3);
+            int n_al = __reduce_add_sync(full, ev_reason == 4), n_ra = __reduce_add_sync(full, ev_reason == 5);
+            int n_tr = __reduce_add_sync(full, ev_trunc), n_vi = __reduce_add_sync(full, viol);
+            double d_ret = ev_ret, d_ret2 = (double)ev_ret * (double)ev_ret, d_alt = ev_alt, d_tilt = ev_tilt, d_fuel = ev_fuel;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                d_ret += __shfl_xor_sync(full, d_ret, o); d_ret2 += __shfl_xor_sync(full, d_ret2, o);
+                d_alt += __shfl_xor_sync(full, d_alt, o); d_tilt += __shfl_xor_sync(full, d_tilt, o);
+                d_fuel += __shfl_xor_sync(full, d_fuel, o);
+            }
+            if (lane == 0) {
+                double *s = s_stat + warp * TVC_NSTAT;
+                s[0] = n_ep; s[1] = d_ret; s[2] = d_ret2; s[3] = n_len; s[4] = n_succ; s[5] = n_cr; s[6] = n_ti;
+                s[7] = n_al; s[8] = n_ra; s[9] = n_tr; s[10] = n_vi; s[11] = d_alt; s[12] = d_tilt; s[13] = d_fuel;
+                s[14] = 0.0; s[15] = 0.0;
+            }
+            __syncthreads();
+            if (tid < TVC_NSTAT) {
+                double s = 0.0;
+#pragma unroll
+                for (int w = 0; w < TVC_WARPS; w++) s += s_stat[w * TVC_NSTAT + tid];
+                if (s != 0.0) st.partial[(long long)blockIdx.x * TVC_NSTAT + tid] += s;
+            }
+            __syncthreads();
+        }
+    }
+
+    if (live) {
+        store_env(st, X, i, e);
+#pragma unroll
+        for (int k = 0; k < 10; k++) io.obs[10 * i + k] = obs[k];
+        if (io.reward_sum) io.reward_sum[i] = rsum;
+        if (io.actions_last) reinterpret_cast<float2 *>(io.actions_last)[i] = make_float2(a0, a1);
+    }
+    // ---- teardown: release TMEM ----
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem_base) : "memory");
+    }
+}
+
+}  // namespace
+
+void tvc_rollout_free(tvc_handle *h) {
+    if (!h || !h->rollout_ws) return;
+    RolloutWs *ws = static_cast<RolloutWs *>(h->rollout_ws);
+    cudaFree(ws->img);
+    delete ws;
+    h->rollout_ws = nullptr;
+}
+
+extern "C" int tvc_rollout(tvc_handle *h, const tvc_actor_weights *w, int32_t T, const tvc_rollout_io *u, tvc_stream stream) {
+    if (!h) { tvc_set_err("handle is NULL"); return TVC_E_BADARG; }
+    if (!w || !w->w1 || !w->b1 || !w->w2 || !w->b2 || !w->w3 || !w->b3) { tvc_set_err("tvc_rollout: NULL weight pointer"); return TVC_E_BADARG; }
+    if (!u || !u->obs) { tvc_set_err("tvc_rollout: io.obs (current observation, [N,10]) must be non-NULL"); return TVC_E_BADARG; }
+    if (T < 1 || T > 65536) { tvc_set_err("tvc_rollout: T out of range [1,65536]"); return TVC_E_BADARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!h->rollout_ws) {
+        RolloutWs *ws = new (std::nothrow) RolloutWs();
+        if (!ws) { tvc_set_err("out of host memory"); return TVC_E_NOMEM; }
+        cudaError_t e = cudaMalloc((void **)&ws->img, W2_BYTES + W1_BYTES + VEC_BYTES);
+        if (e != cudaSuccess) { delete ws; tvc_set_err(cudaGetErrorString(e)); return TVC_E_CUDA; }
+        h->rollout_ws = ws;
+    }
+    RolloutWs *ws = static_cast<RolloutWs *>(h->rollout_ws);
+    pack_actor_kernel<<<64, 128, 0, s>>>(*w, ws->img);
+    RolloutIO io;
+    io.obs = u->obs; io.reward_sum = u->reward_sum; io.actions_last = u->actions_last; io.actions_all = u->actions_all;
+    io.reward_all = u->reward_all; io.T = T; io.deterministic = u->deterministic;
+    io.t0 = (unsigned long long)h->lifetime_steps;
+    const bool X = h->cur.contract == TVC_CONTRACT_X;
+    const int dv = h->cur.diversity_mode;
+    cudaError_t e = cudaSuccess;
+#define GO(XX, DD)                                                                                                   \
+    do {                                                                                                             \
+        e = cudaFuncSetAttribute(rollout_kernel<XX, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL); \
+        if (e == cudaSuccess) rollout_kernel<XX, DD><<<h->grid, TVC_BLOCK, SMEM_TOTAL, s>>>(h->dc, h->st, ws->img, io); \
+    } while (0)
+    if (X) { if (dv == 0) GO(true, 0); else if (dv == 1) GO(true, 1); else GO(true, 2); }
+    else   { if (dv == 0) GO(false, 0); else if (dv == 1) GO(false, 1); else GO(false, 2); }
+#undef GO
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { tvc_set_err(std::string("rollout_kernel: ") + cudaGetErrorString(e)); return TVC_E_CUDA; }
+    h->lifetime_steps += T;
+    h->stat_steps += T;
+    return TVC_OK;
 }
