@@ -44,6 +44,14 @@ def _peaks():
     return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
+def _bf16_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["bf16_tflops_sustained"])
+    except Exception:  # noqa: BLE001
+        return 1400.0
+
+
 def _traffic():
     """dram bytes per launch of the step kernel from the committed ncu --set full capture, or None."""
     p = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
@@ -265,6 +273,35 @@ def run_ours(args):
                                 "us_per_step": us, "env_steps_per_sec": 4096 / (us * 1e-6)}
         small.close()
 
+        # configs[3]: fused rollout, 65,536 envs, SAC actor MLP 2x256 (bf16 tcgen05) inside the step loop, T=64
+        if not args.no_rollout:
+            nr, T = 65536, 64
+            torch.manual_seed(0)
+            nn = torch.nn
+            net = nn.Sequential(nn.Linear(10, 256), nn.ReLU(), nn.Linear(256, 256), nn.ReLU(), nn.Linear(256, 4)).to(dev)
+            w = dict(w1=net[0].weight.detach(), b1=net[0].bias.detach(), w2=net[2].weight.detach(), b2=net[2].bias.detach(),
+                     w3=net[4].weight.detach(), b3=net[4].bias.detach())
+            ro = BatchedEngine(nr, _workload_cfg(A), device=local)
+            ro.reset()
+            for wu in range(4):                     # 256 steps: warm-up + episode desynchronisation
+                ro.rollout(w, T)
+            torch.cuda.synchronize(dev)
+            reps = 5
+            e0.record()
+            for r in range(reps):
+                ro.rollout(w, T)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            rms = e0.elapsed_time(e1) / reps
+            flops = 138240.0 * nr * T
+            extra["fused_rollout"] = {"workload": "configs[3]: 65536 envs, T=64 steps/launch, actor 10-256-256-4 (bf16 tcgen05.mma, "
+                                                  "fp32 accumulate in TMEM), Contract X full DR, K=10",
+                                      "ms_per_launch": rms, "env_steps_per_sec": nr * T / (rms * 1e-3),
+                                      "actor_tflops": flops / (rms * 1e-3) / 1e12,
+                                      "tensor_peak_tflops": _bf16_peak(), "note": "physics-bound: the MLP is a small share"}
+            launches += reps + 4
+            ro.close()
+
         # end-to-end through the public VectorEnv API with HOST (numpy) actions and results
         venv = RocketTVCVectorEnv(n, config={}, contract="X", device=local, final_info=False)
         venv.reset(seed=42)
@@ -331,6 +368,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--no-rollout", action="store_true", help="skip the fused-rollout (config 4) measurement")
     ap.add_argument("--burn-in", type=int, default=400, help="untimed steps before warm-up (episode desynchronisation)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TVC_ABI_VERSION 3
+#define TVC_ABI_VERSION 4
 
 #define TVC_OBS_DIM 10
 #define TVC_ACT_DIM 2
@@ -70,11 +70,11 @@ typedef struct tvc_config {
     int32_t autoreset;         /* 0: gym.Env semantics; 1: same-step autoreset (VectorEnv) */
     uint32_t quirks;
     int32_t diversity_mode;
-    int32_t contact_iters;
+    int32_t contact_iters;      /* PGS sweeps, first substep of a step (cold start) */
     int32_t ground;
     int32_t delay_steps;  /* X: actuator delay, control steps */
     int32_t thrust_curve; /* X: 0 constant, 1 model-rocket curve */
-    int32_t reserved0;
+    int32_t contact_warm_iters; /* PGS sweeps, later substeps (warm-started from the previous substep) */
     double dt_step;       /* :340 */
     float gradient_penalty, diversity_bonus; /* :83-84 */
     float mass, radius, length, thrust;      /* :412-414, :463 */
@@ -157,7 +157,7 @@ typedef struct tvc_actor_weights {
 } tvc_actor_weights;
 
 typedef struct tvc_rollout_io {
-    float *obs;          /* [N,10] nullable: observation after the last step */
+    float *obs;          /* [N,10] REQUIRED, in/out: the observation returned by the last reset/step/rollout; updated */
     float *reward_sum;   /* [N] nullable: sum of rewards over the T steps */
     float *actions_last; /* [N,2] nullable */
     float *actions_all;  /* [T,N,2] nullable (parity tests) */

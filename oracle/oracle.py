@@ -40,7 +40,8 @@ class BodyParams(C.Structure):
     _fields_ = [("mass", C.c_double), ("inertia", C.c_double * 3), ("lin_damp", C.c_double),
                 ("ang_damp", C.c_double), ("use_gyro", C.c_int32), ("substeps", C.c_int32),
                 ("gravity", C.c_double * 3), ("dt_step", C.c_double), ("max_vel", C.c_double),
-                ("ground", C.c_int32), ("contact_iters", C.c_int32), ("radius", C.c_double),
+                ("ground", C.c_int32), ("contact_iters", C.c_int32), ("warm_iters", C.c_int32), ("reserved_", C.c_int32),
+                ("radius", C.c_double),
                 ("half_len", C.c_double), ("cg", C.c_double), ("mu", C.c_double), ("mu_spin", C.c_double),
                 ("mu_roll", C.c_double), ("restitution", C.c_double), ("rest_threshold", C.c_double),
                 ("erp", C.c_double), ("margin", C.c_double)]
@@ -54,7 +55,8 @@ class Body(C.Structure):
 class Config(C.Structure):
     _fields_ = [("contract", C.c_int32), ("substeps", C.c_int32), ("max_episode_steps", C.c_int32),
                 ("autoreset", C.c_int32), ("quirks", C.c_uint32), ("diversity_mode", C.c_int32),
-                ("contact_iters", C.c_int32), ("ground", C.c_int32), ("dt_step", C.c_double),
+                ("contact_iters", C.c_int32), ("ground", C.c_int32), ("contact_warm_iters", C.c_int32), ("reserved_", C.c_int32),
+                ("dt_step", C.c_double),
                 ("gradient_penalty", C.c_double), ("diversity_bonus", C.c_double),
                 ("mass", C.c_double), ("radius", C.c_double), ("length", C.c_double), ("thrust", C.c_double),
                 ("gimbal_max_rad", C.c_double), ("lin_damp", C.c_double), ("ang_damp", C.c_double),

@@ -131,6 +131,7 @@ void orc_body_params_default(orc_body_params *p) {
     p->max_vel = 100.0;
     p->ground = 1;
     p->contact_iters = 8;
+    p->warm_iters = 3;
     p->radius = radius; p->half_len = 0.5 * length; p->cg = 0.0;
     p->mu = 0.3 * 0.8;                       /* ref:456 x ref:350, Bullet combines by product */
     p->mu_spin = 0.1 * 0.8 + 0.1 * 0.3;      /* ref:351,457: Bullet combined torsional friction */
@@ -203,18 +204,23 @@ static void r_matrix_from_quat(const real q[4], real m[9]) {
  *      p0  lowest rim point of the bottom cap,  p1  lowest rim point of the top cap
  *          (direction -(R31,R32)/max(rho, 1e-3): slides to the cap centre as the axis becomes vertical)
  *      f0,f1,f2  three body-fixed rim points of the bottom cap at 0, 120, 240 degrees
- *  - entered only when the lowest candidate is closer than `margin`; then ALL five normal rows are
- *    processed: vn >= -gap/dt (gap >= 0, speculative) or vn >= -erp*gap/dt (gap < 0, Baumgarte),
- *    plus restitution e when approaching faster than the threshold; distant rows never bind
+ *  - entered only when the lowest candidate is closer than `margin` AND some row can bind at all:
+ *    gap_min - 1e-4 < (1+e) (|vz| + |w| reach) dt  (otherwise the stored impulses are cleared); then ALL
+ *    five normal rows are processed: vn >= -gap/dt (gap >= 0, speculative) or vn >= -erp*gap/dt
+ *    (gap < 0, Baumgarte), plus restitution e when approaching faster than the threshold
  *  - per row: normal impulse (lambda >= 0), then the two world-axis tangent rows projected on the
  *    friction disc mu*lambda_n; after the five points, spinning and rolling friction rows limited by
  *    mu_spin / mu_roll times the total normal impulse
- *  - projected Gauss-Seidel on velocities, contact_iters sweeps, no warm start
+ *  - projected Gauss-Seidel on velocities.  The first substep of a step starts cold and runs
+ *    contact_iters sweeps; later substeps are warm-started with the previous substep's 18 impulses
+ *    (applied before sweeping) and run warm_iters sweeps.  Impulses do not persist across steps.
  */
 /* diagnostic counters (not thread-safe; meaningful for serial runs only) */
 long long orc_dbg_substeps = 0, orc_dbg_entered = 0, orc_dbg_canbind = 0;
 
-static void solve_contacts(const orc_body_params *p, real dt, const real R[9], real pz, real v[3], real w[3]) {
+/* lam[18]: accumulated impulses carried between substeps: normal(5), tangent-x(5), tangent-y(5), spin, roll-x, roll-y */
+static void solve_contacts(const orc_body_params *p, real dt, const real R[9], real pz, real v[3], real w[3],
+                           real lam[18], int iters) {
     const real r = (real)p->radius, h = (real)p->half_len, cg = (real)p->cg, margin = (real)p->margin;
     orc_dbg_substeps++;
     const real R31 = R[6], R32 = R[7], R33 = R[8];
@@ -224,13 +230,16 @@ static void solve_contacts(const orc_body_params *p, real dt, const real R[9], r
     const real zb = -h - cg, zt = h - cg;
     const real low = r * (R31 * ux + R32 * uy);          /* = -r*rho outside the regularised zone */
     const real gb = pz + R33 * zb + low, gt = pz + R33 * zt + low;
-    if (!((gb < gt ? gb : gt) < margin)) return;
-    orc_dbg_entered++;
-    {
+    const real gmin = gb < gt ? gb : gt;
+    int enter = gmin < margin;
+    if (enter) {
+        orc_dbg_entered++;
         real hh = h + (cg < 0 ? -cg : cg), reach = R_SQRT(hh * hh + r * r);
         real vmax = (v[2] < 0 ? -v[2] : v[2]) + R_SQRT(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]) * reach;
-        if ((gb < gt ? gb : gt) - (real)1e-4 < ((real)1.0 + (real)p->restitution) * vmax * dt) orc_dbg_canbind++;
+        enter = gmin - (real)1e-4 < ((real)1.0 + (real)p->restitution) * vmax * dt;
+        if (enter) orc_dbg_canbind++;
     }
+    if (!enter) { for (int i = 0; i < 18; i++) lam[i] = 0; return; }
 
     const real c[5][3] = {
         {r * ux, r * uy, zb},
@@ -266,11 +275,24 @@ static void solve_contacts(const orc_body_params *p, real dt, const real R[9], r
         real vn0 = v[2] + w[0] * ay[i] - w[1] * ax[i];
         real rest = (vn0 < -(real)p->rest_threshold) ? -(real)p->restitution * vn0 : (real)0.0;
         tgt[i] = rest + (gap > 0 ? -gap * inv_dt : -(real)p->erp * gap * inv_dt);
-        ln[i] = 0; l1[i] = 0; l2[i] = 0;
+        ln[i] = lam[i]; l1[i] = lam[5 + i]; l2[i] = lam[10 + i];
     }
-    real lsp = 0, lr1 = 0, lr2 = 0;
+    real lsp = lam[15], lr1 = lam[16], lr2 = lam[17];
     const real iW22 = (real)1.0 / W22, iW00 = (real)1.0 / W00, iW11 = (real)1.0 / W11;
-    for (int it = 0; it < p->contact_iters; it++) {
+    /* warm start: apply the stored impulses at the current contact geometry (targets above use the
+     * velocities before this) */
+    for (int i = 0; i < 5; i++) {
+        const real px_ = l1[i], py_ = l2[i], pn_ = ln[i];
+        v[0] += px_ * im; v[1] += py_ * im; v[2] += pn_ * im;
+        const real tx = ay[i] * pn_ - az[i] * py_, ty = az[i] * px_ - ax[i] * pn_, tz = ax[i] * py_ - ay[i] * px_;
+        w[0] += W00 * tx + W01 * ty + W02 * tz;
+        w[1] += W01 * tx + W11 * ty + W12 * tz;
+        w[2] += W02 * tx + W12 * ty + W22 * tz;
+    }
+    w[0] += W02 * lsp + W00 * lr1 + W01 * lr2;
+    w[1] += W12 * lsp + W01 * lr1 + W11 * lr2;
+    w[2] += W22 * lsp + W02 * lr1 + W12 * lr2;
+    for (int it = 0; it < iters; it++) {
         real lsum = 0;
         for (int i = 0; i < 5; i++) {
             /* normal row */
@@ -314,6 +336,8 @@ static void solve_contacts(const orc_body_params *p, real dt, const real R[9], r
             w[0] += W01 * d; w[1] += W11 * d; w[2] += W12 * d;
         }
     }
+    for (int i = 0; i < 5; i++) { lam[i] = ln[i]; lam[5 + i] = l1[i]; lam[10 + i] = l2[i]; }
+    lam[15] = lsp; lam[16] = lr1; lam[17] = lr2;
 }
 
 /* Rows B2, B4, B5, B6: one p.stepSimulation() (ref:477). */
@@ -329,8 +353,8 @@ void orc_step_simulation(const orc_body_params *p, orc_body *b, double *trace) {
         pos[i] = (real)b->pos[i]; v[i] = (real)b->vel[i]; w[i] = (real)b->omega[i];
     }
     for (int i = 0; i < 4; i++) q[i] = (real)b->quat[i];
-    const real inv_m = (real)(1.0 / p->mass);
-    (void)inv_m;
+    real lam[18];
+    for (int i = 0; i < 18; i++) lam[i] = 0;   /* cold start at every control step */
 
     for (int k = 0; k < K; k++) {
         real R[9];
@@ -367,7 +391,7 @@ void orc_step_simulation(const orc_body_params *p, orc_body *b, double *trace) {
             v[i] = r_clamp(v[i] + vd * dt, -maxv, maxv);
         }
         /* B9 (our model): contacts detected at the pre-integration pose, solved on velocities */
-        if (p->ground) solve_contacts(p, dt, R, pos[2], v, w);
+        if (p->ground) solve_contacts(p, dt, R, pos[2], v, w, lam, k == 0 ? p->contact_iters : p->warm_iters);
 
         /* B6: stepPositionsMultiDof -- semi-implicit Euler, exponential map */
         for (int i = 0; i < 3; i++) pos[i] += dt * v[i];
@@ -478,6 +502,7 @@ void orc_config_default(orc_config *c, int contract) {
     c->quirks = contract == ORC_CONTRACT_R ? ORC_Q_ALL_REFERENCE : (ORC_Q_DOUBLE_GRAVITY | ORC_Q_LAGGED_PHASE);
     c->diversity_mode = contract == ORC_CONTRACT_R ? ORC_DIV_EXACT : ORC_DIV_FAST;
     c->contact_iters = 8;
+    c->contact_warm_iters = 3;
     c->ground = 1;
     c->dt_step = 0.02;
     c->gradient_penalty = 0.1; c->diversity_bonus = 0.05;      /* ref:83-84 defaults */
@@ -514,7 +539,7 @@ static void env_params(const orc_config *c, const orc_env *e, orc_body_params *p
     p->cg = cg;
     p->lin_damp = c->lin_damp; p->ang_damp = c->ang_damp;
     p->substeps = c->substeps; p->dt_step = c->dt_step;
-    p->ground = c->ground; p->contact_iters = c->contact_iters;
+    p->ground = c->ground; p->contact_iters = c->contact_iters; p->warm_iters = c->contact_warm_iters;
 }
 
 /* ref:587-606 _get_enhanced_observation */

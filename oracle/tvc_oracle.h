@@ -47,7 +47,9 @@ typedef struct orc_body_params {
     double max_vel;           /* m_maxCoordinateVelocity = 100 */
     /* collision geometry + contact model (our documented model) */
     int32_t ground;           /* 0 = no plane */
-    int32_t contact_iters;
+    int32_t contact_iters;    /* PGS sweeps of the first substep of a step (cold start) */
+    int32_t warm_iters;       /* PGS sweeps of the following substeps (warm-started from the previous substep) */
+    int32_t reserved_;
     double radius, half_len;
     double cg;                /* COM offset from geometric centre along body z */
     double mu, mu_spin, mu_roll;
@@ -97,6 +99,8 @@ typedef struct orc_config {
     int32_t diversity_mode;
     int32_t contact_iters;
     int32_t ground;
+    int32_t contact_warm_iters;
+    int32_t reserved_;
     double dt_step;
     double gradient_penalty, diversity_bonus;
     /* rocket */

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TVC_B200_LIB") or os.path.join(_HERE, "libtvc_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 OBS_DIM, ACT_DIM, NUM_COMPONENTS, NUM_STATS, MAX_DELAY = 10, 2, 12, 16, 4
 CONTRACT_R, CONTRACT_X = 0, 1
 DIV_OFF, DIV_FAST, DIV_EXACT = 0, 1, 2
@@ -35,7 +35,7 @@ class TvcConfig(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("contract", C.c_int32), ("substeps", C.c_int32),
                 ("max_episode_steps", C.c_int32), ("autoreset", C.c_int32), ("quirks", C.c_uint32),
                 ("diversity_mode", C.c_int32), ("contact_iters", C.c_int32), ("ground", C.c_int32),
-                ("delay_steps", C.c_int32), ("thrust_curve", C.c_int32), ("reserved0", C.c_int32),
+                ("delay_steps", C.c_int32), ("thrust_curve", C.c_int32), ("contact_warm_iters", C.c_int32),
                 ("dt_step", C.c_double),
                 ("gradient_penalty", C.c_float), ("diversity_bonus", C.c_float),
                 ("mass", C.c_float), ("radius", C.c_float), ("length", C.c_float), ("thrust", C.c_float),

@@ -263,7 +263,7 @@ const char *tvc_set_err(const std::string &m) { g_err = m; return g_err.c_str();
 static void make_devcfg(const tvc_config &c, DevCfg &d) {
     memset(&d, 0, sizeof(d));
     d.contract = c.contract; d.K = c.substeps; d.max_steps = c.max_episode_steps; d.autoreset = c.autoreset;
-    d.quirks = c.quirks; d.div_mode = c.diversity_mode; d.contact_iters = c.contact_iters; d.ground = c.ground;
+    d.quirks = c.quirks; d.div_mode = c.diversity_mode; d.contact_iters = c.contact_iters; d.warm_iters = c.contact_warm_iters; d.ground = c.ground;
     d.delay = c.delay_steps; d.thrust_curve = c.thrust_curve;
     const double dt = c.dt_step / (double)c.substeps;
     d.dt = (float)dt; d.inv_dt = (float)(1.0 / dt);
@@ -296,6 +296,7 @@ int tvc_config_default(tvc_config *c, int contract) {
     c->quirks = contract == TVC_CONTRACT_R ? TVC_Q_ALL_REFERENCE : (TVC_Q_DOUBLE_GRAVITY | TVC_Q_LAGGED_PHASE);
     c->diversity_mode = contract == TVC_CONTRACT_R ? TVC_DIV_EXACT : TVC_DIV_FAST;
     c->contact_iters = 8;
+    c->contact_warm_iters = 3;
     c->ground = 1;
     c->dt_step = 0.02;
     c->gradient_penalty = 0.1f; c->diversity_bonus = 0.05f;
@@ -322,7 +323,7 @@ static int validate(const tvc_config *c, int64_t n) {
     if (c->max_episode_steps < 1) { tvc_set_err("max_episode_steps < 1"); return TVC_E_BADARG; }
     if (c->diversity_mode < 0 || c->diversity_mode > 2) { tvc_set_err("bad diversity_mode"); return TVC_E_BADARG; }
     if (c->delay_steps < 0 || c->delay_steps > TVC_MAX_DELAY) { tvc_set_err("delay_steps out of range"); return TVC_E_BADARG; }
-    if (c->contact_iters < 0 || c->contact_iters > 256) { tvc_set_err("contact_iters out of range"); return TVC_E_BADARG; }
+    if (c->contact_iters < 0 || c->contact_iters > 256 || c->contact_warm_iters < 0 || c->contact_warm_iters > 256) { tvc_set_err("contact_iters out of range"); return TVC_E_BADARG; }
     if (!(c->dt_step > 0) || !(c->mass > 0) || !(c->radius > 0) || !(c->length > 0)) { tvc_set_err("non-positive physical parameter"); return TVC_E_BADARG; }
     return TVC_OK;
 }

@@ -20,7 +20,7 @@ namespace tvc {
 struct DevCfg {
     int contract, K, max_steps, autoreset;
     unsigned quirks;
-    int div_mode, contact_iters, ground, delay, thrust_curve;
+    int div_mode, contact_iters, warm_iters, ground, delay, thrust_curve;
     float dt, inv_dt;  // substep
     float gp, db;
     float mass, radius, half_len, thrust, gimbal_max;
@@ -191,17 +191,17 @@ __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fm
 // Ground contact: our documented model (DESIGN.md "Contact model"), continuous in the state.
 //   p0 / p1 : lowest rim point of the bottom / top cap, direction -(R31,R32)/max(rho,1e-3)
 //   f0..f2  : body-fixed rim points of the bottom cap at 0, 120, 240 degrees
-// Entered when the lowest candidate is within `margin`; then all five rows are processed
-// (speculative vn >= -gap/dt, Baumgarte for gap < 0, restitution), friction disc per point,
-// spinning / rolling rows limited by the total normal impulse; projected Gauss-Seidel on
-// velocities, contact_iters sweeps, no warm start.  Bullet's own manifold/solver (row B9) is not
+// Entered when the lowest candidate is within `margin` and some row can bind (contact_needed); then
+// all five rows are processed (speculative vn >= -gap/dt, Baumgarte for gap < 0, restitution),
+// friction disc per point, spinning / rolling rows limited by the total normal impulse; projected
+// Gauss-Seidel on velocities: contact_iters sweeps from a cold start in the first substep of a step,
+// warm_iters sweeps warm-started with the previous substep's 18 impulses afterwards.  Bullet's own manifold/solver (row B9) is not
 // reproducible without its source; this model is shared with the oracle by specification only.
 // ------------------------------------------------------------------------------------------
-// Broadphase, evaluated per substep by the env's own thread.  The solve is entered when the lowest
-// candidate is within `margin` (the model's rule, as in the oracle) AND some row can bind at all:
-// a row binds only if (1+e) * approach speed * dt exceeds its gap, and the approach speed of any
-// point is bounded by |vz| + |w| * reach -- when that fails the solve is exactly a no-op, so
-// skipping it does not change the result.
+// Entry rule of the contact model (same in the oracle), evaluated per substep by the env's own thread:
+// the lowest candidate is within `margin` AND some row can bind at all -- a row binds only if
+// (1+e) * approach speed * dt exceeds its gap, and the approach speed of any point is bounded by
+// |vz| + |w| * reach.  When the rule fails the stored impulses are cleared.
 __device__ __forceinline__ bool contact_needed(const DevCfg &c, const BodyP &P, const float R[9], float pz, float vz,
                                                float wx, float wy, float wz) {
     const float r = c.radius, h = c.half_len;
@@ -217,8 +217,11 @@ __device__ __forceinline__ bool contact_needed(const DevCfg &c, const BodyP &P, 
     return gmin - 1e-4f < (1.0f + c.restitution) * vmax * c.dt;
 }
 
+// lam: this problem's 18 stored impulses, element j at lam[j * TVC_BLOCK] (shared memory column of the posting
+// thread): normal(5), tangent-x(5), tangent-y(5), spin, roll-x, roll-y.  warm: apply them before sweeping.
 __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, const float R[9], float pz, float &vx,
-                                               float &vy, float &vz, float &wx, float &wy, float &wz) {
+                                               float &vy, float &vz, float &wx, float &wy, float &wz, float *lam,
+                                               bool warm, int iters) {
     const float r = c.radius, h = c.half_len;
     const float R31 = R[6], R32 = R[7];
     const float rho = sqrtf(R31 * R31 + R32 * R32);
@@ -255,11 +258,27 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
         const float vn0 = vz + wx * ay[i] - wy * ax[i];
         const float rest = (vn0 < -c.rest_thr) ? -c.restitution * vn0 : 0.0f;
         tgt[i] = rest + (gap > 0.0f ? -gap * c.inv_dt : -c.erp * gap * c.inv_dt);
-        ln[i] = 0.0f; l1[i] = 0.0f; l2[i] = 0.0f;
+        ln[i] = warm ? lam[i * TVC_BLOCK] : 0.0f;
+        l1[i] = warm ? lam[(5 + i) * TVC_BLOCK] : 0.0f;
+        l2[i] = warm ? lam[(10 + i) * TVC_BLOCK] : 0.0f;
     }
-    float lsp = 0.0f, lr1 = 0.0f, lr2 = 0.0f;
+    float lsp = warm ? lam[15 * TVC_BLOCK] : 0.0f, lr1 = warm ? lam[16 * TVC_BLOCK] : 0.0f, lr2 = warm ? lam[17 * TVC_BLOCK] : 0.0f;
     const float iW22 = 1.0f / W22, iW00 = 1.0f / W00, iW11 = 1.0f / W11;
-    for (int it = 0; it < c.contact_iters; it++) {
+    if (warm) {   // apply the stored impulses at the current contact geometry
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+            const float px_ = l1[i], py_ = l2[i], pn_ = ln[i];
+            vx += px_ * im; vy += py_ * im; vz += pn_ * im;
+            const float tx = ay[i] * pn_ - az[i] * py_, ty = az[i] * px_ - ax[i] * pn_, tz = ax[i] * py_ - ay[i] * px_;
+            wx += W00 * tx + W01 * ty + W02 * tz;
+            wy += W01 * tx + W11 * ty + W12 * tz;
+            wz += W02 * tx + W12 * ty + W22 * tz;
+        }
+        wx += W02 * lsp + W00 * lr1 + W01 * lr2;
+        wy += W12 * lsp + W01 * lr1 + W11 * lr2;
+        wz += W22 * lsp + W02 * lr1 + W12 * lr2;
+    }
+    for (int it = 0; it < iters; it++) {
         float lsum = 0.0f;
 #pragma unroll
         for (int i = 0; i < 5; i++) {
@@ -303,6 +322,9 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
             wx += W01 * d; wy += W11 * d; wz += W12 * d;
         }
     }
+#pragma unroll
+    for (int i = 0; i < 5; i++) { lam[i * TVC_BLOCK] = ln[i]; lam[(5 + i) * TVC_BLOCK] = l1[i]; lam[(10 + i) * TVC_BLOCK] = l2[i]; }
+    lam[15 * TVC_BLOCK] = lsp; lam[16 * TVC_BLOCK] = lr1; lam[17 * TVC_BLOCK] = lr2;
 }
 
 // Shared-memory exchange used to compact ground-contact problems across the CTA: each env that needs
@@ -311,6 +333,8 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
 #define TVC_PROB_FIELDS 15
 struct ContactSmem {
     float f[TVC_PROB_FIELDS][TVC_BLOCK];   // qx qy qz qw pz vx vy vz wx wy wz inv_mass inv_Ixy inv_Iz cg
+    float lam[18][TVC_BLOCK];              // per ENV THREAD: impulses carried between the substeps of one step
+    int owner[TVC_BLOCK];                  // per slot: posting thread | warm flag << 16
     int cnt[TVC_WARPS];
 };
 
@@ -321,6 +345,7 @@ __device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &
     const float dt = c.dt;
     const float ax_ = Fx * P.inv_mass, ay_ = Fy * P.inv_mass, az_ = Fz * P.inv_mass;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    bool have_lam = false;   // cold start at every control step: stored impulses are logically zero
     for (int k = 0; k < c.K; k++) {
         float R[9];
         quat_to_mat(e.qx, e.qy, e.qz, e.qw, R);
@@ -367,6 +392,7 @@ __device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &
                     sm.f[5][slot] = e.vx; sm.f[6][slot] = e.vy; sm.f[7][slot] = e.vz;
                     sm.f[8][slot] = e.wx; sm.f[9][slot] = e.wy; sm.f[10][slot] = e.wz;
                     sm.f[11][slot] = P.inv_mass; sm.f[12][slot] = P.inv_Ixy; sm.f[13][slot] = P.inv_Iz; sm.f[14][slot] = P.cg;
+                    sm.owner[slot] = (int)threadIdx.x | (have_lam ? 0x10000 : 0);
                 }
                 __syncthreads();
                 // rotate the solver warps over the SMSPs (warp w of every CTA sits on SMSP w % 4)
@@ -378,7 +404,9 @@ __device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &
                     Q.inv_mass = sm.f[11][t]; Q.inv_Ixy = sm.f[12][t]; Q.inv_Iz = sm.f[13][t]; Q.cg = sm.f[14][t];
                     float vx = sm.f[5][t], vy = sm.f[6][t], vz = sm.f[7][t];
                     float wx = sm.f[8][t], wy = sm.f[9][t], wz = sm.f[10][t];
-                    solve_contacts(c, Q, Rs, sm.f[4][t], vx, vy, vz, wx, wy, wz);
+                    const int ow = sm.owner[t];
+                    solve_contacts(c, Q, Rs, sm.f[4][t], vx, vy, vz, wx, wy, wz, &sm.lam[0][ow & 0xFFFF], (ow >> 16) != 0,
+                                   k == 0 ? c.contact_iters : c.warm_iters);
                     sm.f[5][t] = vx; sm.f[6][t] = vy; sm.f[7][t] = vz;
                     sm.f[8][t] = wx; sm.f[9][t] = wy; sm.f[10][t] = wz;
                 }
@@ -388,6 +416,7 @@ __device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &
                     e.wx = sm.f[8][slot]; e.wy = sm.f[9][slot]; e.wz = sm.f[10][slot];
                 }
             }
+            have_lam = need;   // entry rule failed -> stored impulses cleared
         }
 
         // B6: semi-implicit Euler + exponential map, q <- dq (x) q, normalise
