@@ -299,7 +299,8 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
             float a2 = l2[i] - vt2 * im2[i];
             const float lim = c.mu * nl;
             const float mag2 = a1 * a1 + a2 * a2;
-            if (mag2 > lim * lim) { const float sc = lim * rsqrtf(mag2); a1 *= sc; a2 *= sc; }
+            const float sc = mag2 > lim * lim ? lim * rsqrtf(mag2) : 1.0f;   // branch-free disc projection
+            a1 *= sc; a2 *= sc;
             const float d1 = a1 - l1[i], d2 = a2 - l2[i];
             l1[i] = a1; l2[i] = a2;
             vx += d1 * im; vy += d2 * im;
@@ -396,7 +397,9 @@ __device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &
                 }
                 __syncthreads();
                 // rotate the solver warps over the SMSPs (warp w of every CTA sits on SMSP w % 4)
-                const int t = (threadIdx.x + 32 * ((blockIdx.x + k) & (TVC_WARPS - 1))) & (TVC_BLOCK - 1);
+                // (co-resident CTAs differ by multiples of the SM count in blockIdx, so fold the high bits in)
+                const unsigned bx = blockIdx.x;
+                const int t = (threadIdx.x + 32 * ((bx + (bx >> 2) + (bx >> 4) + (bx >> 6) + k) & (TVC_WARPS - 1))) & (TVC_BLOCK - 1);
                 if (t < total) {
                     float Rs[9];
                     quat_to_mat(sm.f[0][t], sm.f[1][t], sm.f[2][t], sm.f[3][t], Rs);
