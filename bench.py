@@ -107,9 +107,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+OVERRIDES = {}   # --override key=value (diagnostic what-if runs; the default line uses none)
+
+
 def _workload_cfg(A, env_id_base=0, contract=None):
     contract = A.CONTRACT_X if contract is None else contract
-    return A.default_config(contract, autoreset=1, env_id_base=env_id_base)
+    return A.default_config(contract, autoreset=1, env_id_base=env_id_base, **OVERRIDES)
 
 
 def _oracle_cfg(O):
@@ -336,7 +339,7 @@ def run_ours(args):
                                    "episode-stat reduction every 64 steps (NCCL all-reduce when N>1)",
                        "envs_per_gpu": n, "substeps": 10, "contact_iters": 8, "parallelism": f"env-slab x{world}",
                        "l2": "flushed between timed steps (256 MiB zero-fill, not timed)",
-                       "burn_in_steps": args.burn_in},
+                       "burn_in_steps": args.burn_in, "overrides": dict(OVERRIDES)},
             "env_substeps_per_sec": value * 10,
             "warm_l2": {"ms_per_step": warm_ms, "env_steps_per_sec_per_gpu": n / (warm_ms * 1e-3),
                         "note": "back-to-back launches, state L2-resident (62 MB < 126 MB)"},
@@ -370,7 +373,11 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--no-rollout", action="store_true", help="skip the fused-rollout (config 4) measurement")
     ap.add_argument("--burn-in", type=int, default=400, help="untimed steps before warm-up (episode desynchronisation)")
+    ap.add_argument("--override", action="append", default=[], help="tvc_config field=value (diagnostics only)")
     args = ap.parse_args()
+    for kv in args.override:
+        k, v = kv.split("=")
+        OVERRIDES[k] = float(v) if "." in v else int(v)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -562,6 +562,14 @@ int tvc_get_config(const tvc_handle *h, tvc_config *out) {
     *out = h->cur;
     return TVC_OK;
 }
+#ifdef TVC_PHASE_PROF
+int tvc_debug_phase(unsigned long long *out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, tvc::g_phase, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(tvc::g_phase, z, sizeof(z)); }
+    return 0;
+}
+#endif
 int64_t tvc_num_envs(const tvc_handle *h) { return h ? h->n : -1; }
 int64_t tvc_lifetime_steps(const tvc_handle *h) { return h ? h->lifetime_steps : -1; }
 

@@ -332,6 +332,16 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
 // the solver this substep posts its problem to a slot; the first ceil(M/32) (rotated) warps solve the
 // M problems with (nearly) full lanes instead of every warp running the solver for a few lanes.
 #define TVC_PROB_FIELDS 15
+#ifdef TVC_PHASE_PROF
+// diagnostic build only: cycles per phase of integrate(), summed over warp leaders
+// [0] free-flight  [1] count barrier  [2] post + barrier  [3] solve (solver warps)  [4] wait for solver (others)
+// [5] read-back + pose update  [6] warp-substeps  [7] solver warp-substeps
+__device__ unsigned long long g_phase[8];
+#define PH_T(x) const long long x = clock64()
+#else
+#define PH_T(x)
+#endif
+
 struct ContactSmem {
     float f[TVC_PROB_FIELDS][TVC_BLOCK];   // qx qy qz qw pz vx vy vz wx wy wz inv_mass inv_Ixy inv_Iz cg
     float lam[18][TVC_BLOCK];              // per ENV THREAD: impulses carried between the substeps of one step
@@ -347,7 +357,11 @@ __device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &
     const float ax_ = Fx * P.inv_mass, ay_ = Fy * P.inv_mass, az_ = Fz * P.inv_mass;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     bool have_lam = false;   // cold start at every control step: stored impulses are logically zero
+#ifdef TVC_PHASE_PROF
+    long long ph0 = 0, ph1 = 0, ph2 = 0, ph3 = 0, ph4 = 0, ph5 = 0, phn = 0, phs = 0;
+#endif
     for (int k = 0; k < c.K; k++) {
+        PH_T(t0);
         float R[9];
         quat_to_mat(e.qx, e.qy, e.qz, e.qw, R);
         // B5: base-local angular acceleration, damping k(1 + |w|), no gyroscopic term
@@ -380,8 +394,13 @@ __device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &
             // B9 (our model): contacts detected at the pre-integration pose, solved on velocities
             const bool need = live && contact_needed(c, P, R, e.pz, e.vz, e.wx, e.wy, e.wz);
             const unsigned bal = __ballot_sync(0xffffffffu, need);
+            PH_T(t1);
             if (lane == 0) sm.cnt[warp] = __popc(bal);
             __syncthreads();
+            PH_T(t2);
+#ifdef TVC_PHASE_PROF
+            long long t3 = t2, t4 = t2, t5 = t2; bool solver = false;
+#endif
             int total = 0, base = 0;
 #pragma unroll
             for (int w = 0; w < TVC_WARPS; w++) { const int n = sm.cnt[w]; if (w < warp) base += n; total += n; }
@@ -396,6 +415,9 @@ __device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &
                     sm.owner[slot] = (int)threadIdx.x | (have_lam ? 0x10000 : 0);
                 }
                 __syncthreads();
+#ifdef TVC_PHASE_PROF
+                t3 = clock64();
+#endif
                 // rotate the solver warps over the SMSPs (warp w of every CTA sits on SMSP w % 4)
                 // (co-resident CTAs differ by multiples of the SM count in blockIdx, so fold the high bits in)
                 const unsigned bx = blockIdx.x;
@@ -413,13 +435,27 @@ __device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &
                     sm.f[5][t] = vx; sm.f[6][t] = vy; sm.f[7][t] = vz;
                     sm.f[8][t] = wx; sm.f[9][t] = wy; sm.f[10][t] = wz;
                 }
+#ifdef TVC_PHASE_PROF
+                t4 = clock64(); solver = __any_sync(0xffffffffu, t < total);
+#endif
                 __syncthreads();
+#ifdef TVC_PHASE_PROF
+                t5 = clock64();
+#endif
                 if (need) {
                     e.vx = sm.f[5][slot]; e.vy = sm.f[6][slot]; e.vz = sm.f[7][slot];
                     e.wx = sm.f[8][slot]; e.wy = sm.f[9][slot]; e.wz = sm.f[10][slot];
                 }
             }
             have_lam = need;   // entry rule failed -> stored impulses cleared
+#ifdef TVC_PHASE_PROF
+            {
+                const long long t6 = clock64();
+                ph0 += t1 - t0; ph1 += t2 - t1; ph2 += t3 - t2;
+                if (solver) { ph3 += t4 - t3; phs += 1; ph4 += t5 - t4; } else ph4 += t5 - t3;
+                ph5 += t6 - t5; phn += 1;
+            }
+#endif
         }
 
         // B6: semi-implicit Euler + exponential map, q <- dq (x) q, normalise
@@ -437,6 +473,14 @@ __device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &
         float inv = rsqrtf(nx * nx + ny * ny + nz * nz + nw * nw);
         e.qx = nx * inv; e.qy = ny * inv; e.qz = nz * inv; e.qw = nw * inv;
     }
+#ifdef TVC_PHASE_PROF
+    if (lane == 0) {
+        atomicAdd(&g_phase[0], (unsigned long long)ph0); atomicAdd(&g_phase[1], (unsigned long long)ph1);
+        atomicAdd(&g_phase[2], (unsigned long long)ph2); atomicAdd(&g_phase[3], (unsigned long long)ph3);
+        atomicAdd(&g_phase[4], (unsigned long long)ph4); atomicAdd(&g_phase[5], (unsigned long long)ph5);
+        atomicAdd(&g_phase[6], (unsigned long long)phn); atomicAdd(&g_phase[7], (unsigned long long)phs);
+    }
+#endif
 }
 
 // ref:381-464 reset (rows S13, Q10, Q11, Q15) + Contract X per-episode draws
