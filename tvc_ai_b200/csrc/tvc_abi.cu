@@ -5,6 +5,7 @@
 #include "tvc_internal.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -143,6 +144,164 @@ step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState s
 #pragma unroll
         for (int w = 0; w < TVC_WARPS; w++) s += s_stat[w][threadIdx.x];
         if (s != 0.0) st.partial[(long long)blockIdx.x * TVC_NSTAT + threadIdx.x] += s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// step path v2: sort, then one warp per 32-env group, solver inline, no CTA barriers
+// ------------------------------------------------------------------------------------------
+#define TVC_CHUNK 1024   // envs sorted together (stable partition, near-ground class first)
+
+// Heuristic class of an env for the coming step: may its lowest point come within the contact margin?
+// Only the grouping depends on it (every thread carries the solver), never the results.
+template <bool X>
+__global__ void __launch_bounds__(256)
+classify_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState st) {
+    __shared__ int wcnt[4][8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long base = (long long)blockIdx.x * TVC_CHUNK;
+    if (blockIdx.x == 0 && tid == 0) *st.counter = 0u;
+    unsigned mask[4];
+    const float T = c.dt * (float)c.K;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const long long env = base + j * 256 + tid;
+        bool near = false;
+        if (env < st.n) {
+            const float4 p = st.s0[env], q = st.s1[env], v = st.s2[env], w = st.s3[env];
+            const float cg = X ? fabsf(st.d0[env].z) + fabsf(c.cg_burn) : 0.0f;
+            const float R31 = 2.0f * (q.x * q.z - q.w * q.y), R32 = 2.0f * (q.y * q.z + q.w * q.x);
+            const float R33 = 1.0f - 2.0f * (q.x * q.x + q.y * q.y);
+            const float hh = c.half_len + cg;
+            const float gmin = p.z - fabsf(R33) * hh - c.radius * sqrtf(R31 * R31 + R32 * R32);
+            const float reach = sqrtf(hh * hh + c.radius * c.radius);
+            const float travel = (fabsf(v.z) + sqrtf(w.x * w.x + w.y * w.y + w.z * w.z) * reach) * T;
+            near = gmin - travel < c.margin + 0.03f;
+        }
+        mask[j] = __ballot_sync(0xffffffffu, near);
+        if (lane == 0) wcnt[j][warp] = __popc(mask[j]);
+    }
+    __syncthreads();
+    int total = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int w = 0; w < 8; w++) total += wcnt[j][w];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int before = 0;   // near-class envs ahead of this warp's 32 in linear order (j, warp, lane)
+        for (int jj = 0; jj < 4; jj++)
+            for (int w = 0; w < 8; w++)
+                if (jj < j || (jj == j && w < warp)) before += wcnt[jj][w];
+        const long long env = base + j * 256 + tid;
+        if (env < st.n) {
+            const int lin = j * 256 + tid;
+            const int ahead = before + __popc(mask[j] & ((1u << lane) - 1u));
+            const bool near = (mask[j] >> lane) & 1u;
+            const int pos = near ? ahead : total + (lin - ahead);
+            st.order[base + pos] = (int)env;
+        }
+    }
+}
+
+#ifndef TVC_MIN_BLOCKS_V2
+#define TVC_MIN_BLOCKS_V2 4
+#endif
+template <bool X, int DIV>
+__global__ void __launch_bounds__(TVC_BLOCK, TVC_MIN_BLOCKS_V2)
+step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevState st, const __grid_constant__ DevIO io) {
+    const int lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    const int ngroups = (int)((st.n + 31) / 32);
+    for (;;) {
+        int g = 0;
+        if (lane == 0) g = (int)atomicAdd(st.counter, 1u);
+        g = __shfl_sync(full, g, 0);
+        if (g >= ngroups) break;
+        const long long slot = (long long)g * 32 + lane;
+        const bool live = slot < st.n;
+        int done = 0, viol = 0;
+        int ev_len = 0, ev_succ = 0, ev_reason = 0, ev_trunc = 0;
+        float ev_ret = 0.0f, ev_alt = 0.0f, ev_tilt = 0.0f, ev_fuel = 0.0f;
+        if (live) {
+            const long long i = st.order[slot];
+            const long long gid = c.env_base + i;
+            Env e;
+            load_env(st, X, i, e);
+            float2 a;
+            if (io.actions) a = io.actions[i];
+            else {
+                uint4 rr = philox(c.seed_lo, c.seed_hi, gid, ST_ACTION, (unsigned)io.t, (unsigned)(io.t >> 32));
+                a = make_float2(2.0f * u01(rr.x) - 1.0f, 2.0f * u01(rr.y) - 1.0f);
+            }
+            if (io.actions_out) io.actions_out[i] = a;
+            BodyP P;
+            Forces f;
+            env_pre<X>(c, st, i, e, a.x, a.y, P, f);
+            integrate_thread(c, P, e, f.Fx, f.Fy, f.Fz, f.Tx, f.Ty, f.Tz);
+            StepResult r;
+            env_post<X, DIV>(c, st, i, gid, e, f.a0, f.a1, r);
+            io.reward[i] = r.reward;
+            io.term[i] = (uint8_t)r.terminated;
+            io.trunc[i] = (uint8_t)r.truncated;
+            if (io.altitude) io.altitude[i] = r.alt;
+            if (io.tilt_deg) io.tilt_deg[i] = r.tilt * 57.29577951308232f;
+            if (io.omega_mag) io.omega_mag[i] = r.wmag;
+            if (io.fuel) io.fuel[i] = r.fuel;
+            if (io.position) { io.position[3 * i] = e.px; io.position[3 * i + 1] = e.py; io.position[3 * i + 2] = e.pz; }
+            if (io.phase) io.phase[i] = e.phase;
+            if (io.step) io.step[i] = e.step;
+            if (io.success) io.success[i] = (uint8_t)e.success;
+            if (io.criteria_met) io.criteria_met[i] = (uint8_t)(e.consec >= 10);
+            if (io.comp) {
+#pragma unroll
+                for (int k = 0; k < 12; k++) io.comp[12 * i + k] = r.comp[k];
+            }
+            viol = r.viol;
+            done = r.terminated | r.truncated;
+            if (done) {
+                ev_len = e.step; ev_succ = e.success; ev_reason = r.reason; ev_trunc = r.truncated;
+                ev_ret = e.ep_ret; ev_alt = r.alt; ev_tilt = r.tilt; ev_fuel = r.fuel;
+                if (io.final_obs) {
+                    float2 *f2 = reinterpret_cast<float2 *>(io.final_obs + 10 * i);
+#pragma unroll
+                    for (int k = 0; k < 5; k++) f2[k] = make_float2(r.obs[2 * k], r.obs[2 * k + 1]);
+                }
+                if (c.autoreset) {
+                    reset_env(c, X, gid, e, false);
+                    build_obs(c, X, gid, e, 0, r.obs);
+                }
+            }
+            store_env(st, X, i, e);
+            float2 *o2 = reinterpret_cast<float2 *>(io.obs + 10 * i);
+#pragma unroll
+            for (int k = 0; k < 5; k++) o2[k] = make_float2(r.obs[2 * k], r.obs[2 * k + 1]);
+        }
+        // episode statistics: this group owns row g of `partial` for the whole launch (no atomics, deterministic)
+        if (__any_sync(full, done | viol)) {
+            const int n_ep = __reduce_add_sync(full, done), n_len = __reduce_add_sync(full, ev_len);
+            const int n_succ = __reduce_add_sync(full, done ? ev_succ : 0);
+            const int n_cr = __reduce_add_sync(full, ev_reason == 2), n_ti = __reduce_add_sync(full, ev_reason == 3);
+            const int n_al = __reduce_add_sync(full, ev_reason == 4), n_ra = __reduce_add_sync(full, ev_reason == 5);
+            const int n_tr = __reduce_add_sync(full, ev_trunc), n_vi = __reduce_add_sync(full, viol);
+            double d_ret = ev_ret, d_ret2 = (double)ev_ret * (double)ev_ret, d_alt = ev_alt, d_tilt = ev_tilt, d_fuel = ev_fuel;
+            if (n_ep) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    d_ret += __shfl_xor_sync(full, d_ret, o); d_ret2 += __shfl_xor_sync(full, d_ret2, o);
+                    d_alt += __shfl_xor_sync(full, d_alt, o); d_tilt += __shfl_xor_sync(full, d_tilt, o);
+                    d_fuel += __shfl_xor_sync(full, d_fuel, o);
+                }
+            }
+            double v = 0.0;
+            switch (lane) {
+                case 0: v = n_ep; break;   case 1: v = d_ret; break;  case 2: v = d_ret2; break; case 3: v = n_len; break;
+                case 4: v = n_succ; break; case 5: v = n_cr; break;   case 6: v = n_ti; break;   case 7: v = n_al; break;
+                case 8: v = n_ra; break;   case 9: v = n_tr; break;   case 10: v = n_vi; break;  case 11: v = d_alt; break;
+                case 12: v = d_tilt; break; case 13: v = d_fuel; break; default: break;
+            }
+            if (lane < 14 && v != 0.0) st.partial[(long long)g * TVC_NSTAT + lane] += v;
+        }
     }
 }
 
@@ -356,6 +515,10 @@ int tvc_create(const tvc_config *cfg, int device, int64_t num_envs, tvc_handle *
     tvc_handle *h = new (std::nothrow) tvc_handle();
     if (!h) { tvc_set_err("out of host memory"); return TVC_E_NOMEM; }
     h->device = device; h->n = num_envs; h->base = *cfg; h->cur = *cfg; h->num_sms = prop.multiProcessorCount;
+    {   // TVC_STEP_IMPL=1 selects the legacy CTA-exchange kernel (kept for A/B measurements)
+        const char *impl = getenv("TVC_STEP_IMPL");
+        h->step_impl = (impl && impl[0] == '1') ? 1 : 2;
+    }
     make_devcfg(h->cur, h->dc);
     const size_t n = (size_t)num_envs;
     h->grid = (int)((num_envs + TVC_BLOCK - 1) / TVC_BLOCK);
@@ -371,7 +534,10 @@ int tvc_create(const tvc_config *cfg, int device, int64_t num_envs, tvc_handle *
     }
     if (cfg->diversity_mode == TVC_DIV_FAST) { TRY(dalloc(&s.clipb, 32 * n)); TRY(dalloc(&s.runb, 32 * n)); }
     if (cfg->diversity_mode == TVC_DIV_EXACT) TRY(dalloc(&s.hist, (size_t)TVC_HIST * n));
-    TRY(dalloc(&s.partial, (size_t)h->grid * TVC_NSTAT));
+    h->ngroups = (int)((num_envs + 31) / 32);
+    TRY(dalloc(&s.partial, (size_t)h->ngroups * TVC_NSTAT));
+    TRY(dalloc(&s.order, n));
+    TRY(dalloc(&s.counter, (size_t)4));
     TRY(dalloc(&h->stats_dev, (size_t)TVC_NSTAT));
     {
         cudaError_t e = cudaMallocHost((void **)&h->stats_host, sizeof(double) * TVC_NSTAT);
@@ -395,7 +561,7 @@ int tvc_destroy(tvc_handle *h) {
     DevState &s = h->st;
     cudaFree(s.s0); cudaFree(s.s1); cudaFree(s.s2); cudaFree(s.s3); cudaFree(s.s4);
     cudaFree(s.d0); cudaFree(s.d1); cudaFree(s.ring); cudaFree(s.clipb); cudaFree(s.runb); cudaFree(s.hist);
-    cudaFree(s.delay); cudaFree(s.partial); cudaFree(h->stats_dev);
+    cudaFree(s.delay); cudaFree(s.partial); cudaFree(s.order); cudaFree(s.counter); cudaFree(h->stats_dev);
     cudaFree(h->io_act); cudaFree(h->io_obs); cudaFree(h->io_rew); cudaFree(h->io_term); cudaFree(h->io_trunc); cudaFree(h->io_final);
     tvc_rollout_free(h);
     if (h->stats_host) cudaFreeHost(h->stats_host);
@@ -420,11 +586,31 @@ int tvc_reset(tvc_handle *h, const uint8_t *mask_dev, uint64_t seed, float *obs_
 static int launch_step(tvc_handle *h, const DevIO &io, cudaStream_t s) {
     const bool X = h->cur.contract == TVC_CONTRACT_X;
     const int dv = h->cur.diversity_mode;
+    if (h->step_impl == 1) {   // legacy: thread-per-env CTAs with the shared-memory contact exchange
 #define GO(XX, DD) step_kernel<XX, DD><<<h->grid, TVC_BLOCK, 0, s>>>(h->dc, h->st, io)
-    if (X) { if (dv == 0) GO(true, 0); else if (dv == 1) GO(true, 1); else GO(true, 2); }
-    else   { if (dv == 0) GO(false, 0); else if (dv == 1) GO(false, 1); else GO(false, 2); }
+        if (X) { if (dv == 0) GO(true, 0); else if (dv == 1) GO(true, 1); else GO(true, 2); }
+        else   { if (dv == 0) GO(false, 0); else if (dv == 1) GO(false, 1); else GO(false, 2); }
 #undef GO
-    LAUNCH_OK("step_kernel");
+        LAUNCH_OK("step_kernel");
+    } else {
+        const int cgrid = (int)((h->n + TVC_CHUNK - 1) / TVC_CHUNK);
+        if (X) classify_kernel<true><<<cgrid, 256, 0, s>>>(h->dc, h->st);
+        else classify_kernel<false><<<cgrid, 256, 0, s>>>(h->dc, h->st);
+        LAUNCH_OK("classify_kernel");
+        if (h->v2_grid == 0) {   // persistent grid: resident CTAs of the v2 kernel, capped by the number of groups
+            int per_sm = 0;
+            cudaError_t e = X ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_v2<true, 1>, TVC_BLOCK, 0)
+                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_v2<false, 1>, TVC_BLOCK, 0);
+            if (e != cudaSuccess || per_sm < 1) per_sm = 1;
+            const int want = (h->ngroups + TVC_WARPS - 1) / TVC_WARPS;
+            h->v2_grid = want < per_sm * h->num_sms ? want : per_sm * h->num_sms;
+        }
+#define GO(XX, DD) step_kernel_v2<XX, DD><<<h->v2_grid, TVC_BLOCK, 0, s>>>(h->dc, h->st, io)
+        if (X) { if (dv == 0) GO(true, 0); else if (dv == 1) GO(true, 1); else GO(true, 2); }
+        else   { if (dv == 0) GO(false, 0); else if (dv == 1) GO(false, 1); else GO(false, 2); }
+#undef GO
+        LAUNCH_OK("step_kernel_v2");
+    }
     h->lifetime_steps += 1;
     h->stat_steps += 1;
     return TVC_OK;
@@ -521,7 +707,7 @@ int tvc_episode_stats_dev(tvc_handle *h, double *dev_out, int reset_after, tvc_s
     CHECK_H(h);
     if (!dev_out) { tvc_set_err("dev_out is NULL"); return TVC_E_BADARG; }
     const double steps = (double)h->stat_steps * (double)h->n;
-    stats_reduce_kernel<<<1, 32 * TVC_NSTAT, 0, (cudaStream_t)stream>>>(h->st.partial, h->grid, dev_out, steps, reset_after);
+    stats_reduce_kernel<<<1, 32 * TVC_NSTAT, 0, (cudaStream_t)stream>>>(h->st.partial, h->ngroups, dev_out, steps, reset_after);
     LAUNCH_OK("stats_reduce_kernel");
     if (reset_after) h->stat_steps = 0;
     return TVC_OK;

@@ -46,7 +46,9 @@ struct DevState {
     unsigned *runb;   // [32][N] fast diversity: value == predecessor
     float *hist;      // [1000][N] exact diversity only
     float2 *delay;    // [TVC_MAX_DELAY][N] X: actuator delay ring, slot = step % delay
-    double *partial;  // [grid][16] per-CTA episode statistics
+    double *partial;  // [ceil(N/32)][16] episode statistics rows: one owner (CTA or 32-env group) per row per launch
+    int *order;       // [N] env ids sorted per 1024-env chunk: near-ground envs first (classify_kernel)
+    unsigned *counter;  // work-queue head of step_kernel_v2 (zeroed by classify_kernel)
     long long n;
 };
 
@@ -219,6 +221,7 @@ __device__ __forceinline__ bool contact_needed(const DevCfg &c, const BodyP &P, 
 
 // lam: this problem's 18 stored impulses, element j at lam[j * TVC_BLOCK] (shared memory column of the posting
 // thread): normal(5), tangent-x(5), tangent-y(5), spin, roll-x, roll-y.  warm: apply them before sweeping.
+template <int LS>   // LS: stride between the 18 impulses (TVC_BLOCK for the shared-memory column, 1 for a register array)
 __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, const float R[9], float pz, float &vx,
                                                float &vy, float &vz, float &wx, float &wy, float &wz, float *lam,
                                                bool warm, int iters) {
@@ -258,11 +261,11 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
         const float vn0 = vz + wx * ay[i] - wy * ax[i];
         const float rest = (vn0 < -c.rest_thr) ? -c.restitution * vn0 : 0.0f;
         tgt[i] = rest + (gap > 0.0f ? -gap * c.inv_dt : -c.erp * gap * c.inv_dt);
-        ln[i] = warm ? lam[i * TVC_BLOCK] : 0.0f;
-        l1[i] = warm ? lam[(5 + i) * TVC_BLOCK] : 0.0f;
-        l2[i] = warm ? lam[(10 + i) * TVC_BLOCK] : 0.0f;
+        ln[i] = warm ? lam[i * LS] : 0.0f;
+        l1[i] = warm ? lam[(5 + i) * LS] : 0.0f;
+        l2[i] = warm ? lam[(10 + i) * LS] : 0.0f;
     }
-    float lsp = warm ? lam[15 * TVC_BLOCK] : 0.0f, lr1 = warm ? lam[16 * TVC_BLOCK] : 0.0f, lr2 = warm ? lam[17 * TVC_BLOCK] : 0.0f;
+    float lsp = warm ? lam[15 * LS] : 0.0f, lr1 = warm ? lam[16 * LS] : 0.0f, lr2 = warm ? lam[17 * LS] : 0.0f;
     const float iW22 = 1.0f / W22, iW00 = 1.0f / W00, iW11 = 1.0f / W11;
     if (warm) {   // apply the stored impulses at the current contact geometry
 #pragma unroll
@@ -324,8 +327,8 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
         }
     }
 #pragma unroll
-    for (int i = 0; i < 5; i++) { lam[i * TVC_BLOCK] = ln[i]; lam[(5 + i) * TVC_BLOCK] = l1[i]; lam[(10 + i) * TVC_BLOCK] = l2[i]; }
-    lam[15 * TVC_BLOCK] = lsp; lam[16 * TVC_BLOCK] = lr1; lam[17 * TVC_BLOCK] = lr2;
+    for (int i = 0; i < 5; i++) { lam[i * LS] = ln[i]; lam[(5 + i) * LS] = l1[i]; lam[(10 + i) * LS] = l2[i]; }
+    lam[15 * LS] = lsp; lam[16 * LS] = lr1; lam[17 * LS] = lr2;
 }
 
 // Shared-memory exchange used to compact ground-contact problems across the CTA: each env that needs
@@ -430,7 +433,7 @@ __device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &
                     float vx = sm.f[5][t], vy = sm.f[6][t], vz = sm.f[7][t];
                     float wx = sm.f[8][t], wy = sm.f[9][t], wz = sm.f[10][t];
                     const int ow = sm.owner[t];
-                    solve_contacts(c, Q, Rs, sm.f[4][t], vx, vy, vz, wx, wy, wz, &sm.lam[0][ow & 0xFFFF], (ow >> 16) != 0,
+                    solve_contacts<TVC_BLOCK>(c, Q, Rs, sm.f[4][t], vx, vy, vz, wx, wy, wz, &sm.lam[0][ow & 0xFFFF], (ow >> 16) != 0,
                                    k == 0 ? c.contact_iters : c.warm_iters);
                     sm.f[5][t] = vx; sm.f[6][t] = vy; sm.f[7][t] = vz;
                     sm.f[8][t] = wx; sm.f[9][t] = wy; sm.f[10][t] = wz;
@@ -481,6 +484,67 @@ __device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &
         atomicAdd(&g_phase[6], (unsigned long long)phn); atomicAdd(&g_phase[7], (unsigned long long)phs);
     }
 #endif
+}
+
+// Same K substeps for ONE env on its own thread: no shared memory, no CTA barriers, the contact solver inline with
+// its 18 carried impulses in registers.  Used by step_kernel_v2, whose warps hold envs of one class (near the ground
+// or not) so the `need` branch is nearly warp-uniform.
+__device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P, Env &e, float Fx, float Fy, float Fz,
+                                                 float Tx, float Ty, float Tz) {
+    const float dt = c.dt;
+    const float ax_ = Fx * P.inv_mass, ay_ = Fy * P.inv_mass, az_ = Fz * P.inv_mass;
+    float lam[18];
+#pragma unroll
+    for (int j = 0; j < 18; j++) lam[j] = 0.0f;
+    bool have_lam = false;
+    for (int k = 0; k < c.K; k++) {
+        float R[9];
+        quat_to_mat(e.qx, e.qy, e.qz, e.qw, R);
+        float wl0 = R[0] * e.wx + R[3] * e.wy + R[6] * e.wz;
+        float wl1 = R[1] * e.wx + R[4] * e.wy + R[7] * e.wz;
+        float wl2 = R[2] * e.wx + R[5] * e.wy + R[8] * e.wz;
+        float tl0 = R[0] * Tx + R[3] * Ty + R[6] * Tz;
+        float tl1 = R[1] * Tx + R[4] * Ty + R[7] * Tz;
+        float tl2 = R[2] * Tx + R[5] * Ty + R[8] * Tz;
+        float wn2 = wl0 * wl0 + wl1 * wl1 + wl2 * wl2;
+        float wn = wn2 > 2.220446049250313e-16f ? sqrtf(wn2) : 0.0f;
+        float kd = c.ang_damp + c.ang_damp * wn;
+        float wd0 = tl0 * P.inv_Ixy - wl0 * kd;
+        float wd1 = tl1 * P.inv_Ixy - wl1 * kd;
+        float wd2 = tl2 * P.inv_Iz - wl2 * kd;
+        float dwx = R[0] * wd0 + R[1] * wd1 + R[2] * wd2;
+        float dwy = R[3] * wd0 + R[4] * wd1 + R[5] * wd2;
+        float dwz = R[6] * wd0 + R[7] * wd1 + R[8] * wd2;
+        float vn2 = e.vx * e.vx + e.vy * e.vy + e.vz * e.vz;
+        float vn = vn2 > 2.220446049250313e-16f ? sqrtf(vn2) : 0.0f;
+        float kl = c.lin_damp + c.lin_damp * vn;
+        e.wx = clampf(e.wx + dwx * dt, -100.0f, 100.0f);
+        e.wy = clampf(e.wy + dwy * dt, -100.0f, 100.0f);
+        e.wz = clampf(e.wz + dwz * dt, -100.0f, 100.0f);
+        e.vx = clampf(e.vx + (ax_ - e.vx * kl) * dt, -100.0f, 100.0f);
+        e.vy = clampf(e.vy + (ay_ - e.vy * kl) * dt, -100.0f, 100.0f);
+        e.vz = clampf(e.vz + (az_ - e.vz * kl) * dt, -100.0f, 100.0f);
+        if (c.ground) {
+            const bool need = contact_needed(c, P, R, e.pz, e.vz, e.wx, e.wy, e.wz);
+            if (need)
+                solve_contacts<1>(c, P, R, e.pz, e.vx, e.vy, e.vz, e.wx, e.wy, e.wz, lam, have_lam,
+                                  k == 0 ? c.contact_iters : c.warm_iters);
+            have_lam = need;
+        }
+        e.px += dt * e.vx; e.py += dt * e.vy; e.pz += dt * e.vz;
+        float ang = sqrtf(e.wx * e.wx + e.wy * e.wy + e.wz * e.wz);
+        if (ang * dt > 0.7853981633974483f) ang = 0.7853981633974483f / dt;
+        float sc;
+        if (ang < 0.001f) sc = 0.5f * dt - (dt * dt * dt) * 0.020833333333f * ang * ang;
+        else sc = sinf(0.5f * ang * dt) / ang;
+        float bx = e.wx * sc, by = e.wy * sc, bz = e.wz * sc, cw = cosf(ang * dt * 0.5f);
+        float nx = cw * e.qx + bx * e.qw + by * e.qz - bz * e.qy;
+        float ny = cw * e.qy + by * e.qw + bz * e.qx - bx * e.qz;
+        float nz = cw * e.qz + bz * e.qw + bx * e.qy - by * e.qx;
+        float nw = cw * e.qw - bx * e.qx - by * e.qy - bz * e.qz;
+        float inv = rsqrtf(nx * nx + ny * ny + nz * nz + nw * nw);
+        e.qx = nx * inv; e.qy = ny * inv; e.qz = nz * inv; e.qw = nw * inv;
+    }
 }
 
 // ref:381-464 reset (rows S13, Q10, Q11, Q15) + Contract X per-episode draws
