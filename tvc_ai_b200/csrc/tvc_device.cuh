@@ -84,8 +84,21 @@ struct Env {
 // ------------------------------------------------------------------------------------------
 enum { ST_DR_A = 1, ST_DR_B = 2, ST_NOISE_A = 3, ST_NOISE_B = 4, ST_ACTION = 5, ST_ACTOR = 6, ST_DR_C = 7 };
 
-__device__ __forceinline__ uint4 philox(unsigned seed_lo, unsigned seed_hi, long long gid, unsigned stream,
-                                        unsigned a, unsigned b) {
+// Code size matters here: the step kernels run many desynchronised warps through ~90 KB of straight-line code,
+// and ncu shows instruction-fetch stalls (no_instruction) dominating once the CTA barriers are gone.  So the
+// generators are single out-of-line copies and the hot path uses short, slow-path-free math:
+//   rcp_fast / sqrt_fast : MUFU.RCP / MUFU.RSQ based, <= 2 ulp, operands are well-scaled positive numbers
+//   sincos_small         : degree-9/8 Taylor polynomials, |x| <= 0.8 rad, error < 4e-8
+__device__ __forceinline__ float rcp_fast(float x) { return __fdividef(1.0f, x); }
+__device__ __forceinline__ float sqrt_fast(float x) { return x > 0.0f ? x * rsqrtf(x) : 0.0f; }
+__device__ __forceinline__ void sincos_small(float x, float &s, float &c) {
+    const float x2 = x * x;
+    s = x * (1.0f + x2 * (-1.6666667e-1f + x2 * (8.3333333e-3f + x2 * (-1.9841270e-4f + x2 * 2.7557319e-6f))));
+    c = 1.0f + x2 * (-0.5f + x2 * (4.1666667e-2f + x2 * (-1.3888889e-3f + x2 * (2.4801587e-5f - x2 * 2.7557319e-7f))));
+}
+
+static __device__ __noinline__ uint4 philox(unsigned seed_lo, unsigned seed_hi, long long gid, unsigned stream,
+                                     unsigned a, unsigned b) {
     unsigned c0 = (unsigned)gid, c1 = (unsigned)(((unsigned long long)gid >> 32) & 0xFFFFu) | (stream << 16);
     unsigned c2 = a, c3 = b, k0 = seed_lo, k1 = seed_hi;
 #pragma unroll
@@ -101,10 +114,18 @@ __device__ __forceinline__ uint4 philox(unsigned seed_lo, unsigned seed_hi, long
 // (k + 0.5) / 2^23 : exact in fp32
 __device__ __forceinline__ float u01(unsigned x) { return ((float)(x >> 9) + 0.5f) * (1.0f / 8388608.0f); }
 __device__ __forceinline__ void box_muller(unsigned x0, unsigned x1, float &n0, float &n1) {
-    float r = sqrtf(-2.0f * logf(u01(x0)));
+    float r = sqrt_fast(-2.0f * logf(u01(x0)));
     float s, c;
-    sincosf(6.283185307179586f * u01(x1), &s, &c);
+    sincospif(2.0f * u01(x1), &s, &c);   // exact argument reduction, no Payne-Hanek slow path
     n0 = r * c; n1 = r * s;
+}
+// eight N(0,1) draws for one (env, episode, step) -- one out-of-line copy (sensor noise)
+static __device__ __noinline__ void noise8(unsigned seed_lo, unsigned seed_hi, long long gid, unsigned episode, unsigned step,
+                                    float n[8]) {
+    const uint4 a = philox(seed_lo, seed_hi, gid, ST_NOISE_A, episode, step);
+    const uint4 b = philox(seed_lo, seed_hi, gid, ST_NOISE_B, episode, step);
+    box_muller(a.x, a.y, n[0], n[1]); box_muller(a.z, a.w, n[2], n[3]);
+    box_muller(b.x, b.y, n[4], n[5]); box_muller(b.z, b.w, n[6], n[7]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -113,7 +134,7 @@ __device__ __forceinline__ void box_muller(unsigned x0, unsigned x1, float &n0, 
 // btMatrix3x3::setRotation (ref:546 getMatrixFromQuaternion), row-major
 __device__ __forceinline__ void quat_to_mat(float x, float y, float z, float w, float R[9]) {
     float d = x * x + y * y + z * z + w * w;
-    float s = 2.0f / d;
+    float s = 2.0f * rcp_fast(d);
     float xs = x * s, ys = y * s, zs = z * s;
     float wx = w * xs, wy = w * ys, wz = w * zs;
     float xx = x * xs, xy = x * ys, xz = x * zs;
@@ -128,7 +149,7 @@ __device__ __forceinline__ void quat_to_mat(float x, float y, float z, float w, 
 __device__ __forceinline__ void reported_quat(float x, float y, float z, float w, float &ox, float &oy, float &oz,
                                               float &ow) {
     float d = x * x + y * y + z * z + w * w;
-    float s = 2.0f / d;
+    float s = 2.0f * rcp_fast(d);
     float xx = x * x * s, yy = y * y * s, zz = z * z * s;
     float m00 = 1.0f - (yy + zz), m11 = 1.0f - (xx + zz), m22 = 1.0f - (xx + yy);
     float trace = m00 + m11 + m22;
@@ -180,10 +201,10 @@ __device__ __forceinline__ BodyP body_params(const DevCfg &c, bool X, float mass
     float m = X ? c.mass * mass_scale * (1.0f - c.prop_frac * burnt) : c.mass;
     float cg = X ? cg_off + c.cg_burn * burnt : 0.0f;
     float len = 2.0f * c.half_len;
-    P.mass = m; P.inv_mass = 1.0f / m; P.cg = cg;
+    P.mass = m; P.inv_mass = rcp_fast(m); P.cg = cg;
     P.Ixy = (1.0f / 12.0f) * m * (3.0f * c.radius * c.radius + len * len) + m * cg * cg;   // ref:431
     P.Iz = 0.5f * m * c.radius * c.radius;                                                  // ref:432
-    P.inv_Ixy = 1.0f / P.Ixy; P.inv_Iz = 1.0f / P.Iz;
+    P.inv_Ixy = rcp_fast(P.Ixy); P.inv_Iz = rcp_fast(P.Iz);
     return P;
 }
 
@@ -208,14 +229,14 @@ __device__ __forceinline__ bool contact_needed(const DevCfg &c, const BodyP &P, 
                                                float wx, float wy, float wz) {
     const float r = c.radius, h = c.half_len;
     const float R31 = R[6], R32 = R[7], R33 = R[8];
-    const float rho = sqrtf(R31 * R31 + R32 * R32);
-    const float inv = 1.0f / fmaxf(rho, 1e-3f);
+    const float rho = sqrt_fast(R31 * R31 + R32 * R32);
+    const float inv = rcp_fast(fmaxf(rho, 1e-3f));
     const float low = -r * (R31 * R31 + R32 * R32) * inv;
     const float gmin = pz + fminf(R33 * (-h - P.cg), R33 * (h - P.cg)) + low;
     if (!(gmin < c.margin)) return false;
     const float hh = h + fabsf(P.cg);
-    const float reach = sqrtf(hh * hh + r * r);
-    const float vmax = fabsf(vz) + sqrtf(wx * wx + wy * wy + wz * wz) * reach;
+    const float reach = sqrt_fast(hh * hh + r * r);
+    const float vmax = fabsf(vz) + sqrt_fast(wx * wx + wy * wy + wz * wz) * reach;
     return gmin - 1e-4f < (1.0f + c.restitution) * vmax * c.dt;
 }
 
@@ -227,8 +248,8 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
                                                bool warm, int iters) {
     const float r = c.radius, h = c.half_len;
     const float R31 = R[6], R32 = R[7];
-    const float rho = sqrtf(R31 * R31 + R32 * R32);
-    const float inv = 1.0f / fmaxf(rho, 1e-3f);
+    const float rho = sqrt_fast(R31 * R31 + R32 * R32);
+    const float inv = rcp_fast(fmaxf(rho, 1e-3f));
     const float ux = -R31 * inv, uy = -R32 * inv;
     const float zb = -h - P.cg, zt = h - P.cg;
 
@@ -257,7 +278,7 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
         const float mn = im + (W00 * ay[i] * ay[i] - 2.0f * W01 * ax[i] * ay[i] + W11 * ax[i] * ax[i]);
         const float m1 = im + (W11 * az[i] * az[i] - 2.0f * W12 * az[i] * ay[i] + W22 * ay[i] * ay[i]);
         const float m2 = im + (W00 * az[i] * az[i] - 2.0f * W02 * az[i] * ax[i] + W22 * ax[i] * ax[i]);
-        imn[i] = 1.0f / mn; im1[i] = 1.0f / m1; im2[i] = 1.0f / m2;
+        imn[i] = rcp_fast(mn); im1[i] = rcp_fast(m1); im2[i] = rcp_fast(m2);
         const float vn0 = vz + wx * ay[i] - wy * ax[i];
         const float rest = (vn0 < -c.rest_thr) ? -c.restitution * vn0 : 0.0f;
         tgt[i] = rest + (gap > 0.0f ? -gap * c.inv_dt : -c.erp * gap * c.inv_dt);
@@ -266,7 +287,7 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
         l2[i] = warm ? lam[(10 + i) * LS] : 0.0f;
     }
     float lsp = warm ? lam[15 * LS] : 0.0f, lr1 = warm ? lam[16 * LS] : 0.0f, lr2 = warm ? lam[17 * LS] : 0.0f;
-    const float iW22 = 1.0f / W22, iW00 = 1.0f / W00, iW11 = 1.0f / W11;
+    const float iW22 = rcp_fast(W22), iW00 = rcp_fast(W00), iW11 = rcp_fast(W11);
     if (warm) {   // apply the stored impulses at the current contact geometry
 #pragma unroll
         for (int i = 0; i < 5; i++) {
@@ -375,7 +396,7 @@ __device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &
         float tl1 = R[1] * Tx + R[4] * Ty + R[7] * Tz;
         float tl2 = R[2] * Tx + R[5] * Ty + R[8] * Tz;
         float wn2 = wl0 * wl0 + wl1 * wl1 + wl2 * wl2;
-        float wn = wn2 > 2.220446049250313e-16f ? sqrtf(wn2) : 0.0f;
+        float wn = wn2 > 2.220446049250313e-16f ? sqrt_fast(wn2) : 0.0f;
         float kd = c.ang_damp + c.ang_damp * wn;
         float wd0 = tl0 * P.inv_Ixy - wl0 * kd;
         float wd1 = tl1 * P.inv_Ixy - wl1 * kd;
@@ -384,7 +405,7 @@ __device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &
         float dwy = R[3] * wd0 + R[4] * wd1 + R[5] * wd2;
         float dwz = R[6] * wd0 + R[7] * wd1 + R[8] * wd2;
         float vn2 = e.vx * e.vx + e.vy * e.vy + e.vz * e.vz;
-        float vn = vn2 > 2.220446049250313e-16f ? sqrtf(vn2) : 0.0f;
+        float vn = vn2 > 2.220446049250313e-16f ? sqrt_fast(vn2) : 0.0f;
         float kl = c.lin_damp + c.lin_damp * vn;
         e.wx = clampf(e.wx + dwx * dt, -100.0f, 100.0f);
         e.wy = clampf(e.wy + dwy * dt, -100.0f, 100.0f);
@@ -463,12 +484,13 @@ __device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &
 
         // B6: semi-implicit Euler + exponential map, q <- dq (x) q, normalise
         e.px += dt * e.vx; e.py += dt * e.vy; e.pz += dt * e.vz;
-        float ang = sqrtf(e.wx * e.wx + e.wy * e.wy + e.wz * e.wz);
-        if (ang * dt > 0.7853981633974483f) ang = 0.7853981633974483f / dt;
-        float sc;
-        if (ang < 0.001f) sc = 0.5f * dt - (dt * dt * dt) * 0.020833333333f * ang * ang;
-        else sc = sinf(0.5f * ang * dt) / ang;
-        float bx = e.wx * sc, by = e.wy * sc, bz = e.wz * sc, cw = cosf(ang * dt * 0.5f);
+        float ang = sqrt_fast(e.wx * e.wx + e.wy * e.wy + e.wz * e.wz);
+        if (ang * dt > 0.7853981633974483f) ang = 0.7853981633974483f * c.inv_dt;
+        // sin(x)/ang and cos(x) with x = ang*dt/2 <= pi/8: polynomials (Bullet switches to its own Taylor form below 1e-3)
+        const float hx = 0.5f * ang * dt, hx2 = hx * hx;
+        const float sc = 0.5f * dt * (1.0f + hx2 * (-1.6666667e-1f + hx2 * (8.3333333e-3f + hx2 * (-1.9841270e-4f + hx2 * 2.7557319e-6f))));
+        const float cw = 1.0f + hx2 * (-0.5f + hx2 * (4.1666667e-2f + hx2 * (-1.3888889e-3f + hx2 * 2.4801587e-5f)));
+        float bx = e.wx * sc, by = e.wy * sc, bz = e.wz * sc;
         float nx = cw * e.qx + bx * e.qw + by * e.qz - bz * e.qy;
         float ny = cw * e.qy + by * e.qw + bz * e.qx - bx * e.qz;
         float nz = cw * e.qz + bz * e.qw + bx * e.qy - by * e.qx;
@@ -507,7 +529,7 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
         float tl1 = R[1] * Tx + R[4] * Ty + R[7] * Tz;
         float tl2 = R[2] * Tx + R[5] * Ty + R[8] * Tz;
         float wn2 = wl0 * wl0 + wl1 * wl1 + wl2 * wl2;
-        float wn = wn2 > 2.220446049250313e-16f ? sqrtf(wn2) : 0.0f;
+        float wn = wn2 > 2.220446049250313e-16f ? sqrt_fast(wn2) : 0.0f;
         float kd = c.ang_damp + c.ang_damp * wn;
         float wd0 = tl0 * P.inv_Ixy - wl0 * kd;
         float wd1 = tl1 * P.inv_Ixy - wl1 * kd;
@@ -516,7 +538,7 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
         float dwy = R[3] * wd0 + R[4] * wd1 + R[5] * wd2;
         float dwz = R[6] * wd0 + R[7] * wd1 + R[8] * wd2;
         float vn2 = e.vx * e.vx + e.vy * e.vy + e.vz * e.vz;
-        float vn = vn2 > 2.220446049250313e-16f ? sqrtf(vn2) : 0.0f;
+        float vn = vn2 > 2.220446049250313e-16f ? sqrt_fast(vn2) : 0.0f;
         float kl = c.lin_damp + c.lin_damp * vn;
         e.wx = clampf(e.wx + dwx * dt, -100.0f, 100.0f);
         e.wy = clampf(e.wy + dwy * dt, -100.0f, 100.0f);
@@ -532,12 +554,13 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
             have_lam = need;
         }
         e.px += dt * e.vx; e.py += dt * e.vy; e.pz += dt * e.vz;
-        float ang = sqrtf(e.wx * e.wx + e.wy * e.wy + e.wz * e.wz);
-        if (ang * dt > 0.7853981633974483f) ang = 0.7853981633974483f / dt;
-        float sc;
-        if (ang < 0.001f) sc = 0.5f * dt - (dt * dt * dt) * 0.020833333333f * ang * ang;
-        else sc = sinf(0.5f * ang * dt) / ang;
-        float bx = e.wx * sc, by = e.wy * sc, bz = e.wz * sc, cw = cosf(ang * dt * 0.5f);
+        float ang = sqrt_fast(e.wx * e.wx + e.wy * e.wy + e.wz * e.wz);
+        if (ang * dt > 0.7853981633974483f) ang = 0.7853981633974483f * c.inv_dt;
+        // sin(x)/ang and cos(x) with x = ang*dt/2 <= pi/8: polynomials (Bullet switches to its own Taylor form below 1e-3)
+        const float hx = 0.5f * ang * dt, hx2 = hx * hx;
+        const float sc = 0.5f * dt * (1.0f + hx2 * (-1.6666667e-1f + hx2 * (8.3333333e-3f + hx2 * (-1.9841270e-4f + hx2 * 2.7557319e-6f))));
+        const float cw = 1.0f + hx2 * (-0.5f + hx2 * (4.1666667e-2f + hx2 * (-1.3888889e-3f + hx2 * 2.4801587e-5f)));
+        float bx = e.wx * sc, by = e.wy * sc, bz = e.wz * sc;
         float nx = cw * e.qx + bx * e.qw + by * e.qz - bz * e.qy;
         float ny = cw * e.qy + by * e.qw + bz * e.qx - bx * e.qz;
         float nz = cw * e.qz + bz * e.qw + bx * e.qy - by * e.qx;
@@ -545,6 +568,30 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
         float inv = rsqrtf(nx * nx + ny * ny + nz * nz + nw * nw);
         e.qx = nx * inv; e.qy = ny * inv; e.qz = nz * inv; e.qw = nw * inv;
     }
+}
+
+// Contract X per-episode draws (one out-of-line copy): mass scale, thrust scale, wind x/y, cg offset, initial
+// tilt quaternion (x, y, w) and angular velocity.
+static __device__ __noinline__ void reset_draws(const DevCfg &c, long long gid, int episode, float d[11]) {
+    uint4 a = philox(c.seed_lo, c.seed_hi, gid, ST_DR_A, (unsigned)episode, 0u);
+    uint4 b = philox(c.seed_lo, c.seed_hi, gid, ST_DR_B, (unsigned)episode, 0u);
+    uint4 w = philox(c.seed_lo, c.seed_hi, gid, ST_DR_C, (unsigned)episode, 0u);
+    float n0, n1, n2, n3;
+    box_muller(a.y, a.z, n0, n1);
+    box_muller(b.x, b.y, n2, n3);
+    d[0] = 1.0f + c.mass_var * (2.0f * u01(a.x) - 1.0f);
+    d[1] = clampf(1.0f + c.thrust_std * n0, c.thrust_lo, c.thrust_hi);
+    d[2] = c.wind_std * n1;
+    d[3] = c.wind_std * n2;
+    d[4] = c.cg_max * (2.0f * u01(a.w) - 1.0f);
+    float tx = c.tilt_max * (2.0f * u01(b.z) - 1.0f);
+    float ty = c.tilt_max * (2.0f * u01(b.w) - 1.0f);
+    float ang = sqrtf(tx * tx + ty * ty);
+    float sc = ang < 1e-6f ? 0.5f - ang * ang * (1.0f / 48.0f) : sinf(0.5f * ang) / ang;
+    d[5] = tx * sc; d[6] = ty * sc; d[7] = cosf(0.5f * ang);
+    d[8] = c.omega_max * (2.0f * u01(w.x) - 1.0f);
+    d[9] = c.omega_max * (2.0f * u01(w.y) - 1.0f);
+    d[10] = c.omega_max * (2.0f * u01(w.z) - 1.0f);
 }
 
 // ref:381-464 reset (rows S13, Q10, Q11, Q15) + Contract X per-episode draws
@@ -559,25 +606,11 @@ __device__ __forceinline__ void reset_env(const DevCfg &c, bool X, long long gid
     if (first_time || !(c.quirks & 4u)) { e.has_prev = 0; e.ap0 = 0.0f; e.ap1 = 0.0f; e.hist_count = 0; e.n_clip = 0; e.n_run = 0; }
     e.mass_scale = 1.0f; e.thrust_scale = 1.0f; e.cg_off = 0.0f; e.wind_x = 0.0f; e.wind_y = 0.0f;
     if (X) {
-        uint4 a = philox(c.seed_lo, c.seed_hi, gid, ST_DR_A, (unsigned)e.episode, 0u);
-        uint4 b = philox(c.seed_lo, c.seed_hi, gid, ST_DR_B, (unsigned)e.episode, 0u);
-        uint4 d = philox(c.seed_lo, c.seed_hi, gid, ST_DR_C, (unsigned)e.episode, 0u);
-        float n0, n1, n2, n3;
-        box_muller(a.y, a.z, n0, n1);
-        box_muller(b.x, b.y, n2, n3);
-        e.mass_scale = 1.0f + c.mass_var * (2.0f * u01(a.x) - 1.0f);
-        e.thrust_scale = clampf(1.0f + c.thrust_std * n0, c.thrust_lo, c.thrust_hi);
-        e.wind_x = c.wind_std * n1;
-        e.wind_y = c.wind_std * n2;
-        e.cg_off = c.cg_max * (2.0f * u01(a.w) - 1.0f);
-        float tx = c.tilt_max * (2.0f * u01(b.z) - 1.0f);
-        float ty = c.tilt_max * (2.0f * u01(b.w) - 1.0f);
-        float ang = sqrtf(tx * tx + ty * ty);
-        float sc = ang < 1e-6f ? 0.5f - ang * ang * (1.0f / 48.0f) : sinf(0.5f * ang) / ang;
-        e.qx = tx * sc; e.qy = ty * sc; e.qz = 0.0f; e.qw = cosf(0.5f * ang);
-        e.wx = c.omega_max * (2.0f * u01(d.x) - 1.0f);
-        e.wy = c.omega_max * (2.0f * u01(d.y) - 1.0f);
-        e.wz = c.omega_max * (2.0f * u01(d.z) - 1.0f);
+        float d[11];
+        reset_draws(c, gid, e.episode, d);
+        e.mass_scale = d[0]; e.thrust_scale = d[1]; e.wind_x = d[2]; e.wind_y = d[3]; e.cg_off = d[4];
+        e.qx = d[5]; e.qy = d[6]; e.qz = 0.0f; e.qw = d[7];
+        e.wx = d[8]; e.wy = d[9]; e.wz = d[10];
     }
 }
 
@@ -590,11 +623,8 @@ __device__ __forceinline__ void build_obs(const DevCfg &c, bool X, long long gid
     o[8] = (float)((double)phase_for_obs / 7.0);
     o[9] = fminf(1.0f, (float)e.step / (float)c.max_steps);
     if (X && c.noise_std > 0.0f) {
-        uint4 a = philox(c.seed_lo, c.seed_hi, gid, ST_NOISE_A, (unsigned)e.episode, (unsigned)e.step);
-        uint4 b = philox(c.seed_lo, c.seed_hi, gid, ST_NOISE_B, (unsigned)e.episode, (unsigned)e.step);
         float n[8];
-        box_muller(a.x, a.y, n[0], n[1]); box_muller(a.z, a.w, n[2], n[3]);
-        box_muller(b.x, b.y, n[4], n[5]); box_muller(b.z, b.w, n[6], n[7]);
+        noise8(c.seed_lo, c.seed_hi, gid, (unsigned)e.episode, (unsigned)e.step, n);
 #pragma unroll
         for (int i = 0; i < 7; i++) o[i] += c.noise_std * n[i];
     }
@@ -676,7 +706,7 @@ __device__ __forceinline__ void env_pre(const DevCfg &c, const DevState &st, lon
         float T = c.thrust;
         if (X) T = T * e.thrust_scale * thrust_curve(c.thrust_curve, burn_before);
         float sp, cp, sy, cy;
-        sincosf(pitch, &sp, &cp); sincosf(yaw, &sy, &cy);
+        sincos_small(pitch, sp, cp); sincos_small(yaw, sy, cy);    // |angle| <= gimbal limit (< 0.8 rad)
         float fl0 = T * sy, fl1 = T * sp, fl2 = T * cp * cy;           // Q2 (ref:539-543)
         float R[9];
         quat_to_mat(e.qx, e.qy, e.qz, e.qw, R);
@@ -690,10 +720,10 @@ __device__ __forceinline__ void env_pre(const DevCfg &c, const DevState &st, lon
     }
     {   // ---- S5 (ref:561-585) aerodynamics ----
         float rho = 1.225f * expf(-e.pz / 8400.0f);
-        float vmag = sqrtf(e.vx * e.vx + e.vy * e.vy + e.vz * e.vz);
+        float vmag = sqrt_fast(e.vx * e.vx + e.vy * e.vy + e.vz * e.vz);
         if (vmag > 0.1f) {                                             // Q5
             float dm = 0.5f * rho * (vmag * vmag) * 0.47f * (3.14159265358979f * 0.0025f);
-            float k = -dm / vmag;
+            float k = -dm * rcp_fast(vmag);
             Fx += k * e.vx; Fy += k * e.vy; Fz += k * e.vz;
         }
         float ad = 0.02f * rho;
