@@ -215,7 +215,7 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
     const int ngroups = (int)((st.n + 31) / 32);
     for (;;) {
         int g = 0;
-        if (lane == 0) g = (int)atomicAdd(st.counter, 1u);
+        if (lane == 0) g = (int)atomicAdd(st.counter, 1u);   // dynamic work queue over the sorted 32-env groups
         g = __shfl_sync(full, g, 0);
         if (g >= ngroups) break;
         const long long slot = (long long)g * 32 + lane;
@@ -602,8 +602,10 @@ static int launch_step(tvc_handle *h, const DevIO &io, cudaStream_t s) {
             cudaError_t e = X ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_v2<true, 1>, TVC_BLOCK, 0)
                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_v2<false, 1>, TVC_BLOCK, 0);
             if (e != cudaSuccess || per_sm < 1) per_sm = 1;
-            const int want = (h->ngroups + TVC_WARPS - 1) / TVC_WARPS;
-            h->v2_grid = want < per_sm * h->num_sms ? want : per_sm * h->num_sms;
+            // small batches: one warp per CTA does the work (every group gets its own SM: latency), else 4 per CTA
+            const int cap = per_sm * h->num_sms;
+            const int want = h->ngroups <= cap ? h->ngroups : (h->ngroups + TVC_WARPS - 1) / TVC_WARPS;
+            h->v2_grid = want < cap ? want : cap;
         }
 #define GO(XX, DD) step_kernel_v2<XX, DD><<<h->v2_grid, TVC_BLOCK, 0, s>>>(h->dc, h->st, io)
         if (X) { if (dv == 0) GO(true, 0); else if (dv == 1) GO(true, 1); else GO(true, 2); }

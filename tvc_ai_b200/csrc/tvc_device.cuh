@@ -165,10 +165,13 @@ __device__ __forceinline__ void reported_quat(float x, float y, float z, float w
 }
 
 // pybullet.c getEulerFromQuaternion (ref:614); only pitch and yaw feed the env (quirk Q7)
+static __device__ __noinline__ void euler_gimbal_lock(float x, float y, float sarg, float &pitch, float &yaw) {
+    if (sarg < 0.0f) { pitch = -1.5707963267948966f; yaw = 2.0f * atan2f(x, -y); }
+    else { pitch = 1.5707963267948966f; yaw = 2.0f * atan2f(-x, y); }
+}
 __device__ __forceinline__ void euler_pitch_yaw(float x, float y, float z, float w, float &pitch, float &yaw) {
     float sarg = -2.0f * (x * z - w * y);
-    if (sarg <= -0.99999f) { pitch = -1.5707963267948966f; yaw = 2.0f * atan2f(x, -y); }
-    else if (sarg >= 0.99999f) { pitch = 1.5707963267948966f; yaw = 2.0f * atan2f(-x, y); }
+    if (sarg <= -0.99999f || sarg >= 0.99999f) euler_gimbal_lock(x, y, sarg, pitch, yaw);
     else {
         pitch = asinf(sarg);
         yaw = atan2f(2.0f * (x * y + w * z), w * w + x * x - y * y - z * z);
@@ -225,10 +228,9 @@ __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fm
 // the lowest candidate is within `margin` AND some row can bind at all -- a row binds only if
 // (1+e) * approach speed * dt exceeds its gap, and the approach speed of any point is bounded by
 // |vz| + |w| * reach.  When the rule fails the stored impulses are cleared.
-__device__ __forceinline__ bool contact_needed(const DevCfg &c, const BodyP &P, const float R[9], float pz, float vz,
-                                               float wx, float wy, float wz) {
+__device__ __forceinline__ bool contact_needed_row(const DevCfg &c, const BodyP &P, float R31, float R32, float R33,
+                                                   float pz, float vz, float wx, float wy, float wz) {
     const float r = c.radius, h = c.half_len;
-    const float R31 = R[6], R32 = R[7], R33 = R[8];
     const float rho = sqrt_fast(R31 * R31 + R32 * R32);
     const float inv = rcp_fast(fmaxf(rho, 1e-3f));
     const float low = -r * (R31 * R31 + R32 * R32) * inv;
@@ -238,6 +240,10 @@ __device__ __forceinline__ bool contact_needed(const DevCfg &c, const BodyP &P, 
     const float reach = sqrt_fast(hh * hh + r * r);
     const float vmax = fabsf(vz) + sqrt_fast(wx * wx + wy * wy + wz * wz) * reach;
     return gmin - 1e-4f < (1.0f + c.restitution) * vmax * c.dt;
+}
+__device__ __forceinline__ bool contact_needed(const DevCfg &c, const BodyP &P, const float R[9], float pz, float vz,
+                                               float wx, float wy, float wz) {
+    return contact_needed_row(c, P, R[6], R[7], R[8], pz, vz, wx, wy, wz);
 }
 
 // lam: this problem's 18 stored impulses, element j at lam[j * TVC_BLOCK] (shared memory column of the posting
@@ -366,6 +372,7 @@ __device__ unsigned long long g_phase[8];
 #define PH_T(x)
 #endif
 
+#define TVC_PROB_FIELDS 15
 struct ContactSmem {
     float f[TVC_PROB_FIELDS][TVC_BLOCK];   // qx qy qz qw pz vx vy vz wx wy wz inv_mass inv_Ixy inv_Iz cg
     float lam[18][TVC_BLOCK];              // per ENV THREAD: impulses carried between the substeps of one step
@@ -518,25 +525,22 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
     float lam[18];
 #pragma unroll
     for (int j = 0; j < 18; j++) lam[j] = 0.0f;
-    bool have_lam = false;
+    bool have_lam = false;   // cold start at every control step
+    const float dI = P.inv_Iz - P.inv_Ixy;
     for (int k = 0; k < c.K; k++) {
-        float R[9];
-        quat_to_mat(e.qx, e.qy, e.qz, e.qw, R);
-        float wl0 = R[0] * e.wx + R[3] * e.wy + R[6] * e.wz;
-        float wl1 = R[1] * e.wx + R[4] * e.wy + R[7] * e.wz;
-        float wl2 = R[2] * e.wx + R[5] * e.wy + R[8] * e.wz;
-        float tl0 = R[0] * Tx + R[3] * Ty + R[6] * Tz;
-        float tl1 = R[1] * Tx + R[4] * Ty + R[7] * Tz;
-        float tl2 = R[2] * Tx + R[5] * Ty + R[8] * Tz;
-        float wn2 = wl0 * wl0 + wl1 * wl1 + wl2 * wl2;
+        // B5 with I = diag(a, a, b): R diag(1/a,1/a,1/b) R^T tau = tau/a + (1/b - 1/a)(e.tau) e, e = body axis in the
+        // world frame (third column of R); the k(1+|w|) damping is isotropic.  Only e and the third row of R are needed
+        // outside the contact solver.
+        const float s2 = 2.0f * rcp_fast(e.qx * e.qx + e.qy * e.qy + e.qz * e.qz + e.qw * e.qw);
+        const float xs = e.qx * s2, ys = e.qy * s2, zs = e.qz * s2;
+        const float e0 = e.qx * zs + e.qw * ys, e1 = e.qy * zs - e.qw * xs, e2 = 1.0f - (e.qx * xs + e.qy * ys);
+        const float et = (e0 * Tx + e1 * Ty + e2 * Tz) * dI;
+        float wn2 = e.wx * e.wx + e.wy * e.wy + e.wz * e.wz;
         float wn = wn2 > 2.220446049250313e-16f ? sqrt_fast(wn2) : 0.0f;
         float kd = c.ang_damp + c.ang_damp * wn;
-        float wd0 = tl0 * P.inv_Ixy - wl0 * kd;
-        float wd1 = tl1 * P.inv_Ixy - wl1 * kd;
-        float wd2 = tl2 * P.inv_Iz - wl2 * kd;
-        float dwx = R[0] * wd0 + R[1] * wd1 + R[2] * wd2;
-        float dwy = R[3] * wd0 + R[4] * wd1 + R[5] * wd2;
-        float dwz = R[6] * wd0 + R[7] * wd1 + R[8] * wd2;
+        float dwx = Tx * P.inv_Ixy + et * e0 - e.wx * kd;
+        float dwy = Ty * P.inv_Ixy + et * e1 - e.wy * kd;
+        float dwz = Tz * P.inv_Ixy + et * e2 - e.wz * kd;
         float vn2 = e.vx * e.vx + e.vy * e.vy + e.vz * e.vz;
         float vn = vn2 > 2.220446049250313e-16f ? sqrt_fast(vn2) : 0.0f;
         float kl = c.lin_damp + c.lin_damp * vn;
@@ -547,11 +551,14 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
         e.vy = clampf(e.vy + (ay_ - e.vy * kl) * dt, -100.0f, 100.0f);
         e.vz = clampf(e.vz + (az_ - e.vz * kl) * dt, -100.0f, 100.0f);
         if (c.ground) {
-            const bool need = contact_needed(c, P, R, e.pz, e.vz, e.wx, e.wy, e.wz);
-            if (need)
+            const float R31 = e.qx * zs - e.qw * ys, R32 = e.qy * zs + e.qw * xs;   // third row of R (R33 == e2)
+            if (contact_needed_row(c, P, R31, R32, e2, e.pz, e.vz, e.wx, e.wy, e.wz)) {
+                float R[9];
+                quat_to_mat(e.qx, e.qy, e.qz, e.qw, R);
                 solve_contacts<1>(c, P, R, e.pz, e.vx, e.vy, e.vz, e.wx, e.wy, e.wz, lam, have_lam,
                                   k == 0 ? c.contact_iters : c.warm_iters);
-            have_lam = need;
+                have_lam = true;
+            } else have_lam = false;
         }
         e.px += dt * e.vx; e.py += dt * e.vy; e.pz += dt * e.vz;
         float ang = sqrt_fast(e.wx * e.wx + e.wy * e.wy + e.wz * e.wz);
