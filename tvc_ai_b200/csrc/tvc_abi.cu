@@ -389,19 +389,24 @@ __global__ void info_kernel(const __grid_constant__ DevState st, const __grid_co
     if (io.criteria_met) io.criteria_met[i] = (uint8_t)(e.consec >= 10);
 }
 
-// deterministic reduction of the per-CTA partial rows: one warp per statistic, lane-strided partial sums in
-// a fixed order, then a fixed shuffle tree
-__global__ void stats_reduce_kernel(double *partial, int nblocks, double *out, double steps, int reset_after) {
-    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (k >= TVC_NSTAT) return;
-    double s = 0.0;
-    for (int b = lane; b < nblocks; b += 32) {
-        s += partial[(long long)b * TVC_NSTAT + k];
-        if (reset_after) partial[(long long)b * TVC_NSTAT + k] = 0.0;
+// deterministic reduction of the statistics rows: 512 threads = 32 row-lanes x 16 statistics (each row is one
+// coalesced 128-byte read), row-strided partial sums in a fixed order, then a fixed-order fold over the row-lanes
+__global__ void __launch_bounds__(512)
+stats_reduce_kernel(double *partial, int nrows, double *out, double steps, int reset_after) {
+    __shared__ double s[32][TVC_NSTAT];
+    const int k = threadIdx.x & (TVC_NSTAT - 1), rl = threadIdx.x >> 4;
+    double acc = 0.0;
+    for (int r = rl; r < nrows; r += 32) {
+        acc += partial[(long long)r * TVC_NSTAT + k];
+        if (reset_after) partial[(long long)r * TVC_NSTAT + k] = 0.0;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) out[k] = (k == 14) ? steps : s;
+    s[rl][k] = acc;
+    __syncthreads();
+    if (threadIdx.x < TVC_NSTAT) {
+        double t = 0.0;
+        for (int j = 0; j < 32; j++) t += s[j][threadIdx.x];
+        out[threadIdx.x] = (threadIdx.x == 14) ? steps : t;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -709,7 +714,7 @@ int tvc_episode_stats_dev(tvc_handle *h, double *dev_out, int reset_after, tvc_s
     CHECK_H(h);
     if (!dev_out) { tvc_set_err("dev_out is NULL"); return TVC_E_BADARG; }
     const double steps = (double)h->stat_steps * (double)h->n;
-    stats_reduce_kernel<<<1, 32 * TVC_NSTAT, 0, (cudaStream_t)stream>>>(h->st.partial, h->ngroups, dev_out, steps, reset_after);
+    stats_reduce_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(h->st.partial, h->ngroups, dev_out, steps, reset_after);
     LAUNCH_OK("stats_reduce_kernel");
     if (reset_after) h->stat_steps = 0;
     return TVC_OK;
