@@ -1,0 +1,141 @@
+#!/usr/bin/env python
+"""BASELINE config 5: curriculum "stage 6" (max noise, actuator delay, thrust-curve variation) with an end-to-end SAC
+loop on the batched CUDA env -- everything stays on the GPU (no host round trip per transition).
+
+What it mirrors: the reference's train loop (scripts/train.py:406-533: act -> env.step -> agent.update, periodic
+evaluation, curriculum update), with the batch-of-1 host loop replaced by N envs stepped in one launch, an on-device
+replay buffer and a plain PyTorch SAC learner (SURVEY.md section 8(f) rank 1 in its simplest form).  The learner is
+PyTorch on purpose: only the env path is this repo's product.
+
+    python examples/train_sac_stage6.py --envs 4096 --iters 200
+
+Reports env-steps/s end to end and the learner's share of the wall time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from tvc_ai_b200 import RocketTVCVectorEnv
+from tvc_ai_b200.curriculum import stage6_conditions
+from tvc_ai_b200.evaluate import evaluate
+
+
+def mlp(i, o):
+    return nn.Sequential(nn.Linear(i, 256), nn.ReLU(), nn.Linear(256, 256), nn.ReLU(), nn.Linear(256, o))
+
+
+class Actor(nn.Module):
+    """Legacy SAC actor shape (10-256-256-4 -> mean, log_std), the same network tvc_rollout evaluates in-kernel."""
+
+    def __init__(self):
+        super().__init__()
+        self.net = mlp(10, 4)
+
+    def forward(self, obs, deterministic=False):
+        out = self.net(obs)
+        mean, log_std = out[:, :2], out[:, 2:].clamp(-20, 2)
+        if deterministic:
+            return torch.tanh(mean), None
+        std = log_std.exp()
+        u = mean + std * torch.randn_like(mean)
+        a = torch.tanh(u)
+        logp = (-0.5 * ((u - mean) / std) ** 2 - log_std - 0.9189385).sum(-1) - torch.log(1 - a * a + 1e-6).sum(-1)
+        return a, logp
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs", type=int, default=4096)
+    ap.add_argument("--iters", type=int, default=200)
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--buffer", type=int, default=1 << 20)
+    ap.add_argument("--seed", type=int, default=42)
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(args.seed)
+
+    # stage 6 = stage_5 conditions + sensor noise + actuator delay (3 control steps) + thrust-curve variation
+    env = RocketTVCVectorEnv(args.envs, config={"globals": {"seed": args.seed}}, contract="X", device=0, final_info=False,
+                             delay_steps=3, thrust_curve=1, propellant_fraction=0.2, cg_burn_shift=0.05)
+    env.set_curriculum(stage6_conditions())
+    obs, _ = env.reset(seed=args.seed, options={"return_torch": True})
+    obs = obs.clone()
+
+    actor, q1, q2 = Actor().to(dev), mlp(12, 1).to(dev), mlp(12, 1).to(dev)
+    q1t, q2t = mlp(12, 1).to(dev), mlp(12, 1).to(dev)
+    q1t.load_state_dict(q1.state_dict()), q2t.load_state_dict(q2.state_dict())
+    opt_a = torch.optim.Adam(actor.parameters(), lr=3e-4)
+    opt_q = torch.optim.Adam(list(q1.parameters()) + list(q2.parameters()), lr=3e-4)
+    alpha, gamma, tau, rscale = 0.2, 0.99, 0.005, 0.01
+
+    B = args.buffer
+    buf = dict(s=torch.zeros((B, 10), device=dev), a=torch.zeros((B, 2), device=dev), r=torch.zeros(B, device=dev),
+               s2=torch.zeros((B, 10), device=dev), d=torch.zeros(B, device=dev))
+    head, filled = 0, 0
+    t_env = t_learn = 0.0
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    for it in range(args.iters):
+        ev[0].record()
+        with torch.no_grad():
+            act, _ = actor(obs)
+        nobs, rew, term, trunc, infos = env.step(act.contiguous())
+        done = term | trunc
+        # same-step autoreset: the successor state of a finished env is its terminal observation
+        s2 = torch.where(done[:, None], infos["final_observation"], nobs)
+        n = args.envs
+        idx = (head + torch.arange(n, device=dev)) % B
+        buf["s"][idx], buf["a"][idx], buf["r"][idx], buf["s2"][idx] = obs, act, rew * rscale, s2
+        buf["d"][idx] = term.float()
+        head, filled = (head + n) % B, min(filled + n, B)
+        obs = nobs.clone()
+        ev[1].record()
+        # ---- one SAC update per env step ----
+        j = torch.randint(0, filled, (args.batch,), device=dev)
+        s, a, r, sn, d = buf["s"][j], buf["a"][j], buf["r"][j], buf["s2"][j], buf["d"][j]
+        with torch.no_grad():
+            an, lpn = actor(sn)
+            qn = torch.min(q1t(torch.cat([sn, an], 1)), q2t(torch.cat([sn, an], 1))).squeeze(-1) - alpha * lpn
+            y = r + gamma * (1 - d) * qn
+        sa = torch.cat([s, a], 1)
+        lq = F.mse_loss(q1(sa).squeeze(-1), y) + F.mse_loss(q2(sa).squeeze(-1), y)
+        opt_q.zero_grad(set_to_none=True), lq.backward(), opt_q.step()
+        ap_, lp = actor(s)
+        sap = torch.cat([s, ap_], 1)
+        la = (alpha * lp - torch.min(q1(sap), q2(sap)).squeeze(-1)).mean()
+        opt_a.zero_grad(set_to_none=True), la.backward(), opt_a.step()
+        with torch.no_grad():
+            for p, pt in zip(list(q1.parameters()) + list(q2.parameters()), list(q1t.parameters()) + list(q2t.parameters())):
+                pt.mul_(1 - tau).add_(p, alpha=tau)
+        ev[2].record()
+        torch.cuda.synchronize()
+        t_env += ev[0].elapsed_time(ev[1])
+        t_learn += ev[1].elapsed_time(ev[2])
+    wall = time.perf_counter() - wall0
+    stats = env.episode_stats()
+    env.close()
+    pol = lambda o: actor(o, deterministic=True)[0]   # noqa: E731
+    evalm = evaluate(pol, episodes=64, contract="X", conditions=stage6_conditions(), delay_steps=3, thrust_curve=1)
+    print(json.dumps({
+        "config": "stage 6: wind 3 N, mass +-30 %, initial tilt 0.7 rad, sensor noise 0.02, actuator delay 3 steps, thrust curve",
+        "envs": args.envs, "iters": args.iters, "env_steps": args.envs * args.iters,
+        "env_steps_per_sec_end_to_end": args.envs * args.iters / wall,
+        "env_ms_per_iter": t_env / args.iters, "learner_ms_per_iter": t_learn / args.iters,
+        "learner_share_of_device_time": t_learn / (t_env + t_learn),
+        "episodes": stats["episodes"], "train_success_rate": stats["successes"] / max(stats["episodes"], 1),
+        "eval": evalm}))
+
+
+if __name__ == "__main__":
+    main()
