@@ -224,13 +224,13 @@ def run_ours(args):
         flush.zero_()
         starts[k].record()
         eng.step(pool[k % 16], want_final=False)
-        launches += 1
+        launches += 2            # classify_kernel + step_kernel_v2
         ends[k].record()
         if (k + 1) % 64 == 0:   # episode-statistics reduction (+ NCCL all-reduce over NVLink when N>1), side stream
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
                 D.allreduce_stats(eng.stats_device(False))
-            launches += 1
+            launches += 1        # stats_reduce_kernel
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
@@ -302,7 +302,7 @@ def run_ours(args):
                                       "ms_per_launch": rms, "env_steps_per_sec": nr * T / (rms * 1e-3),
                                       "actor_tflops": flops / (rms * 1e-3) / 1e12,
                                       "tensor_peak_tflops": _bf16_peak(), "note": "physics-bound: the MLP is a small share"}
-            launches += reps + 4
+            launches += 2 * (reps + 4)   # pack_actor_kernel + rollout_kernel per call
             ro.close()
 
         # end-to-end through the public VectorEnv API with HOST (numpy) actions and results
@@ -324,7 +324,7 @@ def run_ours(args):
                         "d2h_bytes_per_step": n * (40 + 4 + 1 + 1 + 40), "ms_per_step": 1e3 * e2e_dt,
                         "n_gpus_measured": 1,
                         "api": "RocketTVCVectorEnv.step(numpy) -> tvc_step_host (pinned host buffers, sync inside)"}
-        launches += ke
+        launches += 2 * ke
 
     if rank == 0:
         peak, peak_src = _peaks()
@@ -345,8 +345,9 @@ def run_ours(args):
                         "note": "back-to-back launches, state L2-resident (62 MB < 126 MB)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": _traffic(), "peak_source": peak_src,
-                         "kernel": "step_kernel<X=true,DIV=fast>", "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP_X,
-                         "note": "compute-bound kernel (contact PGS + transcendental mix); see DESIGN.md and profiles/"},
+                         "kernel": "step_kernel_v2<X=true,DIV=fast> (+ classify_kernel, 7 us)",
+                         "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP_X,
+                         "note": "instruction-bound (contact PGS chain, 50 % of issue slots); see DESIGN.md section 6 and profiles/"},
             "gpu_launches": launches,
             "clocks": clocks,
             "region_wall_ms": 1e3 * wall,

@@ -373,17 +373,20 @@ __device__ unsigned long long g_phase[8];
 #endif
 
 #define TVC_PROB_FIELDS 15
-struct ContactSmem {
-    float f[TVC_PROB_FIELDS][TVC_BLOCK];   // qx qy qz qw pz vx vy vz wx wy wz inv_mass inv_Ixy inv_Iz cg
-    float lam[18][TVC_BLOCK];              // per ENV THREAD: impulses carried between the substeps of one step
-    int owner[TVC_BLOCK];                  // per slot: posting thread | warm flag << 16
-    int cnt[TVC_WARPS];
+template <int B>   // B = threads (= envs) per CTA
+struct ContactSmemT {
+    float f[TVC_PROB_FIELDS][B];   // qx qy qz qw pz vx vy vz wx wy wz inv_mass inv_Ixy inv_Iz cg
+    float lam[18][B];              // per ENV THREAD: impulses carried between the substeps of one step
+    int owner[B];                  // per slot: posting thread | warm flag << 16
+    int cnt[B / 32];
 };
+typedef ContactSmemT<TVC_BLOCK> ContactSmem;
 
 // Rows B2, B4, B5, B6: K substeps with the world-frame force F and torque T held constant (Q3).
 // Block-cooperative: EVERY thread of the CTA must call this (threads without an env pass live=false).
+template <int B>
 __device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &e, float Fx, float Fy, float Fz,
-                                          float Tx, float Ty, float Tz, bool live, ContactSmem &sm) {
+                                          float Tx, float Ty, float Tz, bool live, ContactSmemT<B> &sm) {
     const float dt = c.dt;
     const float ax_ = Fx * P.inv_mass, ay_ = Fy * P.inv_mass, az_ = Fz * P.inv_mass;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -434,7 +437,7 @@ __device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &
 #endif
             int total = 0, base = 0;
 #pragma unroll
-            for (int w = 0; w < TVC_WARPS; w++) { const int n = sm.cnt[w]; if (w < warp) base += n; total += n; }
+            for (int w = 0; w < B / 32; w++) { const int n = sm.cnt[w]; if (w < warp) base += n; total += n; }
             if (total > 0) {                                   // CTA-uniform
                 const int slot = base + __popc(bal & ((1u << lane) - 1u));
                 if (need) {
@@ -452,7 +455,7 @@ __device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &
                 // rotate the solver warps over the SMSPs (warp w of every CTA sits on SMSP w % 4)
                 // (co-resident CTAs differ by multiples of the SM count in blockIdx, so fold the high bits in)
                 const unsigned bx = blockIdx.x;
-                const int t = (threadIdx.x + 32 * ((bx + (bx >> 2) + (bx >> 4) + (bx >> 6) + k) & (TVC_WARPS - 1))) & (TVC_BLOCK - 1);
+                const int t = (threadIdx.x + 32 * ((bx + (bx >> 2) + (bx >> 4) + (bx >> 6) + k) & (B / 32 - 1))) & (B - 1);
                 if (t < total) {
                     float Rs[9];
                     quat_to_mat(sm.f[0][t], sm.f[1][t], sm.f[2][t], sm.f[3][t], Rs);
@@ -461,7 +464,7 @@ __device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &
                     float vx = sm.f[5][t], vy = sm.f[6][t], vz = sm.f[7][t];
                     float wx = sm.f[8][t], wy = sm.f[9][t], wz = sm.f[10][t];
                     const int ow = sm.owner[t];
-                    solve_contacts<TVC_BLOCK>(c, Q, Rs, sm.f[4][t], vx, vy, vz, wx, wy, wz, &sm.lam[0][ow & 0xFFFF], (ow >> 16) != 0,
+                    solve_contacts<B>(c, Q, Rs, sm.f[4][t], vx, vy, vz, wx, wy, wz, &sm.lam[0][ow & 0xFFFF], (ow >> 16) != 0,
                                    k == 0 ? c.contact_iters : c.warm_iters);
                     sm.f[5][t] = vx; sm.f[6][t] = vy; sm.f[7][t] = vz;
                     sm.f[8][t] = wx; sm.f[9][t] = wy; sm.f[10][t] = wz;

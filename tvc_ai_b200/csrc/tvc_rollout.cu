@@ -4,8 +4,8 @@
 // Replaces the get_action -> env.step loop of scripts/train.py:546-603 for the legacy 2x256 SAC actor
 // (shape from scripts/export_tflm.py:85-156, tests/test_agent.py:46-56).
 //
-// sm_100a design: CTA = 128 threads = 128 envs = 128 TMEM lanes (thread i owns env i and accumulator
-// row i).  bf16 weights are packed once into UMMA "K-major, no swizzle" core-matrix images and copied
+// sm_100a design: CTA = 256 threads = 256 envs = two 128-row MMA tiles (thread i owns env i and accumulator
+// row i % 128 of tile i / 128; 8 warps share the resident weights and hide each other's physics latency).  bf16 weights are packed once into UMMA "K-major, no swizzle" core-matrix images and copied
 // into shared memory with one TMA bulk copy (cp.async.bulk) for the whole rollout.  Per step:
 //   obs tile -> smem (bf16)          -> tcgen05.mma M128 N256 K16   (layer 1, accumulators in TMEM)
 //   tcgen05.ld -> bias+ReLU -> smem  -> 16 x tcgen05.mma M128 N256 K16 (layer 2)
@@ -24,10 +24,13 @@ namespace {
 
 constexpr int HID = 256;
 constexpr int K1 = 16;               // layer-1 K (10 obs padded to one UMMA K step)
+constexpr int TM = 128;              // rows (envs) of one MMA tile = TMEM lanes
+constexpr int RB = 256;              // threads (envs) per CTA = NT tiles; 8 warps share the resident weights
+constexpr int NT = RB / TM;
 constexpr uint32_t W1_BYTES = HID * K1 * 2;        // 8 KB   image [K1/8][256][8] bf16
 constexpr uint32_t W2_BYTES = HID * HID * 2;       // 128 KB image [256/8][256][8] bf16
-constexpr uint32_t A1_BYTES = TVC_BLOCK * K1 * 2;  // 4 KB   obs tile [K1/8][128][8] bf16
-constexpr uint32_t H1_BYTES = TVC_BLOCK * HID * 2; // 64 KB  hidden tile [256/8][128][8] bf16
+constexpr uint32_t A1_BYTES = TM * K1 * 2;         // 4 KB   obs tile [K1/8][128][8] bf16 (one per tile)
+constexpr uint32_t H1_BYTES = TM * HID * 2;        // 64 KB  hidden tile [256/8][128][8] bf16 (shared by the tiles in turn)
 constexpr uint32_t VEC_FLOATS = HID + HID + 4 * HID + 4;   // b1, b2, W3[4][256], b3
 constexpr uint32_t VEC_BYTES = ((VEC_FLOATS * 4 + 15) / 16) * 16;
 
@@ -35,11 +38,11 @@ constexpr uint32_t VEC_BYTES = ((VEC_FLOATS * 4 + 15) / 16) * 16;
 constexpr uint32_t OFF_W2 = 0;
 constexpr uint32_t OFF_W1 = OFF_W2 + W2_BYTES;
 constexpr uint32_t OFF_A1 = OFF_W1 + W1_BYTES;
-constexpr uint32_t OFF_H1 = OFF_A1 + A1_BYTES;          // also the contact-exchange area during physics
+constexpr uint32_t OFF_H1 = OFF_A1 + NT * A1_BYTES;     // also the contact-exchange area during physics
 constexpr uint32_t OFF_VEC = OFF_H1 + H1_BYTES;
-constexpr uint32_t OFF_BAR = OFF_VEC + VEC_BYTES;       // 2 mbarriers + tmem base
+constexpr uint32_t OFF_BAR = OFF_VEC + VEC_BYTES;       // weight barrier, one MMA barrier per tile, tmem base
 constexpr uint32_t SMEM_TOTAL = OFF_BAR + 64;
-static_assert(sizeof(ContactSmem) <= H1_BYTES, "contact exchange must fit in the hidden-tile area");
+static_assert(sizeof(ContactSmemT<RB>) <= H1_BYTES, "contact exchange must fit in the hidden-tile area");
 static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 
 // UMMA instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=128 (cute::UMMA::InstrDescriptor)
@@ -152,32 +155,35 @@ struct RolloutIO {
 };
 
 template <bool X, int DIV>
-__global__ void __launch_bounds__(TVC_BLOCK, 1)
+__global__ void __launch_bounds__(RB, 1)
 rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState st, const uint8_t *__restrict__ img,
                const __grid_constant__ RolloutIO io) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long i = (long long)blockIdx.x * TVC_BLOCK + tid;
+    const int tile = tid / TM, row = tid % TM;          // this thread's MMA tile and accumulator row
+    const long long i = (long long)blockIdx.x * RB + tid;
     const bool live = i < st.n;
     const long long gid = c.env_base + i;
 
     const uint32_t s_base = smem_u32(smem);
-    const uint32_t bar_w = s_base + OFF_BAR, bar_mma = s_base + OFF_BAR + 8;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 16);
+    const uint32_t bar_w = s_base + OFF_BAR;
+    const uint32_t bar_mma = s_base + OFF_BAR + 8 + 8 * tile;   // this tile's MMA-completion barrier
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 8 + 8 * NT);
     const float *b1 = reinterpret_cast<const float *>(smem + OFF_VEC);
     const float *b2 = b1 + HID;
     const float *w3 = b2 + HID;
     const float *b3 = w3 + 4 * HID;
-    ContactSmem &s_contact = *reinterpret_cast<ContactSmem *>(smem + OFF_H1);
+    ContactSmemT<RB> &s_contact = *reinterpret_cast<ContactSmemT<RB> *>(smem + OFF_H1);
 
-    // ---- one-time setup: barriers, TMEM (256 columns), weights via TMA bulk copy ----
+    // ---- one-time setup: barriers, TMEM (256 accumulator columns per tile), weights via TMA bulk copy ----
     if (tid == 0) {
         mbar_init(bar_w, 1);
-        mbar_init(bar_mma, 1);
+#pragma unroll
+        for (int j = 0; j < NT; j++) mbar_init(s_base + OFF_BAR + 8 + 8 * j, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" :: "r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -206,75 +212,86 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
     }
     mbar_wait(bar_w, 0);
 
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);   // this warp's 32 TMEM lanes
+    // warp w reads TMEM lanes 32*(w%4)..+31; tile j accumulates in columns [256 j, 256 j + 256)
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(tile * HID);
     uint32_t mma_phase = 0;
     float rsum = 0.0f, a0 = 0.0f, a1 = 0.0f;
-    int done = 0, viol = 0;   // statistics are accumulated per CTA at the end of every step
+    int done = 0, viol = 0;
 
     for (int t = 0; t < io.T; t++) {
-        // ---- layer 1 operand: obs row -> bf16 tile [2][128][8] ----
+        // ---- layer 1 operands: every env writes its obs row into its tile's bf16 operand [2][128][8] ----
         {
             uint4 c0 = make_uint4(pack_bf16(obs[0], obs[1]), pack_bf16(obs[2], obs[3]), pack_bf16(obs[4], obs[5]), pack_bf16(obs[6], obs[7]));
             uint4 c1 = make_uint4(pack_bf16(obs[8], obs[9]), 0u, 0u, 0u);
-            *reinterpret_cast<uint4 *>(smem + OFF_A1 + tid * 16) = c0;
-            *reinterpret_cast<uint4 *>(smem + OFF_A1 + TVC_BLOCK * 16 + tid * 16) = c1;
+            uint8_t *a1p = smem + OFF_A1 + tile * A1_BYTES;
+            *reinterpret_cast<uint4 *>(a1p + row * 16) = c0;
+            *reinterpret_cast<uint4 *>(a1p + TM * 16 + row * 16) = c1;
         }
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (tid == 0) {   // layer 1 of every tile is issued up front: tile 1's MMA overlaps tile 0's epilogue
             tc_fence_after();
-            mma_bf16(tmem_base, umma_desc(s_base + OFF_A1, TVC_BLOCK * 16, 128), umma_desc(s_base + OFF_W1, HID * 16, 128), 0u);
-            mma_commit(bar_mma);
-        }
-        mbar_wait(bar_mma, mma_phase);
-        mma_phase ^= 1u;
-        tc_fence_after();
-        // ---- epilogue 1: bias + ReLU -> bf16 hidden tile [32][128][8] (thread-contiguous 16-byte stores) ----
-#pragma unroll 1
-        for (int ch = 0; ch < 8; ch++) {
-            uint32_t v[32];
-            tmem_ld32(taddr + ch * 32, v);
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                float h[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) h[j] = fmaxf(__uint_as_float(v[8 * q + j]) + b1[ch * 32 + 8 * q + j], 0.0f);
-                *reinterpret_cast<uint4 *>(smem + OFF_H1 + (ch * 4 + q) * (TVC_BLOCK * 16) + tid * 16) =
-                    make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+            for (int j = 0; j < NT; j++) {
+                mma_bf16(tmem_base + j * HID, umma_desc(s_base + OFF_A1 + j * A1_BYTES, TM * 16, 128),
+                         umma_desc(s_base + OFF_W1, HID * 16, 128), 0u);
+                mma_commit(s_base + OFF_BAR + 8 + 8 * j);
             }
         }
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        // ---- layer 2: 16 K-steps of M128 N256 K16 ----
-        if (tid == 0) {
-            tc_fence_after();
-#pragma unroll
-            for (int kk = 0; kk < HID / 16; kk++)
-                mma_bf16(tmem_base, umma_desc(s_base + OFF_H1 + kk * 2 * (TVC_BLOCK * 16), TVC_BLOCK * 16, 128),
-                         umma_desc(s_base + OFF_W2 + kk * 2 * (HID * 16), HID * 16, 128), kk > 0 ? 1u : 0u);
-            mma_commit(bar_mma);
-        }
-        mbar_wait(bar_mma, mma_phase);
-        mma_phase ^= 1u;
-        tc_fence_after();
-        // ---- epilogue 2 + head: h2 = ReLU(d + b2); out[k] += h2 * W3[k][:] ----
         float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f, o3 = 0.0f;
 #pragma unroll 1
-        for (int ch = 0; ch < 8; ch++) {
-            uint32_t v[32];
-            tmem_ld32(taddr + ch * 32, v);
+        for (int j = 0; j < NT; j++) {   // the tiles take turns on the single hidden-tile buffer
+            if (tile == j) {
+                mbar_wait(bar_mma, mma_phase);
+                tc_fence_after();
+                // epilogue 1: bias + ReLU -> bf16 hidden tile [32][128][8] (thread-contiguous 16-byte stores)
+#pragma unroll 1
+                for (int ch = 0; ch < 8; ch++) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + ch * 32, v);
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const int col = ch * 32 + j;
-                const float h = fmaxf(__uint_as_float(v[j]) + b2[col], 0.0f);
-                o0 = fmaf(h, w3[col], o0); o1 = fmaf(h, w3[HID + col], o1);
-                o2 = fmaf(h, w3[2 * HID + col], o2); o3 = fmaf(h, w3[3 * HID + col], o3);
+                    for (int q = 0; q < 4; q++) {
+                        float h[8];
+#pragma unroll
+                        for (int jj = 0; jj < 8; jj++) h[jj] = fmaxf(__uint_as_float(v[8 * q + jj]) + b1[ch * 32 + 8 * q + jj], 0.0f);
+                        *reinterpret_cast<uint4 *>(smem + OFF_H1 + (ch * 4 + q) * (TM * 16) + row * 16) =
+                            make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+                    }
+                }
+                fence_async_smem();
+                tc_fence_before();
             }
+            __syncthreads();
+            if (tid == 0) {   // layer 2 of tile j: 16 K-steps of M128 N256 K16
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < HID / 16; kk++)
+                    mma_bf16(tmem_base + j * HID, umma_desc(s_base + OFF_H1 + kk * 2 * (TM * 16), TM * 16, 128),
+                             umma_desc(s_base + OFF_W2 + kk * 2 * (HID * 16), HID * 16, 128), kk > 0 ? 1u : 0u);
+                mma_commit(s_base + OFF_BAR + 8 + 8 * j);
+            }
+            if (tile == j) {
+                mbar_wait(bar_mma, mma_phase ^ 1u);
+                tc_fence_after();
+                // epilogue 2 + head: h2 = ReLU(d + b2); out[k] += h2 * W3[k][:]
+#pragma unroll 1
+                for (int ch = 0; ch < 8; ch++) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + ch * 32, v);
+#pragma unroll
+                    for (int jj = 0; jj < 32; jj++) {
+                        const int col = ch * 32 + jj;
+                        const float h = fmaxf(__uint_as_float(v[jj]) + b2[col], 0.0f);
+                        o0 = fmaf(h, w3[col], o0); o1 = fmaf(h, w3[HID + col], o1);
+                        o2 = fmaf(h, w3[2 * HID + col], o2); o3 = fmaf(h, w3[3 * HID + col], o3);
+                    }
+                }
+                tc_fence_before();
+            }
+            __syncthreads();   // tile j's layer-2 MMAs have completed (its threads waited): the hidden tile is free again
         }
-        tc_fence_before();
-        __syncthreads();   // all TMEM reads retired and the hidden tile is free: the area now serves the contact exchange
+        // each tile's barrier completed two phases this step -> parity unchanged
         // ---- action: tanh(mean + exp(clamp(log_std)) * eps), eps from Philox stream 6 ----
         const float mean0 = o0 + b3[0], mean1 = o1 + b3[1];
         const float ls0 = clampf(o2 + b3[2], -20.0f, 2.0f), ls1 = clampf(o3 + b3[3], -20.0f, 2.0f);
@@ -287,7 +304,7 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
         a0 = tanhf(mean0 + expf(ls0) * e0);
         a1 = tanhf(mean1 + expf(ls1) * e1);
 
-        // ---- env step (same device code as step_kernel) ----
+        // ---- env step (same device code as the legacy step kernel; the hidden-tile area is the contact exchange) ----
         BodyP P;
         Forces f;
         if (live) env_pre<X>(c, st, i, e, a0, a1, P, f);
@@ -295,7 +312,7 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
             P = body_params(c, false, 1.0f, 0.0f, 1.0f);
             f.Fx = f.Fy = f.Fz = f.Tx = f.Ty = f.Tz = f.a0 = f.a1 = 0.0f;
         }
-        integrate(c, P, e, f.Fx, f.Fy, f.Fz, f.Tx, f.Ty, f.Tz, live, s_contact);
+        integrate<RB>(c, P, e, f.Fx, f.Fy, f.Fz, f.Tx, f.Ty, f.Tz, live, s_contact);
         done = 0; viol = 0;
         int ev_len = 0, ev_succ = 0, ev_reason = 0, ev_trunc = 0;
         float ev_ret = 0.0f, ev_alt = 0.0f, ev_tilt = 0.0f, ev_fuel = 0.0f;
@@ -318,11 +335,11 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
 #pragma unroll
             for (int k = 0; k < 10; k++) obs[k] = r.obs[k];
         }
-        // ---- episode statistics (same scheme as step_kernel; the contact area is idle now) ----
+        // ---- episode statistics (same scheme as the step kernels; the contact area is idle now) ----
         __syncthreads();
         const int any_ev = __syncthreads_or(done | viol);
         if (any_ev) {
-            double *s_stat = reinterpret_cast<double *>(smem + OFF_H1);   // [4][16] doubles
+            double *s_stat = reinterpret_cast<double *>(smem + OFF_H1);   // [RB/32][16] doubles
             const unsigned full = 0xffffffffu;
             int n_ep = __reduce_add_sync(full, done), n_len = __reduce_add_sync(full, ev_len);
             int n_succ = __reduce_add_sync(full, done ? ev_succ : 0);
@@ -346,7 +363,7 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
             if (tid < TVC_NSTAT) {
                 double s = 0.0;
 #pragma unroll
-                for (int w = 0; w < TVC_WARPS; w++) s += s_stat[w * TVC_NSTAT + tid];
+                for (int w = 0; w < RB / 32; w++) s += s_stat[w * TVC_NSTAT + tid];
                 if (s != 0.0) st.partial[(long long)blockIdx.x * TVC_NSTAT + tid] += s;
             }
             __syncthreads();
@@ -365,7 +382,7 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem_base) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem_base) : "memory");
     }
 }
 
@@ -404,7 +421,7 @@ extern "C" int tvc_rollout(tvc_handle *h, const tvc_actor_weights *w, int32_t T,
 #define GO(XX, DD)                                                                                                   \
     do {                                                                                                             \
         e = cudaFuncSetAttribute(rollout_kernel<XX, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL); \
-        if (e == cudaSuccess) rollout_kernel<XX, DD><<<h->grid, TVC_BLOCK, SMEM_TOTAL, s>>>(h->dc, h->st, ws->img, io); \
+        if (e == cudaSuccess) rollout_kernel<XX, DD><<<(int)((h->n + RB - 1) / RB), RB, SMEM_TOTAL, s>>>(h->dc, h->st, ws->img, io); \
     } while (0)
     if (X) { if (dv == 0) GO(true, 0); else if (dv == 1) GO(true, 1); else GO(true, 2); }
     else   { if (dv == 0) GO(false, 0); else if (dv == 1) GO(false, 1); else GO(false, 2); }
