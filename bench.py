@@ -233,7 +233,6 @@ def run_ours(args):
             launches += 1        # stats_reduce_kernel
     barrier()
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop()
     per = [s.elapsed_time(e) for s, e in zip(starts, ends)]
     ms = sum(per) / K
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -305,27 +304,36 @@ def run_ours(args):
             launches += 2 * (reps + 4)   # pack_actor_kernel + rollout_kernel per call
             ro.close()
 
-        # end-to-end through the public VectorEnv API with HOST (numpy) actions and results
-        venv = RocketTVCVectorEnv(n, config={}, contract="X", device=local, final_info=False)
-        venv.reset(seed=42)
-        import numpy as np
-        host_actions = [np.random.default_rng(i).uniform(-1, 1, (n, 2)).astype(np.float32) for i in range(4)]
-        for w in range(3):
-            venv.step(host_actions[w % 4])
-        ke = max(5, min(K, 30))
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        for k in range(ke):
-            venv.step(host_actions[k % 4])
-        torch.cuda.synchronize(dev)
-        e2e_dt = (time.perf_counter() - t0) / ke
-        venv.close()
-        extra["e2e"] = {"value": n / e2e_dt, "unit": "env-steps/s", "h2d_bytes_per_step": n * 8,
-                        "d2h_bytes_per_step": n * (40 + 4 + 1 + 1 + 40), "ms_per_step": 1e3 * e2e_dt,
-                        "n_gpus_measured": 1,
-                        "api": "RocketTVCVectorEnv.step(numpy) -> tvc_step_host (pinned host buffers, sync inside)"}
-        launches += 2 * ke
+    # end-to-end through the public VectorEnv API with HOST (numpy) buffers, every rank (its own env slab): the
+    # timed region contains, per step, the H2D copy of the actions and the D2H copies of obs / reward / flags /
+    # final observations (tvc_step_host: pinned host buffers, stream sync inside the call)
+    import numpy as np
+    venv = RocketTVCVectorEnv(n, config={}, contract="X", device=local, final_info=False, copy_outputs=False,
+                              env_id_base=rank * n, **OVERRIDES)
+    venv.reset(seed=42)
+    host_actions = [np.random.default_rng(100 * rank + i).uniform(-1, 1, (n, 2)).astype(np.float32) for i in range(4)]
+    for w in range(3):
+        venv.step(host_actions[w % 4])
+    ke = max(5, min(K, 30))
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(ke):
+        o_h, r_h, te_h, tr_h, _ = venv.step(host_actions[k % 4])
+    torch.cuda.synchronize(dev)
+    e2e_dt = (time.perf_counter() - t0) / ke
+    e2e_check = float(r_h[:16].sum())      # touch the result on the host
+    venv.close()
+    te = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_dt = float(te.item())
+    launches += 2 * ke
+    extra["e2e"] = {"value": total_envs / e2e_dt, "unit": "env-steps/s", "h2d_bytes_per_step": n * 8,
+                    "d2h_bytes_per_step": n * (40 + 4 + 1 + 1 + 40), "ms_per_step": 1e3 * e2e_dt, "n_gpus_measured": world,
+                    "bytes_are": "per GPU", "result_checksum": e2e_check,
+                    "api": "RocketTVCVectorEnv.step(numpy, copy_outputs=False) -> tvc_step_host (pinned host buffers, sync inside)"}
 
+    clocks = sampler.stop()   # sampled from the start of the timed region to the end of the e2e measurement (all under load)
     if rank == 0:
         peak, peak_src = _peaks()
         per_launch_bytes = ALGO_BYTES_PER_ENV_STEP_X * n

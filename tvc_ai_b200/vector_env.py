@@ -26,7 +26,7 @@ class RocketTVCVectorEnv:
 
     def __init__(self, num_envs: int, config: Optional[dict] = None, max_episode_steps: int = 1000,
                  contract: str | int = "R", device: Optional[int] = None, env_id_base: int = 0,
-                 final_info: bool = True, **engine_over):
+                 final_info: bool = True, copy_outputs: bool = True, **engine_over):
         if isinstance(contract, str):
             contract = {"R": A.CONTRACT_R, "X": A.CONTRACT_X}[contract.upper()]
         self.num_envs = int(num_envs)
@@ -42,6 +42,9 @@ class RocketTVCVectorEnv:
         self.render_mode = None
         self.closed = False
         self._want_final_info = bool(final_info)
+        # numpy path: True returns fresh arrays every step (Gymnasium semantics); False returns views of the pinned
+        # host buffers tvc_step_host writes into (valid until the next step) and float32 rewards -- no host copies
+        self._copy_outputs = bool(copy_outputs)
 
     # ------------------------------------------------------------------
     def reset(self, *, seed: Optional[int] = None, options: Optional[dict] = None):
@@ -81,7 +84,8 @@ class RocketTVCVectorEnv:
         if actions.shape != (self.num_envs, 2):
             raise ValueError(f"actions must have shape {(self.num_envs, 2)}, got {actions.shape}")
         obs, rew, term, trunc, final = self.engine.step_host(actions, want_final=True)
-        obs, rew, term, trunc = obs.copy(), rew.astype(np.float64), term.copy(), trunc.copy()
+        if self._copy_outputs:
+            obs, rew, term, trunc = obs.copy(), rew.astype(np.float64), term.copy(), trunc.copy()
         done = term | trunc
         infos = {}
         if done.any():
@@ -92,7 +96,7 @@ class RocketTVCVectorEnv:
                     fo[i] = final[i].copy()
             else:
                 # large batches: dense [N,10] array, valid where the mask is set (no per-env Python loop)
-                fo = final.copy()
+                fo = final.copy() if self._copy_outputs else final
             infos["final_observation"] = fo
             infos["_final_observation"] = done
         return obs, rew, term, trunc, infos
