@@ -2,6 +2,10 @@ import os, sys, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ['TVC_B200_LIB'] = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tvc_ai_b200', 'libtvc_b200_prof.so')
 import torch
+
+from tvc_ai_b200 import build as _B
+_B.build_phase_profiler()
+os.environ['TVC_STEP_IMPL'] = '1'   # the counters live in the legacy CTA-exchange kernel
 from tvc_ai_b200 import _abi as A
 from tvc_ai_b200.engine import BatchedEngine
 n = 262144

@@ -42,3 +42,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         print(res.stderr)
     return LIB
+
+
+def build_phase_profiler() -> str:
+    """Diagnostic build with clock64 phase counters in the legacy CTA-exchange integrate() (tools/phase_prof.py)."""
+    out = os.path.join(_HERE, "libtvc_b200_prof.so")
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-DTVC_PHASE_PROF", "-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    env = dict(os.environ)
+    env.pop("CC", None), env.pop("CXX", None)
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return out
