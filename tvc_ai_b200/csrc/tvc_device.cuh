@@ -521,6 +521,7 @@ __device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &
 // Same K substeps for ONE env on its own thread: no shared memory, no CTA barriers, the contact solver inline with
 // its 18 carried impulses in registers.  Used by step_kernel_v2, whose warps hold envs of one class (near the ground
 // or not) so the `need` branch is nearly warp-uniform.
+template <bool LOCKSTEP>   // LOCKSTEP: the CTA's warps re-align at every substep (every thread of the CTA must call this)
 __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P, Env &e, float Fx, float Fy, float Fz,
                                                  float Tx, float Ty, float Tz) {
     const float dt = c.dt;
@@ -531,6 +532,7 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
     bool have_lam = false;   // cold start at every control step
     const float dI = P.inv_Iz - P.inv_Ixy;
     for (int k = 0; k < c.K; k++) {
+        if (LOCKSTEP) __syncthreads();
         // B5 with I = diag(a, a, b): R diag(1/a,1/a,1/b) R^T tau = tau/a + (1/b - 1/a)(e.tau) e, e = body axis in the
         // world frame (third column of R); the k(1+|w|) damping is isotropic.  Only e and the third row of R are needed
         // outside the contact solver.
