@@ -468,6 +468,7 @@ static void make_devcfg(const tvc_config &c, DevCfg &d) {
     d.delay = c.delay_steps; d.thrust_curve = c.thrust_curve;
     const double dt = c.dt_step / (double)c.substeps;
     d.dt = (float)dt; d.inv_dt = (float)(1.0 / dt);
+    d.inv_max_steps = (float)(1.0 / (double)c.max_episode_steps);
     d.gp = c.gradient_penalty; d.db = c.diversity_bonus;
     d.mass = c.mass; d.radius = c.radius; d.half_len = 0.5f * c.length; d.thrust = c.thrust; d.gimbal_max = c.gimbal_max_rad;
     d.lin_damp = c.lin_damp; d.ang_damp = c.ang_damp;
