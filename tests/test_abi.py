@@ -90,3 +90,34 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "tvc_oracle.h" not in txt, f
+
+
+def test_error_codes_without_a_gpu(lib_built):
+    """Error behaviour of the C ABI (include/tvc_b200.h): negative codes + tvc_last_error(), never an exception or exit.
+    Argument validation happens before any CUDA call, so these run on the CPU box."""
+    from tvc_ai_b200 import _abi as A
+    L = A.load()
+    h = C.c_void_p()
+    cfg = A.default_config(A.CONTRACT_R)
+    assert L.tvc_config_default(None, 0) == -1 and b"bad argument" in L.tvc_last_error()
+    assert L.tvc_config_default(C.byref(cfg), 7) == -1
+    bad = A.default_config(A.CONTRACT_R)
+    bad.abi_version = 1
+    assert L.tvc_create(C.byref(bad), 0, 16, C.byref(h)) == -4 and b"abi_version" in L.tvc_last_error()      # TVC_E_ABI
+    assert L.tvc_create(C.byref(cfg), 0, 0, C.byref(h)) == -1 and b"num_envs" in L.tvc_last_error()          # TVC_E_BADARG
+    assert L.tvc_create(C.byref(cfg), 0, 16, None) == -1
+    for field, value in (("substeps", 0), ("substeps", 65), ("max_episode_steps", 0), ("diversity_mode", 3),
+                         ("delay_steps", 5), ("contact_iters", -1), ("contract", 2), ("mass", 0.0), ("dt_step", 0.0)):
+        c2 = A.default_config(A.CONTRACT_X)
+        setattr(c2, field, value)
+        assert L.tvc_create(C.byref(c2), 0, 16, C.byref(h)) == -1, field
+        assert not h.value
+    # NULL handles are rejected everywhere
+    assert L.tvc_step(None, None, None, None, None, None, None, None) == -1 and b"handle" in L.tvc_last_error()
+    assert L.tvc_reset(None, None, 0, None, None) == -1
+    assert L.tvc_destroy(None) == 0
+    assert L.tvc_num_envs(None) == -1 and L.tvc_state_bytes(None) == 0
+    import torch
+    if not torch.cuda.is_available():
+        rc = L.tvc_create(C.byref(cfg), 0, 16, C.byref(h))
+        assert rc in (-2, -1) and not h.value          # no device: CUDA error, still no crash

@@ -369,3 +369,39 @@ def test_vector_env_numpy_and_torch_paths(lib_built):
     st = v.episode_stats()
     assert st["episodes"] >= total_done and st["steps"] == 61 * n
     v.close()
+
+
+def test_edge_sizes_and_argument_checks(lib_built):
+    """Ragged and extreme batch sizes (1, 31, 33, 129 envs; 2^20 envs), NULL-output rejection, mask reset."""
+    from tvc_ai_b200 import _abi as A
+    import ctypes as C
+    for n in (1, 31, 33, 129):
+        eng = _engine(n, A.CONTRACT_X, autoreset=1)
+        eng.reset()
+        for _ in range(45):
+            obs, rew, term, trunc = eng.step(None)
+        assert obs.shape == (n, 10) and bool(torch.isfinite(obs).all()) and bool(torch.isfinite(rew).all())
+        s = eng.stats()
+        assert s[14] == 45 * n and (n < 31 or s[0] >= 1)
+        eng.close()
+    big = _engine(1 << 20, A.CONTRACT_X, autoreset=1)
+    big.reset()
+    for _ in range(5):
+        obs, rew, term, trunc = big.step(None)
+    st = big.get_state()
+    assert np.all(np.abs(np.linalg.norm(st["quat"], axis=1) - 1) < 1e-5) and np.all(st["step"] == 5)
+    assert big.stats()[14] == 5 * (1 << 20)
+    # masked reset touches only the selected envs
+    mask = torch.zeros(1 << 20, dtype=torch.uint8, device="cuda")
+    mask[::2] = 1
+    big.reset(mask=mask)
+    st = big.get_state()
+    assert np.all(st["step"][::2] == 0) and np.all(st["step"][1::2] == 5)
+    # NULL outputs are rejected with a message, not a crash
+    L = A.load()
+    assert L.tvc_step(big.h, None, None, None, None, None, None, None) == -1 and b"non-NULL" in L.tvc_last_error()
+    with pytest.raises((TypeError, ValueError)):
+        big.step(torch.zeros((3, 2), device="cuda"))
+    with pytest.raises(TypeError):
+        big.step(torch.zeros((1 << 20, 2), dtype=torch.float64, device="cuda"))
+    big.close()
