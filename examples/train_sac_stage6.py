@@ -3,8 +3,9 @@
 loop on the batched CUDA env -- everything stays on the GPU (no host round trip per transition).
 
 What it mirrors: the reference's train loop (scripts/train.py:406-533: act -> env.step -> agent.update, periodic
-evaluation, curriculum update), with the batch-of-1 host loop replaced by N envs stepped in one launch, an on-device
-replay buffer and a plain PyTorch SAC learner (SURVEY.md section 8(f) rank 1 in its simplest form).  The learner is
+evaluation, curriculum update), with the batch-of-1 host loop replaced by the fused rollout kernel (the actor is evaluated on tensor
+cores inside the env loop and the kernel writes the transitions itself), an on-device replay buffer and a plain PyTorch SAC
+learner (SURVEY.md section 8(f) rank 1 in its simplest form).  The learner is
 PyTorch on purpose: only the env path is this repo's product.
 
     python examples/train_sac_stage6.py --envs 4096 --iters 200
@@ -59,6 +60,7 @@ def main():
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--buffer", type=int, default=1 << 20)
+    ap.add_argument("--rollout-steps", type=int, default=8, help="env steps per fused-rollout launch")
     ap.add_argument("--seed", type=int, default=42)
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -68,8 +70,7 @@ def main():
     env = RocketTVCVectorEnv(args.envs, config={"globals": {"seed": args.seed}}, contract="X", device=0, final_info=False,
                              delay_steps=3, thrust_curve=1, propellant_fraction=0.2, cg_burn_shift=0.05)
     env.set_curriculum(stage6_conditions())
-    obs, _ = env.reset(seed=args.seed, options={"return_torch": True})
-    obs = obs.clone()
+    env.reset(seed=args.seed, options={"return_torch": True})
 
     actor, q1, q2 = Actor().to(dev), mlp(12, 1).to(dev), mlp(12, 1).to(dev)
     q1t, q2t = mlp(12, 1).to(dev), mlp(12, 1).to(dev)
@@ -79,8 +80,16 @@ def main():
     alpha, gamma, tau, rscale = 0.2, 0.99, 0.005, 0.01
 
     B = args.buffer
+    T = args.rollout_steps
     buf = dict(s=torch.zeros((B, 10), device=dev), a=torch.zeros((B, 2), device=dev), r=torch.zeros(B, device=dev),
                s2=torch.zeros((B, 10), device=dev), d=torch.zeros(B, device=dev))
+    # the fused rollout kernel acts with the actor's current weights for T steps per launch and writes the transitions
+    # itself (tvc_rollout_io.obs_all / next_obs_all / ...): no host round trip and no per-step torch forward for acting
+    n = args.envs
+    tr = dict(obs=torch.zeros((T, n, 10), device=dev), actions=torch.zeros((T, n, 2), device=dev),
+              reward=torch.zeros((T, n), device=dev), next_obs=torch.zeros((T, n, 10), device=dev),
+              terminated=torch.zeros((T, n), dtype=torch.uint8, device=dev), truncated=torch.zeros((T, n), dtype=torch.uint8, device=dev))
+    eng = env.engine
     head, filled = 0, 0
     t_env = t_learn = 0.0
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -88,36 +97,35 @@ def main():
     wall0 = time.perf_counter()
     for it in range(args.iters):
         ev[0].record()
-        with torch.no_grad():
-            act, _ = actor(obs)
-        nobs, rew, term, trunc, infos = env.step(act.contiguous())
-        done = term | trunc
-        # same-step autoreset: the successor state of a finished env is its terminal observation
-        s2 = torch.where(done[:, None], infos["final_observation"], nobs)
-        n = args.envs
-        idx = (head + torch.arange(n, device=dev)) % B
-        buf["s"][idx], buf["a"][idx], buf["r"][idx], buf["s2"][idx] = obs, act, rew * rscale, s2
-        buf["d"][idx] = term.float()
-        head, filled = (head + n) % B, min(filled + n, B)
-        obs = nobs.clone()
+        lin = [m for m in actor.net if isinstance(m, nn.Linear)]
+        w = dict(w1=lin[0].weight.detach(), b1=lin[0].bias.detach(), w2=lin[1].weight.detach(), b2=lin[1].bias.detach(),
+                 w3=lin[2].weight.detach(), b3=lin[2].bias.detach())
+        eng.rollout(w, T, transitions=tr)
+        m = T * n
+        idx = (head + torch.arange(m, device=dev)) % B
+        buf["s"][idx], buf["a"][idx] = tr["obs"].reshape(m, 10), tr["actions"].reshape(m, 2)
+        buf["r"][idx], buf["s2"][idx] = tr["reward"].reshape(m) * rscale, tr["next_obs"].reshape(m, 10)
+        buf["d"][idx] = tr["terminated"].reshape(m).float()
+        head, filled = (head + m) % B, min(filled + m, B)
         ev[1].record()
-        # ---- one SAC update per env step ----
-        j = torch.randint(0, filled, (args.batch,), device=dev)
-        s, a, r, sn, d = buf["s"][j], buf["a"][j], buf["r"][j], buf["s2"][j], buf["d"][j]
-        with torch.no_grad():
-            an, lpn = actor(sn)
-            qn = torch.min(q1t(torch.cat([sn, an], 1)), q2t(torch.cat([sn, an], 1))).squeeze(-1) - alpha * lpn
-            y = r + gamma * (1 - d) * qn
-        sa = torch.cat([s, a], 1)
-        lq = F.mse_loss(q1(sa).squeeze(-1), y) + F.mse_loss(q2(sa).squeeze(-1), y)
-        opt_q.zero_grad(set_to_none=True), lq.backward(), opt_q.step()
-        ap_, lp = actor(s)
-        sap = torch.cat([s, ap_], 1)
-        la = (alpha * lp - torch.min(q1(sap), q2(sap)).squeeze(-1)).mean()
-        opt_a.zero_grad(set_to_none=True), la.backward(), opt_a.step()
-        with torch.no_grad():
-            for p, pt in zip(list(q1.parameters()) + list(q2.parameters()), list(q1t.parameters()) + list(q2t.parameters())):
-                pt.mul_(1 - tau).add_(p, alpha=tau)
+        # ---- SAC updates (one per rollout step) ----
+        for _ in range(T):
+            j = torch.randint(0, filled, (args.batch,), device=dev)
+            s, a, r, sn, d = buf["s"][j], buf["a"][j], buf["r"][j], buf["s2"][j], buf["d"][j]
+            with torch.no_grad():
+                an, lpn = actor(sn)
+                qn = torch.min(q1t(torch.cat([sn, an], 1)), q2t(torch.cat([sn, an], 1))).squeeze(-1) - alpha * lpn
+                y = r + gamma * (1 - d) * qn
+            sa = torch.cat([s, a], 1)
+            lq = F.mse_loss(q1(sa).squeeze(-1), y) + F.mse_loss(q2(sa).squeeze(-1), y)
+            opt_q.zero_grad(set_to_none=True), lq.backward(), opt_q.step()
+            ap_, lp = actor(s)
+            sap = torch.cat([s, ap_], 1)
+            la = (alpha * lp - torch.min(q1(sap), q2(sap)).squeeze(-1)).mean()
+            opt_a.zero_grad(set_to_none=True), la.backward(), opt_a.step()
+            with torch.no_grad():
+                for p, pt in zip(list(q1.parameters()) + list(q2.parameters()), list(q1t.parameters()) + list(q2t.parameters())):
+                    pt.mul_(1 - tau).add_(p, alpha=tau)
         ev[2].record()
         torch.cuda.synchronize()
         t_env += ev[0].elapsed_time(ev[1])
@@ -129,8 +137,8 @@ def main():
     evalm = evaluate(pol, episodes=64, contract="X", conditions=stage6_conditions(), delay_steps=3, thrust_curve=1)
     print(json.dumps({
         "config": "stage 6: wind 3 N, mass +-30 %, initial tilt 0.7 rad, sensor noise 0.02, actuator delay 3 steps, thrust curve",
-        "envs": args.envs, "iters": args.iters, "env_steps": args.envs * args.iters,
-        "env_steps_per_sec_end_to_end": args.envs * args.iters / wall,
+        "envs": args.envs, "iters": args.iters, "rollout_steps": T, "env_steps": args.envs * args.iters * T,
+        "env_steps_per_sec_end_to_end": args.envs * args.iters * T / wall, "acting": "tvc_rollout (tcgen05 actor in-kernel)",
         "env_ms_per_iter": t_env / args.iters, "learner_ms_per_iter": t_learn / args.iters,
         "learner_share_of_device_time": t_learn / (t_env + t_learn),
         "episodes": stats["episodes"], "train_success_rate": stats["successes"] / max(stats["episodes"], 1),

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TVC_ABI_VERSION 4
+#define TVC_ABI_VERSION 5
 
 #define TVC_OBS_DIM 10
 #define TVC_ACT_DIM 2
@@ -160,9 +160,15 @@ typedef struct tvc_rollout_io {
     float *obs;          /* [N,10] REQUIRED, in/out: the observation returned by the last reset/step/rollout; updated */
     float *reward_sum;   /* [N] nullable: sum of rewards over the T steps */
     float *actions_last; /* [N,2] nullable */
-    float *actions_all;  /* [T,N,2] nullable (parity tests) */
+    float *actions_all;  /* [T,N,2] nullable */
     float *reward_all;   /* [T,N] nullable */
     int32_t deterministic; /* 1: a = tanh(mean) */
+    int32_t reserved;
+    /* transition record for an on-device replay buffer; all nullable */
+    float *obs_all;        /* [T,N,10] observation the actor saw at step t */
+    float *next_obs_all;   /* [T,N,10] successor observation (the terminal one when the episode ended at step t) */
+    uint8_t *terminated_all; /* [T,N] */
+    uint8_t *truncated_all;  /* [T,N] */
 } tvc_rollout_io;
 
 int tvc_abi_version(void);

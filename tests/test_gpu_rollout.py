@@ -101,3 +101,29 @@ def test_rollout_noise_is_philox_stream_6(lib_built, oracle_mod):
     out2 = b.rollout(w, T, deterministic=False, record=True)
     assert torch.equal(out2["actions_all"], out["actions_all"])     # same seed, same ids -> same noise
     a.close(), b.close()
+
+
+def test_rollout_transition_record_feeds_a_replay_buffer(lib_built):
+    """tvc_rollout writes (obs, action, reward, next_obs, terminated, truncated) for every step straight into caller
+    tensors (on-device replay feed): they must equal what stepping the same actions through tvc_step returns."""
+    net, w = _actor(1)
+    n, T = 700, 10
+    a, b = _engines(n)
+    dev = a.device
+    tr = dict(obs=torch.zeros((T, n, 10), device=dev), actions=torch.zeros((T, n, 2), device=dev),
+              reward=torch.zeros((T, n), device=dev), next_obs=torch.zeros((T, n, 10), device=dev),
+              terminated=torch.zeros((T, n), dtype=torch.uint8, device=dev), truncated=torch.zeros((T, n), dtype=torch.uint8, device=dev))
+    a.rollout(w, T, deterministic=False, transitions=tr)
+    torch.cuda.synchronize()
+    n_done = 0
+    for t in range(T):
+        assert torch.allclose(tr["obs"][t], b.obs, atol=1e-5)
+        obs, rew, term, trunc = b.step(tr["actions"][t].contiguous())
+        done = (term | trunc).bool()
+        nxt = torch.where(done[:, None], b.final_obs, obs)
+        assert torch.equal(tr["terminated"][t], term) and torch.equal(tr["truncated"][t], trunc)
+        assert torch.allclose(tr["next_obs"][t], nxt, atol=1e-5)
+        assert torch.allclose(tr["reward"][t], rew, rtol=1e-5, atol=1e-4)
+        n_done += int(done.sum())
+    assert bool((tr["actions"].abs() <= 1).all())
+    a.close(), b.close()

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TVC_B200_LIB") or os.path.join(_HERE, "libtvc_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 OBS_DIM, ACT_DIM, NUM_COMPONENTS, NUM_STATS, MAX_DELAY = 10, 2, 12, 16, 4
 CONTRACT_R, CONTRACT_X = 0, 1
 DIV_OFF, DIV_FAST, DIV_EXACT = 0, 1, 2
@@ -83,7 +83,9 @@ class TvcActorWeights(C.Structure):
 
 class TvcRolloutIO(C.Structure):
     _fields_ = [("obs", C.c_void_p), ("reward_sum", C.c_void_p), ("actions_last", C.c_void_p),
-                ("actions_all", C.c_void_p), ("reward_all", C.c_void_p), ("deterministic", C.c_int32)]
+                ("actions_all", C.c_void_p), ("reward_all", C.c_void_p), ("deterministic", C.c_int32),
+                ("reserved", C.c_int32), ("obs_all", C.c_void_p), ("next_obs_all", C.c_void_p),
+                ("terminated_all", C.c_void_p), ("truncated_all", C.c_void_p)]
 
 
 _lib = None

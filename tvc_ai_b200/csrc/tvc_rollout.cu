@@ -150,6 +150,8 @@ __global__ void pack_actor_kernel(tvc_actor_weights w, uint8_t *img) {
 struct RolloutIO {
     float *obs;          // [N,10] in: current observation; out: observation after the last step
     float *reward_sum, *actions_last, *actions_all, *reward_all;
+    float *obs_all, *next_obs_all;
+    uint8_t *term_all, *trunc_all;
     int T, deterministic;
     unsigned long long t0;   // lifetime step of the first rollout step (Philox counters)
 };
@@ -219,6 +221,11 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
     int done = 0, viol = 0;
 
     for (int t = 0; t < io.T; t++) {
+        if (io.obs_all && live) {   // transition record: the observation the actor sees at step t
+            float2 *o2 = reinterpret_cast<float2 *>(io.obs_all + ((long long)t * st.n + i) * 10);
+#pragma unroll
+            for (int k = 0; k < 5; k++) o2[k] = make_float2(obs[2 * k], obs[2 * k + 1]);
+        }
         // ---- layer 1 operands: every env writes its obs row into its tile's bf16 operand [2][128][8] ----
         {
             uint4 c0 = make_uint4(pack_bf16(obs[0], obs[1]), pack_bf16(obs[2], obs[3]), pack_bf16(obs[4], obs[5]), pack_bf16(obs[6], obs[7]));
@@ -324,6 +331,13 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
             if (io.reward_all) io.reward_all[(long long)t * st.n + i] = r.reward;
             viol = r.viol;
             done = r.terminated | r.truncated;
+            if (io.term_all) io.term_all[(long long)t * st.n + i] = (uint8_t)r.terminated;
+            if (io.trunc_all) io.trunc_all[(long long)t * st.n + i] = (uint8_t)r.truncated;
+            if (io.next_obs_all) {   // successor observation before any autoreset (the terminal one when done)
+                float2 *o2 = reinterpret_cast<float2 *>(io.next_obs_all + ((long long)t * st.n + i) * 10);
+#pragma unroll
+                for (int k = 0; k < 5; k++) o2[k] = make_float2(r.obs[2 * k], r.obs[2 * k + 1]);
+            }
             if (done) {
                 ev_len = e.step; ev_succ = e.success; ev_reason = r.reason; ev_trunc = r.truncated;
                 ev_ret = e.ep_ret; ev_alt = r.alt; ev_tilt = r.tilt; ev_fuel = r.fuel;
@@ -414,6 +428,7 @@ extern "C" int tvc_rollout(tvc_handle *h, const tvc_actor_weights *w, int32_t T,
     RolloutIO io;
     io.obs = u->obs; io.reward_sum = u->reward_sum; io.actions_last = u->actions_last; io.actions_all = u->actions_all;
     io.reward_all = u->reward_all; io.T = T; io.deterministic = u->deterministic;
+    io.obs_all = u->obs_all; io.next_obs_all = u->next_obs_all; io.term_all = u->terminated_all; io.trunc_all = u->truncated_all;
     io.t0 = (unsigned long long)h->lifetime_steps;
     const bool X = h->cur.contract == TVC_CONTRACT_X;
     const int dv = h->cur.diversity_mode;

@@ -208,8 +208,11 @@ class BatchedEngine:
         return int(self.L.tvc_lifetime_steps(self.h))
 
     # ------------------------------------------------------------------ fused rollout
-    def rollout(self, weights: dict, T: int, deterministic: bool = False, record: bool = False):
-        """T env steps per launch with the 2x256 SAC actor evaluated in-kernel (tvc_rollout)."""
+    def rollout(self, weights: dict, T: int, deterministic: bool = False, record: bool = False, transitions: dict | None = None):
+        """T env steps per launch with the 2x256 SAC actor evaluated in-kernel (tvc_rollout).
+
+        transitions: optional dict of preallocated CUDA tensors the kernel fills directly (on-device replay feed):
+        obs [T,N,10], actions [T,N,2], reward [T,N], next_obs [T,N,10], terminated [T,N] u8, truncated [T,N] u8."""
         w = A.TvcActorWeights()
         keep = []
         for k in ("w1", "b1", "w2", "b2", "w3", "b3"):
@@ -224,6 +227,10 @@ class BatchedEngine:
             out["actions_all"] = torch.zeros((T, self.n, 2), dtype=torch.float32, device=self.device)
             out["reward_all"] = torch.zeros((T, self.n), dtype=torch.float32, device=self.device)
             io.actions_all, io.reward_all = out["actions_all"].data_ptr(), out["reward_all"].data_ptr()
+        if transitions is not None:
+            io.obs_all, io.next_obs_all = transitions["obs"].data_ptr(), transitions["next_obs"].data_ptr()
+            io.actions_all, io.reward_all = transitions["actions"].data_ptr(), transitions["reward"].data_ptr()
+            io.terminated_all, io.truncated_all = transitions["terminated"].data_ptr(), transitions["truncated"].data_ptr()
         io.deterministic = int(deterministic)
         A.check(self.L.tvc_rollout(self.h, C.byref(w), int(T), C.byref(io), self._stream()), "tvc_rollout")
         out["_keep"] = keep
