@@ -4,8 +4,9 @@
 // Replaces the get_action -> env.step loop of scripts/train.py:546-603 for the legacy 2x256 SAC actor
 // (shape from scripts/export_tflm.py:85-156, tests/test_agent.py:46-56).
 //
-// sm_100a design: CTA = 256 threads = 256 envs = two 128-row MMA tiles (thread i owns env i and accumulator
-// row i % 128 of tile i / 128; 8 warps share the resident weights and hide each other's physics latency).  bf16 weights are packed once into UMMA "K-major, no swizzle" core-matrix images and copied
+// sm_100a design: CTA = 512 threads = 512 envs = four 128-row MMA tiles (thread i owns env i and accumulator
+// row i % 128 of tile i / 128; the 16 warps share the resident weights and hide each other's physics latency;
+// the tiles alternate between two 256-column TMEM accumulator sets and take turns on one hidden-tile buffer).  bf16 weights are packed once into UMMA "K-major, no swizzle" core-matrix images and copied
 // into shared memory with one TMA bulk copy (cp.async.bulk) for the whole rollout.  Per step:
 //   obs tile -> smem (bf16)          -> tcgen05.mma M128 N256 K16   (layer 1, accumulators in TMEM)
 //   tcgen05.ld -> bias+ReLU -> smem  -> 16 x tcgen05.mma M128 N256 K16 (layer 2)
@@ -25,7 +26,11 @@ namespace {
 constexpr int HID = 256;
 constexpr int K1 = 16;               // layer-1 K (10 obs padded to one UMMA K step)
 constexpr int TM = 128;              // rows (envs) of one MMA tile = TMEM lanes
-constexpr int RB = 256;              // threads (envs) per CTA = NT tiles; 8 warps share the resident weights
+#ifndef TVC_ROLLOUT_BLOCK
+#define TVC_ROLLOUT_BLOCK 512
+#endif
+constexpr int RB = TVC_ROLLOUT_BLOCK; // threads (envs) per CTA = NT tiles; the warps share the resident weights
+constexpr int NSET = 2;              // TMEM accumulator column sets (256 columns each); tile j uses set j % 2
 constexpr int NT = RB / TM;
 constexpr uint32_t W1_BYTES = HID * K1 * 2;        // 8 KB   image [K1/8][256][8] bf16
 constexpr uint32_t W2_BYTES = HID * HID * 2;       // 128 KB image [256/8][256][8] bf16
@@ -42,7 +47,8 @@ constexpr uint32_t OFF_H1 = OFF_A1 + NT * A1_BYTES;     // also the contact-exch
 constexpr uint32_t OFF_VEC = OFF_H1 + H1_BYTES;
 constexpr uint32_t OFF_BAR = OFF_VEC + VEC_BYTES;       // weight barrier, one MMA barrier per tile, tmem base
 constexpr uint32_t SMEM_TOTAL = OFF_BAR + 64;
-static_assert(sizeof(ContactSmemT<RB>) <= H1_BYTES, "contact exchange must fit in the hidden-tile area");
+static_assert(sizeof(ContactSmemT<RB>) <= NT * A1_BYTES + H1_BYTES, "contact exchange must fit in the operand + hidden-tile area");
+static_assert(NT >= 2 && NT % 2 == 0, "tiles alternate between two TMEM column sets");
 static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 
 // UMMA instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=128 (cute::UMMA::InstrDescriptor)
@@ -169,19 +175,20 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
 
     const uint32_t s_base = smem_u32(smem);
     const uint32_t bar_w = s_base + OFF_BAR;
-    const uint32_t bar_mma = s_base + OFF_BAR + 8 + 8 * tile;   // this tile's MMA-completion barrier
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 8 + 8 * NT);
+    const int set = tile % NSET;                                 // this tile's TMEM column set and MMA barrier
+    const uint32_t bar_mma = s_base + OFF_BAR + 8 + 8 * set;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 8 + 8 * NSET);
     const float *b1 = reinterpret_cast<const float *>(smem + OFF_VEC);
     const float *b2 = b1 + HID;
     const float *w3 = b2 + HID;
     const float *b3 = w3 + 4 * HID;
-    ContactSmemT<RB> &s_contact = *reinterpret_cast<ContactSmemT<RB> *>(smem + OFF_H1);
+    ContactSmemT<RB> &s_contact = *reinterpret_cast<ContactSmemT<RB> *>(smem + OFF_A1);   // operand + hidden tiles are idle during physics
 
     // ---- one-time setup: barriers, TMEM (256 accumulator columns per tile), weights via TMA bulk copy ----
     if (tid == 0) {
         mbar_init(bar_w, 1);
 #pragma unroll
-        for (int j = 0; j < NT; j++) mbar_init(s_base + OFF_BAR + 8 + 8 * j, 1);
+        for (int j = 0; j < NSET; j++) mbar_init(s_base + OFF_BAR + 8 + 8 * j, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -214,8 +221,8 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
     }
     mbar_wait(bar_w, 0);
 
-    // warp w reads TMEM lanes 32*(w%4)..+31; tile j accumulates in columns [256 j, 256 j + 256)
-    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(tile * HID);
+    // warp w reads TMEM lanes 32*(w%4)..+31; tile j accumulates in column set j % 2: columns [256 set, 256 set + 256)
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(set * HID);
     uint32_t mma_phase = 0;
     float rsum = 0.0f, a0 = 0.0f, a1 = 0.0f;
     int done = 0, viol = 0;
@@ -237,10 +244,10 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {   // layer 1 of every tile is issued up front: tile 1's MMA overlaps tile 0's epilogue
+        if (tid == 0) {   // layer 1 of the first two tiles is issued up front: tile 1's MMA overlaps tile 0's epilogue
             tc_fence_after();
 #pragma unroll
-            for (int j = 0; j < NT; j++) {
+            for (int j = 0; j < NSET; j++) {
                 mma_bf16(tmem_base + j * HID, umma_desc(s_base + OFF_A1 + j * A1_BYTES, TM * 16, 128),
                          umma_desc(s_base + OFF_W1, HID * 16, 128), 0u);
                 mma_commit(s_base + OFF_BAR + 8 + 8 * j);
@@ -274,9 +281,9 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < HID / 16; kk++)
-                    mma_bf16(tmem_base + j * HID, umma_desc(s_base + OFF_H1 + kk * 2 * (TM * 16), TM * 16, 128),
+                    mma_bf16(tmem_base + (j % NSET) * HID, umma_desc(s_base + OFF_H1 + kk * 2 * (TM * 16), TM * 16, 128),
                              umma_desc(s_base + OFF_W2 + kk * 2 * (HID * 16), HID * 16, 128), kk > 0 ? 1u : 0u);
-                mma_commit(s_base + OFF_BAR + 8 + 8 * j);
+                mma_commit(s_base + OFF_BAR + 8 + 8 * (j % NSET));
             }
             if (tile == j) {
                 mbar_wait(bar_mma, mma_phase ^ 1u);
@@ -297,8 +304,14 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
                 tc_fence_before();
             }
             __syncthreads();   // tile j's layer-2 MMAs have completed (its threads waited): the hidden tile is free again
+            if (tid == 0 && j + NSET < NT) {   // column set j % 2 has been read out: start layer 1 of tile j + 2 in it
+                tc_fence_after();
+                mma_bf16(tmem_base + (j % NSET) * HID, umma_desc(s_base + OFF_A1 + (j + NSET) * A1_BYTES, TM * 16, 128),
+                         umma_desc(s_base + OFF_W1, HID * 16, 128), 0u);
+                mma_commit(s_base + OFF_BAR + 8 + 8 * (j % NSET));
+            }
         }
-        // each tile's barrier completed two phases this step -> parity unchanged
+        // every column-set barrier completed 2 * NT / NSET (an even number of) phases this step -> parity unchanged
         // ---- action: tanh(mean + exp(clamp(log_std)) * eps), eps from Philox stream 6 ----
         const float mean0 = o0 + b3[0], mean1 = o1 + b3[1];
         const float ls0 = clampf(o2 + b3[2], -20.0f, 2.0f), ls1 = clampf(o3 + b3[3], -20.0f, 2.0f);
@@ -353,7 +366,7 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
         __syncthreads();
         const int any_ev = __syncthreads_or(done | viol);
         if (any_ev) {
-            double *s_stat = reinterpret_cast<double *>(smem + OFF_H1);   // [RB/32][16] doubles
+            double *s_stat = reinterpret_cast<double *>(smem + OFF_H1 + 32768);   // [RB/32][16] doubles, clear of the contact area's head
             const unsigned full = 0xffffffffu;
             int n_ep = __reduce_add_sync(full, done), n_len = __reduce_add_sync(full, ev_len);
             int n_succ = __reduce_add_sync(full, done ? ev_succ : 0);
