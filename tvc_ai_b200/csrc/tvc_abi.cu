@@ -155,21 +155,32 @@ step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState s
 #endif
 #define TVC_EPT (TVC_CHUNK / 256)   // envs per classify thread
 
-// Heuristic class of an env for the coming step: may its lowest point come within the contact margin?
+// Heuristic class of an env for the coming step: 0 = its lowest point touches the ground now (measured: such envs need
+// the contact solve in 9.4 of the 10 substeps), 1 = it may come within reach during the step, 2 = airborne.
 // Only the grouping depends on it (every thread carries the solver), never the results.
+//
+// Each 1024-env chunk is sorted by class (stable), its class counts go to goff[c][chunk + 1], and the last CTA to finish
+// turns the counts into exclusive scans over the chunks.  step_kernel_v2 then walks ONE global sequence -- all class-0
+// envs, all class-1 envs, all class-2 envs -- so that a CTA's warps hold groups of the same class (a CTA whose warps
+// re-align at every substep would otherwise park three airborne warps behind one solver warp) and the long class-0
+// groups start first.  Deterministic: no atomics on data, the sequence depends on the states only.
+#define TVC_NOW_GAP 0.008f     // class 0: lower bound of the lowest point's height below this
+#define TVC_MAYBE_GAP 0.02f    // class 1: that bound minus the first-order travel over the step below this
 template <bool X>
 __global__ void __launch_bounds__(256)
 classify_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState st) {
-    __shared__ int wcnt[TVC_EPT][8];
+    __shared__ int wcnt[3][TVC_EPT][8];
+    __shared__ int s_scan[8];
+    __shared__ int s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long base = (long long)blockIdx.x * TVC_CHUNK;
-    if (blockIdx.x == 0 && tid == 0) *st.counter = 0u;
-    unsigned mask[TVC_EPT];
+    const int nc = st.nchunks;
+    unsigned mask[3][TVC_EPT];
     const float T = c.dt * (float)c.K;
 #pragma unroll
     for (int j = 0; j < TVC_EPT; j++) {
         const long long env = base + j * 256 + tid;
-        bool near = false;
+        int cls = 3;
         if (env < st.n) {
             const float4 p = st.s0[env], q = st.s1[env], v = st.s2[env], w = st.s3[env];
             const float cg = X ? fabsf(st.d0[env].z) + fabsf(c.cg_burn) : 0.0f;
@@ -179,32 +190,85 @@ classify_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevSta
             const float gmin = p.z - fabsf(R33) * hh - c.radius * sqrtf(R31 * R31 + R32 * R32);
             const float reach = sqrtf(hh * hh + c.radius * c.radius);
             const float travel = (fabsf(v.z) + sqrtf(w.x * w.x + w.y * w.y + w.z * w.z) * reach) * T;
-            near = gmin - travel < c.margin + 0.03f;
+            cls = gmin < TVC_NOW_GAP ? 0 : (gmin - travel < TVC_MAYBE_GAP ? 1 : 2);
+            if (!c.ground) cls = 2;
         }
-        mask[j] = __ballot_sync(0xffffffffu, near);
-        if (lane == 0) wcnt[j][warp] = __popc(mask[j]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            mask[k][j] = __ballot_sync(0xffffffffu, cls == k);
+            if (lane == 0) wcnt[k][j][warp] = __popc(mask[k][j]);
+        }
     }
     __syncthreads();
-    int total = 0;
+    int total[3] = {0, 0, 0};
 #pragma unroll
-    for (int j = 0; j < TVC_EPT; j++)
+    for (int k = 0; k < 3; k++)
 #pragma unroll
-        for (int w = 0; w < 8; w++) total += wcnt[j][w];
+        for (int j = 0; j < TVC_EPT; j++)
+#pragma unroll
+            for (int w = 0; w < 8; w++) total[k] += wcnt[k][j][w];
 #pragma unroll
     for (int j = 0; j < TVC_EPT; j++) {
-        int before = 0;   // near-class envs ahead of this warp's 32 in linear order (j, warp, lane)
-        for (int jj = 0; jj < TVC_EPT; jj++)
-            for (int w = 0; w < 8; w++)
-                if (jj < j || (jj == j && w < warp)) before += wcnt[jj][w];
         const long long env = base + j * 256 + tid;
         if (env < st.n) {
-            const int lin = j * 256 + tid;
-            const int ahead = before + __popc(mask[j] & ((1u << lane) - 1u));
-            const bool near = (mask[j] >> lane) & 1u;
-            const int pos = near ? ahead : total + (lin - ahead);
-            st.order[base + pos] = (int)env;
+            const int k = (mask[0][j] >> lane) & 1u ? 0 : ((mask[1][j] >> lane) & 1u ? 1 : 2);
+            int before = 0;   // envs of the same class ahead of this warp's 32 in linear order (j, warp, lane)
+            for (int jj = 0; jj < TVC_EPT; jj++)
+                for (int w = 0; w < 8; w++)
+                    if (jj < j || (jj == j && w < warp)) before += wcnt[k][jj][w];
+            const unsigned mk = k == 0 ? mask[0][j] : (k == 1 ? mask[1][j] : mask[2][j]);
+            const int rank = before + __popc(mk & ((1u << lane) - 1u));
+            const int start = k == 0 ? 0 : (k == 1 ? total[0] : total[0] + total[1]);
+            st.order[base + start + rank] = (int)env;
         }
     }
+    // per-chunk counts, then the last CTA to arrive scans them (threadfence + ticket)
+    if (tid < 3) st.goff[tid * (nc + 1) + blockIdx.x + 1] = tid == 0 ? total[0] : (tid == 1 ? total[1] : total[2]);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&st.counter[1], 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int k = 0; k < 3; k++) {
+        volatile int *o = st.goff + k * (nc + 1);
+        int carry = 0;
+        for (int t0 = 0; t0 < nc; t0 += 256) {
+            const int idx = t0 + tid;
+            int v = idx < nc ? o[idx + 1] : 0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += u; }
+            if (lane == 31) s_scan[warp] = v;
+            __syncthreads();
+            int wbase = 0, tile = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) { const int sv = s_scan[w]; if (w < warp) wbase += sv; tile += sv; }
+            if (idx < nc) o[idx + 1] = carry + wbase + v;
+            carry += tile;
+            __syncthreads();
+        }
+        if (tid == 0) o[0] = 0;
+    }
+    if (tid == 0) { st.counter[0] = 0u; st.counter[1] = 0u; }
+}
+
+// Position p of the global class-ordered sequence -> env id (binary search over the chunk scans of p's class).
+__device__ __forceinline__ int env_at(const DevState &st, int p) {
+    const int nc = st.nchunks;
+    const int *g0 = st.goff, *g1 = st.goff + (nc + 1), *g2 = st.goff + 2 * (nc + 1);
+    const int T0 = g0[nc], T1 = g1[nc];
+    const int k = p < T0 ? 0 : (p < T0 + T1 ? 1 : 2);
+    const int q = p - (k == 0 ? 0 : (k == 1 ? T0 : T0 + T1));
+    const int *o = k == 0 ? g0 : (k == 1 ? g1 : g2);
+    int lo = 0, hi = nc;   // o[lo] <= q < o[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (o[mid] <= q) lo = mid; else hi = mid;
+    }
+    int intra = q - o[lo];
+    if (k >= 1) intra += g0[lo + 1] - g0[lo];
+    if (k == 2) intra += g1[lo + 1] - g1[lo];
+    return st.order[(long long)lo * TVC_CHUNK + intra];
 }
 
 #ifndef TVC_MIN_BLOCKS_V2
@@ -253,7 +317,7 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
         Forces f;
         long long i = 0, gid = 0;
         if (live) {
-            i = st.order[slot];
+            i = env_at(st, (int)slot);
             gid = c.env_base + i;
             load_env(st, X, i, e);
             float2 a;
@@ -580,6 +644,8 @@ int tvc_create(const tvc_config *cfg, int device, int64_t num_envs, tvc_handle *
     h->ngroups = (int)((num_envs + 31) / 32);
     TRY(dalloc(&s.partial, (size_t)h->ngroups * TVC_NSTAT));
     TRY(dalloc(&s.order, n));
+    s.nchunks = (int)((num_envs + TVC_CHUNK - 1) / TVC_CHUNK);
+    TRY(dalloc(&s.goff, (size_t)3 * (s.nchunks + 1)));
     TRY(dalloc(&s.counter, (size_t)4));
     TRY(dalloc(&h->stats_dev, (size_t)TVC_NSTAT));
     {
@@ -604,7 +670,7 @@ int tvc_destroy(tvc_handle *h) {
     DevState &s = h->st;
     cudaFree(s.s0); cudaFree(s.s1); cudaFree(s.s2); cudaFree(s.s3); cudaFree(s.s4);
     cudaFree(s.d0); cudaFree(s.d1); cudaFree(s.ring); cudaFree(s.clipb); cudaFree(s.runb); cudaFree(s.hist);
-    cudaFree(s.delay); cudaFree(s.partial); cudaFree(s.order); cudaFree(s.counter); cudaFree(h->stats_dev);
+    cudaFree(s.delay); cudaFree(s.partial); cudaFree(s.order); cudaFree(s.goff); cudaFree(s.counter); cudaFree(h->stats_dev);
     cudaFree(h->io_act); cudaFree(h->io_obs); cudaFree(h->io_rew); cudaFree(h->io_term); cudaFree(h->io_trunc); cudaFree(h->io_final);
     tvc_rollout_free(h);
     if (h->stats_host) cudaFreeHost(h->stats_host);
@@ -636,7 +702,7 @@ static int launch_step(tvc_handle *h, const DevIO &io, cudaStream_t s) {
 #undef GO
         LAUNCH_OK("step_kernel");
     } else {
-        const int cgrid = (int)((h->n + TVC_CHUNK - 1) / TVC_CHUNK);
+        const int cgrid = h->st.nchunks;
         if (X) classify_kernel<true><<<cgrid, 256, 0, s>>>(h->dc, h->st);
         else classify_kernel<false><<<cgrid, 256, 0, s>>>(h->dc, h->st);
         LAUNCH_OK("classify_kernel");

@@ -48,8 +48,10 @@ struct DevState {
     float *hist;      // [1000][N] exact diversity only
     float2 *delay;    // [TVC_MAX_DELAY][N] X: actuator delay ring, slot = step % delay
     double *partial;  // [ceil(N/32)][16] episode statistics rows: one owner (CTA or 32-env group) per row per launch
-    int *order;       // [N] env ids sorted per 1024-env chunk: near-ground envs first (classify_kernel)
-    unsigned *counter;  // work-queue head of step_kernel_v2 (zeroed by classify_kernel)
+    int *order;       // [N] env ids sorted per 1024-env chunk by class: in contact, may touch, airborne (classify_kernel)
+    int *goff;        // [3][nchunks + 1] exclusive scans over the chunks of the per-chunk class counts (goff[c][0] = 0)
+    unsigned *counter;  // [0] work-queue head of step_kernel_v2 (zeroed by classify_kernel), [1] classify_kernel's ticket
+    int nchunks;
     long long n;
 };
 
