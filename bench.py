@@ -224,7 +224,7 @@ def run_ours(args):
         flush.zero_()
         starts[k].record()
         eng.step(pool[k % 16], want_final=False)
-        launches += 2            # classify_kernel + step_kernel_v2
+        launches += 3            # classify_kernel + step_kernel_v2 + reset_done_kernel
         ends[k].record()
         if (k + 1) % 64 == 0:   # episode-statistics reduction (+ NCCL all-reduce over NVLink when N>1), side stream
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -322,15 +322,18 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     e2e_dt = (time.perf_counter() - t0) / ke
     e2e_check = float(r_h[:16].sum())      # touch the result on the host
+    done_rows = int((te_h | tr_h).sum())   # final-observation rows the last step wrote into the pinned host buffer
     venv.close()
     te = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_dt = float(te.item())
-    launches += 2 * ke
+    launches += 3 * ke
     extra["e2e"] = {"value": total_envs / e2e_dt, "unit": "env-steps/s", "h2d_bytes_per_step": n * 8,
-                    "d2h_bytes_per_step": n * (40 + 4 + 1 + 1 + 40), "ms_per_step": 1e3 * e2e_dt, "n_gpus_measured": world,
+                    "d2h_bytes_per_step": n * (40 + 4 + 1 + 1) + done_rows * 40, "ms_per_step": 1e3 * e2e_dt, "n_gpus_measured": world,
                     "bytes_are": "per GPU", "result_checksum": e2e_check,
+                    "d2h_note": f"obs 40 B + reward 4 B + 2 flag bytes per env by copy engine; the final observations of the {done_rows} "
+                                "envs that ended an episode in the (last) step are stored by the kernel straight into the pinned host buffer",
                     "api": "RocketTVCVectorEnv.step(numpy, copy_outputs=False) -> tvc_step_host (pinned host buffers, sync inside)"}
 
     clocks = sampler.stop()   # sampled from the start of the timed region to the end of the e2e measurement (all under load)
@@ -353,7 +356,7 @@ def run_ours(args):
                         "note": "back-to-back launches, state L2-resident (62 MB < 126 MB)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": _traffic(), "peak_source": peak_src,
-                         "kernel": "step_kernel_v2<X=true,DIV=fast> (+ classify_kernel, 7 us)",
+                         "kernel": "step_kernel_v2<X=true,DIV=fast> (+ classify_kernel and reset_done_kernel)",
                          "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP_X,
                          "note": "instruction-bound (contact PGS chain, 50 % of issue slots); see DESIGN.md section 6 and profiles/"},
             "gpu_launches": launches,

@@ -249,7 +249,7 @@ classify_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevSta
         }
         if (tid == 0) o[0] = 0;
     }
-    if (tid == 0) { st.counter[0] = 0u; st.counter[1] = 0u; }
+    if (tid == 0) { st.counter[0] = 0u; st.counter[1] = 0u; st.counter[2] = 0u; }
 }
 
 // Position p of the global class-ordered sequence -> env id (binary search over the chunk scans of p's class).
@@ -301,7 +301,13 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
         if (s_g0 >= ngroups) break;
         g = s_g0 + (threadIdx.x >> 5);
         const long long slot = (long long)g * 32 + lane;
+#ifdef TVC_DBG   // timing experiments only (env TVC_DBG_ONLY): 0 = only the in-contact / may-touch groups, 1 = only the airborne groups
+        const int near_end = st.goff[st.nchunks] + st.goff[2 * st.nchunks + 1];
+        const bool skip = c.dbg_only == 0 ? (slot >= near_end) : (c.dbg_only == 1 ? (slot + 31 < near_end) : false);
+        const bool live = g < ngroups && slot < st.n && !skip;
+#else
         const bool live = g < ngroups && slot < st.n;
+#endif
 #else
         if (lane == 0) g = (int)atomicAdd(st.counter, 1u);   // dynamic work queue over the sorted 32-env groups
         g = __shfl_sync(full, g, 0);
@@ -368,15 +374,24 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
 #pragma unroll
                     for (int k = 0; k < 5; k++) f2[k] = make_float2(r.obs[2 * k], r.obs[2 * k + 1]);
                 }
-                if (c.autoreset) {
-                    reset_env(c, X, gid, e, false);
-                    build_obs(c, X, gid, e, 0, r.obs);
-                }
             }
             store_env(st, X, i, e);
             float2 *o2 = reinterpret_cast<float2 *>(io.obs + 10 * i);
 #pragma unroll
             for (int k = 0; k < 5; k++) o2[k] = make_float2(r.obs[2 * k], r.obs[2 * k + 1]);
+        }
+        // Same-step autoreset is deferred: ~1 env in 38 ends its episode per step, i.e. 1-2 lanes per warp would walk
+        // through the per-episode Philox draws and a second observation here (10 % of this kernel's warp-instructions
+        // at 1.7 live lanes).  The terminal state and observation are stored above; reset_done_kernel re-initialises
+        // the listed envs with full warps and overwrites their observation rows.  List order is arbitrary, results are not.
+        if (c.autoreset) {
+            const unsigned dm = __ballot_sync(full, done != 0);
+            if (dm) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(&st.counter[2], (unsigned)__popc(dm));
+                base = __shfl_sync(full, base, 0);
+                if (done) st.done_list[base + __popc(dm & ((1u << lane) - 1u))] = (int)i;
+            }
         }
         // episode statistics: this group owns row g of `partial` for the whole launch (no atomics, deterministic)
         if (__any_sync(full, done | viol)) {
@@ -424,6 +439,28 @@ reset_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState 
         build_obs(c, X, gid, e, 0, o);
 #pragma unroll
         for (int k = 0; k < 10; k++) obs[10 * i + k] = o[k];
+    }
+}
+
+// Second half of the same-step autoreset of step_kernel_v2: ref:381-464 reset + the reset observation for the envs
+// listed in done_list (their terminal state was stored by the step kernel; every Env field round-trips through
+// store_env / load_env, so this equals resetting in place).
+template <bool X>
+__global__ void __launch_bounds__(TVC_BLOCK)
+reset_done_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState st, float *obs) {
+    const unsigned nd = st.counter[2];
+    for (unsigned k = blockIdx.x * TVC_BLOCK + threadIdx.x; k < nd; k += gridDim.x * TVC_BLOCK) {
+        const long long i = st.done_list[k];
+        const long long gid = c.env_base + i;
+        Env e;
+        load_env(st, X, i, e);
+        reset_env(c, X, gid, e, false);
+        store_env(st, X, i, e);
+        float o[10];
+        build_obs(c, X, gid, e, 0, o);
+        float2 *o2 = reinterpret_cast<float2 *>(obs + 10 * i);
+#pragma unroll
+        for (int j = 0; j < 5; j++) o2[j] = make_float2(o[2 * j], o[2 * j + 1]);
     }
 }
 
@@ -647,6 +684,7 @@ int tvc_create(const tvc_config *cfg, int device, int64_t num_envs, tvc_handle *
     s.nchunks = (int)((num_envs + TVC_CHUNK - 1) / TVC_CHUNK);
     TRY(dalloc(&s.goff, (size_t)3 * (s.nchunks + 1)));
     TRY(dalloc(&s.counter, (size_t)4));
+    TRY(dalloc(&s.done_list, n));
     TRY(dalloc(&h->stats_dev, (size_t)TVC_NSTAT));
     {
         cudaError_t e = cudaMallocHost((void **)&h->stats_host, sizeof(double) * TVC_NSTAT);
@@ -670,7 +708,7 @@ int tvc_destroy(tvc_handle *h) {
     DevState &s = h->st;
     cudaFree(s.s0); cudaFree(s.s1); cudaFree(s.s2); cudaFree(s.s3); cudaFree(s.s4);
     cudaFree(s.d0); cudaFree(s.d1); cudaFree(s.ring); cudaFree(s.clipb); cudaFree(s.runb); cudaFree(s.hist);
-    cudaFree(s.delay); cudaFree(s.partial); cudaFree(s.order); cudaFree(s.goff); cudaFree(s.counter); cudaFree(h->stats_dev);
+    cudaFree(s.delay); cudaFree(s.partial); cudaFree(s.order); cudaFree(s.goff); cudaFree(s.counter); cudaFree(s.done_list); cudaFree(h->stats_dev);
     cudaFree(h->io_act); cudaFree(h->io_obs); cudaFree(h->io_rew); cudaFree(h->io_term); cudaFree(h->io_trunc); cudaFree(h->io_final);
     tvc_rollout_free(h);
     if (h->stats_host) cudaFreeHost(h->stats_host);
@@ -693,6 +731,9 @@ int tvc_reset(tvc_handle *h, const uint8_t *mask_dev, uint64_t seed, float *obs_
 }
 
 static int launch_step(tvc_handle *h, const DevIO &io, cudaStream_t s) {
+#ifdef TVC_DBG
+    { const char *e = getenv("TVC_DBG_ONLY"); h->dc.dbg_only = e ? atoi(e) : -1; }
+#endif
     const bool X = h->cur.contract == TVC_CONTRACT_X;
     const int dv = h->cur.diversity_mode;
     if (h->step_impl == 1) {   // legacy: thread-per-env CTAs with the shared-memory contact exchange
@@ -722,6 +763,13 @@ static int launch_step(tvc_handle *h, const DevIO &io, cudaStream_t s) {
         else   { if (dv == 0) GO(false, 0); else if (dv == 1) GO(false, 1); else GO(false, 2); }
 #undef GO
         LAUNCH_OK("step_kernel_v2");
+        if (h->cur.autoreset) {   // deferred same-step autoreset of the envs the step kernel listed
+            const int want = (int)((h->n / 16 + TVC_BLOCK - 1) / TVC_BLOCK) + 1;
+            const int rgrid = want < 2 * h->num_sms ? want : 2 * h->num_sms;
+            if (X) reset_done_kernel<true><<<rgrid, TVC_BLOCK, 0, s>>>(h->dc, h->st, io.obs);
+            else reset_done_kernel<false><<<rgrid, TVC_BLOCK, 0, s>>>(h->dc, h->st, io.obs);
+            LAUNCH_OK("reset_done_kernel");
+        }
     }
     h->lifetime_steps += 1;
     h->stat_steps += 1;
@@ -767,14 +815,30 @@ int tvc_step_host(tvc_handle *h, const float *actions_host, float *obs_host, flo
     }
     cudaStream_t s = h->own_stream;
     if (actions_host) CUDA_OK(cudaMemcpyAsync(h->io_act, actions_host, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, s));
-    int rc = tvc_step(h, actions_host ? h->io_act : nullptr, h->io_obs, h->io_rew, h->io_term, h->io_trunc,
-                      final_obs_host ? h->io_final : nullptr, (tvc_stream)s);
+    // Final observations exist only for the ~3 % of envs whose episode ended in this step.  When the caller's buffer is
+    // pinned (device-mapped) host memory the kernel stores those rows straight into it over PCIe and the dense
+    // [N,10] device-to-host copy (40 B per env) disappears; pageable memory takes the staged copy below.
+    float *final_dev = nullptr;
+    bool final_direct = false;
+    if (final_obs_host) {
+        if (final_obs_host != h->final_host_seen) {
+            cudaPointerAttributes at;
+            h->final_host_seen = final_obs_host;
+            h->final_host_dev = nullptr;
+            if (cudaPointerGetAttributes(&at, final_obs_host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+                h->final_host_dev = (float *)at.devicePointer;
+            else (void)cudaGetLastError();
+        }
+        final_direct = h->final_host_dev != nullptr;
+        final_dev = final_direct ? h->final_host_dev : h->io_final;
+    }
+    int rc = tvc_step(h, actions_host ? h->io_act : nullptr, h->io_obs, h->io_rew, h->io_term, h->io_trunc, final_dev, (tvc_stream)s);
     if (rc) return rc;
     CUDA_OK(cudaMemcpyAsync(obs_host, h->io_obs, sizeof(float) * 10 * n, cudaMemcpyDeviceToHost, s));
     CUDA_OK(cudaMemcpyAsync(reward_host, h->io_rew, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
     CUDA_OK(cudaMemcpyAsync(terminated_host, h->io_term, n, cudaMemcpyDeviceToHost, s));
     CUDA_OK(cudaMemcpyAsync(truncated_host, h->io_trunc, n, cudaMemcpyDeviceToHost, s));
-    if (final_obs_host) CUDA_OK(cudaMemcpyAsync(final_obs_host, h->io_final, sizeof(float) * 10 * n, cudaMemcpyDeviceToHost, s));
+    if (final_obs_host && !final_direct) CUDA_OK(cudaMemcpyAsync(final_obs_host, h->io_final, sizeof(float) * 10 * n, cudaMemcpyDeviceToHost, s));
     CUDA_OK(cudaStreamSynchronize(s));
     return TVC_OK;
 }

@@ -31,6 +31,7 @@ struct DevCfg {
     float mu, mu_spin, mu_roll, restitution, rest_thr, erp, margin;
     unsigned seed_lo, seed_hi;
     long long env_base;
+    int dbg_only;   // diagnostic builds (-DTVC_DBG) only
 };
 
 // Persistent per-env state, SoA planes of 16-byte groups (coalesced LDG.128/STG.128).
@@ -50,7 +51,9 @@ struct DevState {
     double *partial;  // [ceil(N/32)][16] episode statistics rows: one owner (CTA or 32-env group) per row per launch
     int *order;       // [N] env ids sorted per 1024-env chunk by class: in contact, may touch, airborne (classify_kernel)
     int *goff;        // [3][nchunks + 1] exclusive scans over the chunks of the per-chunk class counts (goff[c][0] = 0)
-    unsigned *counter;  // [0] work-queue head of step_kernel_v2 (zeroed by classify_kernel), [1] classify_kernel's ticket
+    unsigned *counter;  // [0] work-queue head of step_kernel_v2 (zeroed by classify_kernel), [1] classify_kernel's ticket,
+                        // [2] length of done_list (zeroed by classify_kernel)
+    int *done_list;     // [N] envs whose episode ended in this step (step_kernel_v2 appends, reset_done_kernel consumes)
     int nchunks;
     long long n;
 };
@@ -96,6 +99,9 @@ enum { ST_DR_A = 1, ST_DR_B = 2, ST_NOISE_A = 3, ST_NOISE_B = 4, ST_ACTION = 5, 
 __device__ __forceinline__ float rcp_fast(float x) { return __fdividef(1.0f, x); }
 __device__ __forceinline__ float sqrt_fast(float x) { return x > 0.0f ? x * rsqrtf(x) : 0.0f; }
 __device__ __forceinline__ float rsqrt_fast(float x) { return rsqrtf(x); }
+// operand known to be a normal number (callers clamp it away from the subnormal range): one MUFU.RSQ, without the
+// subnormal pre/post-scaling rsqrtf() carries
+__device__ __forceinline__ float rsqrt_normal(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void sincos_small(float x, float &s, float &c) {
     const float x2 = x * x;
     s = x * (1.0f + x2 * (-1.6666667e-1f + x2 * (8.3333333e-3f + x2 * (-1.9841270e-4f + x2 * 2.7557319e-6f))));
@@ -278,6 +284,10 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
     const float cly[5] = {r * uy, r * uy, 0.0f, 0.8660254037844386f * r, -0.8660254037844386f * r};
     float ax[5], ay[5], az[5], tgt[5], imn[5], im1[5], im2[5];
     float ln[5], l1[5], l2[5];
+    // Point 1 (the top cap) is far from the plane in every upright pose: its normal row then cannot bind
+    // (tgt <= vn with a zero stored impulse), which makes the row, its friction rows and its warm-start term exact
+    // no-ops.  It is therefore visited lazily: each sweep tests `tgt > vn` (and "any stored impulse"), and only a
+    // thread that passes computes the point's effective masses and runs the row.  Same results as visiting it always.
 #pragma unroll
     for (int i = 0; i < 5; i++) {
         const float cz = i == 1 ? zt : zb;
@@ -285,11 +295,13 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
         ay[i] = R[3] * clx[i] + R[4] * cly[i] + R[5] * cz;
         az[i] = R[6] * clx[i] + R[7] * cly[i] + R[8] * cz;
         const float gap = pz + az[i];
-        // effective masses for n = z, t1 = x, t2 = y at arm (ax,ay,az)
-        const float mn = im + (W00 * ay[i] * ay[i] - 2.0f * W01 * ax[i] * ay[i] + W11 * ax[i] * ax[i]);
-        const float m1 = im + (W11 * az[i] * az[i] - 2.0f * W12 * az[i] * ay[i] + W22 * ay[i] * ay[i]);
-        const float m2 = im + (W00 * az[i] * az[i] - 2.0f * W02 * az[i] * ax[i] + W22 * ax[i] * ax[i]);
-        imn[i] = rcp_fast(mn); im1[i] = rcp_fast(m1); im2[i] = rcp_fast(m2);
+        if (i != 1) {
+            // effective masses for n = z, t1 = x, t2 = y at arm (ax,ay,az)
+            const float mn = im + (W00 * ay[i] * ay[i] - 2.0f * W01 * ax[i] * ay[i] + W11 * ax[i] * ax[i]);
+            const float m1 = im + (W11 * az[i] * az[i] - 2.0f * W12 * az[i] * ay[i] + W22 * ay[i] * ay[i]);
+            const float m2 = im + (W00 * az[i] * az[i] - 2.0f * W02 * az[i] * ax[i] + W22 * ax[i] * ax[i]);
+            imn[i] = rcp_fast(mn); im1[i] = rcp_fast(m1); im2[i] = rcp_fast(m2);
+        } else { imn[i] = 0.0f; im1[i] = 0.0f; im2[i] = 0.0f; }
         const float vn0 = vz + wx * ay[i] - wy * ax[i];
         const float rest = (vn0 < -c.rest_thr) ? -c.restitution * vn0 : 0.0f;
         tgt[i] = rest + (gap > 0.0f ? -gap * c.inv_dt : -c.erp * gap * c.inv_dt);
@@ -302,6 +314,7 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
     if (warm) {   // apply the stored impulses at the current contact geometry
 #pragma unroll
         for (int i = 0; i < 5; i++) {
+            if (i == 1 && ln[1] == 0.0f && l1[1] == 0.0f && l2[1] == 0.0f) continue;   // adds exact zeros
             const float px_ = l1[i], py_ = l2[i], pn_ = ln[i];
             vx += px_ * im; vy += py_ * im; vz += pn_ * im;
             const float tx = ay[i] * pn_ - az[i] * py_, ty = az[i] * px_ - ax[i] * pn_, tz = ax[i] * py_ - ay[i] * px_;
@@ -319,6 +332,15 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
         for (int i = 0; i < 5; i++) {
             // normal row
             const float vn = vz + wx * ay[i] - wy * ax[i];
+            if (i == 1) {
+                if (!(tgt[1] > vn || ln[1] > 0.0f || l1[1] != 0.0f || l2[1] != 0.0f)) continue;   // exact no-op
+                if (imn[1] == 0.0f) {
+                    const float mn = im + (W00 * ay[1] * ay[1] - 2.0f * W01 * ax[1] * ay[1] + W11 * ax[1] * ax[1]);
+                    const float m1 = im + (W11 * az[1] * az[1] - 2.0f * W12 * az[1] * ay[1] + W22 * ay[1] * ay[1]);
+                    const float m2 = im + (W00 * az[1] * az[1] - 2.0f * W02 * az[1] * ax[1] + W22 * ax[1] * ax[1]);
+                    imn[1] = rcp_fast(mn); im1[1] = rcp_fast(m1); im2[1] = rcp_fast(m2);
+                }
+            }
             const float nl = fmaxf(ln[i] + (tgt[i] - vn) * imn[i], 0.0f);
             const float d = nl - ln[i];
             ln[i] = nl;
@@ -334,15 +356,15 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
             float a2 = l2[i] - vt2 * im2[i];
             const float lim = c.mu * nl;
             const float mag2 = a1 * a1 + a2 * a2;
-            const float sc = mag2 > lim * lim ? lim * rsqrt_fast(fmaxf(mag2, 1e-30f)) : 1.0f;   // branch-free disc projection
+            const float sc = mag2 > lim * lim ? lim * rsqrt_normal(fmaxf(mag2, 1e-30f)) : 1.0f;   // branch-free disc projection
             a1 *= sc; a2 *= sc;
             const float d1 = a1 - l1[i], d2 = a2 - l2[i];
             l1[i] = a1; l2[i] = a2;
             vx += d1 * im; vy += d2 * im;
             const float tx = -az[i] * d2, ty = az[i] * d1, tz = ax[i] * d2 - ay[i] * d1;
-            wx += W00 * tx + W01 * ty + W02 * tz;
-            wy += W01 * tx + W11 * ty + W12 * tz;
-            wz += W02 * tx + W12 * ty + W22 * tz;
+            wx = fmaf(W00, tx, fmaf(W01, ty, fmaf(W02, tz, wx)));   // three FFMA per component, no separate add
+            wy = fmaf(W01, tx, fmaf(W11, ty, fmaf(W12, tz, wy)));
+            wz = fmaf(W02, tx, fmaf(W12, ty, fmaf(W22, tz, wz)));
         }
         {   // spinning / rolling friction rows, limited by the total normal impulse
             float lim = c.mu_spin * lsum;
@@ -536,6 +558,7 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
     for (int j = 0; j < 18; j++) lam[j] = 0.0f;
     bool have_lam = false;   // cold start at every control step
     const float dI = P.inv_Iz - P.inv_Ixy;
+    const float far_z = 1.001f * (c.half_len + fabsf(P.cg) + c.radius) + c.margin;
     for (int k = 0; k < c.K; k++) {
         if (LOCKSTEP) __syncthreads();
         // B5 with I = diag(a, a, b): R diag(1/a,1/a,1/b) R^T tau = tau/a + (1/b - 1/a)(e.tau) e, e = body axis in the
@@ -560,7 +583,9 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
         e.vx = clampf(e.vx + (ax_ - e.vx * kl) * dt, -100.0f, 100.0f);
         e.vy = clampf(e.vy + (ay_ - e.vy * kl) * dt, -100.0f, 100.0f);
         e.vz = clampf(e.vz + (az_ - e.vz * kl) * dt, -100.0f, 100.0f);
-        if (c.ground) {
+        // the lowest point of the body is never lower than pz - 1.001 (h + |cg| + r): above `far_z` the entry rule fails
+        // without evaluating it (same decision, one compare for the airborne envs)
+        if (c.ground && e.pz < far_z) {
             const float R31 = e.qx * zs - e.qw * ys, R32 = e.qy * zs + e.qw * xs;   // third row of R (R33 == e2)
             if (contact_needed_row(c, P, R31, R32, e2, e.pz, e.vz, e.wx, e.wy, e.wz)) {
                 float R[9];
@@ -569,7 +594,7 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
                                   k == 0 ? c.contact_iters : c.warm_iters);
                 have_lam = true;
             } else have_lam = false;
-        }
+        } else have_lam = false;
         e.px += dt * e.vx; e.py += dt * e.vy; e.pz += dt * e.vz;
         float ang = sqrt_fast(e.wx * e.wx + e.wy * e.wy + e.wz * e.wz);
         if (ang * dt > 0.7853981633974483f) ang = 0.7853981633974483f * c.inv_dt;
