@@ -313,6 +313,51 @@ def test_sharding_invariance_and_determinism(lib_built):
         e.close()
 
 
+def test_deferred_autoreset_and_large_batch_sharding_bit_exact(lib_built, monkeypatch):
+    """The step path picks its launch plan by batch size: small batches reset finished envs inside the step kernel,
+    large ones list them for reset_done_kernel, and the class-ordered work sequence differs with every sharding.
+    None of that may change a single bit: (a) the same 8,192 envs stepped with either plan, 120 steps (free fall,
+    impacts, resting contact, terminations and resets); (b) one 98,304-env engine (deferred plan) against two
+    49,152-env shards (in-place plan), 80 steps.  Final observations are compared where an episode ended."""
+    from tvc_ai_b200 import _abi as A
+
+    def run(envs, steps, defer, base=0):
+        if defer is None:
+            monkeypatch.delenv("TVC_STEP_DEFER", raising=False)
+        else:
+            monkeypatch.setenv("TVC_STEP_DEFER", "1" if defer else "0")
+        e = _engine(envs, A.CONTRACT_X, autoreset=1, env_id_base=base)
+        e.reset()
+        out = []
+        for _ in range(steps):
+            o, r, t, tr = e.step(None, want_final=True)[:4]
+            done = t | tr
+            out.append((o.clone(), r.clone(), t.clone(), tr.clone(), (e.final_obs * done[:, None]).clone()))
+        st = e.stats()
+        e.close()
+        return out, st
+
+    a, sa = run(8192, 120, False)
+    b, sb = run(8192, 120, True)
+    assert sa[0] > 1000 and sa[5] > 0 and sa[6] > 0            # episodes ended by crash and by tilt
+    for k, (x, y) in enumerate(zip(a, b)):
+        for u, v in zip(x, y):
+            assert torch.equal(u, v), f"step {k}: in-place and deferred autoreset differ"
+    np.testing.assert_array_equal(sa, sb)
+
+    n = 98304
+    full, sf = run(n, 80, None)
+    lo, sl = run(n // 2, 80, None)
+    hi, sh = run(n // 2, 80, None, base=n // 2)
+    for k in range(80):
+        for u, v, w in zip(full[k], lo[k], hi[k]):
+            assert torch.equal(u, torch.cat([v, w])), f"step {k}: sharded and unsharded runs differ"
+    idx = [0, 3, 4, 5, 6, 7, 8, 9, 10, 14]
+    np.testing.assert_array_equal(sf[idx], (sl + sh)[idx])
+    np.testing.assert_allclose(sf, sl + sh, rtol=1e-12)
+    assert sf[0] > 10000
+
+
 def test_facade_matches_reference_api(lib_built, golden_dir):
     """Drop-in boundary: the single-env facade returns the reference's types and info keys
     (scripts/train.py:537-641) and reproduces the zero-action golden run."""

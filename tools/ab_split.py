@@ -9,7 +9,7 @@ import torch
 from tvc_ai_b200 import _abi as A
 from tvc_ai_b200.engine import BatchedEngine
 
-n = 262144
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
 dev = torch.device("cuda", 0)
 eng = BatchedEngine(n, A.default_config(A.CONTRACT_X, autoreset=1), device=0)
 eng.reset()
@@ -36,5 +36,5 @@ for rep in range(12):
         eng.step(pool[b % 16], want_final=False)
 for k, v in res.items():
     v = sorted(v)
-    print(f"SPLIT mode {k}: median {v[len(v) // 2]:.4f} ms  min {v[0]:.4f}", flush=True)
+    print(f"SPLIT n={n} mode {k}: median {v[len(v) // 2]:.4f} ms  min {v[0]:.4f}", flush=True)
 eng.close()

@@ -280,14 +280,24 @@ __device__ __forceinline__ int env_at(const DevState &st, int p) {
 #ifndef TVC_V2_NO_LOCKSTEP
 #define TVC_V2_LOCKSTEP 1   // measured: 0.1767 -> 0.164 ms per step (shared instruction fetches); larger CTAs / chunks lose
 #endif
-template <bool X, int DIV>
+// DEFER: finished envs are listed for reset_done_kernel (large batches) instead of being reset in place (small batches,
+// where one launch fewer matters more than the idle lanes).
+// A split into an airborne-part kernel at twice the occupancy (64 registers, solver out of line) followed by a near-ground
+// kernel was measured: 0.150 ms against 0.125 ms for this single kernel -- the FP32-pipe-bound solver warps and the
+// latency-bound airborne warps hide each other only when they share the SM sub-partitions.
+template <bool X, int DIV, bool DEFER>
 __global__ void __launch_bounds__(TVC_V2_BLOCK, TVC_MIN_BLOCKS_V2)
 step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevState st, const __grid_constant__ DevIO io) {
     const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
     const int ngroups = (int)((st.n + 31) / 32);
+    const int g_base = 0;
+    unsigned *const queue = &st.counter[0];
 #ifdef TVC_V2_LOCKSTEP
     __shared__ int s_g0;
+#endif
+#ifdef TVC_PHASE_PROF2
+    long long pt_prev = clock64();
 #endif
     for (;;) {
         int g = 0;
@@ -296,7 +306,7 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
         // they fetch the same instruction lines: ncu shows the GPC instruction cache at 80 % of its request rate and a
         // 76 % hit rate in the SM instruction cache when 16 warps per SM wander through the ~57 KB kernel on their own
         __syncthreads();
-        if (threadIdx.x == 0) s_g0 = (int)atomicAdd(st.counter, (unsigned)(TVC_V2_BLOCK / 32));
+        if (threadIdx.x == 0) s_g0 = g_base + (int)atomicAdd(queue, (unsigned)(TVC_V2_BLOCK / 32));
         __syncthreads();
         if (s_g0 >= ngroups) break;
         g = s_g0 + (threadIdx.x >> 5);
@@ -309,7 +319,7 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
         const bool live = g < ngroups && slot < st.n;
 #endif
 #else
-        if (lane == 0) g = (int)atomicAdd(st.counter, 1u);   // dynamic work queue over the sorted 32-env groups
+        if (lane == 0) g = g_base + (int)atomicAdd(queue, 1u);   // dynamic work queue over the sorted 32-env groups
         g = __shfl_sync(full, g, 0);
         if (g >= ngroups) break;
         const long long slot = (long long)g * 32 + lane;
@@ -322,6 +332,10 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
         BodyP P;
         Forces f;
         long long i = 0, gid = 0;
+#ifdef TVC_PHASE_PROF2
+        const long long pt0 = clock64();
+        Ph2 ph2s = {0u, 0u, 0u}; Ph2 *ph2 = &ph2s;
+#endif
         if (live) {
             i = env_at(st, (int)slot);
             gid = c.env_base + i;
@@ -340,11 +354,13 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
             P = body_params(c, false, 1.0f, 0.0f, 1.0f);
             f.Fx = f.Fy = f.Fz = f.Tx = f.Ty = f.Tz = f.a0 = f.a1 = 0.0f;
         }
+        PH2_CLK(pt1);
 #ifdef TVC_V2_LOCKSTEP
-        integrate_thread<true>(c, P, e, f.Fx, f.Fy, f.Fz, f.Tx, f.Ty, f.Tz);
+        integrate_thread<true>(c, P, e, f.Fx, f.Fy, f.Fz, f.Tx, f.Ty, f.Tz PH2_PASS);
 #else
-        if (live) integrate_thread<false>(c, P, e, f.Fx, f.Fy, f.Fz, f.Tx, f.Ty, f.Tz);
+        if (live) integrate_thread<false>(c, P, e, f.Fx, f.Fy, f.Fz, f.Tx, f.Ty, f.Tz PH2_PASS);
 #endif
+        PH2_CLK(pt2);
         if (live) {
             StepResult r;
             env_post<X, DIV>(c, st, i, gid, e, f.a0, f.a1, r);
@@ -374,17 +390,21 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
 #pragma unroll
                     for (int k = 0; k < 5; k++) f2[k] = make_float2(r.obs[2 * k], r.obs[2 * k + 1]);
                 }
+                if (!DEFER && c.autoreset) {   // small batches: reset in place (one launch fewer)
+                    reset_env(c, X, gid, e, false);
+                    build_obs(c, X, gid, e, 0, r.obs);
+                }
             }
             store_env(st, X, i, e);
             float2 *o2 = reinterpret_cast<float2 *>(io.obs + 10 * i);
 #pragma unroll
             for (int k = 0; k < 5; k++) o2[k] = make_float2(r.obs[2 * k], r.obs[2 * k + 1]);
         }
-        // Same-step autoreset is deferred: ~1 env in 38 ends its episode per step, i.e. 1-2 lanes per warp would walk
+        // Same-step autoreset is deferred (DEFER): ~1 env in 38 ends its episode per step, i.e. 1-2 lanes per warp would walk
         // through the per-episode Philox draws and a second observation here (10 % of this kernel's warp-instructions
         // at 1.7 live lanes).  The terminal state and observation are stored above; reset_done_kernel re-initialises
         // the listed envs with full warps and overwrites their observation rows.  List order is arbitrary, results are not.
-        if (c.autoreset) {
+        if (DEFER && c.autoreset) {
             const unsigned dm = __ballot_sync(full, done != 0);
             if (dm) {
                 unsigned base = 0;
@@ -393,6 +413,25 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
                 if (done) st.done_list[base + __popc(dm & ((1u << lane) - 1u))] = (int)i;
             }
         }
+#ifdef TVC_PHASE_PROF2
+        {
+            const long long pt3 = clock64();
+            const int cls = ((long long)g * 32 < (long long)st.goff[st.nchunks] + st.goff[2 * st.nchunks + 1]) ? 0 : 1;   // by position, any MODE
+            const unsigned tot = (unsigned)(pt2 - pt1);
+            const unsigned v1 = __reduce_max_sync(full, (unsigned)(pt1 - pt0)), v3 = __reduce_max_sync(full, ph2s.setup);
+            const unsigned v4 = __reduce_max_sync(full, ph2s.sweeps), v5 = __reduce_max_sync(full, (unsigned)(pt3 - pt2));
+            const unsigned v7 = __reduce_max_sync(full, ph2s.bar), vt = __reduce_max_sync(full, tot);
+            if (lane == 0 && g < ngroups) {
+                atomicAdd(&g_ph2[cls][0], (unsigned long long)(pt0 - pt_prev));
+                atomicAdd(&g_ph2[cls][1], (unsigned long long)v1);
+                atomicAdd(&g_ph2[cls][2], (unsigned long long)(vt - v3 - v4 - v7));
+                atomicAdd(&g_ph2[cls][3], (unsigned long long)v3); atomicAdd(&g_ph2[cls][4], (unsigned long long)v4);
+                atomicAdd(&g_ph2[cls][5], (unsigned long long)v5); atomicAdd(&g_ph2[cls][6], 1ull);
+                atomicAdd(&g_ph2[cls][7], (unsigned long long)v7);
+            }
+            pt_prev = clock64();
+        }
+#endif
         // episode statistics: this group owns row g of `partial` for the whole launch (no atomics, deterministic)
         if (__any_sync(full, done | viol)) {
             const int n_ep = __reduce_add_sync(full, done), n_len = __reduce_add_sync(full, ev_len);
@@ -749,27 +788,34 @@ static int launch_step(tvc_handle *h, const DevIO &io, cudaStream_t s) {
         LAUNCH_OK("classify_kernel");
         if (h->v2_grid == 0) {   // persistent grid: resident CTAs of the v2 kernel, capped by the number of groups
             int per_sm = 0;
-            cudaError_t e = X ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_v2<true, 1>, TVC_V2_BLOCK, 0)
-                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_v2<false, 1>, TVC_V2_BLOCK, 0);
+            cudaError_t e = X ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_v2<true, 1, true>, TVC_V2_BLOCK, 0)
+                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_v2<false, 1, true>, TVC_V2_BLOCK, 0);
             if (e != cudaSuccess || per_sm < 1) per_sm = 1;
-            // small batches: one warp per CTA does the work (every group gets its own SM: latency), else 4 per CTA
             const int cap = per_sm * h->num_sms;
             const int wpb = TVC_V2_BLOCK / 32;
-            const int want = h->ngroups <= cap ? h->ngroups : (h->ngroups + wpb - 1) / wpb;
+            const int ctas = (h->ngroups + wpb - 1) / wpb;
+            // small batches (every group resident at once): finished envs are reset in place -> two launches per step
+            const char *force = getenv("TVC_STEP_DEFER");   // tests / diagnostics: 0 or 1 overrides the choice
+            h->v2_defer = force ? (force[0] == '1') : (ctas > cap);
+            const int want = h->ngroups <= cap ? h->ngroups : ctas;
             h->v2_grid = want < cap ? want : cap;
         }
-#define GO(XX, DD) step_kernel_v2<XX, DD><<<h->v2_grid, TVC_V2_BLOCK, 0, s>>>(h->dc, h->st, io)
-        if (X) { if (dv == 0) GO(true, 0); else if (dv == 1) GO(true, 1); else GO(true, 2); }
-        else   { if (dv == 0) GO(false, 0); else if (dv == 1) GO(false, 1); else GO(false, 2); }
-#undef GO
+#define GO(XX, DD, FF) step_kernel_v2<XX, DD, FF><<<h->v2_grid, TVC_V2_BLOCK, 0, s>>>(h->dc, h->st, io)
+#define GO3(FF) do { \
+        if (X) { if (dv == 0) GO(true, 0, FF); else if (dv == 1) GO(true, 1, FF); else GO(true, 2, FF); } \
+        else   { if (dv == 0) GO(false, 0, FF); else if (dv == 1) GO(false, 1, FF); else GO(false, 2, FF); } } while (0)
+        const bool defer = h->v2_defer && h->cur.autoreset;
+        if (defer) GO3(true); else GO3(false);
         LAUNCH_OK("step_kernel_v2");
-        if (h->cur.autoreset) {   // deferred same-step autoreset of the envs the step kernel listed
+        if (defer) {   // deferred same-step autoreset of the envs the step kernel listed
             const int want = (int)((h->n / 16 + TVC_BLOCK - 1) / TVC_BLOCK) + 1;
             const int rgrid = want < 2 * h->num_sms ? want : 2 * h->num_sms;
             if (X) reset_done_kernel<true><<<rgrid, TVC_BLOCK, 0, s>>>(h->dc, h->st, io.obs);
             else reset_done_kernel<false><<<rgrid, TVC_BLOCK, 0, s>>>(h->dc, h->st, io.obs);
             LAUNCH_OK("reset_done_kernel");
         }
+#undef GO3
+#undef GO
     }
     h->lifetime_steps += 1;
     h->stat_steps += 1;
@@ -924,6 +970,14 @@ int tvc_get_config(const tvc_handle *h, tvc_config *out) {
     *out = h->cur;
     return TVC_OK;
 }
+#ifdef TVC_PHASE_PROF2
+int tvc_debug_phase2(unsigned long long *out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, tvc::g_ph2, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(tvc::g_ph2, z, sizeof(z)); }
+    return 0;
+}
+#endif
 #ifdef TVC_PHASE_PROF
 int tvc_debug_phase(unsigned long long *out, int reset) {
     cudaDeviceSynchronize();

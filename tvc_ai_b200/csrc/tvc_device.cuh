@@ -257,12 +257,28 @@ __device__ __forceinline__ bool contact_needed(const DevCfg &c, const BodyP &P, 
     return contact_needed_row(c, P, R[6], R[7], R[8], pz, vz, wx, wy, wz);
 }
 
+#ifdef TVC_PHASE_PROF2
+// diagnostic build only (tools/phase_prof2.py): clock64 cycles per phase of step_kernel_v2, per class of group
+// (0 = in contact / may touch, 1 = airborne), max over the lanes of a warp, summed over the groups:
+// [0] pull (barrier + queue) [1] index + loads + env_pre [2] substeps outside the solver [3] solver entry (geometry,
+// effective masses, warm start) [4] sweeps [5] env_post + stores [6] groups [7] substep barrier wait
+__device__ unsigned long long g_ph2[2][8];
+struct Ph2 { unsigned setup, sweeps, bar; };
+#define PH2_ARG , Ph2 *ph2
+#define PH2_PASS , ph2
+#define PH2_CLK(x) const long long x = clock64()
+#else
+#define PH2_ARG
+#define PH2_PASS
+#define PH2_CLK(x)
+#endif
 // lam: this problem's 18 stored impulses, element j at lam[j * TVC_BLOCK] (shared memory column of the posting
 // thread): normal(5), tangent-x(5), tangent-y(5), spin, roll-x, roll-y.  warm: apply them before sweeping.
 template <int LS>   // LS: stride between the 18 impulses (TVC_BLOCK for the shared-memory column, 1 for a register array)
 __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, const float R[9], float pz, float &vx,
                                                float &vy, float &vz, float &wx, float &wy, float &wz, float *lam,
-                                               bool warm, int iters) {
+                                               bool warm, int iters PH2_ARG) {
+    PH2_CLK(pc0);
     const float r = c.radius, h = c.half_len;
     const float R31 = R[6], R32 = R[7];
     const float rho = sqrt_fast(R31 * R31 + R32 * R32);
@@ -326,6 +342,7 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
         wy += W12 * lsp + W01 * lr1 + W11 * lr2;
         wz += W22 * lsp + W02 * lr1 + W12 * lr2;
     }
+    PH2_CLK(pc1);
     for (int it = 0; it < iters; it++) {
         float lsum = 0.0f;
 #pragma unroll
@@ -383,6 +400,9 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
 #pragma unroll
     for (int i = 0; i < 5; i++) { lam[i * LS] = ln[i]; lam[(5 + i) * LS] = l1[i]; lam[(10 + i) * LS] = l2[i]; }
     lam[15 * LS] = lsp; lam[16 * LS] = lr1; lam[17 * LS] = lr2;
+#ifdef TVC_PHASE_PROF2
+    { const long long pc2 = clock64(); ph2->setup += (unsigned)(pc1 - pc0); ph2->sweeps += (unsigned)(pc2 - pc1); }
+#endif
 }
 
 // Shared-memory exchange used to compact ground-contact problems across the CTA: each env that needs
@@ -414,6 +434,9 @@ typedef ContactSmemT<TVC_BLOCK> ContactSmem;
 template <int B>
 __device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &e, float Fx, float Fy, float Fz,
                                           float Tx, float Ty, float Tz, bool live, ContactSmemT<B> &sm) {
+#ifdef TVC_PHASE_PROF2
+    Ph2 ph2s = {0u, 0u, 0u}; Ph2 *ph2 = &ph2s;
+#endif
     const float dt = c.dt;
     const float ax_ = Fx * P.inv_mass, ay_ = Fy * P.inv_mass, az_ = Fz * P.inv_mass;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -492,7 +515,7 @@ __device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &
                     float wx = sm.f[8][t], wy = sm.f[9][t], wz = sm.f[10][t];
                     const int ow = sm.owner[t];
                     solve_contacts<B>(c, Q, Rs, sm.f[4][t], vx, vy, vz, wx, wy, wz, &sm.lam[0][ow & 0xFFFF], (ow >> 16) != 0,
-                                   k == 0 ? c.contact_iters : c.warm_iters);
+                                   k == 0 ? c.contact_iters : c.warm_iters PH2_PASS);
                     sm.f[5][t] = vx; sm.f[6][t] = vy; sm.f[7][t] = vz;
                     sm.f[8][t] = wx; sm.f[9][t] = wy; sm.f[10][t] = wz;
                 }
@@ -550,7 +573,7 @@ __device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &
 // or not) so the `need` branch is nearly warp-uniform.
 template <bool LOCKSTEP>   // LOCKSTEP: the CTA's warps re-align at every substep (every thread of the CTA must call this)
 __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P, Env &e, float Fx, float Fy, float Fz,
-                                                 float Tx, float Ty, float Tz) {
+                                                 float Tx, float Ty, float Tz PH2_ARG) {
     const float dt = c.dt;
     const float ax_ = Fx * P.inv_mass, ay_ = Fy * P.inv_mass, az_ = Fz * P.inv_mass;
     float lam[18];
@@ -560,7 +583,11 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
     const float dI = P.inv_Iz - P.inv_Ixy;
     const float far_z = 1.001f * (c.half_len + fabsf(P.cg) + c.radius) + c.margin;
     for (int k = 0; k < c.K; k++) {
+#ifdef TVC_PHASE_PROF2
+        { const long long b0 = clock64(); if (LOCKSTEP) __syncthreads(); ph2->bar += (unsigned)(clock64() - b0); }
+#else
         if (LOCKSTEP) __syncthreads();
+#endif
         // B5 with I = diag(a, a, b): R diag(1/a,1/a,1/b) R^T tau = tau/a + (1/b - 1/a)(e.tau) e, e = body axis in the
         // world frame (third column of R); the k(1+|w|) damping is isotropic.  Only e and the third row of R are needed
         // outside the contact solver.
@@ -591,7 +618,7 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
                 float R[9];
                 quat_to_mat(e.qx, e.qy, e.qz, e.qw, R);
                 solve_contacts<1>(c, P, R, e.pz, e.vx, e.vy, e.vz, e.wx, e.wy, e.wz, lam, have_lam,
-                                  k == 0 ? c.contact_iters : c.warm_iters);
+                                  k == 0 ? c.contact_iters : c.warm_iters PH2_PASS);
                 have_lam = true;
             } else have_lam = false;
         } else have_lam = false;
