@@ -271,6 +271,43 @@ __device__ __forceinline__ int env_at(const DevState &st, int p) {
     return st.order[(long long)lo * TVC_CHUNK + intra];
 }
 
+// The same lookup for the 32 consecutive positions of one group, warp-cooperatively: the lanes probe 32 chunk boundaries
+// per round trip (two rounds for 1,024 chunks instead of ten dependent loads per lane), then every lane walks forward
+// from the chunk of the group's first position.  A group that straddles a class boundary takes the per-lane search.
+__device__ __forceinline__ int env_at_group(const DevState &st, int p, int lane, bool valid) {
+#ifdef TVC_NO_COOP_SEARCH
+    return valid ? env_at(st, p) : 0;
+#else
+    const unsigned full = 0xffffffffu;
+    const int nc = st.nchunks;
+    const int *g0 = st.goff, *g1 = st.goff + (nc + 1), *g2 = st.goff + 2 * (nc + 1);
+    const int T0 = g0[nc], T1 = g1[nc];
+    const int k = p < T0 ? 0 : (p < T0 + T1 ? 1 : 2);
+    const int k0 = __shfl_sync(full, k, 0);
+    if (!__all_sync(full, k == k0 || !valid)) return valid ? env_at(st, p) : 0;
+    const int q = p - (k0 == 0 ? 0 : (k0 == 1 ? T0 : T0 + T1));
+    const int q0 = __shfl_sync(full, q, 0);
+    const int *o = k0 == 0 ? g0 : (k0 == 1 ? g1 : g2);
+    int lo = 0, hi = nc;   // o[lo] <= q0 < o[hi]
+    while (hi - lo > 1) {
+        const int step = (hi - lo + 31) >> 5;
+        int idx = lo + step * (lane + 1);
+        idx = idx > hi ? hi : idx;
+        const int m = __popc(__ballot_sync(full, o[idx] <= q0));   // probes are monotone in the lane index
+        int nlo = lo + step * m, nhi = lo + step * (m + 1);
+        lo = nlo > hi ? hi : nlo;
+        hi = nhi > hi ? hi : nhi;
+    }
+    if (!valid) return 0;
+    int ch = lo, end = o[ch + 1];
+    while (q >= end) { ch++; end = o[ch + 1]; }   // valid positions lie below o[nc]
+    int intra = q - o[ch];
+    if (k0 >= 1) intra += g0[ch + 1] - g0[ch];
+    if (k0 == 2) intra += g1[ch + 1] - g1[ch];
+    return st.order[(long long)ch * TVC_CHUNK + intra];
+#endif
+}
+
 #ifndef TVC_MIN_BLOCKS_V2
 #define TVC_MIN_BLOCKS_V2 4
 #endif
@@ -336,8 +373,8 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
         const long long pt0 = clock64();
         Ph2 ph2s = {0u, 0u, 0u}; Ph2 *ph2 = &ph2s;
 #endif
+        i = env_at_group(st, (int)slot, lane, live);
         if (live) {
-            i = env_at(st, (int)slot);
             gid = c.env_base + i;
             load_env(st, X, i, e);
             float2 a;
