@@ -785,9 +785,10 @@ int tvc_destroy(tvc_handle *h) {
     cudaFree(s.s0); cudaFree(s.s1); cudaFree(s.s2); cudaFree(s.s3); cudaFree(s.s4);
     cudaFree(s.d0); cudaFree(s.d1); cudaFree(s.ring); cudaFree(s.clipb); cudaFree(s.runb); cudaFree(s.hist);
     cudaFree(s.delay); cudaFree(s.partial); cudaFree(s.order); cudaFree(s.goff); cudaFree(s.counter); cudaFree(s.done_list); cudaFree(h->stats_dev);
-    cudaFree(h->io_act); cudaFree(h->io_obs); cudaFree(h->io_rew); cudaFree(h->io_term); cudaFree(h->io_trunc); cudaFree(h->io_final);
+    cudaFree(h->io_act); cudaFree(h->io_obs) /* the obs|reward|flags slab */; cudaFree(h->io_final);
     tvc_rollout_free(h);
     if (h->stats_host) cudaFreeHost(h->stats_host);
+    if (h->act_pinned) cudaFreeHost(h->act_pinned);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return TVC_OK;
@@ -890,14 +891,31 @@ int tvc_step_host(tvc_handle *h, const float *actions_host, float *obs_host, flo
     if (!h->io_obs) {   // one-time staging buffers (not on the steady-state step path)
         int rc;
         if ((rc = dalloc(&h->io_act, 2 * n))) return rc;
-        if ((rc = dalloc(&h->io_obs, 10 * n))) return rc;
-        if ((rc = dalloc(&h->io_rew, n))) return rc;
-        if ((rc = dalloc(&h->io_term, n))) return rc;
-        if ((rc = dalloc(&h->io_trunc, n))) return rc;
+        // obs | reward | terminated | truncated in ONE slab, so that a caller whose host buffers are laid out the same way
+        // gets a single device-to-host copy of 46 bytes per env
+        uint8_t *slab = nullptr;
+        if ((rc = dalloc(&slab, 46 * n))) return rc;
+        h->io_obs = (float *)slab; h->io_rew = (float *)(slab + 40 * n); h->io_term = slab + 44 * n; h->io_trunc = slab + 45 * n;
+    }
+    if (final_obs_host && !h->io_final) {   // only needed for pageable final_obs buffers; allocated up front to keep the path simple
+        int rc;
         if ((rc = dalloc(&h->io_final, 10 * n))) return rc;
     }
     cudaStream_t s = h->own_stream;
-    if (actions_host) CUDA_OK(cudaMemcpyAsync(h->io_act, actions_host, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, s));
+    if (actions_host) {
+        // pinned caller memory goes to the copy engine as it is; pageable memory is staged through the handle's own
+        // pinned buffer first (an asynchronous copy from pageable memory would stage inside the driver anyway)
+        const float *src = actions_host;
+        cudaPointerAttributes at;
+        const bool pinned = cudaPointerGetAttributes(&at, actions_host) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        if (!pinned) {
+            (void)cudaGetLastError();
+            if (!h->act_pinned) CUDA_OK(cudaMallocHost((void **)&h->act_pinned, sizeof(float) * 2 * n));
+            memcpy(h->act_pinned, actions_host, sizeof(float) * 2 * n);
+            src = h->act_pinned;
+        }
+        CUDA_OK(cudaMemcpyAsync(h->io_act, src, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, s));
+    }
     // Final observations exist only for the ~3 % of envs whose episode ended in this step.  When the caller's buffer is
     // pinned (device-mapped) host memory the kernel stores those rows straight into it over PCIe and the dense
     // [N,10] device-to-host copy (40 B per env) disappears; pageable memory takes the staged copy below.
@@ -917,10 +935,15 @@ int tvc_step_host(tvc_handle *h, const float *actions_host, float *obs_host, flo
     }
     int rc = tvc_step(h, actions_host ? h->io_act : nullptr, h->io_obs, h->io_rew, h->io_term, h->io_trunc, final_dev, (tvc_stream)s);
     if (rc) return rc;
-    CUDA_OK(cudaMemcpyAsync(obs_host, h->io_obs, sizeof(float) * 10 * n, cudaMemcpyDeviceToHost, s));
-    CUDA_OK(cudaMemcpyAsync(reward_host, h->io_rew, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
-    CUDA_OK(cudaMemcpyAsync(terminated_host, h->io_term, n, cudaMemcpyDeviceToHost, s));
-    CUDA_OK(cudaMemcpyAsync(truncated_host, h->io_trunc, n, cudaMemcpyDeviceToHost, s));
+    const uint8_t *ob = (const uint8_t *)obs_host;
+    if ((const uint8_t *)reward_host == ob + 40 * n && terminated_host == ob + 44 * n && truncated_host == ob + 45 * n) {
+        CUDA_OK(cudaMemcpyAsync(obs_host, h->io_obs, 46 * n, cudaMemcpyDeviceToHost, s));
+    } else {
+        CUDA_OK(cudaMemcpyAsync(obs_host, h->io_obs, sizeof(float) * 10 * n, cudaMemcpyDeviceToHost, s));
+        CUDA_OK(cudaMemcpyAsync(reward_host, h->io_rew, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
+        CUDA_OK(cudaMemcpyAsync(terminated_host, h->io_term, n, cudaMemcpyDeviceToHost, s));
+        CUDA_OK(cudaMemcpyAsync(truncated_host, h->io_trunc, n, cudaMemcpyDeviceToHost, s));
+    }
     if (final_obs_host && !final_direct) CUDA_OK(cudaMemcpyAsync(final_obs_host, h->io_final, sizeof(float) * 10 * n, cudaMemcpyDeviceToHost, s));
     CUDA_OK(cudaStreamSynchronize(s));
     return TVC_OK;

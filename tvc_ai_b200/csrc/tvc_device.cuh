@@ -95,7 +95,8 @@ enum { ST_DR_A = 1, ST_DR_B = 2, ST_NOISE_A = 3, ST_NOISE_B = 4, ST_ACTION = 5, 
 // generators are single out-of-line copies and the hot path uses short, slow-path-free math:
 //   rcp_fast / sqrt_fast : MUFU.RCP / MUFU.RSQ based, <= 2 ulp, operands are well-scaled positive numbers
 //   sincos_small         : degree-9/8 Taylor polynomials, |x| <= 0.8 rad, error < 4e-8
-// (raw rcp/sqrt/rsqrt.approx.ftz inline PTX was measured too: fewer instructions but 10 % slower end to end)
+// (an earlier build, then bound by instruction fetch, measured raw `asm volatile` rcp/sqrt/rsqrt.approx.ftz 10 % slower;
+//  with the class-ordered sequence the plain-asm single-MUFU rsqrt below is the faster form)
 __device__ __forceinline__ float rcp_fast(float x) { return __fdividef(1.0f, x); }
 // operand known to be a normal number (callers clamp it away from the subnormal range): one MUFU.RSQ, without the
 // subnormal pre/post-scaling rsqrtf() carries

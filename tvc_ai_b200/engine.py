@@ -53,6 +53,7 @@ class BatchedEngine:
         self.final_obs = torch.zeros((n, A.OBS_DIM), dtype=torch.float32, device=dev)
         self._info = None
         self._host = None
+        self._pinned_act = None
         self._stats_dev = torch.zeros(A.NUM_STATS, dtype=torch.float64, device=dev)
 
     # ------------------------------------------------------------------ lifecycle
@@ -147,19 +148,33 @@ class BatchedEngine:
         if self._host is None:
             n = self.n
             pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()  # noqa: E731
-            self._host = dict(act=pin((n, 2), torch.float32), obs=pin((n, 10), torch.float32),
-                              rew=pin((n,), torch.float32), term=pin((n,), torch.uint8),
-                              trunc=pin((n,), torch.uint8), final=pin((n, 10), torch.float32))
+            # obs | reward | terminated | truncated share one pinned slab (46 B per env, the library's own staging
+            # layout): tvc_step_host then needs a single device-to-host copy
+            slab = pin((46 * n,), torch.uint8)
+            self._host = dict(slab=slab,
+                              obs=slab[:40 * n].view(torch.float32).view(n, 10),
+                              rew=slab[40 * n:44 * n].view(torch.float32),
+                              term=slab[44 * n:45 * n], trunc=slab[45 * n:46 * n],
+                              final=pin((n, 10), torch.float32))
         hb = self._host
         ap = None
         if actions_np is not None:
-            hb["act"].numpy()[...] = np.asarray(actions_np, np.float32).reshape(self.n, 2)
-            ap = C.c_void_p(hb["act"].data_ptr())
+            # the library copies straight from pinned memory (e.g. `pinned_actions()`) and stages pageable arrays itself
+            act = np.ascontiguousarray(actions_np, np.float32)
+            if act.size != 2 * self.n:
+                raise ValueError(f"actions must have shape ({self.n}, 2)")
+            ap = C.c_void_p(act.ctypes.data)
         A.check(self.L.tvc_step_host(self.h, ap, C.c_void_p(hb["obs"].data_ptr()), C.c_void_p(hb["rew"].data_ptr()),
                                      C.c_void_p(hb["term"].data_ptr()), C.c_void_p(hb["trunc"].data_ptr()),
                                      C.c_void_p(hb["final"].data_ptr()) if want_final else None), "tvc_step_host")
         return (hb["obs"].numpy(), hb["rew"].numpy(), hb["term"].numpy().view(np.bool_),
                 hb["trunc"].numpy().view(np.bool_), hb["final"].numpy() if want_final else None)
+
+    def pinned_actions(self) -> np.ndarray:
+        """A pinned (page-locked) [N,2] float32 array: actions written here go to the device without a staging copy."""
+        if self._pinned_act is None:
+            self._pinned_act = torch.zeros((self.n, 2), dtype=torch.float32).pin_memory()
+        return self._pinned_act.numpy()
 
     # ------------------------------------------------------------------ state / info / stats
     def get_state(self) -> np.ndarray:

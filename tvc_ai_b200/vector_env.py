@@ -80,6 +80,11 @@ class RocketTVCVectorEnv:
             infos["_final_info"] = done
         return obs, rew, term_b, trunc_b, infos
 
+    def pinned_actions(self) -> np.ndarray:
+        """Pinned [N,2] float32 buffer: a policy that writes its actions here and passes it to `step` avoids the staging
+        copy a pageable array needs (the copy engine reads pinned host memory directly)."""
+        return self.engine.pinned_actions()
+
     def _step_numpy(self, actions):
         if actions.shape != (self.num_envs, 2):
             raise ValueError(f"actions must have shape {(self.num_envs, 2)}, got {actions.shape}")
