@@ -153,7 +153,11 @@ step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState s
 #ifndef TVC_CHUNK
 #define TVC_CHUNK 1024   // envs sorted together (stable partition, near-ground class first)
 #endif
-#define TVC_EPT (TVC_CHUNK / 256)   // envs per classify thread
+#ifndef TVC_CLS_THREADS
+#define TVC_CLS_THREADS 256    // (512 measured equal, 1,024 -- one env per thread -- 3 % slower end to end)
+#endif
+#define TVC_CLS_WARPS (TVC_CLS_THREADS / 32)
+#define TVC_EPT (TVC_CHUNK / TVC_CLS_THREADS)   // envs per classify thread
 
 // Heuristic class of an env for the coming step: 0 = its lowest point touches the ground now (measured: such envs need
 // the contact solve in 9.4 of the 10 substeps), 1 = it may come within reach during the step, 2 = airborne.
@@ -166,32 +170,40 @@ step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState s
 // groups start first.  Deterministic: no atomics on data, the sequence depends on the states only.
 #define TVC_NOW_GAP 0.008f     // class 0: lower bound of the lowest point's height below this
 #define TVC_MAYBE_GAP 0.02f    // class 1: that bound minus the first-order travel over the step below this
-template <bool X>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ int class_of(const DevCfg &c, bool X, float pz, float qx, float qy, float qz, float qw, float vz,
+                                        float wx, float wy, float wz, float cg_off) {
+    if (!c.ground) return 2;
+    const float cg = X ? fabsf(cg_off) + fabsf(c.cg_burn) : 0.0f;
+    const float R31 = 2.0f * (qx * qz - qw * qy), R32 = 2.0f * (qy * qz + qw * qx);
+    const float R33 = 1.0f - 2.0f * (qx * qx + qy * qy);
+    const float hh = c.half_len + cg;
+    const float gmin = pz - fabsf(R33) * hh - c.radius * sqrtf(R31 * R31 + R32 * R32);
+    const float reach = sqrtf(hh * hh + c.radius * c.radius);
+    const float travel = (fabsf(vz) + sqrtf(wx * wx + wy * wy + wz * wz) * reach) * (c.dt * (float)c.K);
+    return gmin < TVC_NOW_GAP ? 0 : (gmin - travel < TVC_MAYBE_GAP ? 1 : 2);
+}
+// FROM_STATE: compute the classes from the state planes (80 B per env; first step, or after a reset / set_state / rollout
+// touched the state behind the step path's back).  Otherwise read the class byte that step_kernel_v2 and
+// reset_done_kernel left for every env at the end of the previous step (1 B per env).
+template <bool X, bool FROM_STATE>
+__global__ void __launch_bounds__(TVC_CLS_THREADS)
 classify_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState st) {
-    __shared__ int wcnt[3][TVC_EPT][8];
-    __shared__ int s_scan[8];
+    __shared__ int wcnt[3][TVC_EPT][TVC_CLS_WARPS];
+    __shared__ int s_scan[TVC_CLS_WARPS];
     __shared__ int s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long base = (long long)blockIdx.x * TVC_CHUNK;
     const int nc = st.nchunks;
     unsigned mask[3][TVC_EPT];
-    const float T = c.dt * (float)c.K;
 #pragma unroll
     for (int j = 0; j < TVC_EPT; j++) {
-        const long long env = base + j * 256 + tid;
+        const long long env = base + j * TVC_CLS_THREADS + tid;
         int cls = 3;
         if (env < st.n) {
-            const float4 p = st.s0[env], q = st.s1[env], v = st.s2[env], w = st.s3[env];
-            const float cg = X ? fabsf(st.d0[env].z) + fabsf(c.cg_burn) : 0.0f;
-            const float R31 = 2.0f * (q.x * q.z - q.w * q.y), R32 = 2.0f * (q.y * q.z + q.w * q.x);
-            const float R33 = 1.0f - 2.0f * (q.x * q.x + q.y * q.y);
-            const float hh = c.half_len + cg;
-            const float gmin = p.z - fabsf(R33) * hh - c.radius * sqrtf(R31 * R31 + R32 * R32);
-            const float reach = sqrtf(hh * hh + c.radius * c.radius);
-            const float travel = (fabsf(v.z) + sqrtf(w.x * w.x + w.y * w.y + w.z * w.z) * reach) * T;
-            cls = gmin < TVC_NOW_GAP ? 0 : (gmin - travel < TVC_MAYBE_GAP ? 1 : 2);
-            if (!c.ground) cls = 2;
+            if (FROM_STATE) {
+                const float4 p = st.s0[env], q = st.s1[env], v = st.s2[env], w = st.s3[env];
+                cls = class_of(c, X, p.z, q.x, q.y, q.z, q.w, v.z, w.x, w.y, w.z, X ? st.d0[env].z : 0.0f);
+            } else cls = st.cls[env];
         }
 #pragma unroll
         for (int k = 0; k < 3; k++) {
@@ -206,15 +218,15 @@ classify_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevSta
 #pragma unroll
         for (int j = 0; j < TVC_EPT; j++)
 #pragma unroll
-            for (int w = 0; w < 8; w++) total[k] += wcnt[k][j][w];
+            for (int w = 0; w < TVC_CLS_WARPS; w++) total[k] += wcnt[k][j][w];
 #pragma unroll
     for (int j = 0; j < TVC_EPT; j++) {
-        const long long env = base + j * 256 + tid;
+        const long long env = base + j * TVC_CLS_THREADS + tid;
         if (env < st.n) {
             const int k = (mask[0][j] >> lane) & 1u ? 0 : ((mask[1][j] >> lane) & 1u ? 1 : 2);
             int before = 0;   // envs of the same class ahead of this warp's 32 in linear order (j, warp, lane)
             for (int jj = 0; jj < TVC_EPT; jj++)
-                for (int w = 0; w < 8; w++)
+                for (int w = 0; w < TVC_CLS_WARPS; w++)
                     if (jj < j || (jj == j && w < warp)) before += wcnt[k][jj][w];
             const unsigned mk = k == 0 ? mask[0][j] : (k == 1 ? mask[1][j] : mask[2][j]);
             const int rank = before + __popc(mk & ((1u << lane) - 1u));
@@ -222,6 +234,7 @@ classify_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevSta
             st.order[base + start + rank] = (int)env;
         }
     }
+    asm volatile("griddepcontrol.launch_dependents;");   // step_kernel_v2 may be scheduled; it waits for this whole grid
     // per-chunk counts, then the last CTA to arrive scans them (threadfence + ticket)
     if (tid < 3) st.goff[tid * (nc + 1) + blockIdx.x + 1] = tid == 0 ? total[0] : (tid == 1 ? total[1] : total[2]);
     __threadfence();
@@ -233,7 +246,7 @@ classify_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevSta
     for (int k = 0; k < 3; k++) {
         volatile int *o = st.goff + k * (nc + 1);
         int carry = 0;
-        for (int t0 = 0; t0 < nc; t0 += 256) {
+        for (int t0 = 0; t0 < nc; t0 += TVC_CLS_THREADS) {
             const int idx = t0 + tid;
             int v = idx < nc ? o[idx + 1] : 0;
 #pragma unroll
@@ -242,7 +255,7 @@ classify_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevSta
             __syncthreads();
             int wbase = 0, tile = 0;
 #pragma unroll
-            for (int w = 0; w < 8; w++) { const int sv = s_scan[w]; if (w < warp) wbase += sv; tile += sv; }
+            for (int w = 0; w < TVC_CLS_WARPS; w++) { const int sv = s_scan[w]; if (w < warp) wbase += sv; tile += sv; }
             if (idx < nc) o[idx + 1] = carry + wbase + v;
             carry += tile;
             __syncthreads();
@@ -325,6 +338,8 @@ __device__ __forceinline__ int env_at_group(const DevState &st, int p, int lane,
 template <bool X, int DIV, bool DEFER>
 __global__ void __launch_bounds__(TVC_V2_BLOCK, TVC_MIN_BLOCKS_V2)
 step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevState st, const __grid_constant__ DevIO io) {
+    // launched with programmatic stream serialization: everything above this line may overlap classify_kernel's tail
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
     const int ngroups = (int)((st.n + 31) / 32);
@@ -433,6 +448,7 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
                 }
             }
             store_env(st, X, i, e);
+            st.cls[i] = (uint8_t)class_of(c, X, e.pz, e.qx, e.qy, e.qz, e.qw, e.vz, e.wx, e.wy, e.wz, e.cg_off);   // for the next step's sort
             float2 *o2 = reinterpret_cast<float2 *>(io.obs + 10 * i);
 #pragma unroll
             for (int k = 0; k < 5; k++) o2[k] = make_float2(r.obs[2 * k], r.obs[2 * k + 1]);
@@ -524,6 +540,7 @@ reset_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState 
 template <bool X>
 __global__ void __launch_bounds__(TVC_BLOCK)
 reset_done_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState st, float *obs) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic dependent launch behind step_kernel_v2
     const unsigned nd = st.counter[2];
     for (unsigned k = blockIdx.x * TVC_BLOCK + threadIdx.x; k < nd; k += gridDim.x * TVC_BLOCK) {
         const long long i = st.done_list[k];
@@ -532,6 +549,7 @@ reset_done_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevS
         load_env(st, X, i, e);
         reset_env(c, X, gid, e, false);
         store_env(st, X, i, e);
+        st.cls[i] = (uint8_t)class_of(c, X, e.pz, e.qx, e.qy, e.qz, e.qw, e.vz, e.wx, e.wy, e.wz, e.cg_off);
         float o[10];
         build_obs(c, X, gid, e, 0, o);
         float2 *o2 = reinterpret_cast<float2 *>(obs + 10 * i);
@@ -637,6 +655,20 @@ const char *tvc_set_err(const std::string &m) { g_err = m; return g_err.c_str();
             return TVC_E_CUDA;                                                                     \
         }                                                                                          \
     } while (0)
+
+// Launch with the programmatic-stream-serialization attribute: the kernel may be scheduled while its predecessor in the
+// stream drains; it calls griddepcontrol.wait before touching anything the predecessor wrote.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_dep(void (*kernel)(KArgs...), int grid, int block, cudaStream_t s, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 
 static void make_devcfg(const tvc_config &c, DevCfg &d) {
     memset(&d, 0, sizeof(d));
@@ -761,6 +793,7 @@ int tvc_create(const tvc_config *cfg, int device, int64_t num_envs, tvc_handle *
     TRY(dalloc(&s.goff, (size_t)3 * (s.nchunks + 1)));
     TRY(dalloc(&s.counter, (size_t)4));
     TRY(dalloc(&s.done_list, n));
+    TRY(dalloc(&s.cls, n));
     TRY(dalloc(&h->stats_dev, (size_t)TVC_NSTAT));
     {
         cudaError_t e = cudaMallocHost((void **)&h->stats_host, sizeof(double) * TVC_NSTAT);
@@ -784,7 +817,7 @@ int tvc_destroy(tvc_handle *h) {
     DevState &s = h->st;
     cudaFree(s.s0); cudaFree(s.s1); cudaFree(s.s2); cudaFree(s.s3); cudaFree(s.s4);
     cudaFree(s.d0); cudaFree(s.d1); cudaFree(s.ring); cudaFree(s.clipb); cudaFree(s.runb); cudaFree(s.hist);
-    cudaFree(s.delay); cudaFree(s.partial); cudaFree(s.order); cudaFree(s.goff); cudaFree(s.counter); cudaFree(s.done_list); cudaFree(h->stats_dev);
+    cudaFree(s.delay); cudaFree(s.partial); cudaFree(s.order); cudaFree(s.goff); cudaFree(s.counter); cudaFree(s.done_list); cudaFree(s.cls); cudaFree(h->stats_dev);
     cudaFree(h->io_act); cudaFree(h->io_obs) /* the obs|reward|flags slab */; cudaFree(h->io_final);
     tvc_rollout_free(h);
     if (h->stats_host) cudaFreeHost(h->stats_host);
@@ -804,6 +837,7 @@ int tvc_reset(tvc_handle *h, const uint8_t *mask_dev, uint64_t seed, float *obs_
     if (h->cur.contract == TVC_CONTRACT_X) reset_kernel<true><<<h->grid, TVC_BLOCK, 0, s>>>(h->dc, h->st, mask_dev, obs_out_dev, 0);
     else reset_kernel<false><<<h->grid, TVC_BLOCK, 0, s>>>(h->dc, h->st, mask_dev, obs_out_dev, 0);
     LAUNCH_OK("reset_kernel");
+    h->cls_valid = false;
     return TVC_OK;
 }
 
@@ -821,9 +855,15 @@ static int launch_step(tvc_handle *h, const DevIO &io, cudaStream_t s) {
         LAUNCH_OK("step_kernel");
     } else {
         const int cgrid = h->st.nchunks;
-        if (X) classify_kernel<true><<<cgrid, 256, 0, s>>>(h->dc, h->st);
-        else classify_kernel<false><<<cgrid, 256, 0, s>>>(h->dc, h->st);
+        if (!h->cls_valid) {   // the class bytes do not describe the current state: classify from the state planes
+            if (X) classify_kernel<true, true><<<cgrid, TVC_CLS_THREADS, 0, s>>>(h->dc, h->st);
+            else classify_kernel<false, true><<<cgrid, TVC_CLS_THREADS, 0, s>>>(h->dc, h->st);
+        } else {
+            if (X) classify_kernel<true, false><<<cgrid, TVC_CLS_THREADS, 0, s>>>(h->dc, h->st);
+            else classify_kernel<false, false><<<cgrid, TVC_CLS_THREADS, 0, s>>>(h->dc, h->st);
+        }
         LAUNCH_OK("classify_kernel");
+        h->cls_valid = true;   // the step kernel (and reset_done_kernel) leave fresh class bytes behind
         if (h->v2_grid == 0) {   // persistent grid: resident CTAs of the v2 kernel, capped by the number of groups
             int per_sm = 0;
             cudaError_t e = X ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_v2<true, 1, true>, TVC_V2_BLOCK, 0)
@@ -833,12 +873,13 @@ static int launch_step(tvc_handle *h, const DevIO &io, cudaStream_t s) {
             const int wpb = TVC_V2_BLOCK / 32;
             const int ctas = (h->ngroups + wpb - 1) / wpb;
             // small batches (every group resident at once): finished envs are reset in place -> two launches per step
+            { const char *p = getenv("TVC_PDL"); h->pdl = !(p && p[0] == '0'); }   // diagnostics: TVC_PDL=0 launches plainly
             const char *force = getenv("TVC_STEP_DEFER");   // tests / diagnostics: 0 or 1 overrides the choice
             h->v2_defer = force ? (force[0] == '1') : (ctas > cap);
             const int want = h->ngroups <= cap ? h->ngroups : ctas;
             h->v2_grid = want < cap ? want : cap;
         }
-#define GO(XX, DD, FF) step_kernel_v2<XX, DD, FF><<<h->v2_grid, TVC_V2_BLOCK, 0, s>>>(h->dc, h->st, io)
+#define GO(XX, DD, FF) (void)launch_dep(step_kernel_v2<XX, DD, FF>, h->v2_grid, TVC_V2_BLOCK, s, h->pdl, h->dc, h->st, io)
 #define GO3(FF) do { \
         if (X) { if (dv == 0) GO(true, 0, FF); else if (dv == 1) GO(true, 1, FF); else GO(true, 2, FF); } \
         else   { if (dv == 0) GO(false, 0, FF); else if (dv == 1) GO(false, 1, FF); else GO(false, 2, FF); } } while (0)
@@ -848,8 +889,8 @@ static int launch_step(tvc_handle *h, const DevIO &io, cudaStream_t s) {
         if (defer) {   // deferred same-step autoreset of the envs the step kernel listed
             const int want = (int)((h->n / 16 + TVC_BLOCK - 1) / TVC_BLOCK) + 1;
             const int rgrid = want < 2 * h->num_sms ? want : 2 * h->num_sms;
-            if (X) reset_done_kernel<true><<<rgrid, TVC_BLOCK, 0, s>>>(h->dc, h->st, io.obs);
-            else reset_done_kernel<false><<<rgrid, TVC_BLOCK, 0, s>>>(h->dc, h->st, io.obs);
+            if (X) (void)launch_dep(reset_done_kernel<true>, rgrid, TVC_BLOCK, s, h->pdl, h->dc, h->st, io.obs);
+            else (void)launch_dep(reset_done_kernel<false>, rgrid, TVC_BLOCK, s, h->pdl, h->dc, h->st, io.obs);
             LAUNCH_OK("reset_done_kernel");
         }
 #undef GO3
@@ -968,6 +1009,7 @@ int tvc_set_state(tvc_handle *h, const void *dev_blob, size_t bytes, tvc_stream 
     if (h->cur.contract == TVC_CONTRACT_X) set_state_kernel<true><<<g, 128, 0, (cudaStream_t)stream>>>(h->st, (const tvc_env_state *)dev_blob, TVC_MAX_DELAY);
     else set_state_kernel<false><<<g, 128, 0, (cudaStream_t)stream>>>(h->st, (const tvc_env_state *)dev_blob, 0);
     LAUNCH_OK("set_state_kernel");
+    h->cls_valid = false;
     return TVC_OK;
 }
 
@@ -1021,6 +1063,7 @@ int tvc_set_curriculum(tvc_handle *h, const tvc_stage_conditions *c) {
     n.seed = h->cur.seed;
     h->cur = n;
     make_devcfg(h->cur, h->dc);
+    h->cls_valid = false;
     return TVC_OK;
 }
 

@@ -54,6 +54,7 @@ struct DevState {
     unsigned *counter;  // [0] work-queue head of step_kernel_v2 (zeroed by classify_kernel), [1] classify_kernel's ticket,
                         // [2] length of done_list (zeroed by classify_kernel)
     int *done_list;     // [N] envs whose episode ended in this step (step_kernel_v2 appends, reset_done_kernel consumes)
+    uint8_t *cls;       // [N] class of every env for the NEXT step's sort (written at the end of a step)
     int nchunks;
     long long n;
 };
