@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(TVC_CLS_THREADS)
 classify_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState st) {
     __shared__ int wcnt[3][TVC_EPT][TVC_CLS_WARPS];
     __shared__ int s_scan[TVC_CLS_WARPS];
+    __shared__ int s_pre[3][32], s_tot[3];
     __shared__ int s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long base = (long long)blockIdx.x * TVC_CHUNK;
@@ -212,33 +213,35 @@ classify_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevSta
         }
     }
     __syncthreads();
-    int total[3] = {0, 0, 0};
+    // exclusive prefix of the 32 (j, warp) counts of each class: warp k scans class k (TVC_CHUNK / 32 == 32 entries)
+    static_assert(TVC_EPT * TVC_CLS_WARPS == 32, "one warp scans the per-warp counts of a chunk");
+    if (warp < 3) {
+        const int cnt = wcnt[warp][lane / TVC_CLS_WARPS][lane % TVC_CLS_WARPS];
+        int v = cnt;
 #pragma unroll
-    for (int k = 0; k < 3; k++)
-#pragma unroll
-        for (int j = 0; j < TVC_EPT; j++)
-#pragma unroll
-            for (int w = 0; w < TVC_CLS_WARPS; w++) total[k] += wcnt[k][j][w];
+        for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += u; }
+        s_pre[warp][lane] = v - cnt;
+        if (lane == 31) {
+            s_tot[warp] = v;
+            st.goff[warp * (nc + 1) + blockIdx.x + 1] = v;   // per-chunk count; the last CTA to arrive scans them
+            __threadfence();
+        }
+    }
+    __syncthreads();
+    const int t0c = s_tot[0], t1c = s_tot[1];
 #pragma unroll
     for (int j = 0; j < TVC_EPT; j++) {
         const long long env = base + j * TVC_CLS_THREADS + tid;
         if (env < st.n) {
             const int k = (mask[0][j] >> lane) & 1u ? 0 : ((mask[1][j] >> lane) & 1u ? 1 : 2);
-            int before = 0;   // envs of the same class ahead of this warp's 32 in linear order (j, warp, lane)
-            for (int jj = 0; jj < TVC_EPT; jj++)
-                for (int w = 0; w < TVC_CLS_WARPS; w++)
-                    if (jj < j || (jj == j && w < warp)) before += wcnt[k][jj][w];
             const unsigned mk = k == 0 ? mask[0][j] : (k == 1 ? mask[1][j] : mask[2][j]);
-            const int rank = before + __popc(mk & ((1u << lane) - 1u));
-            const int start = k == 0 ? 0 : (k == 1 ? total[0] : total[0] + total[1]);
+            // envs of the same class ahead of this one in linear order (j, warp, lane)
+            const int rank = s_pre[k][j * TVC_CLS_WARPS + warp] + __popc(mk & ((1u << lane) - 1u));
+            const int start = k == 0 ? 0 : (k == 1 ? t0c : t0c + t1c);
             st.order[base + start + rank] = (int)env;
         }
     }
     asm volatile("griddepcontrol.launch_dependents;");   // step_kernel_v2 may be scheduled; it waits for this whole grid
-    // per-chunk counts, then the last CTA to arrive scans them (threadfence + ticket)
-    if (tid < 3) st.goff[tid * (nc + 1) + blockIdx.x + 1] = tid == 0 ? total[0] : (tid == 1 ? total[1] : total[2]);
-    __threadfence();
-    __syncthreads();
     if (tid == 0) s_last = (atomicAdd(&st.counter[1], 1u) == gridDim.x - 1);
     __syncthreads();
     if (!s_last) return;
