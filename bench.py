@@ -52,12 +52,28 @@ def _bf16_peak():
         return 1400.0
 
 
-def _traffic():
-    """dram bytes per launch of the step kernel from the committed ncu --set full capture, or None."""
+def _issue_roofline(ms, clocks):
+    """Second roofline of the step path: warp-instructions issued per clock and SM sub-partition (count from the committed
+    ncu capture, time and clock measured live) against the issue limit of 1.0 and the measured FP32 ceilings."""
+    wi = _traffic("warp_instructions_per_step")
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    if not wi:
+        return None
+    ipc = wi / (148 * 4 * ms * 1e-3 * mhz * 1e6)
+    return {"bound": "issue", "achieved": ipc, "peak": 1.0, "unit": "warp-instructions/clk/SM sub-partition", "frac": ipc,
+            "warp_instructions_per_step": wi,
+            "fp32_ceilings": {"ffma_three_register_sources": 0.65, "ffma_two_shared_sources": 0.93,
+                              "source": "tools/micro/fp32_rate.cu on this pool's B200 (profiles/r01_fp32_rate_microbench.txt)"},
+            "note": "the PGS sweeps (30 % of the instructions) run at 0.57-0.66 with four solver warps per sub-partition, i.e. at the "
+                    "three-register-source FFMA rate; the remainder is dependent-issue / memory latency"}
+
+
+def _traffic(key="dram_bytes_per_launch"):
+    """A per-launch figure of the step path from the committed ncu --set full capture (DRAM bytes, warp-instructions), or None."""
     p = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("dram_bytes_per_launch")
+            return json.load(open(p)).get(key)
         except Exception:  # noqa: BLE001
             return None
     return None
@@ -363,7 +379,10 @@ def run_ours(args):
                          "traffic": _traffic(), "peak_source": peak_src,
                          "kernel": "step_kernel_v2<X=true,DIV=fast> (+ classify_kernel and reset_done_kernel)",
                          "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP_X,
-                         "note": "instruction-bound (contact PGS chain, 50 % of issue slots); see DESIGN.md section 6 and profiles/"},
+                         "note": "not DRAM-bound (ncu: 8 % of DRAM throughput): ~7,000 thread-instructions per env-step; the in-contact "
+                                 "quarter of the envs runs FP32-pipe-bound PGS sweeps, the rest is latency-bound; see issue_roofline, "
+                                 "DESIGN.md section 6 and profiles/"},
+            "issue_roofline": _issue_roofline(ms, clocks),
             "gpu_launches": launches,
             "clocks": clocks,
             "region_wall_ms": 1e3 * wall,
