@@ -416,6 +416,42 @@ def test_vector_env_numpy_and_torch_paths(lib_built):
     v.close()
 
 
+def test_host_buffer_paths_equal_device_path(lib_built):
+    """tvc_step_host takes three routes depending on the caller's memory: pinned or pageable action buffers, one
+    obs|reward|flags slab or four separate result buffers, final observations stored by the kernel straight into
+    pinned host memory or staged through a device buffer.  Every route must return what the device-pointer path
+    returns, bit for bit (100,000 envs -> deferred autoreset plan, 70 steps: contact, terminations, resets)."""
+    import ctypes as C
+    from tvc_ai_b200 import _abi as A
+    n, steps = 100_000, 70
+    dev_eng = _engine(n, A.CONTRACT_X, autoreset=1)
+    pin_eng = _engine(n, A.CONTRACT_X, autoreset=1)      # pinned actions, slab results, zero-copy final rows
+    pag_eng = _engine(n, A.CONTRACT_X, autoreset=1)      # pageable actions, separate pageable result buffers
+    for e in (dev_eng, pin_eng, pag_eng):
+        e.reset()
+    pinned_act = pin_eng.pinned_actions()
+    o2, r2 = np.zeros((n, 10), np.float32), np.zeros(n, np.float32)
+    t2, tr2, f2 = np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.zeros((n, 10), np.float32)
+    ptr = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+    ended = 0
+    for t in range(steps):
+        a = np.random.default_rng(1000 + t).uniform(-1, 1, (n, 2)).astype(np.float32)
+        od, rd, td, trd = dev_eng.step(torch.from_numpy(a).cuda(), want_final=True)
+        od, rd, td, trd, fd = od.cpu().numpy(), rd.cpu().numpy(), td.cpu().numpy(), trd.cpu().numpy(), dev_eng.final_obs.cpu().numpy()
+        pinned_act[...] = a
+        o1, r1, t1, tr1, f1 = pin_eng.step_host(pinned_act, want_final=True)
+        A.check(pag_eng.L.tvc_step_host(pag_eng.h, ptr(a), ptr(o2), ptr(r2), ptr(t2), ptr(tr2), ptr(f2)), "tvc_step_host")
+        done = (td | trd).astype(bool)
+        ended += int(done.sum())
+        for name, (o, r, te, tr, f) in (("pinned", (o1, r1, t1.view(np.uint8), tr1.view(np.uint8), f1)), ("pageable", (o2, r2, t2, tr2, f2))):
+            assert np.array_equal(o, od) and np.array_equal(r, rd), f"step {t}: {name} host path differs (obs / reward)"
+            assert np.array_equal(te, td) and np.array_equal(tr, trd), f"step {t}: {name} host path differs (flags)"
+            assert np.array_equal(f[done], fd[done]), f"step {t}: {name} host path differs (final observations)"
+    assert ended > 5000
+    for e in (dev_eng, pin_eng, pag_eng):
+        e.close()
+
+
 def test_edge_sizes_and_argument_checks(lib_built):
     """Ragged and extreme batch sizes (1, 31, 33, 129 envs; 2^20 envs), NULL-output rejection, mask reset."""
     from tvc_ai_b200 import _abi as A
