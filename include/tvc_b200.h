@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TVC_ABI_VERSION 5
+#define TVC_ABI_VERSION 6
 
 #define TVC_OBS_DIM 10
 #define TVC_ACT_DIM 2
@@ -196,6 +196,12 @@ int tvc_step_ex(tvc_handle *h, const tvc_step_io *io, tvc_stream stream);
  * This is the end-to-end call the Python VectorEnv facade makes for numpy inputs. */
 int tvc_step_host(tvc_handle *h, const float *actions_host, float *obs_host, float *reward_host,
                   uint8_t *terminated_host, uint8_t *truncated_host, float *final_obs_host);
+/* The same call split in two: enqueue (copies and kernels go to the handle's own stream, nothing is waited for; the
+ * host buffers must stay untouched until the sync) and wait.  Several handles -- env slabs of one VectorEnv -- enqueued
+ * back to back overlap one slab's device-to-host copy with the next slab's kernels (RocketTVCHostPipelineEnv). */
+int tvc_step_host_async(tvc_handle *h, const float *actions_host, float *obs_host, float *reward_host,
+                        uint8_t *terminated_host, uint8_t *truncated_host, float *final_obs_host);
+int tvc_host_sync(tvc_handle *h);
 
 /* Fused rollout: T env steps per launch with the SAC actor MLP evaluated inside the loop
  * (replaces train.py:546-603's get_action -> step loop for the legacy 2x256 actor). */

@@ -452,6 +452,42 @@ def test_host_buffer_paths_equal_device_path(lib_built):
         e.close()
 
 
+def test_host_pipeline_env_equals_single_engine(lib_built):
+    """RocketTVCHostPipelineEnv (env slabs with their own handles and streams, asynchronous host steps) returns the
+    trajectories of one engine over all envs, bit for bit, for 1, 2 and 3 (ragged) slabs; its statistics add up."""
+    from tvc_ai_b200 import _abi as A
+    from tvc_ai_b200.vector_env import RocketTVCHostPipelineEnv
+    n, steps = 20_000, 60
+    ref = _engine(n, A.CONTRACT_X, autoreset=1)
+    ref.reset(seed=7)
+    want = []
+    for t in range(steps):
+        a = np.random.default_rng(50 + t).uniform(-1, 1, (n, 2)).astype(np.float32)
+        o, r, te, tr = ref.step(torch.from_numpy(a).cuda(), want_final=True)
+        want.append((o.cpu().numpy(), r.cpu().numpy(), te.cpu().numpy().astype(bool), tr.cpu().numpy().astype(bool),
+                     ref.final_obs.cpu().numpy()))
+    sref = ref.stats()
+    ref.close()
+    for slabs in (1, 2, 3):
+        env = RocketTVCHostPipelineEnv(n, config={}, contract="X", slabs=slabs)
+        assert sum(hi - lo for lo, hi in env._ranges) == n
+        env.reset(seed=7)
+        buf = env.pinned_actions()
+        for t in range(steps):
+            buf[...] = np.random.default_rng(50 + t).uniform(-1, 1, (n, 2)).astype(np.float32)
+            o, r, te, tr, infos = env.step(buf)
+            wo, wr, wte, wtr, wf = want[t]
+            assert np.array_equal(o, wo) and np.array_equal(r, wr) and np.array_equal(te, wte) and np.array_equal(tr, wtr), \
+                f"{slabs} slabs, step {t}: pipelined host env differs from the single engine"
+            d = wte | wtr
+            if d.any():
+                assert np.array_equal(infos["_final_observation"], d) and np.array_equal(infos["final_observation"][d], wf[d])
+        st = env.episode_stats()
+        idx = [0, 3, 4, 5, 6, 7, 8, 9, 10, 14]
+        assert [st[A.STAT_NAMES[i]] for i in idx] == [sref[i] for i in idx]
+        env.close()
+
+
 def test_edge_sizes_and_argument_checks(lib_built):
     """Ragged and extreme batch sizes (1, 31, 33, 129 envs; 2^20 envs), NULL-output rejection, mask reset."""
     from tvc_ai_b200 import _abi as A

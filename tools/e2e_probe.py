@@ -34,3 +34,18 @@ timeit("engine.step_host(None, want_final=False)", lambda k: eng.step_host(None,
 def dev_step(k):
     eng.step(pool[k % 8], want_final=False); torch.cuda.synchronize()
 timeit("engine.step(device actions) + sync", dev_step)
+
+# slab-pipelined host env
+from tvc_ai_b200.vector_env import RocketTVCHostPipelineEnv
+venv.close()
+for slabs in (1, 2, 3, 4):
+    env = RocketTVCHostPipelineEnv(n, config={}, contract="X", device=0, slabs=slabs)
+    env.reset(seed=42)
+    for e_, (lo, hi) in zip(env.engines, env._ranges):
+        for b in range(400):
+            e_.step(pool[b % 8][lo:hi].contiguous(), want_final=False)
+    torch.cuda.synchronize()
+    buf = env.pinned_actions()
+    buf[...] = acts[0]
+    timeit(f"RocketTVCHostPipelineEnv(slabs={slabs}).step(pinned)", lambda k: env.step(buf))
+    env.close()

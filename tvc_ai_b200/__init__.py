@@ -9,7 +9,7 @@ Importing the package does not need a GPU; constructing an env does (no CPU fall
 from . import _abi  # noqa: F401
 from ._abi import CONTRACT_R, CONTRACT_X  # noqa: F401
 
-__all__ = ["EnhancedRocketTVCEnv", "MissionPhase", "RocketTVCVectorEnv", "BatchedEngine", "CurriculumManager",
+__all__ = ["EnhancedRocketTVCEnv", "MissionPhase", "RocketTVCVectorEnv", "RocketTVCHostPipelineEnv", "BatchedEngine", "CurriculumManager",
            "make_training_env", "make_evaluation_env", "make_debug_env", "CONTRACT_R", "CONTRACT_X"]
 
 
@@ -21,6 +21,9 @@ def __getattr__(name):
     if name == "RocketTVCVectorEnv":
         from .vector_env import RocketTVCVectorEnv
         return RocketTVCVectorEnv
+    if name == "RocketTVCHostPipelineEnv":
+        from .vector_env import RocketTVCHostPipelineEnv
+        return RocketTVCHostPipelineEnv
     if name == "BatchedEngine":
         from .engine import BatchedEngine
         return BatchedEngine

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TVC_B200_LIB") or os.path.join(_HERE, "libtvc_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 OBS_DIM, ACT_DIM, NUM_COMPONENTS, NUM_STATS, MAX_DELAY = 10, 2, 12, 16, 4
 CONTRACT_R, CONTRACT_X = 0, 1
 DIV_OFF, DIV_FAST, DIV_EXACT = 0, 1, 2
@@ -26,7 +26,7 @@ STAT_NAMES = ("episodes", "sum_return", "sum_return_sq", "sum_length", "successe
               "sum_final_altitude", "sum_final_tilt", "sum_fuel_left", "steps", "reserved")
 
 EXPORTS = ("tvc_abi_version", "tvc_last_error", "tvc_config_default", "tvc_create", "tvc_destroy", "tvc_reset",
-           "tvc_step", "tvc_step_ex", "tvc_step_host", "tvc_rollout", "tvc_state_bytes", "tvc_get_state",
+           "tvc_step", "tvc_step_ex", "tvc_step_host", "tvc_step_host_async", "tvc_host_sync", "tvc_rollout", "tvc_state_bytes", "tvc_get_state",
            "tvc_set_state", "tvc_read_info", "tvc_episode_stats", "tvc_episode_stats_dev", "tvc_set_curriculum",
            "tvc_get_config", "tvc_num_envs", "tvc_lifetime_steps")
 
@@ -112,6 +112,8 @@ def load(path: str | None = None):
     L.tvc_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.tvc_step_ex.argtypes = [vp, C.POINTER(TvcStepIO), vp]
     L.tvc_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.tvc_step_host_async.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.tvc_host_sync.argtypes = [vp]
     L.tvc_rollout.argtypes = [vp, C.POINTER(TvcActorWeights), i32, C.POINTER(TvcRolloutIO), vp]
     L.tvc_state_bytes.argtypes = [vp]
     L.tvc_state_bytes.restype = C.c_size_t

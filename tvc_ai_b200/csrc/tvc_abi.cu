@@ -927,11 +927,27 @@ int tvc_step(tvc_handle *h, const float *actions_dev, float *obs_dev, float *rew
     return tvc_step_ex(h, &u, stream);
 }
 
+int tvc_host_sync(tvc_handle *h) {
+    CHECK_H(h);
+    CUDA_OK(cudaStreamSynchronize(h->own_stream));
+    h->host_pending = false;
+    return TVC_OK;
+}
+
 int tvc_step_host(tvc_handle *h, const float *actions_host, float *obs_host, float *reward_host, uint8_t *terminated_host,
                   uint8_t *truncated_host, float *final_obs_host) {
+    int rc = tvc_step_host_async(h, actions_host, obs_host, reward_host, terminated_host, truncated_host, final_obs_host);
+    if (rc) return rc;
+    return tvc_host_sync(h);
+}
+
+int tvc_step_host_async(tvc_handle *h, const float *actions_host, float *obs_host, float *reward_host, uint8_t *terminated_host,
+                        uint8_t *truncated_host, float *final_obs_host) {
     CHECK_H(h);
     if (!obs_host || !reward_host || !terminated_host || !truncated_host) { tvc_set_err("tvc_step_host: NULL output"); return TVC_E_BADARG; }
     const size_t n = (size_t)h->n;
+    if (h->host_pending) CUDA_OK(cudaStreamSynchronize(h->own_stream));   // a second enqueue without tvc_host_sync: drain first
+    h->host_pending = true;
     if (!h->io_obs) {   // one-time staging buffers (not on the steady-state step path)
         int rc;
         if ((rc = dalloc(&h->io_act, 2 * n))) return rc;
@@ -989,7 +1005,6 @@ int tvc_step_host(tvc_handle *h, const float *actions_host, float *obs_host, flo
         CUDA_OK(cudaMemcpyAsync(truncated_host, h->io_trunc, n, cudaMemcpyDeviceToHost, s));
     }
     if (final_obs_host && !final_direct) CUDA_OK(cudaMemcpyAsync(final_obs_host, h->io_final, sizeof(float) * 10 * n, cudaMemcpyDeviceToHost, s));
-    CUDA_OK(cudaStreamSynchronize(s));
     return TVC_OK;
 }
 

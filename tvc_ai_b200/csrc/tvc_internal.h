@@ -28,6 +28,7 @@ struct tvc_handle {
     // staging for tvc_step_host
     float *io_act = nullptr, *io_obs = nullptr, *io_rew = nullptr, *io_final = nullptr;
     uint8_t *io_term = nullptr, *io_trunc = nullptr;
+    bool host_pending = false;                // tvc_step_host_async enqueued, tvc_host_sync not yet called
     float *act_pinned = nullptr;              // pinned staging for pageable action buffers (tvc_step_host)
     const float *final_host_seen = nullptr;   // last final_obs_host pointer classified by tvc_step_host
     float *final_host_dev = nullptr;          // its device alias when it is pinned (mapped) host memory, else NULL

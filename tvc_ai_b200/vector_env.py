@@ -9,6 +9,7 @@ call); torch CUDA in -> torch CUDA out, zero-copy views of the engine's buffers.
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Optional
 
 import numpy as np
@@ -135,3 +136,77 @@ class RocketTVCVectorEnv:
             self.close()
         except Exception:  # noqa: BLE001
             pass
+
+
+class RocketTVCHostPipelineEnv:
+    """The numpy (host-buffer) side of `RocketTVCVectorEnv` for large batches, pipelined over env slabs.
+
+    The envs are split into `slabs` contiguous slabs, each with its own engine (handle, state, stream; `env_id_base`
+    keeps the global env ids, so the trajectories are those of one big engine, bit for bit).  `step()` enqueues every
+    slab's host step (`tvc_step_host_async`: H2D of its actions, kernels, D2H of its results) and then waits for all of
+    them: the copy engines move slab k's results to the host while the SMs step slab k+1.  Results land in pinned arrays
+    owned by this object and are returned as views (valid until the next step), Gymnasium `VectorEnv.step` shapes.
+    """
+
+    def __init__(self, num_envs: int, config: Optional[dict] = None, max_episode_steps: int = 1000,
+                 contract: str | int = "X", device: Optional[int] = None, env_id_base: int = 0, slabs: int = 2,
+                 **engine_over):
+        if isinstance(contract, str):
+            contract = {"R": A.CONTRACT_R, "X": A.CONTRACT_X}[contract.upper()]
+        self.num_envs = int(num_envs)
+        slabs = max(1, min(int(slabs), self.num_envs))
+        edges = [round(k * self.num_envs / slabs) for k in range(slabs + 1)]
+        self._ranges = [(edges[k], edges[k + 1]) for k in range(slabs) if edges[k + 1] > edges[k]]
+        self.engines = [BatchedEngine(hi - lo, engine_config_from_yaml(config, contract, max_episode_steps, autoreset=1,
+                                                                       env_id_base=int(env_id_base) + lo, **engine_over),
+                                      device=device) for lo, hi in self._ranges]
+        self.single_observation_space = spaces.observation_space()
+        self.single_action_space = spaces.action_space()
+        self.observation_space = spaces.batch_space(self.single_observation_space, self.num_envs)
+        self.action_space = spaces.batch_space(self.single_action_space, self.num_envs)
+        n = self.num_envs
+        pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()  # noqa: E731
+        self._t = dict(act=pin((n, 2), torch.float32), obs=pin((n, 10), torch.float32), rew=pin((n,), torch.float32),
+                       term=pin((n,), torch.uint8), trunc=pin((n,), torch.uint8), final=pin((n, 10), torch.float32))
+        self._np = {k: v.numpy() for k, v in self._t.items()}
+        self.closed = False
+
+    def pinned_actions(self) -> np.ndarray:
+        """Pinned [N,2] float32 buffer; pass it to `step` after writing the actions into it (no staging copy)."""
+        return self._np["act"]
+
+    def reset(self, *, seed: Optional[int] = None, options: Optional[dict] = None):
+        obs = self._np["obs"]
+        for eng, (lo, hi) in zip(self.engines, self._ranges):
+            obs[lo:hi] = eng.reset(seed=int(seed) if seed is not None else 0).cpu().numpy()
+        return obs.copy(), {}
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, np.float32)
+        if a.shape != (self.num_envs, 2):
+            raise ValueError(f"actions must have shape {(self.num_envs, 2)}, got {a.shape}")
+        b = self._np
+        vp = lambda arr, lo: C.c_void_p(arr.ctypes.data + lo * arr.strides[0])  # noqa: E731
+        for eng, (lo, hi) in zip(self.engines, self._ranges):
+            A.check(eng.L.tvc_step_host_async(eng.h, vp(a, lo), vp(b["obs"], lo), vp(b["rew"], lo), vp(b["term"], lo),
+                                              vp(b["trunc"], lo), vp(b["final"], lo)), "tvc_step_host_async")
+        for eng in self.engines:
+            A.check(eng.L.tvc_host_sync(eng.h), "tvc_host_sync")
+        term, trunc = b["term"].view(np.bool_), b["trunc"].view(np.bool_)
+        done = term | trunc
+        infos = {"final_observation": b["final"], "_final_observation": done} if done.any() else {}
+        return b["obs"], b["rew"], term, trunc, infos
+
+    def episode_stats(self, reset_after: bool = False) -> dict:
+        s = sum(eng.stats(reset_after) for eng in self.engines)
+        return dict(zip(A.STAT_NAMES, s.tolist()))
+
+    def set_curriculum(self, conditions: dict):
+        for eng in self.engines:
+            eng.set_curriculum(conditions)
+
+    def close(self, **kwargs):
+        if not self.closed:
+            for eng in self.engines:
+                eng.close()
+            self.closed = True
