@@ -305,10 +305,14 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
     const float cly[5] = {r * uy, r * uy, 0.0f, 0.8660254037844386f * r, -0.8660254037844386f * r};
     float ax[5], ay[5], az[5], tgt[5], imn[5], im1[5], im2[5];
     float ln[5], l1[5], l2[5];
-    // Point 1 (the top cap) is far from the plane in every upright pose: its normal row then cannot bind
-    // (tgt <= vn with a zero stored impulse), which makes the row, its friction rows and its warm-start term exact
-    // no-ops.  It is therefore visited lazily: each sweep tests `tgt > vn` (and "any stored impulse"), and only a
-    // thread that passes computes the point's effective masses and runs the row.  Same results as visiting it always.
+    // A row whose normal constraint cannot bind (tgt <= vn with zero stored impulses) is an exact no-op together with its
+    // friction rows and its warm-start term.  That is the normal case for the top cap (point 1) in every upright pose
+    // and for most of the body-fixed rim points: measured with the oracle, an env in contact stands on its rim at a
+    // median tilt of 21 degrees with 0.8 of the three fixed points within 4 mm of the plane.  Points 1-4 are therefore
+    // visited lazily: each sweep tests `tgt > vn` (and "any stored impulse"), and only a thread that passes computes
+    // the point's effective masses and runs the row.  Same results as visiting every row always.  (Sorting the
+    // in-contact envs further by their set of near-ground rim points, so that whole warps skip the same rows, was
+    // measured: 0.1074 ms against 0.1036 without -- ten classes scatter a group's 32 envs over more cache lines.)
 #pragma unroll
     for (int i = 0; i < 5; i++) {
         const float cz = i == 1 ? zt : zb;
@@ -316,13 +320,13 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
         ay[i] = R[3] * clx[i] + R[4] * cly[i] + R[5] * cz;
         az[i] = R[6] * clx[i] + R[7] * cly[i] + R[8] * cz;
         const float gap = pz + az[i];
-        if (i != 1) {
+        if (i == 0) {
             // effective masses for n = z, t1 = x, t2 = y at arm (ax,ay,az)
             const float mn = im + (W00 * ay[i] * ay[i] - 2.0f * W01 * ax[i] * ay[i] + W11 * ax[i] * ax[i]);
             const float m1 = im + (W11 * az[i] * az[i] - 2.0f * W12 * az[i] * ay[i] + W22 * ay[i] * ay[i]);
             const float m2 = im + (W00 * az[i] * az[i] - 2.0f * W02 * az[i] * ax[i] + W22 * ax[i] * ax[i]);
             imn[i] = rcp_fast(mn); im1[i] = rcp_fast(m1); im2[i] = rcp_fast(m2);
-        } else { imn[i] = 0.0f; im1[i] = 0.0f; im2[i] = 0.0f; }
+        } else { imn[i] = 0.0f; im1[i] = 0.0f; im2[i] = 0.0f; }   // lazily, in the first sweep that needs them
         const float vn0 = vz + wx * ay[i] - wy * ax[i];
         const float rest = (vn0 < -c.rest_thr) ? -c.restitution * vn0 : 0.0f;
         tgt[i] = rest + (gap > 0.0f ? -gap * c.inv_dt : -c.erp * gap * c.inv_dt);
@@ -335,7 +339,7 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
     if (warm) {   // apply the stored impulses at the current contact geometry
 #pragma unroll
         for (int i = 0; i < 5; i++) {
-            if (i == 1 && ln[1] == 0.0f && l1[1] == 0.0f && l2[1] == 0.0f) continue;   // adds exact zeros
+            if (i != 0 && ln[i] == 0.0f && l1[i] == 0.0f && l2[i] == 0.0f) continue;   // adds exact zeros
             const float px_ = l1[i], py_ = l2[i], pn_ = ln[i];
             vx += px_ * im; vy += py_ * im; vz += pn_ * im;
             const float tx = ay[i] * pn_ - az[i] * py_, ty = az[i] * px_ - ax[i] * pn_, tz = ax[i] * py_ - ay[i] * px_;
@@ -354,13 +358,13 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
         for (int i = 0; i < 5; i++) {
             // normal row
             const float vn = vz + wx * ay[i] - wy * ax[i];
-            if (i == 1) {
-                if (!(tgt[1] > vn || ln[1] > 0.0f || l1[1] != 0.0f || l2[1] != 0.0f)) continue;   // exact no-op
-                if (imn[1] == 0.0f) {
-                    const float mn = im + (W00 * ay[1] * ay[1] - 2.0f * W01 * ax[1] * ay[1] + W11 * ax[1] * ax[1]);
-                    const float m1 = im + (W11 * az[1] * az[1] - 2.0f * W12 * az[1] * ay[1] + W22 * ay[1] * ay[1]);
-                    const float m2 = im + (W00 * az[1] * az[1] - 2.0f * W02 * az[1] * ax[1] + W22 * ax[1] * ax[1]);
-                    imn[1] = rcp_fast(mn); im1[1] = rcp_fast(m1); im2[1] = rcp_fast(m2);
+            if (i != 0) {
+                if (!(tgt[i] > vn || ln[i] > 0.0f || l1[i] != 0.0f || l2[i] != 0.0f)) continue;   // exact no-op
+                if (imn[i] == 0.0f) {
+                    const float mn = im + (W00 * ay[i] * ay[i] - 2.0f * W01 * ax[i] * ay[i] + W11 * ax[i] * ax[i]);
+                    const float m1 = im + (W11 * az[i] * az[i] - 2.0f * W12 * az[i] * ay[i] + W22 * ay[i] * ay[i]);
+                    const float m2 = im + (W00 * az[i] * az[i] - 2.0f * W02 * az[i] * ax[i] + W22 * ax[i] * ax[i]);
+                    imn[i] = rcp_fast(mn); im1[i] = rcp_fast(m1); im2[i] = rcp_fast(m2);
                 }
             }
             const float nl = fmaxf(ln[i] + (tgt[i] - vn) * imn[i], 0.0f);
