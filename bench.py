@@ -64,8 +64,9 @@ def _issue_roofline(ms, clocks):
             "warp_instructions_per_step": wi,
             "fp32_ceilings": {"ffma_three_register_sources": 0.65, "ffma_two_shared_sources": 0.93,
                               "source": "tools/micro/fp32_rate.cu on this pool's B200 (profiles/r01_fp32_rate_microbench.txt)"},
-            "note": "the PGS sweeps (30 % of the instructions) run at 0.57-0.66 with four solver warps per sub-partition, i.e. at the "
-                    "three-register-source FFMA rate; the remainder is dependent-issue / memory latency"}
+            "note": "with the lazy contact rows the step is a single wave of dependent chains (1,750 near-ground groups of ~45 us, 6,450 "
+                    "airborne groups of ~13 us on 2,368 warp slots): neither more warps (5 CTAs/SM spill-free: no gain) nor a pipe limit "
+                    "bounds it, the instruction count along each warp's chain does; see DESIGN.md section 6"}
 
 
 def _traffic(key="dram_bytes_per_launch"):
@@ -379,9 +380,9 @@ def run_ours(args):
                          "traffic": _traffic(), "peak_source": peak_src,
                          "kernel": "step_kernel_v2<X=true,DIV=fast> (+ classify_kernel and reset_done_kernel)",
                          "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP_X,
-                         "note": "not DRAM-bound (ncu: 8 % of DRAM throughput): ~7,000 thread-instructions per env-step; the in-contact "
-                                 "quarter of the envs runs FP32-pipe-bound PGS sweeps, the rest is latency-bound; see issue_roofline, "
-                                 "DESIGN.md section 6 and profiles/"},
+                         "note": "not DRAM-bound (ncu: 8 % of DRAM throughput): ~5,000 thread-instructions per env-step in dependent chains "
+                                 "(contact PGS for the in-contact quarter of the envs, ten substeps, Euler angles, reward, Philox noise for all); "
+                                 "see issue_roofline, DESIGN.md section 6 and profiles/"},
             "issue_roofline": _issue_roofline(ms, clocks),
             "gpu_launches": launches,
             "clocks": clocks,
