@@ -241,7 +241,7 @@ def run_ours(args):
         flush.zero_()
         starts[k].record()
         eng.step(pool[k % 16], want_final=False)
-        launches += 3            # classify_kernel + step_kernel_v2 + reset_done_kernel
+        launches += 2            # step_kernel_v2 + the closing sort kernel (classify_kernel with the deferred resets)
         ends[k].record()
         if (k + 1) % 64 == 0:   # episode-statistics reduction (+ NCCL all-reduce over NVLink when N>1), side stream
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -350,7 +350,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_dt = float(te.item())
-    launches += 3 * ke
+    launches += 2 * ke
     extra["e2e"] = {"value": total_envs / e2e_dt, "unit": "env-steps/s", "h2d_bytes_per_step": n * 8,
                     "d2h_bytes_per_step": n * (40 + 4 + 1 + 1) + done_rows * 40, "ms_per_step": 1e3 * e2e_dt, "n_gpus_measured": world,
                     "bytes_are": "per GPU", "result_checksum": e2e_check,
@@ -378,7 +378,7 @@ def run_ours(args):
                         "note": "back-to-back launches, state L2-resident (62 MB < 126 MB)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": _traffic(), "peak_source": peak_src,
-                         "kernel": "step_kernel_v2<X=true,DIV=fast> (+ classify_kernel and reset_done_kernel)",
+                         "kernel": "step_kernel_v2<X=true,DIV=fast> (+ the closing sort / deferred-reset kernel)",
                          "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP_X,
                          "note": "not DRAM-bound (ncu: 8 % of DRAM throughput): ~5,000 thread-instructions per env-step in dependent chains "
                                  "(contact PGS for the in-contact quarter of the envs, ten substeps, Euler angles, reward, Philox noise for all); "

@@ -183,18 +183,62 @@ __device__ __forceinline__ int class_of(const DevCfg &c, bool X, float pz, float
     return gmin < TVC_NOW_GAP ? 0 : (gmin - travel < TVC_MAYBE_GAP ? 1 : 2);
 }
 // FROM_STATE: compute the classes from the state planes (80 B per env; first step, or after a reset / set_state / rollout
-// touched the state behind the step path's back).  Otherwise read the class byte that step_kernel_v2 and
-// reset_done_kernel left for every env at the end of the previous step (1 B per env).
-template <bool X, bool FROM_STATE>
+// touched the state behind the step path's back).  Otherwise read the class byte step_kernel_v2 left for every env
+// (1 B per env) -- this instantiation CLOSES a step and prepares the next one's sequence.
+// RESET (large batches, same-step autoreset): before sorting, the envs the step kernel marked 0xFF are compacted per chunk
+// and re-initialised by as many threads (ref:381-464 reset + the reset observation; their terminal state was stored by
+// the step kernel and every Env field round-trips through store_env / load_env, so this equals resetting in place).
+// One launch does what a separate reset kernel and the next step's classify did (-8 us per step).
+template <bool X, bool FROM_STATE, bool RESET>
 __global__ void __launch_bounds__(TVC_CLS_THREADS)
-classify_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState st) {
+classify_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState st, float *obs) {
     __shared__ int wcnt[3][TVC_EPT][TVC_CLS_WARPS];
     __shared__ int s_scan[TVC_CLS_WARPS];
     __shared__ int s_pre[3][32], s_tot[3];
     __shared__ int s_last;
+    __shared__ uint8_t s_cls[RESET ? TVC_CHUNK : 4];
+    __shared__ unsigned short s_done[RESET ? TVC_CHUNK : 2];
+    __shared__ int s_ndone;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long base = (long long)blockIdx.x * TVC_CHUNK;
     const int nc = st.nchunks;
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // behind step_kernel_v2 when it closes a step
+    if (RESET) {
+        if (tid == 0) s_ndone = 0;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < TVC_EPT; j++) {
+            const int li = j * TVC_CLS_THREADS + tid;
+            const long long env = base + li;
+            const int cl = env < st.n ? (int)st.cls[env] : 3;
+            s_cls[li] = (uint8_t)cl;
+            const unsigned dm = __ballot_sync(0xffffffffu, cl == 0xFF);
+            if (dm) {
+                int pos = 0;
+                if (lane == 0) pos = atomicAdd(&s_ndone, __popc(dm));
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+                if (cl == 0xFF) s_done[pos + __popc(dm & ((1u << lane) - 1u))] = (unsigned short)li;
+            }
+        }
+        __syncthreads();
+        for (int k = tid; k < s_ndone; k += TVC_CLS_THREADS) {   // list order is arbitrary, results are not
+            const int li = s_done[k];
+            const long long i = base + li, gid = c.env_base + i;
+            Env e;
+            load_env(st, X, i, e);
+            reset_env(c, X, gid, e, false);
+            store_env(st, X, i, e);
+            const uint8_t nc_ = (uint8_t)class_of(c, X, e.pz, e.qx, e.qy, e.qz, e.qw, e.vz, e.wx, e.wy, e.wz, e.cg_off);
+            s_cls[li] = nc_;
+            st.cls[i] = nc_;   // never leave a stale "reset me" mark behind
+            float o[10];
+            build_obs(c, X, gid, e, 0, o);
+            float2 *o2 = reinterpret_cast<float2 *>(obs + 10 * i);
+#pragma unroll
+            for (int q = 0; q < 5; q++) o2[q] = make_float2(o[2 * q], o[2 * q + 1]);
+        }
+        __syncthreads();
+    }
     unsigned mask[3][TVC_EPT];
 #pragma unroll
     for (int j = 0; j < TVC_EPT; j++) {
@@ -204,7 +248,8 @@ classify_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevSta
             if (FROM_STATE) {
                 const float4 p = st.s0[env], q = st.s1[env], v = st.s2[env], w = st.s3[env];
                 cls = class_of(c, X, p.z, q.x, q.y, q.z, q.w, v.z, w.x, w.y, w.z, X ? st.d0[env].z : 0.0f);
-            } else cls = st.cls[env];
+            } else if (RESET) cls = s_cls[j * TVC_CLS_THREADS + tid];
+            else cls = st.cls[env];
         }
 #pragma unroll
         for (int k = 0; k < 3; k++) {
@@ -265,7 +310,7 @@ classify_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevSta
         }
         if (tid == 0) o[0] = 0;
     }
-    if (tid == 0) { st.counter[0] = 0u; st.counter[1] = 0u; st.counter[2] = 0u; }
+    if (tid == 0) { st.counter[0] = 0u; st.counter[1] = 0u; }
 }
 
 // Position p of the global class-ordered sequence -> env id (binary search over the chunk scans of p's class).
@@ -333,7 +378,7 @@ __device__ __forceinline__ int env_at_group(const DevState &st, int p, int lane,
 #ifndef TVC_V2_NO_LOCKSTEP
 #define TVC_V2_LOCKSTEP 1   // measured: 0.1767 -> 0.164 ms per step (shared instruction fetches); larger CTAs / chunks lose
 #endif
-// DEFER: finished envs are listed for reset_done_kernel (large batches) instead of being reset in place (small batches,
+// DEFER: finished envs are marked for the closing sort kernel (large batches) instead of being reset in place (small batches,
 // where one launch fewer matters more than the idle lanes).
 // A split into an airborne-part kernel at twice the occupancy (64 registers, solver out of line) followed by a near-ground
 // kernel was measured: 0.150 ms against 0.125 ms for this single kernel -- the FP32-pipe-bound solver warps and the
@@ -451,24 +496,18 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
                 }
             }
             store_env(st, X, i, e);
-            st.cls[i] = (uint8_t)class_of(c, X, e.pz, e.qx, e.qy, e.qz, e.qw, e.vz, e.wx, e.wy, e.wz, e.cg_off);   // for the next step's sort
+            // class byte for the next step's sort; 0xFF = "episode ended, reset me" (DEFER, consumed by the sort kernel)
+            st.cls[i] = (DEFER && done && c.autoreset) ? (uint8_t)0xFF
+                        : (uint8_t)class_of(c, X, e.pz, e.qx, e.qy, e.qz, e.qw, e.vz, e.wx, e.wy, e.wz, e.cg_off);
             float2 *o2 = reinterpret_cast<float2 *>(io.obs + 10 * i);
 #pragma unroll
             for (int k = 0; k < 5; k++) o2[k] = make_float2(r.obs[2 * k], r.obs[2 * k + 1]);
         }
         // Same-step autoreset is deferred (DEFER): ~1 env in 38 ends its episode per step, i.e. 1-2 lanes per warp would walk
         // through the per-episode Philox draws and a second observation here (10 % of this kernel's warp-instructions
-        // at 1.7 live lanes).  The terminal state and observation are stored above; reset_done_kernel re-initialises
-        // the listed envs with full warps and overwrites their observation rows.  List order is arbitrary, results are not.
-        if (DEFER && c.autoreset) {
-            const unsigned dm = __ballot_sync(full, done != 0);
-            if (dm) {
-                unsigned base = 0;
-                if (lane == 0) base = atomicAdd(&st.counter[2], (unsigned)__popc(dm));
-                base = __shfl_sync(full, base, 0);
-                if (done) st.done_list[base + __popc(dm & ((1u << lane) - 1u))] = (int)i;
-            }
-        }
+        // at 1.7 live lanes).  The terminal state and observation are stored above and the env is marked in its class
+        // byte; the sort kernel that closes the step (classify_kernel<X, false, true>) compacts the marked envs of its
+        // chunk, re-initialises them and overwrites their observation rows before it sorts.
 #ifdef TVC_PHASE_PROF2
         {
             const long long pt3 = clock64();
@@ -534,30 +573,6 @@ reset_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState 
         build_obs(c, X, gid, e, 0, o);
 #pragma unroll
         for (int k = 0; k < 10; k++) obs[10 * i + k] = o[k];
-    }
-}
-
-// Second half of the same-step autoreset of step_kernel_v2: ref:381-464 reset + the reset observation for the envs
-// listed in done_list (their terminal state was stored by the step kernel; every Env field round-trips through
-// store_env / load_env, so this equals resetting in place).
-template <bool X>
-__global__ void __launch_bounds__(TVC_BLOCK)
-reset_done_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState st, float *obs) {
-    asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic dependent launch behind step_kernel_v2
-    const unsigned nd = st.counter[2];
-    for (unsigned k = blockIdx.x * TVC_BLOCK + threadIdx.x; k < nd; k += gridDim.x * TVC_BLOCK) {
-        const long long i = st.done_list[k];
-        const long long gid = c.env_base + i;
-        Env e;
-        load_env(st, X, i, e);
-        reset_env(c, X, gid, e, false);
-        store_env(st, X, i, e);
-        st.cls[i] = (uint8_t)class_of(c, X, e.pz, e.qx, e.qy, e.qz, e.qw, e.vz, e.wx, e.wy, e.wz, e.cg_off);
-        float o[10];
-        build_obs(c, X, gid, e, 0, o);
-        float2 *o2 = reinterpret_cast<float2 *>(obs + 10 * i);
-#pragma unroll
-        for (int j = 0; j < 5; j++) o2[j] = make_float2(o[2 * j], o[2 * j + 1]);
     }
 }
 
@@ -795,7 +810,6 @@ int tvc_create(const tvc_config *cfg, int device, int64_t num_envs, tvc_handle *
     s.nchunks = (int)((num_envs + TVC_CHUNK - 1) / TVC_CHUNK);
     TRY(dalloc(&s.goff, (size_t)3 * (s.nchunks + 1)));
     TRY(dalloc(&s.counter, (size_t)4));
-    TRY(dalloc(&s.done_list, n));
     TRY(dalloc(&s.cls, n));
     TRY(dalloc(&h->stats_dev, (size_t)TVC_NSTAT));
     {
@@ -820,7 +834,7 @@ int tvc_destroy(tvc_handle *h) {
     DevState &s = h->st;
     cudaFree(s.s0); cudaFree(s.s1); cudaFree(s.s2); cudaFree(s.s3); cudaFree(s.s4);
     cudaFree(s.d0); cudaFree(s.d1); cudaFree(s.ring); cudaFree(s.clipb); cudaFree(s.runb); cudaFree(s.hist);
-    cudaFree(s.delay); cudaFree(s.partial); cudaFree(s.order); cudaFree(s.goff); cudaFree(s.counter); cudaFree(s.done_list); cudaFree(s.cls); cudaFree(h->stats_dev);
+    cudaFree(s.delay); cudaFree(s.partial); cudaFree(s.order); cudaFree(s.goff); cudaFree(s.counter); cudaFree(s.cls); cudaFree(h->stats_dev);
     cudaFree(h->io_act); cudaFree(h->io_obs) /* the obs|reward|flags slab */; cudaFree(h->io_final);
     tvc_rollout_free(h);
     if (h->stats_host) cudaFreeHost(h->stats_host);
@@ -840,7 +854,7 @@ int tvc_reset(tvc_handle *h, const uint8_t *mask_dev, uint64_t seed, float *obs_
     if (h->cur.contract == TVC_CONTRACT_X) reset_kernel<true><<<h->grid, TVC_BLOCK, 0, s>>>(h->dc, h->st, mask_dev, obs_out_dev, 0);
     else reset_kernel<false><<<h->grid, TVC_BLOCK, 0, s>>>(h->dc, h->st, mask_dev, obs_out_dev, 0);
     LAUNCH_OK("reset_kernel");
-    h->cls_valid = false;
+    h->order_valid = false;
     return TVC_OK;
 }
 
@@ -858,15 +872,11 @@ static int launch_step(tvc_handle *h, const DevIO &io, cudaStream_t s) {
         LAUNCH_OK("step_kernel");
     } else {
         const int cgrid = h->st.nchunks;
-        if (!h->cls_valid) {   // the class bytes do not describe the current state: classify from the state planes
-            if (X) classify_kernel<true, true><<<cgrid, TVC_CLS_THREADS, 0, s>>>(h->dc, h->st);
-            else classify_kernel<false, true><<<cgrid, TVC_CLS_THREADS, 0, s>>>(h->dc, h->st);
-        } else {
-            if (X) classify_kernel<true, false><<<cgrid, TVC_CLS_THREADS, 0, s>>>(h->dc, h->st);
-            else classify_kernel<false, false><<<cgrid, TVC_CLS_THREADS, 0, s>>>(h->dc, h->st);
+        if (!h->order_valid) {   // first step, or the state was changed behind the step path's back: sort from the state planes
+            if (X) classify_kernel<true, true, false><<<cgrid, TVC_CLS_THREADS, 0, s>>>(h->dc, h->st, nullptr);
+            else classify_kernel<false, true, false><<<cgrid, TVC_CLS_THREADS, 0, s>>>(h->dc, h->st, nullptr);
+            LAUNCH_OK("classify_kernel");
         }
-        LAUNCH_OK("classify_kernel");
-        h->cls_valid = true;   // the step kernel (and reset_done_kernel) leave fresh class bytes behind
         if (h->v2_grid == 0) {   // persistent grid: resident CTAs of the v2 kernel, capped by the number of groups
             int per_sm = 0;
             cudaError_t e = X ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_v2<true, 1, true>, TVC_V2_BLOCK, 0)
@@ -889,13 +899,16 @@ static int launch_step(tvc_handle *h, const DevIO &io, cudaStream_t s) {
         const bool defer = h->v2_defer && h->cur.autoreset;
         if (defer) GO3(true); else GO3(false);
         LAUNCH_OK("step_kernel_v2");
-        if (defer) {   // deferred same-step autoreset of the envs the step kernel listed
-            const int want = (int)((h->n / 16 + TVC_BLOCK - 1) / TVC_BLOCK) + 1;
-            const int rgrid = want < 2 * h->num_sms ? want : 2 * h->num_sms;
-            if (X) (void)launch_dep(reset_done_kernel<true>, rgrid, TVC_BLOCK, s, h->pdl, h->dc, h->st, io.obs);
-            else (void)launch_dep(reset_done_kernel<false>, rgrid, TVC_BLOCK, s, h->pdl, h->dc, h->st, io.obs);
-            LAUNCH_OK("reset_done_kernel");
+        // close the step: (reset the finished envs of every chunk and) sort for the next step from the class bytes
+        if (defer) {
+            if (X) (void)launch_dep(classify_kernel<true, false, true>, cgrid, TVC_CLS_THREADS, s, h->pdl, h->dc, h->st, io.obs);
+            else (void)launch_dep(classify_kernel<false, false, true>, cgrid, TVC_CLS_THREADS, s, h->pdl, h->dc, h->st, io.obs);
+        } else {
+            if (X) (void)launch_dep(classify_kernel<true, false, false>, cgrid, TVC_CLS_THREADS, s, h->pdl, h->dc, h->st, io.obs);
+            else (void)launch_dep(classify_kernel<false, false, false>, cgrid, TVC_CLS_THREADS, s, h->pdl, h->dc, h->st, io.obs);
         }
+        LAUNCH_OK("classify_kernel (end of step)");
+        h->order_valid = true;
 #undef GO3
 #undef GO
     }
@@ -1027,7 +1040,7 @@ int tvc_set_state(tvc_handle *h, const void *dev_blob, size_t bytes, tvc_stream 
     if (h->cur.contract == TVC_CONTRACT_X) set_state_kernel<true><<<g, 128, 0, (cudaStream_t)stream>>>(h->st, (const tvc_env_state *)dev_blob, TVC_MAX_DELAY);
     else set_state_kernel<false><<<g, 128, 0, (cudaStream_t)stream>>>(h->st, (const tvc_env_state *)dev_blob, 0);
     LAUNCH_OK("set_state_kernel");
-    h->cls_valid = false;
+    h->order_valid = false;
     return TVC_OK;
 }
 
@@ -1081,7 +1094,7 @@ int tvc_set_curriculum(tvc_handle *h, const tvc_stage_conditions *c) {
     n.seed = h->cur.seed;
     h->cur = n;
     make_devcfg(h->cur, h->dc);
-    h->cls_valid = false;
+    h->order_valid = false;
     return TVC_OK;
 }
 

@@ -51,10 +51,8 @@ struct DevState {
     double *partial;  // [ceil(N/32)][16] episode statistics rows: one owner (CTA or 32-env group) per row per launch
     int *order;       // [N] env ids sorted per 1024-env chunk by class: in contact, may touch, airborne (classify_kernel)
     int *goff;        // [3][nchunks + 1] exclusive scans over the chunks of the per-chunk class counts (goff[c][0] = 0)
-    unsigned *counter;  // [0] work-queue head of step_kernel_v2 (zeroed by classify_kernel), [1] classify_kernel's ticket,
-                        // [2] length of done_list (zeroed by classify_kernel)
-    int *done_list;     // [N] envs whose episode ended in this step (step_kernel_v2 appends, reset_done_kernel consumes)
-    uint8_t *cls;       // [N] class of every env for the NEXT step's sort (written at the end of a step)
+    unsigned *counter;  // [0] work-queue head of step_kernel_v2 (zeroed by classify_kernel), [1] classify_kernel's ticket
+    uint8_t *cls;       // [N] class of every env for the next step's sort (written by step_kernel_v2; 0xFF = reset me)
     int nchunks;
     long long n;
 };

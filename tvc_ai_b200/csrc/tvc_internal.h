@@ -12,9 +12,9 @@ struct tvc_handle {
     int grid = 0;       // CTAs of TVC_BLOCK envs (legacy step kernel, rollout kernel)
     int ngroups = 0;    // 32-env groups (step_kernel_v2 work items, statistics rows)
     int v2_grid = 0;    // persistent grid of step_kernel_v2 (computed on first launch)
-    bool cls_valid = false;  // st.cls describes the current state (false after reset / set_state / rollout / legacy steps)
-    bool pdl = true;         // programmatic dependent launch of step_kernel_v2 / reset_done_kernel behind their predecessor
-    bool v2_defer = false;   // large batches: finished envs go to reset_done_kernel; small ones are reset in place
+    bool order_valid = false;  // the sorted sequence describes the current state (false after reset / set_state / rollout / curriculum)
+    bool pdl = true;         // programmatic dependent launch of step_kernel_v2 and of the closing sort kernel
+    bool v2_defer = false;   // large batches: finished envs are reset by the closing sort kernel; small ones in place
     int step_impl = 2;  // 2: sorted warp-per-group kernel, 1: legacy CTA-exchange kernel
     tvc_config base;   // as created
     tvc_config cur;    // after tvc_set_curriculum

@@ -457,7 +457,7 @@ extern "C" int tvc_rollout(tvc_handle *h, const tvc_actor_weights *w, int32_t T,
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { tvc_set_err(std::string("rollout_kernel: ") + cudaGetErrorString(e)); return TVC_E_CUDA; }
     h->lifetime_steps += T;
-    h->cls_valid = false;   // the rollout moved the envs behind the step path's class bytes
+    h->order_valid = false;   // the rollout moved the envs behind the step path's sorted sequence
     h->stat_steps += T;
     return TVC_OK;
 }
