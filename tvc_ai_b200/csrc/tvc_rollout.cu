@@ -332,7 +332,13 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
             P = body_params(c, false, 1.0f, 0.0f, 1.0f);
             f.Fx = f.Fy = f.Fz = f.Tx = f.Ty = f.Tz = f.a0 = f.a1 = 0.0f;
         }
+#if !defined(TVC_ROLLOUT_CTA_EXCHANGE) && !defined(TVC_PHASE_PROF2)
+        // every thread solves its own env's contacts (the lazy rows 1-4 made the solve short enough: 4.31 -> 4.03 ms per
+        // launch against compacting the contact problems across the CTA through shared memory with two barriers per substep)
+        if (live) integrate_thread<false>(c, P, e, f.Fx, f.Fy, f.Fz, f.Tx, f.Ty, f.Tz);
+#else
         integrate<RB>(c, P, e, f.Fx, f.Fy, f.Fz, f.Tx, f.Ty, f.Tz, live, s_contact);
+#endif
         done = 0; viol = 0;
         int ev_len = 0, ev_succ = 0, ev_reason = 0, ev_trunc = 0;
         float ev_ret = 0.0f, ev_alt = 0.0f, ev_tilt = 0.0f, ev_fuel = 0.0f;
