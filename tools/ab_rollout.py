@@ -23,14 +23,15 @@ ro.reset()
 for _ in range(4):
     ro.rollout(w, T)
 torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-reps = 6
-e0.record()
-for _ in range(reps):
+reps = 24
+ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+for a, b in ev:
+    a.record()
     out = ro.rollout(w, T)
-e1.record()
+    b.record()
 torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / reps
+per = sorted(a.elapsed_time(b) for a, b in ev)
+ms = per[len(per) // 2]
 st = ro.stats()
-print(f"ABR {tag}: {ms:.3f} ms per {T}-step launch of {nr} envs -> {nr * T / (ms * 1e-3):.3e} env-steps/s  episodes {st[0]:.0f} sum_return {st[1]:.6e}", flush=True)
+print(f"ABR {tag}: median {ms:.3f} (min {per[0]:.3f}, max {per[-1]:.3f}) ms per {T}-step launch of {nr} envs -> {nr * T / (ms * 1e-3):.3e} env-steps/s  episodes {st[0]:.0f} sum_return {st[1]:.6e}", flush=True)
 ro.close()

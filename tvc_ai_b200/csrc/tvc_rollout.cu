@@ -183,6 +183,7 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
     const float *w3 = b2 + HID;
     const float *b3 = w3 + 4 * HID;
     ContactSmemT<RB> &s_contact = *reinterpret_cast<ContactSmemT<RB> *>(smem + OFF_A1);   // operand + hidden tiles are idle during physics
+    (void)s_contact; (void)bar_mma;   // used by the TVC_ROLLOUT_CTA_EXCHANGE / TVC_ROLLOUT_TILE_TURNS builds only
 
     // ---- one-time setup: barriers, TMEM (256 accumulator columns per tile), weights via TMA bulk copy ----
     if (tid == 0) {
@@ -224,6 +225,7 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
     // warp w reads TMEM lanes 32*(w%4)..+31; tile j accumulates in column set j % 2: columns [256 set, 256 set + 256)
     const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(set * HID);
     uint32_t mma_phase = 0;
+    (void)taddr;
     float rsum = 0.0f, a0 = 0.0f, a1 = 0.0f;
     int done = 0, viol = 0;
 
@@ -233,6 +235,121 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
 #pragma unroll
             for (int k = 0; k < 5; k++) o2[k] = make_float2(obs[2 * k], obs[2 * k + 1]);
         }
+        float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f, o3 = 0.0f;
+#ifndef TVC_ROLLOUT_TILE_TURNS
+        // All 16 warps work on every tile's epilogues: warp w may read TMEM lanes 32 (w % 4) .. +31 of ANY column, so for each
+        // tile it takes row 32 (w % 4) + lane and the 64 accumulator columns 64 (w / 4) .. +63.  (With one tile's four warps
+        // doing its 256-column epilogues while the other twelve wait, the MLP cost 19 of the 63 us per step.)  The head's
+        // partial sums of a row's four column groups meet through shared memory at the end; layer 2 of tile j runs on the
+        // tensor core while the warps are in the second epilogue of tile j - 1.
+        {
+            const int q = warp & 3, m = warp >> 2;            // TMEM lane quarter, column group
+            const int r = q * 32 + lane;                      // accumulator row handled in every tile
+            const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+            const uint32_t bar_set0 = s_base + OFF_BAR + 8, bar_set1 = s_base + OFF_BAR + 16;
+            {   // layer 1 operands: every env writes its obs row into its own tile's bf16 operand [2][128][8]
+                uint4 c0 = make_uint4(pack_bf16(obs[0], obs[1]), pack_bf16(obs[2], obs[3]), pack_bf16(obs[4], obs[5]), pack_bf16(obs[6], obs[7]));
+                uint4 c1 = make_uint4(pack_bf16(obs[8], obs[9]), 0u, 0u, 0u);
+                uint8_t *a1p = smem + OFF_A1 + tile * A1_BYTES;
+                *reinterpret_cast<uint4 *>(a1p + row * 16) = c0;
+                *reinterpret_cast<uint4 *>(a1p + TM * 16 + row * 16) = c1;
+            }
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {   // layer 1 of tiles 0 and 1 into column sets 0 and 1
+                tc_fence_after();
+#pragma unroll
+                for (int j = 0; j < NSET; j++) {
+                    mma_bf16(tmem_base + j * HID, umma_desc(s_base + OFF_A1 + j * A1_BYTES, TM * 16, 128),
+                             umma_desc(s_base + OFF_W1, HID * 16, 128), 0u);
+                    mma_commit(s_base + OFF_BAR + 8 + 8 * j);
+                }
+            }
+            float po[NT][4];
+#pragma unroll
+            for (int j = 0; j < NT; j++) { po[j][0] = 0.0f; po[j][1] = 0.0f; po[j][2] = 0.0f; po[j][3] = 0.0f; }
+            uint32_t ph0 = mma_phase, ph1 = mma_phase;        // running parities of the two column-set barriers
+#pragma unroll
+            for (int j = 0; j <= NT; j++) {
+                if (j < NT) {
+                    const int sj = j % NSET;
+                    // layer 1 of tile j has landed in set sj (and layer 2 of tile j - 1 has released the hidden tile, below)
+                    if (sj == 0) { mbar_wait(bar_set0, ph0); ph0 ^= 1u; } else { mbar_wait(bar_set1, ph1); ph1 ^= 1u; }
+                    tc_fence_after();
+                    // epilogue 1 of tile j: bias + ReLU -> bf16 hidden tile [32][128][8], this thread's 64 columns of row r
+#pragma unroll
+                    for (int hh = 0; hh < 2; hh++) {
+                        uint32_t v[32];
+                        const int cb = m * 64 + hh * 32;
+                        tmem_ld32(tq + (uint32_t)(sj * HID + cb), v);
+#pragma unroll
+                        for (int qq = 0; qq < 4; qq++) {
+                            float h[8];
+#pragma unroll
+                            for (int jj = 0; jj < 8; jj++) h[jj] = fmaxf(__uint_as_float(v[8 * qq + jj]) + b1[cb + 8 * qq + jj], 0.0f);
+                            *reinterpret_cast<uint4 *>(smem + OFF_H1 + ((cb >> 3) + qq) * (TM * 16) + r * 16) =
+                                make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+                        }
+                    }
+                    fence_async_smem();
+                    tc_fence_before();
+                    __syncthreads();
+                    if (tid == 0) {   // layer 2 of tile j: 16 K-steps of M128 N256 K16 over the hidden tile
+                        tc_fence_after();
+#pragma unroll
+                        for (int kk = 0; kk < HID / 16; kk++)
+                            mma_bf16(tmem_base + sj * HID, umma_desc(s_base + OFF_H1 + kk * 2 * (TM * 16), TM * 16, 128),
+                                     umma_desc(s_base + OFF_W2 + kk * 2 * (HID * 16), HID * 16, 128), kk > 0 ? 1u : 0u);
+                        mma_commit(s_base + OFF_BAR + 8 + 8 * sj);
+                    }
+                }
+                if (j > 0) {
+                    // epilogue 2 + head of tile j - 1 (its layer 2 was waited for below, before the hidden tile was reused)
+                    const int jp = j - 1, sp = jp % NSET;
+#pragma unroll
+                    for (int hh = 0; hh < 2; hh++) {
+                        uint32_t v[32];
+                        const int cb = m * 64 + hh * 32;
+                        tmem_ld32(tq + (uint32_t)(sp * HID + cb), v);
+#pragma unroll
+                        for (int jj = 0; jj < 32; jj++) {
+                            const int col = cb + jj;
+                            const float h = fmaxf(__uint_as_float(v[jj]) + b2[col], 0.0f);
+                            po[jp][0] = fmaf(h, w3[col], po[jp][0]); po[jp][1] = fmaf(h, w3[HID + col], po[jp][1]);
+                            po[jp][2] = fmaf(h, w3[2 * HID + col], po[jp][2]); po[jp][3] = fmaf(h, w3[3 * HID + col], po[jp][3]);
+                        }
+                    }
+                    tc_fence_before();
+                }
+                if (j < NT) {
+                    // layer 2 of tile j must be complete before anything touches the hidden tile again / reads its set
+                    const int sj = j % NSET;
+                    if (sj == 0) { mbar_wait(bar_set0, ph0); ph0 ^= 1u; } else { mbar_wait(bar_set1, ph1); ph1 ^= 1u; }
+                    tc_fence_after();
+                }
+                __syncthreads();   // set (j - 1) % 2 has been read out by every warp; the hidden tile is free
+                if (tid == 0 && j > 0 && j + 1 < NT) {   // layer 1 of tile j + 1 into the set tile j - 1 just left
+                    tc_fence_after();
+                    mma_bf16(tmem_base + ((j + 1) % NSET) * HID, umma_desc(s_base + OFF_A1 + (j + 1) * A1_BYTES, TM * 16, 128),
+                             umma_desc(s_base + OFF_W1, HID * 16, 128), 0u);
+                    mma_commit(s_base + OFF_BAR + 8 + 8 * ((j + 1) % NSET));
+                }
+            }
+            // the head's partial sums: [column group][tile][row] float4 in the (now idle) hidden tile; the env's own thread adds
+            // its four groups in a fixed order
+            float4 *s_part = reinterpret_cast<float4 *>(smem + OFF_H1);
+#pragma unroll
+            for (int j = 0; j < NT; j++) s_part[(m * NT + j) * TM + r] = make_float4(po[j][0], po[j][1], po[j][2], po[j][3]);
+            __syncthreads();
+#pragma unroll
+            for (int mm = 0; mm < 4; mm++) {
+                const float4 pp = s_part[(mm * NT + tile) * TM + row];
+                o0 += pp.x; o1 += pp.y; o2 += pp.z; o3 += pp.w;
+            }
+            __syncthreads();   // the hidden tile is written again in the next step
+        }
+#else
         // ---- layer 1 operands: every env writes its obs row into its tile's bf16 operand [2][128][8] ----
         {
             uint4 c0 = make_uint4(pack_bf16(obs[0], obs[1]), pack_bf16(obs[2], obs[3]), pack_bf16(obs[4], obs[5]), pack_bf16(obs[6], obs[7]));
@@ -253,7 +370,6 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
                 mma_commit(s_base + OFF_BAR + 8 + 8 * j);
             }
         }
-        float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f, o3 = 0.0f;
 #pragma unroll 1
         for (int j = 0; j < NT; j++) {   // the tiles take turns on the single hidden-tile buffer
             if (tile == j) {
@@ -311,6 +427,7 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
                 mma_commit(s_base + OFF_BAR + 8 + 8 * (j % NSET));
             }
         }
+#endif
         // every column-set barrier completed 2 * NT / NSET (an even number of) phases this step -> parity unchanged
         // ---- action: tanh(mean + exp(clamp(log_std)) * eps), eps from Philox stream 6 ----
         const float mean0 = o0 + b3[0], mean1 = o1 + b3[1];
