@@ -526,6 +526,41 @@ def test_step_under_cuda_graph_capture(lib_built):
     eager.close(); graphed.close()
 
 
+def test_long_run_invariants(lib_built):
+    """Soak: 65,536 envs x 1,500 steps (about 2.6 million episodes) with same-step autoreset, in-kernel random actions, full
+    domain randomisation, actuator delay and the thrust curve.  Everything stays finite and inside the model's bounds, the
+    bookkeeping adds up, and a second run reproduces the statistics exactly."""
+    from tvc_ai_b200 import _abi as A
+    n, steps = 65536, 1500
+
+    def run():
+        e = _engine(n, A.CONTRACT_X, autoreset=1, delay_steps=3, thrust_curve=1)
+        e.reset(seed=11)
+        bad = torch.zeros((), dtype=torch.int64, device="cuda")
+        for t in range(steps):
+            o, r, te, tr = e.step(None, want_final=False)
+            if t % 50 == 0:
+                bad += (~torch.isfinite(o)).sum() + (~torch.isfinite(r)).sum() + ((r < -1000.0) | (r > 200.0)).sum()
+        st, stats = e.get_state(), e.stats()
+        e.close()
+        return int(bad.item()), st, stats
+
+    bad, st, stats = run()
+    assert bad == 0
+    assert np.all(np.isfinite(st["pos"])) and np.all(np.isfinite(st["vel"])) and np.all(np.isfinite(st["omega"]))
+    assert np.all(np.abs(np.linalg.norm(st["quat"], axis=1) - 1) < 1e-5)
+    assert np.all(np.abs(st["vel"]) <= 100.0) and np.all(np.abs(st["omega"]) <= 100.0)      # Bullet's per-component clamp (row B5)
+    assert np.all((st["step"] >= 0) & (st["step"] <= 1000)) and np.all((st["burn"] >= 0) & (st["burn"] <= 1000))
+    assert np.all(st["burn"] == st["step"])                                                   # one fuel decrement per step while it lasts
+    assert stats[14] == steps * n
+    episodes = stats[0]
+    assert episodes > 2_000_000 and stats[3] + st["step"].sum() == steps * n                  # finished episode lengths + running ones
+    assert stats[4] + stats[5] + stats[6] + stats[7] + stats[8] + stats[9] >= episodes        # every episode has an end reason
+    bad2, st2, stats2 = run()
+    np.testing.assert_array_equal(stats, stats2)
+    assert np.array_equal(st["pos"], st2["pos"]) and np.array_equal(st["quat"], st2["quat"])
+
+
 def test_edge_sizes_and_argument_checks(lib_built):
     """Ragged and extreme batch sizes (1, 31, 33, 129 envs; 2^20 envs), NULL-output rejection, mask reset."""
     from tvc_ai_b200 import _abi as A
