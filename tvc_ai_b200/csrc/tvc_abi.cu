@@ -168,20 +168,6 @@ step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState s
 // envs, all class-1 envs, all class-2 envs -- so that a CTA's warps hold groups of the same class (a CTA whose warps
 // re-align at every substep would otherwise park three airborne warps behind one solver warp) and the long class-0
 // groups start first.  Deterministic: no atomics on data, the sequence depends on the states only.
-#define TVC_NOW_GAP 0.008f     // class 0: lower bound of the lowest point's height below this
-#define TVC_MAYBE_GAP 0.02f    // class 1: that bound minus the first-order travel over the step below this
-__device__ __forceinline__ int class_of(const DevCfg &c, bool X, float pz, float qx, float qy, float qz, float qw, float vz,
-                                        float wx, float wy, float wz, float cg_off) {
-    if (!c.ground) return 2;
-    const float cg = X ? fabsf(cg_off) + fabsf(c.cg_burn) : 0.0f;
-    const float R31 = 2.0f * (qx * qz - qw * qy), R32 = 2.0f * (qy * qz + qw * qx);
-    const float R33 = 1.0f - 2.0f * (qx * qx + qy * qy);
-    const float hh = c.half_len + cg;
-    const float gmin = pz - fabsf(R33) * hh - c.radius * sqrtf(R31 * R31 + R32 * R32);
-    const float reach = sqrtf(hh * hh + c.radius * c.radius);
-    const float travel = (fabsf(vz) + sqrtf(wx * wx + wy * wy + wz * wz) * reach) * (c.dt * (float)c.K);
-    return gmin < TVC_NOW_GAP ? 0 : (gmin - travel < TVC_MAYBE_GAP ? 1 : 2);
-}
 // FROM_STATE: compute the classes from the state planes (80 B per env; first step, or after a reset / set_state / rollout
 // touched the state behind the step path's back).  Otherwise read the class byte step_kernel_v2 left for every env
 // (1 B per env) -- this instantiation CLOSES a step and prepares the next one's sequence.

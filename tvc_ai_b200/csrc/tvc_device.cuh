@@ -746,6 +746,23 @@ __device__ __forceinline__ void store_env(const DevState &st, bool X, long long 
     }
 }
 
+// Heuristic work class of an env for the coming step (classify_kernel sorts by it; the rollout kernel sorts its CTA by it):
+// 0 = its lowest point touches the ground now, 1 = it may come within reach during the step, 2 = airborne.
+#define TVC_NOW_GAP 0.008f     // class 0: lower bound of the lowest point's height below this
+#define TVC_MAYBE_GAP 0.02f    // class 1: that bound minus the first-order travel over the step below this
+__device__ __forceinline__ int class_of(const DevCfg &c, bool X, float pz, float qx, float qy, float qz, float qw, float vz,
+                                        float wx, float wy, float wz, float cg_off) {
+    if (!c.ground) return 2;
+    const float cg = X ? fabsf(cg_off) + fabsf(c.cg_burn) : 0.0f;
+    const float R31 = 2.0f * (qx * qz - qw * qy), R32 = 2.0f * (qy * qz + qw * qx);
+    const float R33 = 1.0f - 2.0f * (qx * qx + qy * qy);
+    const float hh = c.half_len + cg;
+    const float gmin = pz - fabsf(R33) * hh - c.radius * sqrtf(R31 * R31 + R32 * R32);
+    const float reach = sqrtf(hh * hh + c.radius * c.radius);
+    const float travel = (fabsf(vz) + sqrtf(wx * wx + wy * wy + wz * wz) * reach) * (c.dt * (float)c.K);
+    return gmin < TVC_NOW_GAP ? 0 : (gmin - travel < TVC_MAYBE_GAP ? 1 : 2);
+}
+
 struct StepResult {
     float obs[10];
     float reward;

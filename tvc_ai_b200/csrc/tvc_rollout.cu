@@ -46,7 +46,7 @@ constexpr uint32_t OFF_A1 = OFF_W1 + W1_BYTES;
 constexpr uint32_t OFF_H1 = OFF_A1 + NT * A1_BYTES;     // also the contact-exchange area during physics
 constexpr uint32_t OFF_VEC = OFF_H1 + H1_BYTES;
 constexpr uint32_t OFF_BAR = OFF_VEC + VEC_BYTES;       // weight barrier, one MMA barrier per tile, tmem base
-constexpr uint32_t SMEM_TOTAL = OFF_BAR + 64;
+constexpr uint32_t SMEM_TOTAL = OFF_BAR + 64 + 256;   // barriers + tmem base (64 B), class counts of the in-CTA sort (256 B)
 static_assert(sizeof(ContactSmemT<RB>) <= NT * A1_BYTES + H1_BYTES, "contact exchange must fit in the operand + hidden-tile area");
 static_assert(NT >= 2 && NT % 2 == 0, "tiles alternate between two TMEM column sets");
 static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
@@ -169,9 +169,10 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = tid / TM, row = tid % TM;          // this thread's MMA tile and accumulator row
-    const long long i = (long long)blockIdx.x * RB + tid;
-    const bool live = i < st.n;
-    const long long gid = c.env_base + i;
+    // env held by this thread: fixed at first, re-assigned within the CTA every step (class sort, below)
+    long long i = (long long)blockIdx.x * RB + tid;
+    bool live = i < st.n;
+    long long gid = c.env_base + i;
 
     const uint32_t s_base = smem_u32(smem);
     const uint32_t bar_w = s_base + OFF_BAR;
@@ -441,7 +442,57 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
         a0 = tanhf(mean0 + expf(ls0) * e0);
         a1 = tanhf(mean1 + expf(ls1) * e1);
 
-        // ---- env step (same device code as the legacy step kernel; the hidden-tile area is the contact exchange) ----
+#ifndef TVC_ROLLOUT_NO_SORT
+        // ---- class sort within the CTA: the envs change threads so that warps hold envs of one work class ----
+        // One thread keeps its accumulator row, not its env: a row of an MMA tile is just a slot, so after the action is
+        // known the 512 envs are stably sorted by class (in contact / may touch / airborne) and every thread takes over the
+        // env at its own position -- state, action, reward sum and env index travel through the idle operand + hidden-tile
+        // area (35 words x 512).  Without it every warp holds a few in-contact envs and walks the whole solver path;
+        // with it three or four of the sixteen warps do, and the step is bounded by their (now uncontended) chain.
+        {
+            int *s_cnt = reinterpret_cast<int *>(smem + OFF_BAR + 64);               // [3][RB / 32]
+            float *s_x = reinterpret_cast<float *>(smem + OFF_A1);                   // [35][RB] words
+            static_assert(35u * RB * 4u <= NT * A1_BYTES + H1_BYTES, "env exchange must fit in the operand + hidden-tile area");
+            static_assert(3 * (RB / 32) * 4 <= 256, "class counts fit behind the barriers");
+            const unsigned full = 0xffffffffu;
+            const int cls = live ? class_of(c, X, e.pz, e.qx, e.qy, e.qz, e.qw, e.vz, e.wx, e.wy, e.wz, e.cg_off) : 2;
+            const unsigned m0 = __ballot_sync(full, cls == 0), m1 = __ballot_sync(full, cls == 1), m2 = __ballot_sync(full, cls == 2);
+            if (lane == 0) { s_cnt[warp] = __popc(m0); s_cnt[RB / 32 + warp] = __popc(m1); s_cnt[2 * (RB / 32) + warp] = __popc(m2); }
+            __syncthreads();
+            int before = 0, t0 = 0, t1 = 0;
+#pragma unroll
+            for (int w = 0; w < RB / 32; w++) {
+                const int c0 = s_cnt[w], c1 = s_cnt[RB / 32 + w], c2 = s_cnt[2 * (RB / 32) + w];
+                t0 += c0; t1 += c1;
+                if (w < warp) before += cls == 0 ? c0 : (cls == 1 ? c1 : c2);
+            }
+            const unsigned mk = cls == 0 ? m0 : (cls == 1 ? m1 : m2);
+            const int pos = (cls == 0 ? 0 : (cls == 1 ? t0 : t0 + t1)) + before + __popc(mk & ((1u << lane) - 1u));
+            float w_[35] = {e.px, e.py, e.pz, e.ep_ret, e.qx, e.qy, e.qz, e.qw, e.vx, e.vy, e.vz, __int_as_float(e.step),
+                            e.wx, e.wy, e.wz, __int_as_float(e.burn), __int_as_float(e.phase), __int_as_float(e.success),
+                            __int_as_float(e.has_prev), __int_as_float(e.consec), e.ap0, e.ap1, __int_as_float(e.hist_count),
+                            __int_as_float(e.n_clip), __int_as_float(e.n_run), e.mass_scale, e.thrust_scale, e.cg_off,
+                            e.wind_x, e.wind_y, __int_as_float(e.episode), a0, a1, rsum, __int_as_float((int)(i - (long long)blockIdx.x * RB))};
+#pragma unroll
+            for (int k = 0; k < 35; k++) s_x[k * RB + pos] = w_[k];
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 35; k++) w_[k] = s_x[k * RB + tid];
+            e.px = w_[0]; e.py = w_[1]; e.pz = w_[2]; e.ep_ret = w_[3]; e.qx = w_[4]; e.qy = w_[5]; e.qz = w_[6]; e.qw = w_[7];
+            e.vx = w_[8]; e.vy = w_[9]; e.vz = w_[10]; e.step = __float_as_int(w_[11]);
+            e.wx = w_[12]; e.wy = w_[13]; e.wz = w_[14]; e.burn = __float_as_int(w_[15]); e.phase = __float_as_int(w_[16]);
+            e.success = __float_as_int(w_[17]); e.has_prev = __float_as_int(w_[18]); e.consec = __float_as_int(w_[19]);
+            e.ap0 = w_[20]; e.ap1 = w_[21]; e.hist_count = __float_as_int(w_[22]); e.n_clip = __float_as_int(w_[23]);
+            e.n_run = __float_as_int(w_[24]); e.mass_scale = w_[25]; e.thrust_scale = w_[26]; e.cg_off = w_[27];
+            e.wind_x = w_[28]; e.wind_y = w_[29]; e.episode = __float_as_int(w_[30]);
+            a0 = w_[31]; a1 = w_[32]; rsum = w_[33];
+            i = (long long)blockIdx.x * RB + __float_as_int(w_[34]);
+            live = i < st.n;
+            gid = c.env_base + i;
+            __syncthreads();   // the exchange area is the MLP's operand / hidden-tile area again from the next step on
+        }
+#endif
+        // ---- env step (same device code as the step kernel) ----
         BodyP P;
         Forces f;
         if (live) env_pre<X>(c, st, i, e, a0, a1, P, f);
