@@ -836,6 +836,17 @@ template <bool X, int DIV>
 __device__ __forceinline__ void env_post(const DevCfg &c, const DevState &st, long long i, long long gid, Env &e,
                                          float a0, float a1, StepResult &r) {
     e.step += 1;
+    // the ten-entry reward ring (R8) is read further down: ask for it now, so that its DRAM round trip runs under the
+    // Euler angles, the reward terms and the Philox noise instead of stalling the warp where the values are needed
+    float rv[10];
+#pragma unroll
+    for (int k = 0; k < 10; k++) rv[k] = st.ring[(long long)k * st.n + i];
+    unsigned cw_early = 0u, rw_early = 0u;   // the bit-ring words of this push's slot (fast diversity mode), same reason
+    if (DIV == 1) {
+        const int wi0 = (e.hist_count % TVC_HIST) >> 5;
+        cw_early = st.clipb[(long long)wi0 * st.n + i];
+        rw_early = st.runb[(long long)wi0 * st.n + i];
+    }
 
     // ---- S7 (ref:608-633) ----
     float ox, oy, oz, ow, epitch, eyaw;
@@ -900,9 +911,6 @@ __device__ __forceinline__ void env_post(const DevCfg &c, const DevState &st, lo
     const int len = min(hc, TVC_HIST);
     float last_pushed = 0.0f;
     {
-        float rv[10];
-#pragma unroll
-        for (int k = 0; k < 10; k++) rv[k] = st.ring[(long long)k * st.n + i];
         int ls = (hc + 9) % 10;   // slot of push hc-1
 #pragma unroll
         for (int k = 0; k < 10; k++) if (k == ls) last_pushed = rv[k];
@@ -936,7 +944,7 @@ __device__ __forceinline__ void env_post(const DevCfg &c, const DevState &st, lo
         if (DIV == 1) {
             const int wi = slot >> 5;
             const unsigned bit = 1u << (slot & 31);
-            unsigned cw = st.clipb[(long long)wi * st.n + i], rw = st.runb[(long long)wi * st.n + i];
+            unsigned cw = cw_early, rw = rw_early;
             if (hc >= TVC_HIST) {
                 if (cw & bit) e.n_clip--;
                 if (rw & bit) e.n_run--;
