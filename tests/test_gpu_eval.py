@@ -68,3 +68,32 @@ def test_curriculum_conditions_reach_the_kernel(lib_built):
     with pytest.raises(RuntimeError):
         RocketTVCVectorEnv(4, config={}, contract="R").set_curriculum(cond)   # the reference env has no such coupling
     v.close()
+
+
+@pytest.mark.gpu
+def test_batched_curiosity_matches_single_env_facade(lib_built):
+    """Row S14 / Q14 / Q19 at the VectorEnv boundary: with the same (never-trained) forward model the batched intrinsic
+    reward equals the single-env facade's, including "skipped on the first step of an episode" across an autoreset."""
+    import numpy as np
+    import torch
+    from tvc_ai_b200.env import EnhancedRocketTVCEnv
+    from tvc_ai_b200.vector_env import RocketTVCVectorEnv
+    torch.manual_seed(3)
+    single = EnhancedRocketTVCEnv(config={}, enable_curiosity=True)
+    vec = RocketTVCVectorEnv(4, config={}, contract="R", enable_curiosity=True, curiosity_module=single.curiosity_module)
+    single.reset(seed=0)
+    vec.reset(seed=0)
+    rng = np.random.default_rng(9)
+    episodes = 0
+    for t in range(160):
+        a = rng.uniform(-1, 1, 2).astype(np.float32)
+        o1, r1, te1, tr1, info = single.step(a)
+        o4, r4, te4, tr4, _ = vec.step(torch.from_numpy(np.tile(a, (4, 1))).cuda())
+        assert abs(float(r4[0]) - float(r1)) <= 1e-5 * max(1.0, abs(float(r1))), (t, float(r4[0]), float(r1))
+        assert torch.allclose(r4, r4[0].expand(4))
+        assert bool(te4[0]) == bool(te1) and bool(tr4[0]) == bool(tr1)
+        if te1 or tr1:
+            episodes += 1
+            single.reset(seed=0)          # the vector env reset itself in the same step
+    assert episodes >= 1
+    single.close(); vec.close()

@@ -27,7 +27,8 @@ class RocketTVCVectorEnv:
 
     def __init__(self, num_envs: int, config: Optional[dict] = None, max_episode_steps: int = 1000,
                  contract: str | int = "R", device: Optional[int] = None, env_id_base: int = 0,
-                 final_info: bool = True, copy_outputs: bool = True, **engine_over):
+                 final_info: bool = True, copy_outputs: bool = True, enable_curiosity: bool = False,
+                 curiosity_module=None, **engine_over):
         if isinstance(contract, str):
             contract = {"R": A.CONTRACT_R, "X": A.CONTRACT_X}[contract.upper()]
         self.num_envs = int(num_envs)
@@ -46,6 +47,16 @@ class RocketTVCVectorEnv:
         # numpy path: True returns fresh arrays every step (Gymnasium semantics); False returns views of the pinned
         # host buffers tvc_step_host writes into (valid until the next step) and float32 rewards -- no host copies
         self._copy_outputs = bool(copy_outputs)
+        # Row S14 / quirks Q14, Q19 for the batch (torch path): the reference's never-trained forward model adds
+        # 0.01 * mean((f([s8, a]) - s8')^2) to the clipped reward, skipped on the first step of every episode
+        # (ref:257-269, :496-502).  Off by default, as in the reference's evaluation env (scripts/train.py:329).
+        self.enable_curiosity = bool(enable_curiosity)
+        self.curiosity_module = None
+        if self.enable_curiosity:
+            from .env import CuriosityModule
+            self.curiosity_module = curiosity_module or CuriosityModule(obs_dim=8, action_dim=2, device=self.engine.device)
+            self._prev_s8 = torch.zeros((self.num_envs, 8), device=self.engine.device)
+            self._has_prev = torch.zeros(self.num_envs, dtype=torch.bool, device=self.engine.device)
 
     # ------------------------------------------------------------------
     def reset(self, *, seed: Optional[int] = None, options: Optional[dict] = None):
@@ -53,6 +64,8 @@ class RocketTVCVectorEnv:
         reference's reset is deterministic and ignores it (quirk Q15)."""
         as_torch = bool(options and options.get("return_torch"))
         obs = self.engine.reset(seed=int(seed) if seed is not None else 0)
+        if self.enable_curiosity:
+            self._has_prev.zero_()          # ref:399-401: reset() clears state_history
         return (obs if as_torch else obs.cpu().numpy().copy()), {}
 
     def step(self, actions):
@@ -74,6 +87,17 @@ class RocketTVCVectorEnv:
             info = None
         term_b, trunc_b = term.bool(), trunc.bool()
         done = term_b | trunc_b
+        if self.enable_curiosity:
+            if actions is None:
+                raise ValueError("enable_curiosity needs the actions (in-kernel random actions are not visible to the forward model)")
+            with torch.no_grad():
+                a = actions.reshape(self.num_envs, 2).clamp(-1.0, 1.0)
+                s8_next = torch.where(done[:, None], self.engine.final_obs[:, :8], obs[:, :8])   # the env's own next state
+                pred = self.curiosity_module.forward_model(torch.cat([self._prev_s8, a], dim=1))
+                intrinsic = 0.01 * ((pred - s8_next) ** 2).mean(dim=1)
+                rew = rew + torch.where(self._has_prev, intrinsic, torch.zeros_like(intrinsic))   # a new tensor: the engine's buffer keeps the extrinsic reward
+                self._prev_s8.copy_(obs[:, :8])
+                self._has_prev.copy_(~done)
         infos = {"final_observation": self.engine.final_obs, "_final_observation": done}
         if info is not None:
             infos["final_info"] = {k: info[k] for k in ("altitude", "tilt_deg", "omega_mag", "fuel", "phase", "step",
