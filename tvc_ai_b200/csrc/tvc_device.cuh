@@ -96,7 +96,14 @@ enum { ST_DR_A = 1, ST_DR_B = 2, ST_NOISE_A = 3, ST_NOISE_B = 4, ST_ACTION = 5, 
 //   sincos_small         : degree-9/8 Taylor polynomials, |x| <= 0.8 rad, error < 4e-8
 // (an earlier build, then bound by instruction fetch, measured raw `asm volatile` rcp/sqrt/rsqrt.approx.ftz 10 % slower;
 //  with the class-ordered sequence the plain-asm single-MUFU rsqrt below is the faster form)
+// reciprocal of a well-scaled positive number (masses, inertias, squared norms): one MUFU.RCP.  __fdividef(1, x) carries
+// range handling for |x| > 2^126 (two predicated FMULs, two FSELs per call, 42 call sites: 5 % of the step kernel's
+// instructions and 11 % of its stall samples in the ncu source view)
+#ifdef TVC_RCP_FDIVIDEF
 __device__ __forceinline__ float rcp_fast(float x) { return __fdividef(1.0f, x); }
+#else
+__device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#endif
 // operand known to be a normal number (callers clamp it away from the subnormal range): one MUFU.RSQ, without the
 // subnormal pre/post-scaling rsqrtf() carries
 __device__ __forceinline__ float rsqrt_normal(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
