@@ -536,7 +536,9 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
                 case 8: v = n_ra; break;   case 9: v = n_tr; break;   case 10: v = n_vi; break;  case 11: v = d_alt; break;
                 case 12: v = d_tilt; break; case 13: v = d_fuel; break; default: break;
             }
-            if (lane < 14 && v != 0.0 && g < ngroups) st.partial[(long long)g * TVC_NSTAT + lane] += v;
+            // the row has exactly one writer per launch (this group), so the order-free reduction is still deterministic; as a
+            // reduction it does not make the warp wait for the old value (the read-modify-write stalled on a DRAM round trip)
+            if (lane < 14 && v != 0.0 && g < ngroups) atomicAdd(&st.partial[(long long)g * TVC_NSTAT + lane], v);
         }
     }
 }
@@ -578,7 +580,7 @@ __global__ void get_state_kernel(const __grid_constant__ DevState st, tvc_env_st
     s.ep_return = e.ep_ret;
     s.step = e.step; s.burn = e.burn; s.phase = e.phase; s.success = e.success; s.has_prev = e.has_prev;
     s.consec = e.consec; s.hist_count = e.hist_count; s.episode = e.episode; s.n_clip = e.n_clip; s.n_run = e.n_run;
-    for (int k = 0; k < 10; k++) s.ring10[k] = st.ring[(long long)k * st.n + i];
+    for (int k = 0; k < 10; k++) s.ring10[k] = st.ring[12 * i + k];
     s.mass_scale = e.mass_scale; s.thrust_scale = e.thrust_scale; s.cg_offset = e.cg_off;
     s.wind[0] = e.wind_x; s.wind[1] = e.wind_y;
     if (X) for (int k = 0; k < delay; k++) { float2 d = st.delay[(long long)k * st.n + i]; s.delay_ring[k][0] = d.x; s.delay_ring[k][1] = d.y; }
@@ -601,7 +603,7 @@ __global__ void set_state_kernel(const __grid_constant__ DevState st, const tvc_
     e.mass_scale = s.mass_scale; e.thrust_scale = s.thrust_scale; e.cg_off = s.cg_offset;
     e.wind_x = s.wind[0]; e.wind_y = s.wind[1]; e.episode = s.episode;
     store_env(st, X, i, e);
-    for (int k = 0; k < 10; k++) st.ring[(long long)k * st.n + i] = s.ring10[k];
+    for (int k = 0; k < 10; k++) st.ring[12 * i + k] = s.ring10[k];
     if (X) for (int k = 0; k < delay; k++) st.delay[(long long)k * st.n + i] = make_float2(s.delay_ring[k][0], s.delay_ring[k][1]);
 }
 
@@ -783,7 +785,7 @@ int tvc_create(const tvc_config *cfg, int device, int64_t num_envs, tvc_handle *
     s.n = num_envs;
 #define TRY(x) do { rc = (x); if (rc) { tvc_destroy(h); return rc; } } while (0)
     TRY(dalloc(&s.s0, n)); TRY(dalloc(&s.s1, n)); TRY(dalloc(&s.s2, n)); TRY(dalloc(&s.s3, n)); TRY(dalloc(&s.s4, n));
-    TRY(dalloc(&s.ring, 10 * n));
+    TRY(dalloc(&s.ring, 12 * n));
     if (cfg->contract == TVC_CONTRACT_X) {
         TRY(dalloc(&s.d0, n)); TRY(dalloc(&s.d1, n));
         TRY(dalloc(&s.delay, (size_t)TVC_MAX_DELAY * n));

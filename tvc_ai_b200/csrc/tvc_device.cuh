@@ -43,7 +43,7 @@ struct DevState {
     float4 *s4;  // a_prev0 a_prev1 hist_count(int) div(int): n_clip[0:10) n_run[10:20) | n_distinct
     float4 *d0;  // X: mass_scale thrust_scale cg_offset wind_x
     float4 *d1;  // X: wind_y episode(int) - -
-    float *ring;      // [10][N] last ten clipped totals, slot = push % 10
+    float *ring;      // [N][12] last ten clipped totals per env (48 B, three 16-byte loads), slot = push % 10; 2 floats padding
     unsigned *clipb;  // [32][N] fast diversity: value == -1000
     unsigned *runb;   // [32][N] fast diversity: value == predecessor
     float *hist;      // [1000][N] exact diversity only
@@ -846,8 +846,12 @@ __device__ __forceinline__ void env_post(const DevCfg &c, const DevState &st, lo
     // the ten-entry reward ring (R8) is read further down: ask for it now, so that its DRAM round trip runs under the
     // Euler angles, the reward terms and the Philox noise instead of stalling the warp where the values are needed
     float rv[10];
-#pragma unroll
-    for (int k = 0; k < 10; k++) rv[k] = st.ring[(long long)k * st.n + i];
+    {
+        const float4 *rp = reinterpret_cast<const float4 *>(st.ring + 12 * i);
+        const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2];
+        rv[0] = r0.x; rv[1] = r0.y; rv[2] = r0.z; rv[3] = r0.w; rv[4] = r1.x; rv[5] = r1.y; rv[6] = r1.z; rv[7] = r1.w;
+        rv[8] = r2.x; rv[9] = r2.y;
+    }
     unsigned cw_early = 0u, rw_early = 0u;   // the bit-ring words of this push's slot (fast diversity mode), same reason
     if (DIV == 1) {
         const int wi0 = (e.hist_count % TVC_HIST) >> 5;
@@ -987,7 +991,7 @@ __device__ __forceinline__ void env_post(const DevCfg &c, const DevState &st, lo
             if (cx == 0) e.n_clip++;
             st.hist[(long long)slot * st.n + i] = reward;
         }
-        st.ring[(long long)(hc % 10) * st.n + i] = reward;
+        st.ring[12 * i + (hc % 10)] = reward;
         e.hist_count = hc + 1;
         if (e.hist_count >= 2000000000) e.hist_count -= 1000000000;   // keeps % 10, % 1000 and len
     }
