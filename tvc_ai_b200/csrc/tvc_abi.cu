@@ -361,9 +361,10 @@ __device__ __forceinline__ int env_at_group(const DevState &st, int p, int lane,
 #ifndef TVC_V2_BLOCK
 #define TVC_V2_BLOCK 128
 #endif
-#ifndef TVC_V2_NO_LOCKSTEP
-#define TVC_V2_LOCKSTEP 1   // measured: 0.1767 -> 0.164 ms per step (shared instruction fetches); larger CTAs / chunks lose
-#endif
+// -DTVC_V2_LOCKSTEP: a CTA pulls four consecutive groups at once and its warps re-align at every substep (shared instruction
+// fetches).  That won 7 % while the kernel was 92 KB of code with every contact row always visited (0.1767 -> 0.164 ms); with
+// the class-ordered sequence, the lazy rows and 57 KB of code the barrier costs more than the instruction cache gains:
+// 0.0947 ms with it, 0.0925 ms without.  Default: every warp pulls its own groups and never waits for another warp.
 // DEFER: finished envs are marked for the closing sort kernel (large batches) instead of being reset in place (small batches,
 // where one launch fewer matters more than the idle lanes).
 // A split into an airborne-part kernel at twice the occupancy (64 registers, solver out of line) followed by a near-ground
