@@ -386,6 +386,8 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
 #ifdef TVC_PHASE_PROF2
     long long pt_prev = clock64();
 #endif
+    bool first_pull = true;
+    (void)first_pull;
     for (;;) {
         int g = 0;
 #ifdef TVC_V2_LOCKSTEP
@@ -406,8 +408,15 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
         const bool live = g < ngroups && slot < st.n;
 #endif
 #else
-        if (lane == 0) g = g_base + (int)atomicAdd(queue, 1u);   // dynamic work queue over the sorted 32-env groups
-        g = __shfl_sync(full, g, 0);
+        // every warp's first group is its own index (no atomic: 2,368 warps hitting one counter at t = 0 showed up as 6 % of
+        // the stall samples); after that a dynamic queue over the remaining 32-env groups of the sorted sequence
+        if (first_pull) {
+            g = g_base + (int)(blockIdx.x * (TVC_V2_BLOCK / 32) + (threadIdx.x >> 5));
+            first_pull = false;
+        } else {
+            if (lane == 0) g = g_base + (int)(gridDim.x * (TVC_V2_BLOCK / 32)) + (int)atomicAdd(queue, 1u);
+            g = __shfl_sync(full, g, 0);
+        }
         if (g >= ngroups) break;
         const long long slot = (long long)g * 32 + lane;
         const bool live = slot < st.n;
