@@ -165,9 +165,9 @@ step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState s
 //
 // Each 1024-env chunk is sorted by class (stable), its class counts go to goff[c][chunk + 1], and the last CTA to finish
 // turns the counts into exclusive scans over the chunks.  step_kernel_v2 then walks ONE global sequence -- all class-0
-// envs, all class-1 envs, all class-2 envs -- so that a CTA's warps hold groups of the same class (a CTA whose warps
-// re-align at every substep would otherwise park three airborne warps behind one solver warp) and the long class-0
-// groups start first.  Deterministic: no atomics on data, the sequence depends on the states only.
+// envs, all class-1 envs, all class-2 envs -- so that a warp's 32 envs are of one class (the solver path is walked by
+// full warps or not at all) and the long class-0 groups start first, with the short airborne groups filling in behind and
+// beside them.  Deterministic: no atomics on data, the sequence depends on the states only.
 // FROM_STATE: compute the classes from the state planes (80 B per env; first step, or after a reset / set_state / rollout
 // touched the state behind the step path's back).  Otherwise read the class byte step_kernel_v2 left for every env
 // (1 B per env) -- this instantiation CLOSES a step and prepares the next one's sequence.
