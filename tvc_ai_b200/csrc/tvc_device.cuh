@@ -755,8 +755,12 @@ __device__ __forceinline__ void store_env(const DevState &st, bool X, long long 
 
 // Heuristic work class of an env for the coming step (classify_kernel sorts by it; the rollout kernel sorts its CTA by it):
 // 0 = its lowest point touches the ground now, 1 = it may come within reach during the step, 2 = airborne.
+#ifndef TVC_NOW_GAP
 #define TVC_NOW_GAP 0.008f     // class 0: lower bound of the lowest point's height below this
+#endif
+#ifndef TVC_MAYBE_GAP
 #define TVC_MAYBE_GAP 0.02f    // class 1: that bound minus the first-order travel over the step below this
+#endif
 __device__ __forceinline__ int class_of(const DevCfg &c, bool X, float pz, float qx, float qy, float qz, float qw, float vz,
                                         float wx, float wy, float wz, float cg_off) {
     if (!c.ground) return 2;
