@@ -130,8 +130,8 @@ void orc_body_params_default(orc_body_params *p) {
     p->dt_step = 0.02;
     p->max_vel = 100.0;
     p->ground = 1;
-    p->contact_iters = 8;
-    p->warm_iters = 3;
+    p->contact_iters = 2;
+    p->warm_iters = 1;
     p->radius = radius; p->half_len = 0.5 * length; p->cg = 0.0;
     p->mu = 0.3 * 0.8;                       /* ref:456 x ref:350, Bullet combines by product */
     p->mu_spin = 0.1 * 0.8 + 0.1 * 0.3;      /* ref:351,457: Bullet combined torsional friction */
@@ -181,7 +181,7 @@ typedef double real;
 
 static inline real r_clamp(real x, real lo, real hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
-static void r_matrix_from_quat(const real q[4], real m[9]) {
+static real r_matrix_from_quat(const real q[4], real m[9]) {
     real d = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
     real s = (real)2.0 / d;
     real xs = q[0] * s, ys = q[1] * s, zs = q[2] * s;
@@ -191,6 +191,7 @@ static void r_matrix_from_quat(const real q[4], real m[9]) {
     m[0] = (real)1.0 - (yy + zz); m[1] = xy - wz;                 m[2] = xz + wy;
     m[3] = xy + wz;               m[4] = (real)1.0 - (xx + zz);   m[5] = yz - wx;
     m[6] = xz - wy;               m[7] = yz + wx;                 m[8] = (real)1.0 - (xx + yy);
+    return -(xx + yy);   /* R33 - 1 without the cancellation */
 }
 
 /*
@@ -205,31 +206,93 @@ static void r_matrix_from_quat(const real q[4], real m[9]) {
  *          (direction -(R31,R32)/max(rho, 1e-3): slides to the cap centre as the axis becomes vertical)
  *      f0,f1,f2  three body-fixed rim points of the bottom cap at 0, 120, 240 degrees
  *  - entered only when the lowest candidate is closer than `margin` AND some row can bind at all:
- *    gap_min - 1e-4 < (1+e) (|vz| + |w| reach) dt  (otherwise the stored impulses are cleared); then ALL
- *    five normal rows are processed: vn >= -gap/dt (gap >= 0, speculative) or vn >= -erp*gap/dt
- *    (gap < 0, Baumgarte), plus restitution e when approaching faster than the threshold
- *  - per row: normal impulse (lambda >= 0), then the two world-axis tangent rows projected on the
- *    friction disc mu*lambda_n; after the five points, spinning and rolling friction rows limited by
- *    mu_spin / mu_roll times the total normal impulse
- *  - projected Gauss-Seidel on velocities.  The first substep of a step starts cold and runs
- *    contact_iters sweeps; later substeps are warm-started with the previous substep's 18 impulses
- *    (applied before sweeping) and run warm_iters sweeps.  Impulses do not persist across steps.
+ *    gap_min - 1e-4 < (1+e) (|vz| + |w| reach) dt  (otherwise the stored impulses are cleared)
+ *  - normal target per point: vn >= -gap/dt (gap >= 0, speculative) or vn >= -erp*gap/dt (gap < 0,
+ *    Baumgarte), plus restitution e on the approach speed beyond the threshold (continuous at the threshold).
+ *    The gap is formed as (pz + cz) + cz (nbz - 1) + cx nbx + cy nby so that the two O(0.5) terms cancel first
+ *    and the height update carries a running compensation: the targets divide the gap by dt (x500 at K = 10).
+ *  - BODY-FRAME rows: the angular velocity is carried in the body frame during the solve, so the inverse
+ *    inertia stays diag(1/Ixy, 1/Ixy, 1/Iz) and the large 1/Iz (400 kg^-1 m^-2) only ever multiplies the
+ *    body-z component of a row's angular Jacobian c x d_b (|c_x|, |c_y| <= r), which is small by geometry
+ *    instead of by cancellation.  A solve in which nothing binds leaves omega bit-identical.
+ *  - torsional friction (Bullet's spinning / rolling friction, ref:351-352, :457-458) acts along the body's
+ *    principal axes: axial spin limited by mu_spin * (total normal impulse), the two transverse axes by
+ *    mu_roll * (total normal impulse).  Along principal axes the three rows are decoupled from each other
+ *    (a world-axis formulation couples them through 1/Iz, and a scalar Gauss-Seidel between them needs
+ *    6-8 passes at an impact).
+ *  - block Gauss-Seidel: a point that can bind (target above its normal velocity, or a stored impulse) gets
+ *    its three rows (normal z, tangents x and y, world axes) solved TOGETHER with the point's 3x3 Delassus
+ *    matrix A = (1/m) I + J I^-1 J^T: stick solution p* = p + A^-1 e, accepted when p*_n > 0 and
+ *    |p*_t| <= mu p*_n; otherwise slide: the friction impulse keeps the direction of p*_t at magnitude
+ *    mu p_n and the normal row is re-solved with that coupling (p_n = rhs / (A_nn + mu A_nt . t)); p_n <= 0
+ *    releases the point.  Every branch meets its neighbour continuously.
+ *  - point 0 (the manifold's first point, the one Bullet attaches its torsional rows to) carries the axial spin
+ *    row in its block: rim friction and axial spin are coupled through 1/Iz (a scalar pass between them
+ *    contracts by ~0.67 only).  The block is first solved with the axial row sticking (axis z removed from the
+ *    angular dynamics, contact velocity evaluated at w_z = 0); if the axial impulse that needs stays inside
+ *    its limit the solution is exact, otherwise the axial impulse goes to the limit and the point is solved
+ *    again without the fold (both solutions coincide at the limit).
+ *  - after the five points: the transverse torsional rows (and the axial one if point 0 was not visited).
+ *  - a solve that follows free flight starts cold and runs contact_iters passes; a substep that follows a solve
+ *    is warm-started with its 18 impulses (applied before the passes) and runs warm_iters passes.  Impulses do
+ *    not persist across steps.
  */
 /* diagnostic counters (not thread-safe; meaningful for serial runs only) */
 long long orc_dbg_substeps = 0, orc_dbg_entered = 0, orc_dbg_canbind = 0;
+long long orc_dbg_blocks[4] = {0, 0, 0, 0};   /* release, stick, slide, points 1-4 visited */
 
-/* lam[18]: accumulated impulses carried between substeps: normal(5), tangent-x(5), tangent-y(5), spin, roll-x, roll-y */
-static void solve_contacts(const orc_body_params *p, real dt, const real R[9], real pz, real v[3], real w[3],
-                           real lam[18], int iters) {
+typedef struct { real Jx[3], Jy[3], Jn[3]; } orc_rows;
+
+/* angular Jacobians (body frame) of the three world-axis rows at body-frame arm c: c x d_b */
+static inline void point_rows(const real c[3], const real xb[3], const real yb[3], const real nb[3], orc_rows *J) {
+    J->Jx[0] = c[1] * xb[2] - c[2] * xb[1]; J->Jx[1] = c[2] * xb[0] - c[0] * xb[2]; J->Jx[2] = c[0] * xb[1] - c[1] * xb[0];
+    J->Jy[0] = c[1] * yb[2] - c[2] * yb[1]; J->Jy[1] = c[2] * yb[0] - c[0] * yb[2]; J->Jy[2] = c[0] * yb[1] - c[1] * yb[0];
+    J->Jn[0] = c[1] * nb[2] - c[2] * nb[1]; J->Jn[1] = c[2] * nb[0] - c[0] * nb[2]; J->Jn[2] = c[0] * nb[1] - c[1] * nb[0];
+}
+
+typedef struct { real Axx, Axy, Axn, Ayy, Ayn, Ann; } orc_sym3;
+
+/* one point block: stick / slide / release for the Delassus matrix A and the wanted velocity change e at old impulses
+ * (l1, l2, ln); returns the new impulses */
+static inline void point_block(const orc_sym3 *A, real ex, real ey, real en, real mu, real l1, real l2, real ln,
+                               real *opx, real *opy, real *opn) {
+    const real Axx = A->Axx, Axy = A->Axy, Axn = A->Axn, Ayy = A->Ayy, Ayn = A->Ayn, Ann = A->Ann;
+    const real c00 = Ayy * Ann - Ayn * Ayn, c01 = Axn * Ayn - Axy * Ann, c02 = Axy * Ayn - Axn * Ayy;
+    const real c11 = Axx * Ann - Axn * Axn, c12 = Axy * Axn - Axx * Ayn, c22 = Axx * Ayy - Axy * Axy;
+    const real idet = (real)1.0 / (Axx * c00 + Axy * c01 + Axn * c02);
+    real px = l1 + (c00 * ex + c01 * ey + c02 * en) * idet;
+    real py = l2 + (c01 * ex + c11 * ey + c12 * en) * idet;
+    real pn = ln + (c02 * ex + c12 * ey + c22 * en) * idet;
+    const real mag2 = px * px + py * py, lim = mu * pn;
+    if (pn > 0 && mag2 <= lim * lim) orc_dbg_blocks[1]++;                 /* stick */
+    else if (mag2 > 0) {
+        /* sliding (or a stick solution that pulls): the friction impulse keeps the direction of the stick
+         * impulse at magnitude mu p_n, and the normal row is re-solved with that coupling; p_n <= 0 releases */
+        const real is = (real)1.0 / R_SQRT(mag2), tx = px * is, ty = py * is;
+        real den = Ann + mu * (Axn * tx + Ayn * ty);
+        if (den < (real)0.25 * Ann) den = (real)0.25 * Ann;
+        const real rhs = en + Ann * ln + Axn * l1 + Ayn * l2;
+        pn = rhs / den;
+        if (pn < 0) pn = 0;
+        px = mu * pn * tx; py = mu * pn * ty;
+        orc_dbg_blocks[pn > 0 ? 2 : 0]++;
+    } else { px = 0; py = 0; pn = 0; orc_dbg_blocks[0]++; }              /* release */
+    *opx = px; *opy = py; *opn = pn;
+}
+
+/* lam[18]: impulses carried between the substeps of a step: normal(5), tangent-x(5), tangent-y(5), torsional about the
+ * body axes z (spin), x, y (roll) */
+static void solve_contacts(const orc_body_params *p, real dt, const real R[9], real nz1, real pz, real pzc, real v[3], real w[3],
+                           real lam[18], int *have_lam) {
     const real r = (real)p->radius, h = (real)p->half_len, cg = (real)p->cg, margin = (real)p->margin;
     orc_dbg_substeps++;
-    const real R31 = R[6], R32 = R[7], R33 = R[8];
+    const real R31 = R[6], R32 = R[7];
     const real rho = R_SQRT(R31 * R31 + R32 * R32);
     const real inv = (real)1.0 / (rho > (real)1e-3 ? rho : (real)1e-3);
     const real ux = -R31 * inv, uy = -R32 * inv;
     const real zb = -h - cg, zt = h - cg;
     const real low = r * (R31 * ux + R32 * uy);          /* = -r*rho outside the regularised zone */
-    const real gb = pz + R33 * zb + low, gt = pz + R33 * zt + low;
+    const real gb = ((pz + zb) + pzc) + (zb * nz1 + low), gt = ((pz + zt) + pzc) + (zt * nz1 + low);
     const real gmin = gb < gt ? gb : gt;
     int enter = gmin < margin;
     if (enter) {
@@ -239,7 +302,9 @@ static void solve_contacts(const orc_body_params *p, real dt, const real R[9], r
         enter = gmin - (real)1e-4 < ((real)1.0 + (real)p->restitution) * vmax * dt;
         if (enter) orc_dbg_canbind++;
     }
-    if (!enter) { for (int i = 0; i < 18; i++) lam[i] = 0; return; }
+    if (!enter) { for (int i = 0; i < 18; i++) lam[i] = 0; *have_lam = 0; return; }
+    const int iters = *have_lam ? p->warm_iters : p->contact_iters;
+    *have_lam = 1;
 
     const real c[5][3] = {
         {r * ux, r * uy, zb},
@@ -248,96 +313,109 @@ static void solve_contacts(const orc_body_params *p, real dt, const real R[9], r
         {(real)-0.5 * r, (real)0.8660254037844386 * r, zb},
         {(real)-0.5 * r, (real)-0.8660254037844386 * r, zb},
     };
-    /* world inverse inertia W = R diag(1/I) R^T (symmetric) */
-    const real ia = (real)(1.0 / p->inertia[0]), ib = (real)(1.0 / p->inertia[2]);
-    const real W00 = ia * (R[0] * R[0] + R[1] * R[1]) + ib * R[2] * R[2];
-    const real W01 = ia * (R[0] * R[3] + R[1] * R[4]) + ib * R[2] * R[5];
-    const real W02 = ia * (R[0] * R[6] + R[1] * R[7]) + ib * R[2] * R[8];
-    const real W11 = ia * (R[3] * R[3] + R[4] * R[4]) + ib * R[5] * R[5];
-    const real W12 = ia * (R[3] * R[6] + R[4] * R[7]) + ib * R[5] * R[8];
-    const real W22 = ia * (R[6] * R[6] + R[7] * R[7]) + ib * R[8] * R[8];
+    /* world axes in body coordinates = rows of R; body-frame inverse inertia stays diagonal */
+    const real xb[3] = {R[0], R[1], R[2]}, yb[3] = {R[3], R[4], R[5]}, nb[3] = {R[6], R[7], R[8]};
+    const real Ii[3] = {(real)(1.0 / p->inertia[0]), (real)(1.0 / p->inertia[0]), (real)(1.0 / p->inertia[2])};
+    const real Im[3] = {(real)p->inertia[0], (real)p->inertia[0], (real)p->inertia[2]};
     const real im = (real)(1.0 / p->mass);
-    const real mu = (real)p->mu, mus = (real)p->mu_spin, mur = (real)p->mu_roll;
+    const real mu = (real)p->mu;
+    const real mut[3] = {(real)p->mu_roll, (real)p->mu_roll, (real)p->mu_spin};
     const real inv_dt = (real)1.0 / dt;
+    /* body-frame angular velocity wb0 = R^T w; wt carries the running value, w += R (wt - wb0) at the end */
+    const real wb0[3] = {R[0] * w[0] + R[3] * w[1] + R[6] * w[2], R[1] * w[0] + R[4] * w[1] + R[7] * w[2],
+                         R[2] * w[0] + R[5] * w[1] + R[8] * w[2]};
+    real wt[3] = {wb0[0], wb0[1], wb0[2]};
 
-    real ax[5], ay[5], az[5], tgt[5], imn[5], im1[5], im2[5];
-    real ln[5], l1[5], l2[5];
+    orc_rows J[5];
+    real tgt[5], ln[5], l1[5], l2[5];
     for (int i = 0; i < 5; i++) {
-        ax[i] = R[0] * c[i][0] + R[1] * c[i][1] + R[2] * c[i][2];
-        ay[i] = R[3] * c[i][0] + R[4] * c[i][1] + R[5] * c[i][2];
-        az[i] = R[6] * c[i][0] + R[7] * c[i][1] + R[8] * c[i][2];
-        real gap = pz + az[i];
-        /* effective masses for n = z, t1 = x, t2 = y at arm (ax, ay, az) */
-        real mn = im + (W00 * ay[i] * ay[i] - (real)2.0 * W01 * ax[i] * ay[i] + W11 * ax[i] * ax[i]);
-        real m1 = im + (W11 * az[i] * az[i] - (real)2.0 * W12 * az[i] * ay[i] + W22 * ay[i] * ay[i]);
-        real m2 = im + (W00 * az[i] * az[i] - (real)2.0 * W02 * az[i] * ax[i] + W22 * ax[i] * ax[i]);
-        imn[i] = (real)1.0 / mn; im1[i] = (real)1.0 / m1; im2[i] = (real)1.0 / m2;
-        real vn0 = v[2] + w[0] * ay[i] - w[1] * ax[i];
-        real rest = (vn0 < -(real)p->rest_threshold) ? -(real)p->restitution * vn0 : (real)0.0;
+        point_rows(c[i], xb, yb, nb, &J[i]);
+        /* height of the point above the plane: pz + c.nb = (pz + cz) + cz (nbz - 1) + cx nbx + cy nby */
+        real gap = ((pz + c[i][2]) + pzc) + (c[i][2] * nz1 + (nb[0] * c[i][0] + nb[1] * c[i][1]));
+        real vn0 = v[2] + (wb0[0] * J[i].Jn[0] + wb0[1] * J[i].Jn[1] + wb0[2] * J[i].Jn[2]);
+        real rest = (vn0 < -(real)p->rest_threshold) ? (real)p->restitution * (-vn0 - (real)p->rest_threshold) : (real)0.0;
         tgt[i] = rest + (gap > 0 ? -gap * inv_dt : -(real)p->erp * gap * inv_dt);
         ln[i] = lam[i]; l1[i] = lam[5 + i]; l2[i] = lam[10 + i];
     }
-    real lsp = lam[15], lr1 = lam[16], lr2 = lam[17];
-    const real iW22 = (real)1.0 / W22, iW00 = (real)1.0 / W00, iW11 = (real)1.0 / W11;
-    /* warm start: apply the stored impulses at the current contact geometry (targets above use the
+    real lt[3] = {lam[16], lam[17], lam[15]};    /* torsional impulses about body x, y, z */
+    /* warm start: apply the stored impulses at the current contact geometry (the targets above use the
      * velocities before this) */
     for (int i = 0; i < 5; i++) {
-        const real px_ = l1[i], py_ = l2[i], pn_ = ln[i];
-        v[0] += px_ * im; v[1] += py_ * im; v[2] += pn_ * im;
-        const real tx = ay[i] * pn_ - az[i] * py_, ty = az[i] * px_ - ax[i] * pn_, tz = ax[i] * py_ - ay[i] * px_;
-        w[0] += W00 * tx + W01 * ty + W02 * tz;
-        w[1] += W01 * tx + W11 * ty + W12 * tz;
-        w[2] += W02 * tx + W12 * ty + W22 * tz;
+        if (ln[i] == 0 && l1[i] == 0 && l2[i] == 0) continue;
+        v[0] += l1[i] * im; v[1] += l2[i] * im; v[2] += ln[i] * im;
+        for (int k = 0; k < 3; k++) wt[k] += Ii[k] * (J[i].Jx[k] * l1[i] + J[i].Jy[k] * l2[i] + J[i].Jn[k] * ln[i]);
     }
-    w[0] += W02 * lsp + W00 * lr1 + W01 * lr2;
-    w[1] += W12 * lsp + W01 * lr1 + W11 * lr2;
-    w[2] += W22 * lsp + W02 * lr1 + W12 * lr2;
+    for (int k = 0; k < 3; k++) wt[k] += Ii[k] * lt[k];
+
     for (int it = 0; it < iters; it++) {
         real lsum = 0;
+        int spin_done = 0;
         for (int i = 0; i < 5; i++) {
-            /* normal row */
-            real vn = v[2] + w[0] * ay[i] - w[1] * ax[i];
-            real nl = ln[i] + (tgt[i] - vn) * imn[i];
-            if (nl < 0) nl = 0;
-            real d = nl - ln[i];
-            ln[i] = nl;
-            lsum += nl;
-            v[2] += d * im;
-            w[0] += (W00 * ay[i] - W01 * ax[i]) * d;
-            w[1] += (W01 * ay[i] - W11 * ax[i]) * d;
-            w[2] += (W02 * ay[i] - W12 * ax[i]) * d;
-            /* friction disc */
-            real vt1 = v[0] + w[1] * az[i] - w[2] * ay[i];
-            real vt2 = v[1] + w[2] * ax[i] - w[0] * az[i];
-            real a1 = l1[i] - vt1 * im1[i];
-            real a2 = l2[i] - vt2 * im2[i];
-            real lim = mu * nl;
-            real mag2 = a1 * a1 + a2 * a2;
-            if (mag2 > lim * lim) { real sc = lim / R_SQRT(mag2); a1 *= sc; a2 *= sc; }
-            real d1 = a1 - l1[i], d2 = a2 - l2[i];
-            l1[i] = a1; l2[i] = a2;
-            v[0] += d1 * im; v[1] += d2 * im;
-            real tx = -az[i] * d2, ty = az[i] * d1, tz = ax[i] * d2 - ay[i] * d1;
-            w[0] += W00 * tx + W01 * ty + W02 * tz;
-            w[1] += W01 * tx + W11 * ty + W12 * tz;
-            w[2] += W02 * tx + W12 * ty + W22 * tz;
+            const orc_rows *Ji = &J[i];
+            /* point 0 is solved with the axial row folded in: body axis z (k = 2) is left out of the angular dynamics */
+            const int nk = (i == 0) ? 2 : 3;
+            real un = v[2], ux_ = v[0], uy_ = v[1];
+            for (int k = 0; k < nk; k++) { un += wt[k] * Ji->Jn[k]; ux_ += wt[k] * Ji->Jx[k]; uy_ += wt[k] * Ji->Jy[k]; }
+            const real unz = un + (nk == 2 ? wt[2] * Ji->Jn[2] : (real)0.0);      /* true normal velocity */
+            /* a point whose normal row cannot bind and that holds no impulse is an exact no-op */
+            if (!(tgt[i] > unz || ln[i] > 0 || l1[i] != 0 || l2[i] != 0)) continue;
+            if (i) orc_dbg_blocks[3]++;
+            /* the point's Delassus matrix (symmetric): A_ab = (1/m) delta_ab + sum_k Ii_k Ja_k Jb_k */
+            orc_sym3 A = {im, 0, 0, im, 0, im};
+            for (int k = 0; k < nk; k++) {
+                const real ix = Ii[k] * Ji->Jx[k], iy = Ii[k] * Ji->Jy[k], in_ = Ii[k] * Ji->Jn[k];
+                A.Axx += ix * Ji->Jx[k]; A.Axy += ix * Ji->Jy[k]; A.Axn += ix * Ji->Jn[k];
+                A.Ayy += iy * Ji->Jy[k]; A.Ayn += iy * Ji->Jn[k]; A.Ann += in_ * Ji->Jn[k];
+            }
+            real px, py, pn;
+            point_block(&A, -ux_, -uy_, tgt[i] - un, mu, l1[i], l2[i], ln[i], &px, &py, &pn);
+            real dx = px - l1[i], dy = py - l2[i], dn = pn - ln[i];
+            if (i == 0) {
+                /* the axial impulse that keeps w_z at zero through this block, limited by mu_spin * (this point's new
+                 * normal impulse + what the other points hold) */
+                const real slim = mut[2] * (pn + ln[1] + ln[2] + ln[3] + ln[4]);
+                const real cand = lt[2] - (wt[2] * Im[2] + (Ji->Jx[2] * dx + Ji->Jy[2] * dy + Ji->Jn[2] * dn));
+                if (cand >= -slim && cand <= slim) {
+                    wt[2] = 0;                       /* (exactly: the axial row sticks) */
+                    lt[2] = cand;
+                } else {
+                    /* the axial row slips: its impulse goes to the limit of the OLD normal impulses (what a scalar row
+                     * would see), and the point is solved again with the full angular dynamics */
+                    const real slim0 = mut[2] * (ln[0] + ln[1] + ln[2] + ln[3] + ln[4]);
+                    const real nl = r_clamp(cand, -slim0, slim0);
+                    wt[2] += Ii[2] * (nl - lt[2]);
+                    lt[2] = nl;
+                    const real un3 = un + wt[2] * Ji->Jn[2], ux3 = ux_ + wt[2] * Ji->Jx[2], uy3 = uy_ + wt[2] * Ji->Jy[2];
+                    const real ix = Ii[2] * Ji->Jx[2], iy = Ii[2] * Ji->Jy[2], in_ = Ii[2] * Ji->Jn[2];
+                    A.Axx += ix * Ji->Jx[2]; A.Axy += ix * Ji->Jy[2]; A.Axn += ix * Ji->Jn[2];
+                    A.Ayy += iy * Ji->Jy[2]; A.Ayn += iy * Ji->Jn[2]; A.Ann += in_ * Ji->Jn[2];
+                    point_block(&A, -ux3, -uy3, tgt[i] - un3, mu, l1[i], l2[i], ln[i], &px, &py, &pn);
+                    dx = px - l1[i]; dy = py - l2[i]; dn = pn - ln[i];
+                    wt[2] += Ii[2] * (Ji->Jx[2] * dx + Ji->Jy[2] * dy + Ji->Jn[2] * dn);
+                }
+                spin_done = 1;
+            }
+            v[0] += dx * im; v[1] += dy * im; v[2] += dn * im;
+            for (int k = 0; k < nk; k++) wt[k] += Ii[k] * (Ji->Jx[k] * dx + Ji->Jy[k] * dy + Ji->Jn[k] * dn);
+            l1[i] = px; l2[i] = py; ln[i] = pn;
+            lsum += pn;
         }
-        {   /* spinning / rolling friction, limited by the total normal impulse */
-            real lim = mus * lsum;
-            real nl = r_clamp(lsp - w[2] * iW22, -lim, lim);
-            real d = nl - lsp; lsp = nl;
-            w[0] += W02 * d; w[1] += W12 * d; w[2] += W22 * d;
-            lim = mur * lsum;
-            nl = r_clamp(lr1 - w[0] * iW00, -lim, lim);
-            d = nl - lr1; lr1 = nl;
-            w[0] += W00 * d; w[1] += W01 * d; w[2] += W02 * d;
-            nl = r_clamp(lr2 - w[1] * iW11, -lim, lim);
-            d = nl - lr2; lr2 = nl;
-            w[0] += W01 * d; w[1] += W11 * d; w[2] += W12 * d;
+        /* torsional rows about the body axes x, y (and z when point 0 did not carry it): the impulse that zeroes the
+         * component, limited by mu_k * (total normal impulse) */
+        for (int k = 0; k < (spin_done ? 2 : 3); k++) {
+            const real lim = mut[k] * lsum;
+            const real nl = r_clamp(lt[k] - wt[k] * Im[k], -lim, lim);
+            wt[k] += Ii[k] * (nl - lt[k]);
+            lt[k] = nl;
         }
     }
     for (int i = 0; i < 5; i++) { lam[i] = ln[i]; lam[5 + i] = l1[i]; lam[10 + i] = l2[i]; }
-    lam[15] = lsp; lam[16] = lr1; lam[17] = lr2;
+    lam[15] = lt[2]; lam[16] = lt[0]; lam[17] = lt[1];
+    /* back to the world frame: w += R (wt - wb0) */
+    const real d0 = wt[0] - wb0[0], d1 = wt[1] - wb0[1], d2 = wt[2] - wb0[2];
+    w[0] += R[0] * d0 + R[1] * d1 + R[2] * d2;
+    w[1] += R[3] * d0 + R[4] * d1 + R[5] * d2;
+    w[2] += R[6] * d0 + R[7] * d1 + R[8] * d2;
 }
 
 /* Rows B2, B4, B5, B6: one p.stepSimulation() (ref:477). */
@@ -355,10 +433,12 @@ void orc_step_simulation(const orc_body_params *p, orc_body *b, double *trace) {
     for (int i = 0; i < 4; i++) q[i] = (real)b->quat[i];
     real lam[18];
     for (int i = 0; i < 18; i++) lam[i] = 0;   /* cold start at every control step */
+    int have_lam = 0;                          /* the previous substep ran the solve (warm start) */
+    real pzc = 0;                              /* compensation of the height update, true height = pos[2] + pzc */
 
     for (int k = 0; k < K; k++) {
         real R[9];
-        r_matrix_from_quat(q, R);
+        const real nz1 = r_matrix_from_quat(q, R);
         /* B5: ABA for a lone floating base, in base-local coordinates */
         real wl[3], tl[3], wdl[3], wd[3];
         wl[0] = R[0] * w[0] + R[3] * w[1] + R[6] * w[2];
@@ -391,10 +471,16 @@ void orc_step_simulation(const orc_body_params *p, orc_body *b, double *trace) {
             v[i] = r_clamp(v[i] + vd * dt, -maxv, maxv);
         }
         /* B9 (our model): contacts detected at the pre-integration pose, solved on velocities */
-        if (p->ground) solve_contacts(p, dt, R, pos[2], v, w, lam, k == 0 ? p->contact_iters : p->warm_iters);
+        if (p->ground) solve_contacts(p, dt, R, nz1, pos[2], pzc, v, w, lam, &have_lam);
 
         /* B6: stepPositionsMultiDof -- semi-implicit Euler, exponential map */
-        for (int i = 0; i < 3; i++) pos[i] += dt * v[i];
+        pos[0] += dt * v[0]; pos[1] += dt * v[1];
+        {   /* height with a running compensation (Kahan): the contact targets divide the gap by dt, so the 3e-8
+             * rounding of pz + dt vz per substep would otherwise show up as 1.5e-5 m/s in fp32 at dt = 0.002 */
+            const real y = dt * v[2] + pzc, t = pos[2] + y;
+            pzc = y - (t - pos[2]);
+            pos[2] = t;
+        }
         real ang = R_SQRT(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
         if (ang * dt > (real)(0.25 * PI_D)) ang = (real)(0.5 * (0.5 * PI_D)) / dt;   /* ANGULAR_MOTION_THRESHOLD */
         real sc;
@@ -501,8 +587,8 @@ void orc_config_default(orc_config *c, int contract) {
     c->autoreset = 0;
     c->quirks = contract == ORC_CONTRACT_R ? ORC_Q_ALL_REFERENCE : (ORC_Q_DOUBLE_GRAVITY | ORC_Q_LAGGED_PHASE);
     c->diversity_mode = contract == ORC_CONTRACT_R ? ORC_DIV_EXACT : ORC_DIV_FAST;
-    c->contact_iters = 8;
-    c->contact_warm_iters = 3;
+    c->contact_iters = 2;
+    c->contact_warm_iters = 1;
     c->ground = 1;
     c->dt_step = 0.02;
     c->gradient_penalty = 0.1; c->diversity_bonus = 0.05;      /* ref:83-84 defaults */

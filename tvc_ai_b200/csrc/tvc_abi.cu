@@ -26,129 +26,8 @@ __device__ __forceinline__ void warp_store_obs(float *dst, const float *s_warp, 
     for (int k = lane; k < n2; k += 32) d2[k] = s2[k];
 }
 
-#ifndef TVC_MIN_BLOCKS
-#define TVC_MIN_BLOCKS 4
-#endif
-template <bool X, int DIV>
-__global__ void __launch_bounds__(TVC_BLOCK, TVC_MIN_BLOCKS)
-step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState st, const __grid_constant__ DevIO io) {
-    __shared__ __align__(16) float s_obs[TVC_BLOCK * 10];
-    __shared__ double s_stat[TVC_WARPS][TVC_NSTAT];
-    __shared__ ContactSmem s_contact;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long i = (long long)blockIdx.x * TVC_BLOCK + threadIdx.x;
-    const bool live = i < st.n;
-    const long long gid = c.env_base + i;
-
-    int done = 0, viol = 0;
-    int ev_len = 0, ev_succ = 0, ev_reason = 0, ev_trunc = 0;
-    float ev_ret = 0.0f, ev_alt = 0.0f, ev_tilt = 0.0f, ev_fuel = 0.0f;
-
-    Env e;
-    BodyP P;
-    Forces f;
-    if (live) {
-        load_env(st, X, i, e);
-        float2 a;
-        if (io.actions) a = io.actions[i];
-        else {
-            uint4 rr = philox(c.seed_lo, c.seed_hi, gid, ST_ACTION, (unsigned)io.t, (unsigned)(io.t >> 32));
-            a = make_float2(2.0f * u01(rr.x) - 1.0f, 2.0f * u01(rr.y) - 1.0f);
-        }
-        if (io.actions_out) io.actions_out[i] = a;
-        env_pre<X>(c, st, i, e, a.x, a.y, P, f);
-    } else {   // threads past the end still take part in the CTA-wide contact exchange
-        memset(&e, 0, sizeof(e));
-        e.qw = 1.0f; e.pz = 1.0f;
-        P = body_params(c, false, 1.0f, 0.0f, 1.0f);
-        f.Fx = f.Fy = f.Fz = f.Tx = f.Ty = f.Tz = f.a0 = f.a1 = 0.0f;
-    }
-    integrate(c, P, e, f.Fx, f.Fy, f.Fz, f.Tx, f.Ty, f.Tz, live, s_contact);
-    if (live) {
-        StepResult r;
-        env_post<X, DIV>(c, st, i, gid, e, f.a0, f.a1, r);
-
-        io.reward[i] = r.reward;
-        io.term[i] = (uint8_t)r.terminated;
-        io.trunc[i] = (uint8_t)r.truncated;
-        if (io.altitude) io.altitude[i] = r.alt;
-        if (io.tilt_deg) io.tilt_deg[i] = r.tilt * 57.29577951308232f;
-        if (io.omega_mag) io.omega_mag[i] = r.wmag;
-        if (io.fuel) io.fuel[i] = r.fuel;
-        if (io.position) { io.position[3 * i] = e.px; io.position[3 * i + 1] = e.py; io.position[3 * i + 2] = e.pz; }
-        if (io.phase) io.phase[i] = e.phase;
-        if (io.step) io.step[i] = e.step;
-        if (io.success) io.success[i] = (uint8_t)e.success;
-        if (io.criteria_met) io.criteria_met[i] = (uint8_t)(e.consec >= 10);   // Q18
-        if (io.comp) {
-#pragma unroll
-            for (int k = 0; k < 12; k++) io.comp[12 * i + k] = r.comp[k];
-        }
-        viol = r.viol;
-        done = r.terminated | r.truncated;
-        if (done) {
-            ev_len = e.step; ev_succ = e.success; ev_reason = r.reason; ev_trunc = r.truncated;
-            ev_ret = e.ep_ret; ev_alt = r.alt; ev_tilt = r.tilt; ev_fuel = r.fuel;
-            if (io.final_obs) {
-                float2 *f2 = reinterpret_cast<float2 *>(io.final_obs + 10 * i);
-#pragma unroll
-                for (int k = 0; k < 5; k++) f2[k] = make_float2(r.obs[2 * k], r.obs[2 * k + 1]);
-            }
-            if (c.autoreset) {
-                reset_env(c, X, gid, e, false);
-                build_obs(c, X, gid, e, 0, r.obs);
-            }
-        }
-        store_env(st, X, i, e);
-#pragma unroll
-        for (int k = 0; k < 10; k++) s_obs[threadIdx.x * 10 + k] = r.obs[k];
-    }
-    __syncwarp();
-    warp_store_obs(io.obs, s_obs + warp * 320, (long long)blockIdx.x * TVC_BLOCK + warp * 32, st.n, lane);
-
-    // ---- episode statistics: warp shuffle -> shared -> one owner row per CTA (no atomics) ----
-    const int any_ev = __syncthreads_or(done | viol);
-    if (!any_ev) return;
-    {
-        const unsigned full = 0xffffffffu;
-        int n_ep = __reduce_add_sync(full, done);
-        int n_len = __reduce_add_sync(full, ev_len);
-        int n_succ = __reduce_add_sync(full, done ? ev_succ : 0);
-        int n_cr = __reduce_add_sync(full, ev_reason == 2);
-        int n_ti = __reduce_add_sync(full, ev_reason == 3);
-        int n_al = __reduce_add_sync(full, ev_reason == 4);
-        int n_ra = __reduce_add_sync(full, ev_reason == 5);
-        int n_tr = __reduce_add_sync(full, ev_trunc);
-        int n_vi = __reduce_add_sync(full, viol);
-        double d_ret = ev_ret, d_ret2 = (double)ev_ret * (double)ev_ret, d_alt = ev_alt, d_tilt = ev_tilt, d_fuel = ev_fuel;
-        if (n_ep) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                d_ret += __shfl_xor_sync(full, d_ret, o);
-                d_ret2 += __shfl_xor_sync(full, d_ret2, o);
-                d_alt += __shfl_xor_sync(full, d_alt, o);
-                d_tilt += __shfl_xor_sync(full, d_tilt, o);
-                d_fuel += __shfl_xor_sync(full, d_fuel, o);
-            }
-        }
-        if (lane == 0) {
-            double *s = s_stat[warp];
-            s[0] = n_ep; s[1] = d_ret; s[2] = d_ret2; s[3] = n_len; s[4] = n_succ; s[5] = n_cr; s[6] = n_ti;
-            s[7] = n_al; s[8] = n_ra; s[9] = n_tr; s[10] = n_vi; s[11] = d_alt; s[12] = d_tilt; s[13] = d_fuel;
-            s[14] = 0.0; s[15] = 0.0;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x < TVC_NSTAT) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < TVC_WARPS; w++) s += s_stat[w][threadIdx.x];
-        if (s != 0.0) st.partial[(long long)blockIdx.x * TVC_NSTAT + threadIdx.x] += s;
-    }
-}
-
 // ------------------------------------------------------------------------------------------
-// step path v2: sort, then one warp per 32-env group, solver inline, no CTA barriers
+// step path: sort, then one warp per 32-env group, solver inline, no CTA barriers
 // ------------------------------------------------------------------------------------------
 #ifndef TVC_CHUNK
 #define TVC_CHUNK 1024   // envs sorted together (stable partition, near-ground class first)
@@ -722,8 +601,8 @@ int tvc_config_default(tvc_config *c, int contract) {
     c->autoreset = 0;
     c->quirks = contract == TVC_CONTRACT_R ? TVC_Q_ALL_REFERENCE : (TVC_Q_DOUBLE_GRAVITY | TVC_Q_LAGGED_PHASE);
     c->diversity_mode = contract == TVC_CONTRACT_R ? TVC_DIV_EXACT : TVC_DIV_FAST;
-    c->contact_iters = 8;
-    c->contact_warm_iters = 3;
+    c->contact_iters = 2;
+    c->contact_warm_iters = 1;
     c->ground = 1;
     c->dt_step = 0.02;
     c->gradient_penalty = 0.1f; c->diversity_bonus = 0.05f;
@@ -783,10 +662,6 @@ int tvc_create(const tvc_config *cfg, int device, int64_t num_envs, tvc_handle *
     tvc_handle *h = new (std::nothrow) tvc_handle();
     if (!h) { tvc_set_err("out of host memory"); return TVC_E_NOMEM; }
     h->device = device; h->n = num_envs; h->base = *cfg; h->cur = *cfg; h->num_sms = prop.multiProcessorCount;
-    {   // TVC_STEP_IMPL=1 selects the legacy CTA-exchange kernel (kept for A/B measurements)
-        const char *impl = getenv("TVC_STEP_IMPL");
-        h->step_impl = (impl && impl[0] == '1') ? 1 : 2;
-    }
     make_devcfg(h->cur, h->dc);
     const size_t n = (size_t)num_envs;
     h->grid = (int)((num_envs + TVC_BLOCK - 1) / TVC_BLOCK);
@@ -862,13 +737,7 @@ static int launch_step(tvc_handle *h, const DevIO &io, cudaStream_t s) {
 #endif
     const bool X = h->cur.contract == TVC_CONTRACT_X;
     const int dv = h->cur.diversity_mode;
-    if (h->step_impl == 1) {   // legacy: thread-per-env CTAs with the shared-memory contact exchange
-#define GO(XX, DD) step_kernel<XX, DD><<<h->grid, TVC_BLOCK, 0, s>>>(h->dc, h->st, io)
-        if (X) { if (dv == 0) GO(true, 0); else if (dv == 1) GO(true, 1); else GO(true, 2); }
-        else   { if (dv == 0) GO(false, 0); else if (dv == 1) GO(false, 1); else GO(false, 2); }
-#undef GO
-        LAUNCH_OK("step_kernel");
-    } else {
+    {
         const int cgrid = h->st.nchunks;
         if (!h->order_valid) {   // first step, or the state was changed behind the step path's back: sort from the state planes
             if (X) classify_kernel<true, true, false><<<cgrid, TVC_CLS_THREADS, 0, s>>>(h->dc, h->st, nullptr);

@@ -238,33 +238,38 @@ __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fm
 // Ground contact: our documented model (DESIGN.md "Contact model"), continuous in the state.
 //   p0 / p1 : lowest rim point of the bottom / top cap, direction -(R31,R32)/max(rho,1e-3)
 //   f0..f2  : body-fixed rim points of the bottom cap at 0, 120, 240 degrees
-// Entered when the lowest candidate is within `margin` and some row can bind (contact_needed); then
-// all five rows are processed (speculative vn >= -gap/dt, Baumgarte for gap < 0, restitution),
-// friction disc per point, spinning / rolling rows limited by the total normal impulse; projected
-// Gauss-Seidel on velocities: contact_iters sweeps from a cold start in the first substep of a step,
-// warm_iters sweeps warm-started with the previous substep's 18 impulses afterwards.  Bullet's own manifold/solver (row B9) is not
-// reproducible without its source; this model is shared with the oracle by specification only.
+// Entered when the lowest candidate is within `margin` and some row can bind (contact_needed).  Normal targets:
+// speculative vn >= -gap/dt, Baumgarte for gap < 0, restitution on the approach speed beyond the threshold.  The solve
+// runs in the BODY frame (diagonal inverse inertia: 1/Iz = 400 only ever multiplies the body-z component of a row's
+// angular Jacobian, small by geometry, not by cancellation) as a block Gauss-Seidel: a point that can bind gets its three
+// rows solved together with its 3x3 Delassus matrix (stick / slide along the stick impulse with the normal row re-solved /
+// release -- every branch meets its neighbour continuously); point 0 carries the axial spin row in its block (rim
+// friction and axial spin are coupled through 1/Iz); torsional friction acts along the body's principal axes, where its
+// three rows are decoupled from each other.  A solve that follows free flight runs contact_iters passes from a cold
+// start, one that follows a solve runs warm_iters passes warm-started with the previous substep's 18 impulses.
+// Bullet's own manifold/solver (row B9) is not reproducible without its source; this model is shared with the oracle
+// (oracle/tvc_oracle.c solve_contacts) by specification only.
 // ------------------------------------------------------------------------------------------
 // Entry rule of the contact model (same in the oracle), evaluated per substep by the env's own thread:
 // the lowest candidate is within `margin` AND some row can bind at all -- a row binds only if
 // (1+e) * approach speed * dt exceeds its gap, and the approach speed of any point is bounded by
 // |vz| + |w| * reach.  When the rule fails the stored impulses are cleared.
-__device__ __forceinline__ bool contact_needed_row(const DevCfg &c, const BodyP &P, float R31, float R32, float R33,
-                                                   float pz, float vz, float wx, float wy, float wz) {
+// nz1 = R33 - 1 formed without cancellation, pzc = running compensation of the height update: the gap is assembled as
+// (pz + cz) + cz (R33 - 1) + ..., so that the two O(0.5) terms cancel first (the targets divide the gap by dt).
+__device__ __forceinline__ bool contact_needed_row(const DevCfg &c, const BodyP &P, float R31, float R32, float nz1,
+                                                   float pz, float pzc, float vz, float wx, float wy, float wz) {
     const float r = c.radius, h = c.half_len;
     const float rho = sqrt_fast(R31 * R31 + R32 * R32);
     const float inv = rcp_fast(fmaxf(rho, 1e-3f));
     const float low = -r * (R31 * R31 + R32 * R32) * inv;
-    const float gmin = pz + fminf(R33 * (-h - P.cg), R33 * (h - P.cg)) + low;
+    const float zb = -h - P.cg, zt = h - P.cg;
+    const float gb = ((pz + zb) + pzc) + (zb * nz1 + low), gt = ((pz + zt) + pzc) + (zt * nz1 + low);
+    const float gmin = fminf(gb, gt);
     if (!(gmin < c.margin)) return false;
     const float hh = h + fabsf(P.cg);
     const float reach = sqrt_fast(hh * hh + r * r);
     const float vmax = fabsf(vz) + sqrt_fast(wx * wx + wy * wy + wz * wz) * reach;
     return gmin - 1e-4f < (1.0f + c.restitution) * vmax * c.dt;
-}
-__device__ __forceinline__ bool contact_needed(const DevCfg &c, const BodyP &P, const float R[9], float pz, float vz,
-                                               float wx, float wy, float wz) {
-    return contact_needed_row(c, P, R[6], R[7], R[8], pz, vz, wx, wy, wz);
 }
 
 #ifdef TVC_PHASE_PROF2
@@ -282,11 +287,35 @@ struct Ph2 { unsigned setup, sweeps, bar; };
 #define PH2_PASS
 #define PH2_CLK(x)
 #endif
-// lam: this problem's 18 stored impulses, element j at lam[j * TVC_BLOCK] (shared memory column of the posting
-// thread): normal(5), tangent-x(5), tangent-y(5), spin, roll-x, roll-y.  warm: apply them before sweeping.
-template <int LS>   // LS: stride between the 18 impulses (TVC_BLOCK for the shared-memory column, 1 for a register array)
-__device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, const float R[9], float pz, float &vx,
-                                               float &vy, float &vz, float &wx, float &wy, float &wz, float *lam,
+
+// One point block: the point's Delassus matrix A (symmetric), the wanted change of the contact velocity (ex, ey, en) and
+// the old impulses -> new impulses.  Stick solution p* = p + A^-1 e, accepted when p*_n > 0 and |p*_t| <= mu p*_n;
+// otherwise the friction impulse keeps the direction of p*_t at magnitude mu p_n and the normal row is re-solved with
+// that coupling; p_n <= 0 releases the point.
+__device__ __forceinline__ void point_block(float Axx, float Axy, float Axn, float Ayy, float Ayn, float Ann, float ex, float ey,
+                                            float en, float mu, float l1, float l2, float ln, float &px, float &py, float &pn) {
+    const float c00 = Ayy * Ann - Ayn * Ayn, c01 = Axn * Ayn - Axy * Ann, c02 = Axy * Ayn - Axn * Ayy;
+    const float c11 = Axx * Ann - Axn * Axn, c12 = Axy * Axn - Axx * Ayn, c22 = Axx * Ayy - Axy * Axy;
+    const float idet = rcp_fast(Axx * c00 + Axy * c01 + Axn * c02);
+    px = l1 + (c00 * ex + c01 * ey + c02 * en) * idet;
+    py = l2 + (c01 * ex + c11 * ey + c12 * en) * idet;
+    pn = ln + (c02 * ex + c12 * ey + c22 * en) * idet;
+    const float mag2 = px * px + py * py, lim = mu * pn;
+    if (pn > 0.0f && mag2 <= lim * lim) return;                       // stick
+    if (mag2 > 0.0f) {                                                // slide (or a stick solution that pulls)
+        const float is = rsqrt_normal(fmaxf(mag2, 1e-30f)), tx = px * is, ty = py * is;
+        const float den = fmaxf(Ann + mu * (Axn * tx + Ayn * ty), 0.25f * Ann);
+        const float rhs = en + Ann * ln + Axn * l1 + Ayn * l2;
+        pn = fmaxf(rhs * rcp_fast(den), 0.0f);
+        px = mu * pn * tx; py = mu * pn * ty;
+    } else { px = 0.0f; py = 0.0f; pn = 0.0f; }                       // release
+}
+
+// lam: this env's 18 carried impulses, element j at lam[j * LS]: normal(5), tangent-x(5), tangent-y(5), torsional about the
+// body axes z (spin), x, y (roll).  warm: apply them before the passes.
+template <int LS>
+__device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, const float R[9], float nz1, float pz, float pzc,
+                                               float &vx, float &vy, float &vz, float &wx, float &wy, float &wz, float *lam,
                                                bool warm, int iters PH2_ARG) {
     PH2_CLK(pc0);
     const float r = c.radius, h = c.half_len;
@@ -295,296 +324,150 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
     const float inv = rcp_fast(fmaxf(rho, 1e-3f));
     const float ux = -R31 * inv, uy = -R32 * inv;
     const float zb = -h - P.cg, zt = h - P.cg;
+    const float ia = P.inv_Ixy, ib = P.inv_Iz, im = P.inv_mass, mu = c.mu;
+    // body-frame angular velocity wb0 = R^T w; (w0, w1, w2) carries the running value, w += R (wt - wb0) at the end, so that
+    // a solve in which nothing binds leaves omega bit-identical
+    const float wb0x = R[0] * wx + R[3] * wy + R[6] * wz, wb0y = R[1] * wx + R[4] * wy + R[7] * wz;
+    const float wb0z = R[2] * wx + R[5] * wy + R[8] * wz;
+    float w0 = wb0x, w1 = wb0y, w2 = wb0z;
 
-    // world inverse inertia W = R diag(1/I) R^T (symmetric)
-    const float ia = P.inv_Ixy, ib = P.inv_Iz;
-    const float W00 = ia * (R[0] * R[0] + R[1] * R[1]) + ib * R[2] * R[2];
-    const float W01 = ia * (R[0] * R[3] + R[1] * R[4]) + ib * R[2] * R[5];
-    const float W02 = ia * (R[0] * R[6] + R[1] * R[7]) + ib * R[2] * R[8];
-    const float W11 = ia * (R[3] * R[3] + R[4] * R[4]) + ib * R[5] * R[5];
-    const float W12 = ia * (R[3] * R[6] + R[4] * R[7]) + ib * R[5] * R[8];
-    const float W22 = ia * (R[6] * R[6] + R[7] * R[7]) + ib * R[8] * R[8];
-    const float im = P.inv_mass;
-
-    const float clx[5] = {r * ux, r * ux, r, -0.5f * r, -0.5f * r};
-    const float cly[5] = {r * uy, r * uy, 0.0f, 0.8660254037844386f * r, -0.8660254037844386f * r};
-    float ax[5], ay[5], az[5], tgt[5], imn[5], im1[5], im2[5];
-    float ln[5], l1[5], l2[5];
-    // A row whose normal constraint cannot bind (tgt <= vn with zero stored impulses) is an exact no-op together with its
-    // friction rows and its warm-start term.  That is the normal case for the top cap (point 1) in every upright pose
-    // and for most of the body-fixed rim points: measured with the oracle, an env in contact stands on its rim at a
-    // median tilt of 21 degrees with 0.8 of the three fixed points within 4 mm of the plane.  Points 1-4 are therefore
-    // visited lazily: each sweep tests `tgt > vn` (and "any stored impulse"), and only a thread that passes computes
-    // the point's effective masses and runs the row.  Same results as visiting every row always.  (Sorting the
-    // in-contact envs further by their set of near-ground rim points, so that whole warps skip the same rows, was
-    // measured: 0.1074 ms against 0.1036 without -- ten classes scatter a group's 32 envs over more cache lines.)
+    const float pcx[5] = {r * ux, r * ux, r, -0.5f * r, -0.5f * r};
+    const float pcy[5] = {r * uy, r * uy, 0.0f, 0.8660254037844386f * r, -0.8660254037844386f * r};
+    // angular Jacobians (body frame) of the world-axis rows at body-frame arm c: c x (row of R).  The normal rows of all
+    // five points stay in registers (every pass tests them); the tangent rows of points 1-4 are formed when such a point
+    // binds, which is rare: the top cap in every upright pose, and a body-fixed rim point only binds within ~0.2 mm.
+    float Jn0[5], Jn1[5], Jn2[5], tgt[5], ln[5], l1[5], l2[5];
 #pragma unroll
     for (int i = 0; i < 5; i++) {
         const float cz = i == 1 ? zt : zb;
-        ax[i] = R[0] * clx[i] + R[1] * cly[i] + R[2] * cz;
-        ay[i] = R[3] * clx[i] + R[4] * cly[i] + R[5] * cz;
-        az[i] = R[6] * clx[i] + R[7] * cly[i] + R[8] * cz;
-        const float gap = pz + az[i];
-        if (i == 0) {
-            // effective masses for n = z, t1 = x, t2 = y at arm (ax,ay,az)
-            const float mn = im + (W00 * ay[i] * ay[i] - 2.0f * W01 * ax[i] * ay[i] + W11 * ax[i] * ax[i]);
-            const float m1 = im + (W11 * az[i] * az[i] - 2.0f * W12 * az[i] * ay[i] + W22 * ay[i] * ay[i]);
-            const float m2 = im + (W00 * az[i] * az[i] - 2.0f * W02 * az[i] * ax[i] + W22 * ax[i] * ax[i]);
-            imn[i] = rcp_fast(mn); im1[i] = rcp_fast(m1); im2[i] = rcp_fast(m2);
-        } else { imn[i] = 0.0f; im1[i] = 0.0f; im2[i] = 0.0f; }   // lazily, in the first sweep that needs them
-        const float vn0 = vz + wx * ay[i] - wy * ax[i];
-        const float rest = (vn0 < -c.rest_thr) ? -c.restitution * vn0 : 0.0f;
+        Jn0[i] = pcy[i] * R[8] - cz * R[7]; Jn1[i] = cz * R[6] - pcx[i] * R[8]; Jn2[i] = pcx[i] * R[7] - pcy[i] * R[6];
+        const float gap = ((pz + cz) + pzc) + (cz * nz1 + (R[6] * pcx[i] + R[7] * pcy[i]));
+        const float vn0 = vz + (wb0x * Jn0[i] + wb0y * Jn1[i] + wb0z * Jn2[i]);
+        const float rest = (vn0 < -c.rest_thr) ? c.restitution * (-vn0 - c.rest_thr) : 0.0f;
         tgt[i] = rest + (gap > 0.0f ? -gap * c.inv_dt : -c.erp * gap * c.inv_dt);
         ln[i] = warm ? lam[i * LS] : 0.0f;
         l1[i] = warm ? lam[(5 + i) * LS] : 0.0f;
         l2[i] = warm ? lam[(10 + i) * LS] : 0.0f;
     }
-    float lsp = warm ? lam[15 * LS] : 0.0f, lr1 = warm ? lam[16 * LS] : 0.0f, lr2 = warm ? lam[17 * LS] : 0.0f;
-    const float iW22 = rcp_fast(W22), iW00 = rcp_fast(W00), iW11 = rcp_fast(W11);
+    float lt0 = warm ? lam[16 * LS] : 0.0f, lt1 = warm ? lam[17 * LS] : 0.0f, lt2 = warm ? lam[15 * LS] : 0.0f;
+    // tangent rows of point 0
+    const float Jx0 = pcy[0] * R[2] - zb * R[1], Jx1 = zb * R[0] - pcx[0] * R[2], Jx2 = pcx[0] * R[1] - pcy[0] * R[0];
+    const float Jy0 = pcy[0] * R[5] - zb * R[4], Jy1 = zb * R[3] - pcx[0] * R[5], Jy2 = pcx[0] * R[4] - pcy[0] * R[3];
     if (warm) {   // apply the stored impulses at the current contact geometry
 #pragma unroll
         for (int i = 0; i < 5; i++) {
             if (i != 0 && ln[i] == 0.0f && l1[i] == 0.0f && l2[i] == 0.0f) continue;   // adds exact zeros
-            const float px_ = l1[i], py_ = l2[i], pn_ = ln[i];
-            vx += px_ * im; vy += py_ * im; vz += pn_ * im;
-            const float tx = ay[i] * pn_ - az[i] * py_, ty = az[i] * px_ - ax[i] * pn_, tz = ax[i] * py_ - ay[i] * px_;
-            wx += W00 * tx + W01 * ty + W02 * tz;
-            wy += W01 * tx + W11 * ty + W12 * tz;
-            wz += W02 * tx + W12 * ty + W22 * tz;
+            float jx0 = Jx0, jx1 = Jx1, jx2 = Jx2, jy0 = Jy0, jy1 = Jy1, jy2 = Jy2;
+            if (i != 0) {
+                const float cz = i == 1 ? zt : zb;
+                jx0 = pcy[i] * R[2] - cz * R[1]; jx1 = cz * R[0] - pcx[i] * R[2]; jx2 = pcx[i] * R[1] - pcy[i] * R[0];
+                jy0 = pcy[i] * R[5] - cz * R[4]; jy1 = cz * R[3] - pcx[i] * R[5]; jy2 = pcx[i] * R[4] - pcy[i] * R[3];
+            }
+            vx += l1[i] * im; vy += l2[i] * im; vz += ln[i] * im;
+            w0 += ia * (jx0 * l1[i] + jy0 * l2[i] + Jn0[i] * ln[i]);
+            w1 += ia * (jx1 * l1[i] + jy1 * l2[i] + Jn1[i] * ln[i]);
+            w2 += ib * (jx2 * l1[i] + jy2 * l2[i] + Jn2[i] * ln[i]);
         }
-        wx += W02 * lsp + W00 * lr1 + W01 * lr2;
-        wy += W12 * lsp + W01 * lr1 + W11 * lr2;
-        wz += W22 * lsp + W02 * lr1 + W12 * lr2;
+        w0 += ia * lt0; w1 += ia * lt1; w2 += ib * lt2;
     }
     PH2_CLK(pc1);
     for (int it = 0; it < iters; it++) {
         float lsum = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 5; i++) {
-            // normal row
-            const float vn = vz + wx * ay[i] - wy * ax[i];
-            if (i != 0) {
-                if (!(tgt[i] > vn || ln[i] > 0.0f || l1[i] != 0.0f || l2[i] != 0.0f)) continue;   // exact no-op
-                if (imn[i] == 0.0f) {
-                    const float mn = im + (W00 * ay[i] * ay[i] - 2.0f * W01 * ax[i] * ay[i] + W11 * ax[i] * ax[i]);
-                    const float m1 = im + (W11 * az[i] * az[i] - 2.0f * W12 * az[i] * ay[i] + W22 * ay[i] * ay[i]);
-                    const float m2 = im + (W00 * az[i] * az[i] - 2.0f * W02 * az[i] * ax[i] + W22 * ax[i] * ax[i]);
-                    imn[i] = rcp_fast(mn); im1[i] = rcp_fast(m1); im2[i] = rcp_fast(m2);
+        bool spin_done = false;
+        {   // ---- point 0, with the axial spin row folded in: body axis z is left out of the angular dynamics ----
+            const float un = vz + (w0 * Jn0[0] + w1 * Jn1[0]);
+            const float unz = un + w2 * Jn2[0];                          // true normal velocity
+            if (tgt[0] > unz || ln[0] > 0.0f || l1[0] != 0.0f || l2[0] != 0.0f) {
+                const float ux_ = vx + (w0 * Jx0 + w1 * Jx1), uy_ = vy + (w0 * Jy0 + w1 * Jy1);
+                float Axx = im + ia * (Jx0 * Jx0 + Jx1 * Jx1), Axy = ia * (Jx0 * Jy0 + Jx1 * Jy1), Axn = ia * (Jx0 * Jn0[0] + Jx1 * Jn1[0]);
+                float Ayy = im + ia * (Jy0 * Jy0 + Jy1 * Jy1), Ayn = ia * (Jy0 * Jn0[0] + Jy1 * Jn1[0]);
+                float Ann = im + ia * (Jn0[0] * Jn0[0] + Jn1[0] * Jn1[0]);
+                float px, py, pn;
+                point_block(Axx, Axy, Axn, Ayy, Ayn, Ann, -ux_, -uy_, tgt[0] - un, mu, l1[0], l2[0], ln[0], px, py, pn);
+                float dx = px - l1[0], dy = py - l2[0], dn = pn - ln[0];
+                // the axial impulse that keeps w_z at zero through this block, limited by mu_spin * (this point's new normal
+                // impulse + what the other points hold)
+                const float slim = c.mu_spin * (pn + ln[1] + ln[2] + ln[3] + ln[4]);
+                const float cand = lt2 - (w2 * P.Iz + (Jx2 * dx + Jy2 * dy + Jn2[0] * dn));
+                if (cand >= -slim && cand <= slim) { w2 = 0.0f; lt2 = cand; }
+                else {
+                    // the axial row slips: its impulse goes to the limit of the OLD normal impulses and the point is solved
+                    // again with the full angular dynamics (both solutions coincide at the limit)
+                    const float slim0 = c.mu_spin * (ln[0] + ln[1] + ln[2] + ln[3] + ln[4]);
+                    const float nl = clampf(cand, -slim0, slim0);
+                    w2 += ib * (nl - lt2);
+                    lt2 = nl;
+                    const float un3 = un + w2 * Jn2[0], ux3 = ux_ + w2 * Jx2, uy3 = uy_ + w2 * Jy2;
+                    Axx += ib * Jx2 * Jx2; Axy += ib * Jx2 * Jy2; Axn += ib * Jx2 * Jn2[0];
+                    Ayy += ib * Jy2 * Jy2; Ayn += ib * Jy2 * Jn2[0]; Ann += ib * Jn2[0] * Jn2[0];
+                    point_block(Axx, Axy, Axn, Ayy, Ayn, Ann, -ux3, -uy3, tgt[0] - un3, mu, l1[0], l2[0], ln[0], px, py, pn);
+                    dx = px - l1[0]; dy = py - l2[0]; dn = pn - ln[0];
+                    w2 += ib * (Jx2 * dx + Jy2 * dy + Jn2[0] * dn);
                 }
+                spin_done = true;
+                vx += dx * im; vy += dy * im; vz += dn * im;
+                w0 += ia * (Jx0 * dx + Jy0 * dy + Jn0[0] * dn);
+                w1 += ia * (Jx1 * dx + Jy1 * dy + Jn1[0] * dn);
+                l1[0] = px; l2[0] = py; ln[0] = pn;
+                lsum += pn;
             }
-            const float nl = fmaxf(ln[i] + (tgt[i] - vn) * imn[i], 0.0f);
-            const float d = nl - ln[i];
-            ln[i] = nl;
-            lsum += nl;
-            vz += d * im;
-            wx += (W00 * ay[i] - W01 * ax[i]) * d;
-            wy += (W01 * ay[i] - W11 * ax[i]) * d;
-            wz += (W02 * ay[i] - W12 * ax[i]) * d;
-            // friction disc
-            const float vt1 = vx + wy * az[i] - wz * ay[i];
-            const float vt2 = vy + wz * ax[i] - wx * az[i];
-            float a1 = l1[i] - vt1 * im1[i];
-            float a2 = l2[i] - vt2 * im2[i];
-            const float lim = c.mu * nl;
-            const float mag2 = a1 * a1 + a2 * a2;
-            const float sc = mag2 > lim * lim ? lim * rsqrt_normal(fmaxf(mag2, 1e-30f)) : 1.0f;   // branch-free disc projection
-            a1 *= sc; a2 *= sc;
-            const float d1 = a1 - l1[i], d2 = a2 - l2[i];
-            l1[i] = a1; l2[i] = a2;
-            vx += d1 * im; vy += d2 * im;
-            const float tx = -az[i] * d2, ty = az[i] * d1, tz = ax[i] * d2 - ay[i] * d1;
-            wx = fmaf(W00, tx, fmaf(W01, ty, fmaf(W02, tz, wx)));   // three FFMA per component, no separate add
-            wy = fmaf(W01, tx, fmaf(W11, ty, fmaf(W12, tz, wy)));
-            wz = fmaf(W02, tx, fmaf(W12, ty, fmaf(W22, tz, wz)));
         }
-        {   // spinning / rolling friction rows, limited by the total normal impulse
-            float lim = c.mu_spin * lsum;
-            float nl = clampf(lsp - wz * iW22, -lim, lim);
-            float d = nl - lsp; lsp = nl;
-            wx += W02 * d; wy += W12 * d; wz += W22 * d;
-            lim = c.mu_roll * lsum;
-            nl = clampf(lr1 - wx * iW00, -lim, lim);
-            d = nl - lr1; lr1 = nl;
-            wx += W00 * d; wy += W01 * d; wz += W02 * d;
-            nl = clampf(lr2 - wy * iW11, -lim, lim);
-            d = nl - lr2; lr2 = nl;
-            wx += W01 * d; wy += W11 * d; wz += W12 * d;
+#pragma unroll
+        for (int i = 1; i < 5; i++) {   // ---- points 1-4, visited lazily ----
+            const float un = vz + (w0 * Jn0[i] + w1 * Jn1[i] + w2 * Jn2[i]);
+            if (!(tgt[i] > un || ln[i] > 0.0f || l1[i] != 0.0f || l2[i] != 0.0f)) continue;   // exact no-op
+            const float cz = i == 1 ? zt : zb;
+            const float jx0 = pcy[i] * R[2] - cz * R[1], jx1 = cz * R[0] - pcx[i] * R[2], jx2 = pcx[i] * R[1] - pcy[i] * R[0];
+            const float jy0 = pcy[i] * R[5] - cz * R[4], jy1 = cz * R[3] - pcx[i] * R[5], jy2 = pcx[i] * R[4] - pcy[i] * R[3];
+            const float ux_ = vx + (w0 * jx0 + w1 * jx1 + w2 * jx2), uy_ = vy + (w0 * jy0 + w1 * jy1 + w2 * jy2);
+            const float Axx = im + (ia * (jx0 * jx0 + jx1 * jx1) + ib * jx2 * jx2);
+            const float Axy = ia * (jx0 * jy0 + jx1 * jy1) + ib * jx2 * jy2;
+            const float Axn = ia * (jx0 * Jn0[i] + jx1 * Jn1[i]) + ib * jx2 * Jn2[i];
+            const float Ayy = im + (ia * (jy0 * jy0 + jy1 * jy1) + ib * jy2 * jy2);
+            const float Ayn = ia * (jy0 * Jn0[i] + jy1 * Jn1[i]) + ib * jy2 * Jn2[i];
+            const float Ann = im + (ia * (Jn0[i] * Jn0[i] + Jn1[i] * Jn1[i]) + ib * Jn2[i] * Jn2[i]);
+            float px, py, pn;
+            point_block(Axx, Axy, Axn, Ayy, Ayn, Ann, -ux_, -uy_, tgt[i] - un, mu, l1[i], l2[i], ln[i], px, py, pn);
+            const float dx = px - l1[i], dy = py - l2[i], dn = pn - ln[i];
+            vx += dx * im; vy += dy * im; vz += dn * im;
+            w0 += ia * (jx0 * dx + jy0 * dy + Jn0[i] * dn);
+            w1 += ia * (jx1 * dx + jy1 * dy + Jn1[i] * dn);
+            w2 += ib * (jx2 * dx + jy2 * dy + Jn2[i] * dn);
+            l1[i] = px; l2[i] = py; ln[i] = pn;
+            lsum += pn;
+        }
+        {   // torsional rows about the body axes x, y (and z when point 0 did not carry it): the impulse that zeroes the
+            // component, limited by mu_k * (total normal impulse)
+            const float lr = c.mu_roll * lsum;
+            float nl = clampf(lt0 - w0 * P.Ixy, -lr, lr);
+            w0 += ia * (nl - lt0); lt0 = nl;
+            nl = clampf(lt1 - w1 * P.Ixy, -lr, lr);
+            w1 += ia * (nl - lt1); lt1 = nl;
+            if (!spin_done) {
+                const float ls = c.mu_spin * lsum;
+                nl = clampf(lt2 - w2 * P.Iz, -ls, ls);
+                w2 += ib * (nl - lt2); lt2 = nl;
+            }
         }
     }
 #pragma unroll
     for (int i = 0; i < 5; i++) { lam[i * LS] = ln[i]; lam[(5 + i) * LS] = l1[i]; lam[(10 + i) * LS] = l2[i]; }
-    lam[15 * LS] = lsp; lam[16 * LS] = lr1; lam[17 * LS] = lr2;
+    lam[15 * LS] = lt2; lam[16 * LS] = lt0; lam[17 * LS] = lt1;
+    {   // back to the world frame: w += R (wt - wb0)
+        const float d0 = w0 - wb0x, d1 = w1 - wb0y, d2 = w2 - wb0z;
+        wx += R[0] * d0 + R[1] * d1 + R[2] * d2;
+        wy += R[3] * d0 + R[4] * d1 + R[5] * d2;
+        wz += R[6] * d0 + R[7] * d1 + R[8] * d2;
+    }
 #ifdef TVC_PHASE_PROF2
     { const long long pc2 = clock64(); ph2->setup += (unsigned)(pc1 - pc0); ph2->sweeps += (unsigned)(pc2 - pc1); }
 #endif
 }
 
-// Shared-memory exchange used to compact ground-contact problems across the CTA: each env that needs
-// the solver this substep posts its problem to a slot; the first ceil(M/32) (rotated) warps solve the
-// M problems with (nearly) full lanes instead of every warp running the solver for a few lanes.
-#define TVC_PROB_FIELDS 15
-#ifdef TVC_PHASE_PROF
-// diagnostic build only: cycles per phase of integrate(), summed over warp leaders
-// [0] free-flight  [1] count barrier  [2] post + barrier  [3] solve (solver warps)  [4] wait for solver (others)
-// [5] read-back + pose update  [6] warp-substeps  [7] solver warp-substeps
-__device__ unsigned long long g_phase[8];
-#define PH_T(x) const long long x = clock64()
-#else
-#define PH_T(x)
-#endif
-
-#define TVC_PROB_FIELDS 15
-template <int B>   // B = threads (= envs) per CTA
-struct ContactSmemT {
-    float f[TVC_PROB_FIELDS][B];   // qx qy qz qw pz vx vy vz wx wy wz inv_mass inv_Ixy inv_Iz cg
-    float lam[18][B];              // per ENV THREAD: impulses carried between the substeps of one step
-    int owner[B];                  // per slot: posting thread | warm flag << 16
-    int cnt[B / 32];
-};
-typedef ContactSmemT<TVC_BLOCK> ContactSmem;
-
-// Rows B2, B4, B5, B6: K substeps with the world-frame force F and torque T held constant (Q3).
-// Block-cooperative: EVERY thread of the CTA must call this (threads without an env pass live=false).
-template <int B>
-__device__ __forceinline__ void integrate(const DevCfg &c, const BodyP &P, Env &e, float Fx, float Fy, float Fz,
-                                          float Tx, float Ty, float Tz, bool live, ContactSmemT<B> &sm) {
-#ifdef TVC_PHASE_PROF2
-    Ph2 ph2s = {0u, 0u, 0u}; Ph2 *ph2 = &ph2s;
-#endif
-    const float dt = c.dt;
-    const float ax_ = Fx * P.inv_mass, ay_ = Fy * P.inv_mass, az_ = Fz * P.inv_mass;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    bool have_lam = false;   // cold start at every control step: stored impulses are logically zero
-#ifdef TVC_PHASE_PROF
-    long long ph0 = 0, ph1 = 0, ph2 = 0, ph3 = 0, ph4 = 0, ph5 = 0, phn = 0, phs = 0;
-#endif
-    for (int k = 0; k < c.K; k++) {
-        PH_T(t0);
-        float R[9];
-        quat_to_mat(e.qx, e.qy, e.qz, e.qw, R);
-        // B5: base-local angular acceleration, damping k(1 + |w|), no gyroscopic term
-        float wl0 = R[0] * e.wx + R[3] * e.wy + R[6] * e.wz;
-        float wl1 = R[1] * e.wx + R[4] * e.wy + R[7] * e.wz;
-        float wl2 = R[2] * e.wx + R[5] * e.wy + R[8] * e.wz;
-        float tl0 = R[0] * Tx + R[3] * Ty + R[6] * Tz;
-        float tl1 = R[1] * Tx + R[4] * Ty + R[7] * Tz;
-        float tl2 = R[2] * Tx + R[5] * Ty + R[8] * Tz;
-        float wn2 = wl0 * wl0 + wl1 * wl1 + wl2 * wl2;
-        float wn = wn2 > 2.220446049250313e-16f ? sqrt_fast(wn2) : 0.0f;
-        float kd = c.ang_damp + c.ang_damp * wn;
-        float wd0 = tl0 * P.inv_Ixy - wl0 * kd;
-        float wd1 = tl1 * P.inv_Ixy - wl1 * kd;
-        float wd2 = tl2 * P.inv_Iz - wl2 * kd;
-        float dwx = R[0] * wd0 + R[1] * wd1 + R[2] * wd2;
-        float dwy = R[3] * wd0 + R[4] * wd1 + R[5] * wd2;
-        float dwz = R[6] * wd0 + R[7] * wd1 + R[8] * wd2;
-        float vn2 = e.vx * e.vx + e.vy * e.vy + e.vz * e.vz;
-        float vn = vn2 > 2.220446049250313e-16f ? sqrt_fast(vn2) : 0.0f;
-        float kl = c.lin_damp + c.lin_damp * vn;
-        e.wx = clampf(e.wx + dwx * dt, -100.0f, 100.0f);
-        e.wy = clampf(e.wy + dwy * dt, -100.0f, 100.0f);
-        e.wz = clampf(e.wz + dwz * dt, -100.0f, 100.0f);
-        e.vx = clampf(e.vx + (ax_ - e.vx * kl) * dt, -100.0f, 100.0f);
-        e.vy = clampf(e.vy + (ay_ - e.vy * kl) * dt, -100.0f, 100.0f);
-        e.vz = clampf(e.vz + (az_ - e.vz * kl) * dt, -100.0f, 100.0f);
-
-        if (c.ground) {
-            // B9 (our model): contacts detected at the pre-integration pose, solved on velocities
-            const bool need = live && contact_needed(c, P, R, e.pz, e.vz, e.wx, e.wy, e.wz);
-            const unsigned bal = __ballot_sync(0xffffffffu, need);
-            PH_T(t1);
-            if (lane == 0) sm.cnt[warp] = __popc(bal);
-            __syncthreads();
-            PH_T(t2);
-#ifdef TVC_PHASE_PROF
-            long long t3 = t2, t4 = t2, t5 = t2; bool solver = false;
-#endif
-            int total = 0, base = 0;
-#pragma unroll
-            for (int w = 0; w < B / 32; w++) { const int n = sm.cnt[w]; if (w < warp) base += n; total += n; }
-            if (total > 0) {                                   // CTA-uniform
-                const int slot = base + __popc(bal & ((1u << lane) - 1u));
-                if (need) {
-                    sm.f[0][slot] = e.qx; sm.f[1][slot] = e.qy; sm.f[2][slot] = e.qz; sm.f[3][slot] = e.qw;
-                    sm.f[4][slot] = e.pz;
-                    sm.f[5][slot] = e.vx; sm.f[6][slot] = e.vy; sm.f[7][slot] = e.vz;
-                    sm.f[8][slot] = e.wx; sm.f[9][slot] = e.wy; sm.f[10][slot] = e.wz;
-                    sm.f[11][slot] = P.inv_mass; sm.f[12][slot] = P.inv_Ixy; sm.f[13][slot] = P.inv_Iz; sm.f[14][slot] = P.cg;
-                    sm.owner[slot] = (int)threadIdx.x | (have_lam ? 0x10000 : 0);
-                }
-                __syncthreads();
-#ifdef TVC_PHASE_PROF
-                t3 = clock64();
-#endif
-                // rotate the solver warps over the SMSPs (warp w of every CTA sits on SMSP w % 4)
-                // (co-resident CTAs differ by multiples of the SM count in blockIdx, so fold the high bits in)
-                const unsigned bx = blockIdx.x;
-                const int t = (threadIdx.x + 32 * ((bx + (bx >> 2) + (bx >> 4) + (bx >> 6) + k) & (B / 32 - 1))) & (B - 1);
-                if (t < total) {
-                    float Rs[9];
-                    quat_to_mat(sm.f[0][t], sm.f[1][t], sm.f[2][t], sm.f[3][t], Rs);
-                    BodyP Q;
-                    Q.inv_mass = sm.f[11][t]; Q.inv_Ixy = sm.f[12][t]; Q.inv_Iz = sm.f[13][t]; Q.cg = sm.f[14][t];
-                    float vx = sm.f[5][t], vy = sm.f[6][t], vz = sm.f[7][t];
-                    float wx = sm.f[8][t], wy = sm.f[9][t], wz = sm.f[10][t];
-                    const int ow = sm.owner[t];
-                    solve_contacts<B>(c, Q, Rs, sm.f[4][t], vx, vy, vz, wx, wy, wz, &sm.lam[0][ow & 0xFFFF], (ow >> 16) != 0,
-                                   k == 0 ? c.contact_iters : c.warm_iters PH2_PASS);
-                    sm.f[5][t] = vx; sm.f[6][t] = vy; sm.f[7][t] = vz;
-                    sm.f[8][t] = wx; sm.f[9][t] = wy; sm.f[10][t] = wz;
-                }
-#ifdef TVC_PHASE_PROF
-                t4 = clock64(); solver = __any_sync(0xffffffffu, t < total);
-#endif
-                __syncthreads();
-#ifdef TVC_PHASE_PROF
-                t5 = clock64();
-#endif
-                if (need) {
-                    e.vx = sm.f[5][slot]; e.vy = sm.f[6][slot]; e.vz = sm.f[7][slot];
-                    e.wx = sm.f[8][slot]; e.wy = sm.f[9][slot]; e.wz = sm.f[10][slot];
-                }
-            }
-            have_lam = need;   // entry rule failed -> stored impulses cleared
-#ifdef TVC_PHASE_PROF
-            {
-                const long long t6 = clock64();
-                ph0 += t1 - t0; ph1 += t2 - t1; ph2 += t3 - t2;
-                if (solver) { ph3 += t4 - t3; phs += 1; ph4 += t5 - t4; } else ph4 += t5 - t3;
-                ph5 += t6 - t5; phn += 1;
-            }
-#endif
-        }
-
-        // B6: semi-implicit Euler + exponential map, q <- dq (x) q, normalise
-        e.px += dt * e.vx; e.py += dt * e.vy; e.pz += dt * e.vz;
-        float ang = sqrt_fast(e.wx * e.wx + e.wy * e.wy + e.wz * e.wz);
-        if (ang * dt > 0.7853981633974483f) ang = 0.7853981633974483f * c.inv_dt;
-        // sin(x)/ang and cos(x) with x = ang*dt/2 <= pi/8: polynomials (Bullet switches to its own Taylor form below 1e-3)
-        const float hx = 0.5f * ang * dt, hx2 = hx * hx;
-        const float sc = 0.5f * dt * (1.0f + hx2 * (-1.6666667e-1f + hx2 * (8.3333333e-3f + hx2 * (-1.9841270e-4f + hx2 * 2.7557319e-6f))));
-        const float cw = 1.0f + hx2 * (-0.5f + hx2 * (4.1666667e-2f + hx2 * (-1.3888889e-3f + hx2 * 2.4801587e-5f)));
-        float bx = e.wx * sc, by = e.wy * sc, bz = e.wz * sc;
-        float nx = cw * e.qx + bx * e.qw + by * e.qz - bz * e.qy;
-        float ny = cw * e.qy + by * e.qw + bz * e.qx - bx * e.qz;
-        float nz = cw * e.qz + bz * e.qw + bx * e.qy - by * e.qx;
-        float nw = cw * e.qw - bx * e.qx - by * e.qy - bz * e.qz;
-        float inv = rsqrt_fast(nx * nx + ny * ny + nz * nz + nw * nw);
-        e.qx = nx * inv; e.qy = ny * inv; e.qz = nz * inv; e.qw = nw * inv;
-    }
-#ifdef TVC_PHASE_PROF
-    if (lane == 0) {
-        atomicAdd(&g_phase[0], (unsigned long long)ph0); atomicAdd(&g_phase[1], (unsigned long long)ph1);
-        atomicAdd(&g_phase[2], (unsigned long long)ph2); atomicAdd(&g_phase[3], (unsigned long long)ph3);
-        atomicAdd(&g_phase[4], (unsigned long long)ph4); atomicAdd(&g_phase[5], (unsigned long long)ph5);
-        atomicAdd(&g_phase[6], (unsigned long long)phn); atomicAdd(&g_phase[7], (unsigned long long)phs);
-    }
-#endif
-}
-
-// Same K substeps for ONE env on its own thread: no shared memory, no CTA barriers, the contact solver inline with
-// its 18 carried impulses in registers.  Used by step_kernel_v2, whose warps hold envs of one class (near the ground
-// or not) so the `need` branch is nearly warp-uniform.
+// Rows B2, B4, B5, B6: K substeps for ONE env on its own thread with the world-frame force F and torque T held constant
+// (Q3): no shared memory, no CTA barriers, the contact solver inline with its 18 carried impulses in registers.  Used by
+// step_kernel_v2 and the rollout kernel, whose warps hold envs of one class (near the ground or not), so the contact
+// branch is nearly warp-uniform.
 template <bool LOCKSTEP>   // LOCKSTEP: the CTA's warps re-align at every substep (every thread of the CTA must call this)
 __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P, Env &e, float Fx, float Fy, float Fz,
                                                  float Tx, float Ty, float Tz PH2_ARG) {
@@ -594,6 +477,7 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
 #pragma unroll
     for (int j = 0; j < 18; j++) lam[j] = 0.0f;
     bool have_lam = false;   // cold start at every control step
+    float pzc = 0.0f;        // running compensation of the height update: true height = e.pz + pzc
     const float dI = P.inv_Iz - P.inv_Ixy;
     const float far_z = 1.001f * (c.half_len + fabsf(P.cg) + c.radius) + c.margin;
     for (int k = 0; k < c.K; k++) {
@@ -607,7 +491,8 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
         // outside the contact solver.
         const float s2 = 2.0f * rcp_fast(e.qx * e.qx + e.qy * e.qy + e.qz * e.qz + e.qw * e.qw);
         const float xs = e.qx * s2, ys = e.qy * s2, zs = e.qz * s2;
-        const float e0 = e.qx * zs + e.qw * ys, e1 = e.qy * zs - e.qw * xs, e2 = 1.0f - (e.qx * xs + e.qy * ys);
+        const float nz1 = -(e.qx * xs + e.qy * ys);          // R33 - 1, without the cancellation
+        const float e0 = e.qx * zs + e.qw * ys, e1 = e.qy * zs - e.qw * xs, e2 = 1.0f + nz1;
         const float et = (e0 * Tx + e1 * Ty + e2 * Tz) * dI;
         float wn2 = e.wx * e.wx + e.wy * e.wy + e.wz * e.wz;
         float wn = wn2 > 2.220446049250313e-16f ? sqrt_fast(wn2) : 0.0f;
@@ -628,15 +513,22 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
         // without evaluating it (same decision, one compare for the airborne envs)
         if (c.ground && e.pz < far_z) {
             const float R31 = e.qx * zs - e.qw * ys, R32 = e.qy * zs + e.qw * xs;   // third row of R (R33 == e2)
-            if (contact_needed_row(c, P, R31, R32, e2, e.pz, e.vz, e.wx, e.wy, e.wz)) {
+            if (contact_needed_row(c, P, R31, R32, nz1, e.pz, pzc, e.vz, e.wx, e.wy, e.wz)) {
                 float R[9];
                 quat_to_mat(e.qx, e.qy, e.qz, e.qw, R);
-                solve_contacts<1>(c, P, R, e.pz, e.vx, e.vy, e.vz, e.wx, e.wy, e.wz, lam, have_lam,
-                                  k == 0 ? c.contact_iters : c.warm_iters PH2_PASS);
+                solve_contacts<1>(c, P, R, nz1, e.pz, pzc, e.vx, e.vy, e.vz, e.wx, e.wy, e.wz, lam, have_lam,
+                                  have_lam ? c.warm_iters : c.contact_iters PH2_PASS);
                 have_lam = true;
             } else have_lam = false;
         } else have_lam = false;
-        e.px += dt * e.vx; e.py += dt * e.vy; e.pz += dt * e.vz;
+        // B6: semi-implicit Euler (the height with a running compensation: the contact targets divide the gap by dt, so
+        // the 3e-8 rounding of pz + dt vz per substep would otherwise show up as 1.5e-5 m/s at dt = 0.002)
+        e.px += dt * e.vx; e.py += dt * e.vy;
+        {
+            const float y = __fadd_rn(__fmul_rn(dt, e.vz), pzc), t = __fadd_rn(e.pz, y);
+            pzc = __fsub_rn(y, __fsub_rn(t, e.pz));
+            e.pz = t;
+        }
         float ang = sqrt_fast(e.wx * e.wx + e.wy * e.wy + e.wz * e.wz);
         if (ang * dt > 0.7853981633974483f) ang = 0.7853981633974483f * c.inv_dt;
         // sin(x)/ang and cos(x) with x = ang*dt/2 <= pi/8: polynomials (Bullet switches to its own Taylor form below 1e-3)

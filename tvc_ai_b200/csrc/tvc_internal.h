@@ -15,7 +15,6 @@ struct tvc_handle {
     bool order_valid = false;  // the sorted sequence describes the current state (false after reset / set_state / rollout / curriculum)
     bool pdl = true;         // programmatic dependent launch of step_kernel_v2 and of the closing sort kernel
     bool v2_defer = false;   // large batches: finished envs are reset by the closing sort kernel; small ones in place
-    int step_impl = 2;  // 2: sorted warp-per-group kernel, 1: legacy CTA-exchange kernel
     tvc_config base;   // as created
     tvc_config cur;    // after tvc_set_curriculum
     tvc::DevCfg dc;

@@ -47,7 +47,6 @@ constexpr uint32_t OFF_H1 = OFF_A1 + NT * A1_BYTES;     // also the contact-exch
 constexpr uint32_t OFF_VEC = OFF_H1 + H1_BYTES;
 constexpr uint32_t OFF_BAR = OFF_VEC + VEC_BYTES;       // weight barrier, one MMA barrier per tile, tmem base
 constexpr uint32_t SMEM_TOTAL = OFF_BAR + 64 + 256;   // barriers + tmem base (64 B), class counts of the in-CTA sort (256 B)
-static_assert(sizeof(ContactSmemT<RB>) <= NT * A1_BYTES + H1_BYTES, "contact exchange must fit in the operand + hidden-tile area");
 static_assert(NT >= 2 && NT % 2 == 0, "tiles alternate between two TMEM column sets");
 static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 
@@ -176,15 +175,11 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
 
     const uint32_t s_base = smem_u32(smem);
     const uint32_t bar_w = s_base + OFF_BAR;
-    const int set = tile % NSET;                                 // this tile's TMEM column set and MMA barrier
-    const uint32_t bar_mma = s_base + OFF_BAR + 8 + 8 * set;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 8 + 8 * NSET);
     const float *b1 = reinterpret_cast<const float *>(smem + OFF_VEC);
     const float *b2 = b1 + HID;
     const float *w3 = b2 + HID;
     const float *b3 = w3 + 4 * HID;
-    ContactSmemT<RB> &s_contact = *reinterpret_cast<ContactSmemT<RB> *>(smem + OFF_A1);   // operand + hidden tiles are idle during physics
-    (void)s_contact; (void)bar_mma;   // used by the TVC_ROLLOUT_CTA_EXCHANGE / TVC_ROLLOUT_TILE_TURNS builds only
 
     // ---- one-time setup: barriers, TMEM (256 accumulator columns per tile), weights via TMA bulk copy ----
     if (tid == 0) {
@@ -223,10 +218,7 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
     }
     mbar_wait(bar_w, 0);
 
-    // warp w reads TMEM lanes 32*(w%4)..+31; tile j accumulates in column set j % 2: columns [256 set, 256 set + 256)
-    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(set * HID);
     uint32_t mma_phase = 0;
-    (void)taddr;
     float rsum = 0.0f, a0 = 0.0f, a1 = 0.0f;
     int done = 0, viol = 0;
 
@@ -237,7 +229,6 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
             for (int k = 0; k < 5; k++) o2[k] = make_float2(obs[2 * k], obs[2 * k + 1]);
         }
         float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f, o3 = 0.0f;
-#ifndef TVC_ROLLOUT_TILE_TURNS
         // All 16 warps work on every tile's epilogues: warp w may read TMEM lanes 32 (w % 4) .. +31 of ANY column, so for each
         // tile it takes row 32 (w % 4) + lane and the 64 accumulator columns 64 (w / 4) .. +63.  (With one tile's four warps
         // doing its 256-column epilogues while the other twelve wait, the MLP cost 19 of the 63 us per step.)  The head's
@@ -350,85 +341,6 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
             }
             __syncthreads();   // the hidden tile is written again in the next step
         }
-#else
-        // ---- layer 1 operands: every env writes its obs row into its tile's bf16 operand [2][128][8] ----
-        {
-            uint4 c0 = make_uint4(pack_bf16(obs[0], obs[1]), pack_bf16(obs[2], obs[3]), pack_bf16(obs[4], obs[5]), pack_bf16(obs[6], obs[7]));
-            uint4 c1 = make_uint4(pack_bf16(obs[8], obs[9]), 0u, 0u, 0u);
-            uint8_t *a1p = smem + OFF_A1 + tile * A1_BYTES;
-            *reinterpret_cast<uint4 *>(a1p + row * 16) = c0;
-            *reinterpret_cast<uint4 *>(a1p + TM * 16 + row * 16) = c1;
-        }
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {   // layer 1 of the first two tiles is issued up front: tile 1's MMA overlaps tile 0's epilogue
-            tc_fence_after();
-#pragma unroll
-            for (int j = 0; j < NSET; j++) {
-                mma_bf16(tmem_base + j * HID, umma_desc(s_base + OFF_A1 + j * A1_BYTES, TM * 16, 128),
-                         umma_desc(s_base + OFF_W1, HID * 16, 128), 0u);
-                mma_commit(s_base + OFF_BAR + 8 + 8 * j);
-            }
-        }
-#pragma unroll 1
-        for (int j = 0; j < NT; j++) {   // the tiles take turns on the single hidden-tile buffer
-            if (tile == j) {
-                mbar_wait(bar_mma, mma_phase);
-                tc_fence_after();
-                // epilogue 1: bias + ReLU -> bf16 hidden tile [32][128][8] (thread-contiguous 16-byte stores)
-#pragma unroll 1
-                for (int ch = 0; ch < 8; ch++) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + ch * 32, v);
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        float h[8];
-#pragma unroll
-                        for (int jj = 0; jj < 8; jj++) h[jj] = fmaxf(__uint_as_float(v[8 * q + jj]) + b1[ch * 32 + 8 * q + jj], 0.0f);
-                        *reinterpret_cast<uint4 *>(smem + OFF_H1 + (ch * 4 + q) * (TM * 16) + row * 16) =
-                            make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
-                    }
-                }
-                fence_async_smem();
-                tc_fence_before();
-            }
-            __syncthreads();
-            if (tid == 0) {   // layer 2 of tile j: 16 K-steps of M128 N256 K16
-                tc_fence_after();
-#pragma unroll
-                for (int kk = 0; kk < HID / 16; kk++)
-                    mma_bf16(tmem_base + (j % NSET) * HID, umma_desc(s_base + OFF_H1 + kk * 2 * (TM * 16), TM * 16, 128),
-                             umma_desc(s_base + OFF_W2 + kk * 2 * (HID * 16), HID * 16, 128), kk > 0 ? 1u : 0u);
-                mma_commit(s_base + OFF_BAR + 8 + 8 * (j % NSET));
-            }
-            if (tile == j) {
-                mbar_wait(bar_mma, mma_phase ^ 1u);
-                tc_fence_after();
-                // epilogue 2 + head: h2 = ReLU(d + b2); out[k] += h2 * W3[k][:]
-#pragma unroll 1
-                for (int ch = 0; ch < 8; ch++) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + ch * 32, v);
-#pragma unroll
-                    for (int jj = 0; jj < 32; jj++) {
-                        const int col = ch * 32 + jj;
-                        const float h = fmaxf(__uint_as_float(v[jj]) + b2[col], 0.0f);
-                        o0 = fmaf(h, w3[col], o0); o1 = fmaf(h, w3[HID + col], o1);
-                        o2 = fmaf(h, w3[2 * HID + col], o2); o3 = fmaf(h, w3[3 * HID + col], o3);
-                    }
-                }
-                tc_fence_before();
-            }
-            __syncthreads();   // tile j's layer-2 MMAs have completed (its threads waited): the hidden tile is free again
-            if (tid == 0 && j + NSET < NT) {   // column set j % 2 has been read out: start layer 1 of tile j + 2 in it
-                tc_fence_after();
-                mma_bf16(tmem_base + (j % NSET) * HID, umma_desc(s_base + OFF_A1 + (j + NSET) * A1_BYTES, TM * 16, 128),
-                         umma_desc(s_base + OFF_W1, HID * 16, 128), 0u);
-                mma_commit(s_base + OFF_BAR + 8 + 8 * (j % NSET));
-            }
-        }
-#endif
         // every column-set barrier completed 2 * NT / NSET (an even number of) phases this step -> parity unchanged
         // ---- action: tanh(mean + exp(clamp(log_std)) * eps), eps from Philox stream 6 ----
         const float mean0 = o0 + b3[0], mean1 = o1 + b3[1];
@@ -500,12 +412,12 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
             P = body_params(c, false, 1.0f, 0.0f, 1.0f);
             f.Fx = f.Fy = f.Fz = f.Tx = f.Ty = f.Tz = f.a0 = f.a1 = 0.0f;
         }
-#if !defined(TVC_ROLLOUT_CTA_EXCHANGE) && !defined(TVC_PHASE_PROF2)
-        // every thread solves its own env's contacts (the lazy rows 1-4 made the solve short enough: 4.31 -> 4.03 ms per
-        // launch against compacting the contact problems across the CTA through shared memory with two barriers per substep)
-        if (live) integrate_thread<false>(c, P, e, f.Fx, f.Fy, f.Fz, f.Tx, f.Ty, f.Tz);
+        // every thread solves its own env's contacts inline (same device code as the step kernel)
+#ifdef TVC_PHASE_PROF2
+        Ph2 ph2s = {0u, 0u, 0u};
+        if (live) integrate_thread<false>(c, P, e, f.Fx, f.Fy, f.Fz, f.Tx, f.Ty, f.Tz, &ph2s);
 #else
-        integrate<RB>(c, P, e, f.Fx, f.Fy, f.Fz, f.Tx, f.Ty, f.Tz, live, s_contact);
+        if (live) integrate_thread<false>(c, P, e, f.Fx, f.Fy, f.Fz, f.Tx, f.Ty, f.Tz);
 #endif
         done = 0; viol = 0;
         int ev_len = 0, ev_succ = 0, ev_reason = 0, ev_trunc = 0;
