@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TVC_ABI_VERSION 6
+#define TVC_ABI_VERSION 7
 
 #define TVC_OBS_DIM 10
 #define TVC_ACT_DIM 2
@@ -50,12 +50,36 @@ enum {
 enum { TVC_CONTRACT_R = 0 /* reference-faithful */, TVC_CONTRACT_X = 1 /* extension */ };
 enum { TVC_DIV_OFF = 0, TVC_DIV_FAST = 1, TVC_DIV_EXACT = 2 };
 
-/* quirk switches, SURVEY.md section 8(a) quirk index */
-#define TVC_Q_DOUBLE_GRAVITY   (1u << 0) /* Q1  enhanced_rocket_tvc_env.py:338 + :525-527 */
-#define TVC_Q_KEEP_CRITERIA    (1u << 1) /* Q10 :300, :399-401 */
-#define TVC_Q_KEEP_REWARD_HIST (1u << 2) /* Q11 :301, :82, :172-178 */
-#define TVC_Q_LAGGED_PHASE     (1u << 3) /* Q8/Q9 :481-482 vs :485-493 */
-#define TVC_Q_ALL_REFERENCE    0xFu
+/* Quirk switches, SURVEY.md section 8(a) quirk index (lines of env/enhanced_rocket_tvc_env.py).  A set bit reproduces
+ * the reference's behaviour; the comment says what the cleared bit does instead.  Contract R sets all of them.
+ * Contract X keeps the reference's physics and reward conventions (so that numbers stay comparable and policies
+ * transfer) and clears only the two cross-episode leaks Q10 / Q11, which are meaningless under same-step autoreset.
+ * Quirks without a bit: Q4 (fuel by iterated fp64 subtraction -- reproduced exactly by the integer burn counter), Q15
+ * (deterministic reset: Contract R has no randomness; Contract X draws per-episode conditions), Q18-Q22 (Python-level
+ * typing / info quirks, mirrored by the facade in tvc_ai_b200/env.py). */
+#define TVC_Q_DOUBLE_GRAVITY   (1u << 0)  /* Q1  :338 + :525-527; off: world gravity only */
+#define TVC_Q_KEEP_CRITERIA    (1u << 1)  /* Q10 :300, :399-401; off: reset() clears the success-criteria history */
+#define TVC_Q_KEEP_REWARD_HIST (1u << 2)  /* Q11 :301, :82, :172-178; off: reset() clears previous_action / reward_history */
+#define TVC_Q_LAGGED_PHASE     (1u << 3)  /* Q8/Q9 :481-482 vs :485-493; off: obs and R1 see this step's phase / success */
+#define TVC_Q_THRUST_VECTOR    (1u << 4)  /* Q2  :537-543 thrust 35 [sin yaw, sin pitch, cos pitch cos yaw] (not unit norm);
+                                                  off: the same direction normalised, |F| = thrust */
+#define TVC_Q_FROZEN_FORCES    (1u << 5)  /* Q3  :474-477 forces held constant in the world frame over the substeps;
+                                                  off: thrust force and torque follow the body attitude every substep */
+#define TVC_Q_DRAG_CUTOFF      (1u << 6)  /* Q5  :568-580 no drag below |v| = 0.1 m/s; off: drag at every speed */
+#define TVC_Q_STACKED_DAMPING  (1u << 7)  /* Q6  :583-585 env torque -0.02 rho w on top of Bullet's damping; off: Bullet's only */
+#define TVC_Q_EULER_TILT       (1u << 8)  /* Q7  :614-616 tilt = sqrt(pitch^2 + yaw^2) of the ZYX Euler angles;
+                                                  off: the angle between the body axis and the vertical */
+#define TVC_Q_DIVERSITY_BONUS  (1u << 9)  /* Q12 :220-224; off: no diversity bonus (as diversity_mode = TVC_DIV_OFF) */
+#define TVC_Q_VARIANCE_PENALTY (1u << 10) /* Q13 :213-218; off: no -0.1 var(last 10) penalty */
+#define TVC_Q_CLIP_BEFORE_CURIOSITY (1u << 11) /* Q14 :121-123 vs :495-502 (host side: the facades add the curiosity term);
+                                                  off: the sum including the curiosity term is clipped to [-1000, 200] */
+#define TVC_Q_SUCCESS_MASKS_TRUNCATION (1u << 12) /* Q16 :703-719; off: truncated = step >= max_steps also on success */
+#define TVC_Q_CRASH_IS_COM_HEIGHT (1u << 13) /* Q17 :632 crashed = z_com < 0.1; off: the lowest point of the body is within
+                                                  1 cm of the ground while sinking faster than 2 m/s or tilted beyond 0.52 rad */
+#define TVC_Q_ALL_REFERENCE    0x3FFFu
+#define TVC_Q_CONTRACT_X       (TVC_Q_ALL_REFERENCE & ~(TVC_Q_KEEP_CRITERIA | TVC_Q_KEEP_REWARD_HIST))
+
+#define TVC_SEED_KEEP UINT64_MAX /* tvc_reset: keep the current Philox key (every other value, 0 included, is a seed) */
 
 typedef struct tvc_handle tvc_handle;
 typedef void *tvc_stream; /* cudaStream_t */
@@ -70,11 +94,11 @@ typedef struct tvc_config {
     int32_t autoreset;         /* 0: gym.Env semantics; 1: same-step autoreset (VectorEnv) */
     uint32_t quirks;
     int32_t diversity_mode;
-    int32_t contact_iters;      /* PGS sweeps, first substep of a step (cold start) */
+    int32_t contact_iters;      /* block Gauss-Seidel passes of a solve that follows free flight (cold start) */
     int32_t ground;
     int32_t delay_steps;  /* X: actuator delay, control steps */
     int32_t thrust_curve; /* X: 0 constant, 1 model-rocket curve */
-    int32_t contact_warm_iters; /* PGS sweeps, later substeps (warm-started from the previous substep) */
+    int32_t contact_warm_iters; /* passes of a solve that follows a solve (warm-started from the previous substep) */
     double dt_step;       /* :340 */
     float gradient_penalty, diversity_bonus; /* :83-84 */
     float mass, radius, length, thrust;      /* :412-414, :463 */
@@ -89,6 +113,16 @@ typedef struct tvc_config {
     float init_tilt_max, init_omega_max;
     float propellant_fraction, cg_burn_shift;
     float reserved1;
+    /* contact material of our ground-contact model; defaults = Bullet's combination of
+     * :349-352 (plane) and :455-458 (rocket) */
+    float contact_mu;           /* 0.3 * 0.8 */
+    float contact_mu_spin;      /* 0.1 * 0.8 + 0.1 * 0.3 */
+    float contact_mu_roll;      /* 0.05 * 0.8 + 0.05 * 0.3 */
+    float contact_restitution;  /* 0.1 */
+    float contact_rest_threshold; /* 0.2 m/s */
+    float contact_erp;          /* 0.2 */
+    float contact_margin;       /* 0.05 m */
+    float reserved2;
     uint64_t seed;
     int64_t env_id_base; /* global id of env 0 of this handle: Philox counters use global ids, so
                             results do not depend on how envs are sharded over GPUs */
@@ -132,7 +166,9 @@ typedef struct tvc_step_io {
     tvc_info_soa info;      /* terminal (pre-autoreset) info */
 } tvc_step_io;
 
-/* Portable per-env state blob for tvc_get_state / tvc_set_state (parity tests, checkpoints). */
+/* Portable per-env state blob for tvc_get_state / tvc_set_state (parity tests, checkpoints).  Restoring it into a
+ * fresh handle continues the run bit for bit: it carries the diversity window of TVC_DIV_FAST (the two 1000-bit
+ * rings behind n_clip / n_run); the 1000-value window of TVC_DIV_EXACT travels through tvc_get/set_reward_history. */
 typedef struct tvc_env_state {
     float pos[3];
     float quat[4];
@@ -146,6 +182,7 @@ typedef struct tvc_env_state {
     float ring10[10]; /* slot = push_index % 10 */
     float mass_scale, thrust_scale, cg_offset, wind[2];
     float delay_ring[TVC_MAX_DELAY][2];
+    uint32_t clip_bits[32], run_bits[32]; /* TVC_DIV_FAST: bit p % 1000 of push p */
 } tvc_env_state;
 
 /* SAC actor for the fused rollout (config 4): Linear(10,256)-ReLU-Linear(256,256)-ReLU-Linear(256,4).
@@ -182,7 +219,7 @@ int tvc_create(const tvc_config *cfg, int device, int64_t num_envs, tvc_handle *
 /* replaces close() (:749-753) */
 int tvc_destroy(tvc_handle *h);
 
-/* replaces reset() (:381-407).  mask_dev NULL = all envs.  seed != 0 re-keys the Philox streams
+/* replaces reset() (:381-407).  mask_dev NULL = all envs.  seed != TVC_SEED_KEEP re-keys the Philox streams
  * (Contract X); in Contract R it has no effect on dynamics (quirk Q15). */
 int tvc_reset(tvc_handle *h, const uint8_t *mask_dev, uint64_t seed, float *obs_out_dev, tvc_stream stream);
 
@@ -211,6 +248,9 @@ int tvc_rollout(tvc_handle *h, const tvc_actor_weights *w, int32_t T, const tvc_
 size_t tvc_state_bytes(const tvc_handle *h);
 int tvc_get_state(tvc_handle *h, void *dev_blob, size_t bytes, tvc_stream stream);
 int tvc_set_state(tvc_handle *h, const void *dev_blob, size_t bytes, tvc_stream stream);
+/* TVC_DIV_EXACT only: the per-env 1000-value reward window, [N][1000] float on the device (slot = push % 1000) */
+int tvc_get_reward_history(tvc_handle *h, float *dev_out, size_t bytes, tvc_stream stream);
+int tvc_set_reward_history(tvc_handle *h, const float *dev_in, size_t bytes, tvc_stream stream);
 
 /* _get_enhanced_info (:723-742) for the current state */
 int tvc_read_info(tvc_handle *h, const tvc_info_soa *dev, tvc_stream stream);

@@ -25,7 +25,11 @@ NSTATS = 16
 CONTRACT_R, CONTRACT_X = 0, 1
 DIV_OFF, DIV_FAST, DIV_EXACT = 0, 1, 2
 Q_DOUBLE_GRAVITY, Q_KEEP_CRITERIA, Q_KEEP_REWARD_HIST, Q_LAGGED_PHASE = 1, 2, 4, 8
-Q_ALL_REFERENCE = 0xF
+Q_THRUST_VECTOR, Q_FROZEN_FORCES, Q_DRAG_CUTOFF, Q_STACKED_DAMPING, Q_EULER_TILT = 1 << 4, 1 << 5, 1 << 6, 1 << 7, 1 << 8
+Q_DIVERSITY_BONUS, Q_VARIANCE_PENALTY, Q_CLIP_BEFORE_CURIOSITY = 1 << 9, 1 << 10, 1 << 11
+Q_SUCCESS_MASKS_TRUNCATION, Q_CRASH_IS_COM_HEIGHT = 1 << 12, 1 << 13
+Q_ALL_REFERENCE = 0x3FFF
+Q_CONTRACT_X = Q_ALL_REFERENCE & ~(Q_KEEP_CRITERIA | Q_KEEP_REWARD_HIST)
 
 COMP_NAMES = ("mission_completion", "safety_compliance", "fuel_efficiency", "stability_bonus",
               "control_smoothness", "altitude_maintenance", "crash_penalty", "excessive_tilt",
@@ -49,7 +53,8 @@ class BodyParams(C.Structure):
 
 class Body(C.Structure):
     _fields_ = [("pos", C.c_double * 3), ("quat", C.c_double * 4), ("vel", C.c_double * 3),
-                ("omega", C.c_double * 3), ("force", C.c_double * 3), ("torque", C.c_double * 3)]
+                ("omega", C.c_double * 3), ("force", C.c_double * 3), ("torque", C.c_double * 3),
+                ("thrust_local", C.c_double * 3), ("thrust_arm", C.c_double)]
 
 
 class Config(C.Structure):
@@ -65,7 +70,10 @@ class Config(C.Structure):
                 ("sensor_noise_std", C.c_double), ("init_tilt_max", C.c_double), ("init_omega_max", C.c_double),
                 ("propellant_fraction", C.c_double), ("cg_burn_shift", C.c_double),
                 ("delay_steps", C.c_int32), ("thrust_curve", C.c_int32),
-                ("seed", C.c_uint64), ("env_id_base", C.c_int64)]
+                ("seed", C.c_uint64), ("env_id_base", C.c_int64),
+                ("contact_mu", C.c_double), ("contact_mu_spin", C.c_double), ("contact_mu_roll", C.c_double),
+                ("contact_restitution", C.c_double), ("contact_rest_threshold", C.c_double), ("contact_erp", C.c_double),
+                ("contact_margin", C.c_double)]
 
 
 class Env(C.Structure):

@@ -436,9 +436,19 @@ void orc_step_simulation(const orc_body_params *p, orc_body *b, double *trace) {
     int have_lam = 0;                          /* the previous substep ran the solve (warm start) */
     real pzc = 0;                              /* compensation of the height update, true height = pos[2] + pzc */
 
+    const int follow = b->thrust_local[0] != 0 || b->thrust_local[1] != 0 || b->thrust_local[2] != 0;
+    const real F0[3] = {F[0], F[1], F[2]}, T0[3] = {T[0], T[1], T[2]};
     for (int k = 0; k < K; k++) {
         real R[9];
         const real nz1 = r_matrix_from_quat(q, R);
+        if (follow) {   /* quirk Q3 cleared: the body-fixed thrust and its torque at this substep's attitude */
+            const real fl[3] = {(real)b->thrust_local[0], (real)b->thrust_local[1], (real)b->thrust_local[2]};
+            const real tl[3] = {-(real)b->thrust_arm * fl[1], (real)b->thrust_arm * fl[0], (real)0.0};
+            for (int i = 0; i < 3; i++) {
+                F[i] = F0[i] + (R[3 * i] * fl[0] + R[3 * i + 1] * fl[1] + R[3 * i + 2] * fl[2]);
+                T[i] = T0[i] + (R[3 * i] * tl[0] + R[3 * i + 1] * tl[1]);
+            }
+        }
         /* B5: ABA for a lone floating base, in base-local coordinates */
         real wl[3], tl[3], wdl[3], wd[3];
         wl[0] = R[0] * w[0] + R[3] * w[1] + R[6] * w[2];
@@ -505,7 +515,8 @@ void orc_step_simulation(const orc_body_params *p, orc_body *b, double *trace) {
     for (int i = 0; i < 3; i++) { b->pos[i] = pos[i]; b->vel[i] = v[i]; b->omega[i] = w[i]; }
     for (int i = 0; i < 4; i++) b->quat[i] = q[i];
     /* B4: clearForces() after the loop */
-    for (int i = 0; i < 3; i++) { b->force[i] = 0; b->torque[i] = 0; }
+    for (int i = 0; i < 3; i++) { b->force[i] = 0; b->torque[i] = 0; b->thrust_local[i] = 0; }
+    b->thrust_arm = 0;
 }
 
 /* ------------------------------------------------------------------ */
@@ -585,7 +596,7 @@ void orc_config_default(orc_config *c, int contract) {
     c->substeps = contract == ORC_CONTRACT_R ? 4 : 10;
     c->max_episode_steps = 1000;
     c->autoreset = 0;
-    c->quirks = contract == ORC_CONTRACT_R ? ORC_Q_ALL_REFERENCE : (ORC_Q_DOUBLE_GRAVITY | ORC_Q_LAGGED_PHASE);
+    c->quirks = contract == ORC_CONTRACT_R ? ORC_Q_ALL_REFERENCE : ORC_Q_CONTRACT_X;
     c->diversity_mode = contract == ORC_CONTRACT_R ? ORC_DIV_EXACT : ORC_DIV_FAST;
     c->contact_iters = 2;
     c->contact_warm_iters = 1;
@@ -610,6 +621,13 @@ void orc_config_default(orc_config *c, int contract) {
     c->thrust_hi = c->thrust_hi ? c->thrust_hi : 1.6;
     c->seed = 42;
     c->env_id_base = 0;
+    {   /* contact material: ref:349-352 (plane) x ref:455-458 (rocket), Bullet's combination rules */
+        orc_body_params p;
+        orc_body_params_default(&p);
+        c->contact_mu = p.mu; c->contact_mu_spin = p.mu_spin; c->contact_mu_roll = p.mu_roll;
+        c->contact_restitution = p.restitution; c->contact_rest_threshold = p.rest_threshold;
+        c->contact_erp = p.erp; c->contact_margin = p.margin;
+    }
 }
 
 static void env_params(const orc_config *c, const orc_env *e, orc_body_params *p) {
@@ -626,6 +644,9 @@ static void env_params(const orc_config *c, const orc_env *e, orc_body_params *p
     p->lin_damp = c->lin_damp; p->ang_damp = c->ang_damp;
     p->substeps = c->substeps; p->dt_step = c->dt_step;
     p->ground = c->ground; p->contact_iters = c->contact_iters; p->warm_iters = c->contact_warm_iters;
+    p->mu = c->contact_mu; p->mu_spin = c->contact_mu_spin; p->mu_roll = c->contact_mu_roll;
+    p->restitution = c->contact_restitution; p->rest_threshold = c->contact_rest_threshold;
+    p->erp = c->contact_erp; p->margin = c->contact_margin;
 }
 
 /* ref:587-606 _get_enhanced_observation */
@@ -774,27 +795,39 @@ static void env_step(orc_sim *s, orc_env *e, int64_t gid, const float *act, orc_
         double T = c->thrust;
         if (X) T = T * e->thrust_scale * orc_thrust_curve(c->thrust_curve, burn_before);
         double fl[3] = {T * sin(yaw), T * sin(pitch), T * cos(pitch) * cos(yaw)};   /* Q2 (ref:539-543) */
-        orc_matrix_from_quat(orn, R);
-        double fw[3], off[3] = {0, 0, -(P.half_len + P.cg)}, rel[3], tp[3];
-        matvec(R, fl, fw);
-        matvec(R, off, rel);
-        for (int i = 0; i < 3; i++) tp[i] = b->pos[i] + rel[i];                     /* ref:550 */
-        orc_apply_external_force(b, fw, tp);
+        if (!(c->quirks & ORC_Q_THRUST_VECTOR)) {                                   /* Q2 cleared: same direction, |F| = T */
+            double nrm = sqrt(fl[0] * fl[0] + fl[1] * fl[1] + fl[2] * fl[2]);
+            for (int i = 0; i < 3; i++) fl[i] = fl[i] * (T / nrm);
+        }
+        double off[3] = {0, 0, -(P.half_len + P.cg)};
+        if (c->quirks & ORC_Q_FROZEN_FORCES) {                                      /* Q3: evaluated once, world frame */
+            orc_matrix_from_quat(orn, R);
+            double fw[3], rel[3], tp[3];
+            matvec(R, fl, fw);
+            matvec(R, off, rel);
+            for (int i = 0; i < 3; i++) tp[i] = b->pos[i] + rel[i];                 /* ref:550 */
+            orc_apply_external_force(b, fw, tp);
+        } else {                                                                    /* Q3 cleared: the thrust follows the body */
+            for (int i = 0; i < 3; i++) b->thrust_local[i] = fl[i];
+            b->thrust_arm = off[2];
+        }
     }
     /* ---- S5 (ref:561-585) _apply_aerodynamics ---- */
     {
         double rho = 1.225 * exp(-b->pos[2] / 8400);
         double vmag = sqrt(b->vel[0] * b->vel[0] + b->vel[1] * b->vel[1] + b->vel[2] * b->vel[2]);
-        if (vmag > 0.1) {                          /* Q5 */
+        if (vmag > 0.1 || (!(c->quirks & ORC_Q_DRAG_CUTOFF) && vmag > 0)) {   /* Q5 */
             double area = PI_D * (0.05 * 0.05);
             double dm = 0.5 * rho * (vmag * vmag) * 0.47 * area;
             double df[3];
             for (int i = 0; i < 3; i++) df[i] = dm * (-b->vel[i] / vmag);
             orc_apply_external_force(b, df, b->pos);
         }
-        double ad = 0.02 * rho;
-        double dt3[3] = {-ad * b->omega[0], -ad * b->omega[1], -ad * b->omega[2]};
-        orc_apply_external_torque(b, dt3);
+        if (c->quirks & ORC_Q_STACKED_DAMPING) {   /* Q6 */
+            double ad = 0.02 * rho;
+            double dt3[3] = {-ad * b->omega[0], -ad * b->omega[1], -ad * b->omega[2]};
+            orc_apply_external_torque(b, dt3);
+        }
     }
     if (X) {                                       /* wind: constant world-frame force per episode */
         double w[3] = {e->wind[0], e->wind[1], 0};
@@ -810,11 +843,22 @@ static void env_step(orc_sim *s, orc_env *e, int64_t gid, const float *act, orc_
     orc_reported_quat(b->quat, orn);
     orc_euler_from_quat(orn, rpy);
     double tilt = sqrt(rpy[1] * rpy[1] + rpy[2] * rpy[2]);                 /* Q7 */
+    if (!(c->quirks & ORC_Q_EULER_TILT)) {                                 /* Q7 cleared: angle between body axis and vertical */
+        double sxy = 2.0 * sqrt((orn[0] * orn[0] + orn[1] * orn[1]) * (orn[2] * orn[2] + orn[3] * orn[3]));
+        tilt = atan2(sxy, 1.0 - 2.0 * (orn[0] * orn[0] + orn[1] * orn[1]));
+    }
     double wmag = sqrt(b->omega[0] * b->omega[0] + b->omega[1] * b->omega[1] + b->omega[2] * b->omega[2]);
     double vh = sqrt(b->vel[0] * b->vel[0] + b->vel[1] * b->vel[1]);
     double vv = fabs(b->vel[2]);
     double alt = b->pos[2];
     int crashed = alt < 0.1;                                               /* Q17 */
+    if (!(c->quirks & ORC_Q_CRASH_IS_COM_HEIGHT)) {                        /* Q17 cleared: a hard or tilted touchdown */
+        double cgx = X ? e->cg_offset + c->cg_burn_shift * (1.0 - e->fuel) : 0.0, hl = 0.5 * c->length;
+        double R31 = 2.0 * (orn[0] * orn[2] - orn[3] * orn[1]), R32 = 2.0 * (orn[1] * orn[2] + orn[3] * orn[0]);
+        double R33 = 1.0 - 2.0 * (orn[0] * orn[0] + orn[1] * orn[1]);
+        double low = alt + fmin(R33 * (-hl - cgx), R33 * (hl - cgx)) - c->radius * sqrt(R31 * R31 + R32 * R32);
+        crashed = low < 0.01 && (b->vel[2] < -2.0 || tilt > 0.52);
+    }
     int phase_pre = e->phase, success_pre = e->success;                    /* Q8, Q9 */
 
     /* ---- S9 (ref:635-657) _update_mission_phase ---- */
@@ -874,7 +918,7 @@ static void env_step(orc_sim *s, orc_env *e, int64_t gid, const float *act, orc_
         double mean = np_sum10(r10) / 10.0;
         for (int i = 0; i < 10; i++) { double d = r10[i] - mean; d10[i] = d * d; }
         double var = np_sum10(d10) / 10.0;
-        if (var > 10000) adj -= c->gradient_penalty * var;
+        if (var > 10000 && (c->quirks & ORC_Q_VARIANCE_PENALTY)) adj -= c->gradient_penalty * var;
     }
     int div_flag = 0;
     if (c->diversity_mode == ORC_DIV_EXACT) div_flag = (double)distinct_exact(e) > len * 0.8;
@@ -882,6 +926,7 @@ static void env_step(orc_sim *s, orc_env *e, int64_t gid, const float *act, orc_
         int distinct = len - e->n_run - e->n_clip + (e->n_clip > 0);
         div_flag = (double)distinct > len * 0.8;
     }
+    if (!(c->quirks & ORC_Q_DIVERSITY_BONUS)) div_flag = 0;
     if (div_flag) adj += c->diversity_bonus;
     /* R10: Python sum() over the dict in insertion order, then + adjustment, clip, append */
     double total = 0;
@@ -900,8 +945,10 @@ static void env_step(orc_sim *s, orc_env *e, int64_t gid, const float *act, orc_
 
     /* ---- S11 (ref:697-721) _check_termination ---- */
     int terminated = 0, truncated = 0, reason = 0;
-    if (e->success) { terminated = 1; reason = 1; }                       /* Q16 */
-    else {
+    if (e->success) {                                                     /* Q16 */
+        terminated = 1; reason = 1;
+        if (!(c->quirks & ORC_Q_SUCCESS_MASKS_TRUNCATION) && e->step >= c->max_episode_steps) truncated = 1;
+    } else {
         if (crashed) { terminated = 1; reason = 2; }
         else if (tilt > 0.52) { terminated = 1; reason = 3; }
         else if (alt > 20.0) { terminated = 1; reason = 4; }

@@ -63,6 +63,9 @@ typedef struct orc_body {
     double omega[3];  /* world frame */
     double force[3];  /* accumulated external force, cleared by step */
     double torque[3];
+    /* quirk Q3 cleared: a body-fixed force at (0, 0, thrust_arm), re-evaluated at every substep's attitude; cleared by step */
+    double thrust_local[3];
+    double thrust_arm;
 } orc_body;
 
 void orc_body_params_default(orc_body_params *p);
@@ -83,12 +86,23 @@ void orc_matrix_from_quat(const double q[4], double m[9]);      /* row B8 */
 enum { ORC_CONTRACT_R = 0, ORC_CONTRACT_X = 1 };
 enum { ORC_DIV_OFF = 0, ORC_DIV_FAST = 1, ORC_DIV_EXACT = 2 };
 
-/* quirk switches (SURVEY.md section 8(a) quirk index) */
+/* quirk switches (SURVEY.md section 8(a) quirk index); same bits and meanings as include/tvc_b200.h TVC_Q_* */
 #define ORC_Q_DOUBLE_GRAVITY   (1u << 0)  /* Q1 */
 #define ORC_Q_KEEP_CRITERIA    (1u << 1)  /* Q10: criteria history survives reset */
 #define ORC_Q_KEEP_REWARD_HIST (1u << 2)  /* Q11: previous_action + reward_history survive reset */
 #define ORC_Q_LAGGED_PHASE     (1u << 3)  /* Q8/Q9: obs + R1 use the pre-update phase / success */
-#define ORC_Q_ALL_REFERENCE    (0xFu)
+#define ORC_Q_THRUST_VECTOR    (1u << 4)  /* Q2; off: normalised direction */
+#define ORC_Q_FROZEN_FORCES    (1u << 5)  /* Q3; off: thrust follows the body every substep */
+#define ORC_Q_DRAG_CUTOFF      (1u << 6)  /* Q5; off: drag at every speed */
+#define ORC_Q_STACKED_DAMPING  (1u << 7)  /* Q6; off: no env damping torque */
+#define ORC_Q_EULER_TILT       (1u << 8)  /* Q7; off: angle between body axis and vertical */
+#define ORC_Q_DIVERSITY_BONUS  (1u << 9)  /* Q12; off: no bonus */
+#define ORC_Q_VARIANCE_PENALTY (1u << 10) /* Q13; off: no penalty */
+#define ORC_Q_CLIP_BEFORE_CURIOSITY (1u << 11) /* Q14 (host side) */
+#define ORC_Q_SUCCESS_MASKS_TRUNCATION (1u << 12) /* Q16; off: truncation flag also on success */
+#define ORC_Q_CRASH_IS_COM_HEIGHT (1u << 13) /* Q17; off: hard or tilted touchdown */
+#define ORC_Q_ALL_REFERENCE    (0x3FFFu)
+#define ORC_Q_CONTRACT_X       (ORC_Q_ALL_REFERENCE & ~(ORC_Q_KEEP_CRITERIA | ORC_Q_KEEP_REWARD_HIST))
 
 typedef struct orc_config {
     int32_t contract;
@@ -119,6 +133,8 @@ typedef struct orc_config {
     int32_t thrust_curve;       /* 0 constant, 1 model-rocket curve */
     uint64_t seed;
     int64_t env_id_base;
+    /* contact material of our ground-contact model */
+    double contact_mu, contact_mu_spin, contact_mu_roll, contact_restitution, contact_rest_threshold, contact_erp, contact_margin;
 } orc_config;
 
 typedef struct orc_env {

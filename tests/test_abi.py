@@ -70,6 +70,13 @@ def test_defaults_match_reference_constants(lib_built):
     x = _abi.default_config(_abi.CONTRACT_X)
     assert x.substeps == 10 and abs(x.mass_variation - 0.3) < 1e-7 and x.wind_std == 3.0
     assert abs(x.sensor_noise_std - 0.02) < 1e-7 and abs(x.thrust_std - 0.2) < 1e-7
+    # Contract X keeps every reference convention except the two cross-episode leaks (Q10, Q11)
+    assert x.quirks == _abi.Q_CONTRACT_X == _abi.Q_ALL_REFERENCE & ~(_abi.Q_KEEP_CRITERIA | _abi.Q_KEEP_REWARD_HIST)
+    # contact material: Bullet's combination of ref:349-352 (plane) and ref:455-458 (rocket)
+    for cc in (c, x):
+        assert abs(cc.contact_mu - 0.24) < 1e-7 and abs(cc.contact_mu_spin - 0.11) < 1e-7 and abs(cc.contact_mu_roll - 0.055) < 1e-7
+        assert abs(cc.contact_restitution - 0.1) < 1e-7 and abs(cc.contact_erp - 0.2) < 1e-7 and abs(cc.contact_margin - 0.05) < 1e-7
+        assert (cc.contact_iters, cc.contact_warm_iters) == (2, 1)
 
 
 def test_no_cpu_fallback_without_gpu(lib_built):
@@ -105,9 +112,13 @@ def test_error_codes_without_a_gpu(lib_built):
     bad.abi_version = 1
     assert L.tvc_create(C.byref(bad), 0, 16, C.byref(h)) == -4 and b"abi_version" in L.tvc_last_error()      # TVC_E_ABI
     assert L.tvc_create(C.byref(cfg), 0, 0, C.byref(h)) == -1 and b"num_envs" in L.tvc_last_error()          # TVC_E_BADARG
+    assert L.tvc_create(C.byref(cfg), 0, 2 ** 31 - 1000, C.byref(h)) == -1 and b"num_envs" in L.tvc_last_error()   # env ids are int32
     assert L.tvc_create(C.byref(cfg), 0, 16, None) == -1
     for field, value in (("substeps", 0), ("substeps", 65), ("max_episode_steps", 0), ("diversity_mode", 3),
-                         ("delay_steps", 5), ("contact_iters", -1), ("contract", 2), ("mass", 0.0), ("dt_step", 0.0)):
+                         ("delay_steps", 5), ("contact_iters", -1), ("contract", 2), ("mass", 0.0), ("dt_step", 0.0),
+                         ("gimbal_max_rad", 0.9), ("gimbal_max_rad", 0.0), ("mass_variation", 1.0), ("mass_variation", -0.1),
+                         ("thrust_lo", 2.0), ("propellant_fraction", 1.0), ("contact_mu", -0.1), ("contact_margin", 0.0),
+                         ("contact_restitution", 1.5), ("quirks", 1 << 20)):
         c2 = A.default_config(A.CONTRACT_X)
         setattr(c2, field, value)
         assert L.tvc_create(C.byref(c2), 0, 16, C.byref(h)) == -1, field

@@ -320,6 +320,147 @@ def test_episode_statistics_match_oracle(lib_built, oracle_mod, parity_record):
     eng.close()
 
 
+QUIRK_BITS = ["DOUBLE_GRAVITY", "KEEP_CRITERIA", "KEEP_REWARD_HIST", "LAGGED_PHASE", "THRUST_VECTOR", "FROZEN_FORCES",
+              "DRAG_CUTOFF", "STACKED_DAMPING", "EULER_TILT", "DIVERSITY_BONUS", "VARIANCE_PENALTY", "SUCCESS_MASKS_TRUNCATION",
+              "CRASH_IS_COM_HEIGHT"]
+
+
+@pytest.mark.parametrize("bit", QUIRK_BITS)
+def test_quirk_switches_device_equals_oracle(lib_built, oracle_mod, parity_record, bit):
+    """Every quirk switch (include/tvc_b200.h TVC_Q_*) cleared on its own: the device follows the oracle (what the cleared
+    bit means is pinned on the CPU by tests/test_quirks.py).  Contract R, 48 envs x 45 steps (fall, touchdown, tilt-over,
+    crash, autoreset), teacher-forced from identical float32 states."""
+    O = oracle_mod
+    from tvc_ai_b200 import _abi as A
+    n, T, K = 48, 45, 4
+    q = A.Q_ALL_REFERENCE & ~getattr(A, "Q_" + bit)
+    assert getattr(A, "Q_" + bit) == getattr(O, "Q_" + bit)
+    acts = np.load(os.path.join(os.path.dirname(__file__), "golden", "actions_pcg64_42.npy"))
+    over = dict(autoreset=1, quirks=q, max_episode_steps=40)
+    sim = _oracle(O, n, O.CONTRACT_R, diversity_mode=O.DIV_FAST, **over)
+    eng = _engine(n, A.CONTRACT_R, diversity_mode=A.DIV_FAST, **over)
+    eng.reset()
+    rng = np.random.default_rng(3)
+    scale = rng.uniform(0.0, 1.0, (n, 1))
+    worst_free, worst_contact, worst_rew, mism, near, div_flips = 0.0, 0.0, 0.0, 0, 0, 0
+    for t in range(T):
+        for i in range(n):
+            _round_body_f32(sim.env(i))
+        eng.set_state(_state_from_oracle(O, sim, eng.get_state()))
+        pre = np.array([_body13(sim.env(i)) for i in range(n)])
+        a = (acts[t][None, :] * scale).astype(np.float32)
+        obs_o, rew_o, term_o, trunc_o, outs = sim.step(a, threads=4)
+        fin_o = np.stack([np.frombuffer(o.final_obs, np.float32) for o in outs])
+        obs_d, rew_d, term_d, trunc_d, info = eng.step_ex(torch.from_numpy(a).cuda())
+        term_d, trunc_d = term_d.cpu().numpy().astype(bool), trunc_d.cpu().numpy().astype(bool)
+        done_o = term_o | trunc_o
+        comp_d = info["reward_components"].cpu().numpy()
+        cmp_d = np.where(done_o[:, None], eng.final_obs.cpu().numpy(), obs_d.cpu().numpy())
+        cmp_o = np.where(done_o[:, None], fin_o, obs_o)
+        err = (np.abs(cmp_d - cmp_o) / np.maximum(1.0, np.abs(cmp_o))).max(axis=1)
+        rd = rew_d.cpu().numpy()
+        for i in range(n):
+            if term_d[i] != term_o[i] or trunc_d[i] != trunc_o[i]:
+                mism += 1
+                near += int(_near_threshold(outs[i]))
+                continue
+            contact = min(_lowest_gap(pre[i][:3], pre[i][3:7]), outs[i].position[2] - 0.55) < 0.06
+            if contact:
+                worst_contact = max(worst_contact, float(err[i]))
+            else:
+                worst_free = max(worst_free, float(err[i]))
+            flip = comp_d[i][11] != outs[i].comp[11]
+            div_flips += int(flip)
+            if not _near_threshold(outs[i]) and abs(outs[i].comp[10]) < 900 and not flip:
+                worst_rew = max(worst_rew, abs(rd[i] - rew_o[i]) / max(1.0, abs(rew_o[i])))
+    rec = dict(cleared=bit, free_flight_max=worst_free, contact_max=worst_contact, reward_rel_max=worst_rew,
+               flag_mismatches=mism, of_which_near_threshold=near, diversity_flips=div_flips,
+               episodes=float(sim.stats()[0]))
+    parity_record[f"quirk_cleared/{bit}"] = rec
+    assert rec["episodes"] >= n
+    assert mism == near and near <= 2, rec
+    assert worst_free <= K * 1e-5 and worst_contact <= CONTACT_MAX_R and worst_rew <= 2e-4, rec
+    eng.close()
+
+
+def test_state_blob_restores_into_a_fresh_handle(lib_built):
+    """tvc_get_state -> tvc_set_state into a NEW handle continues the run bit for bit, after more than 1000 steps (the
+    1000-entry diversity window is full and leaving values are being retired): Contract X with the bit rings, delay ring
+    and thrust curve, and Contract R with the exact window (tvc_get/set_reward_history)."""
+    from tvc_ai_b200 import _abi as A
+
+    def acts(n, t, dev):
+        g = torch.Generator(device=dev); g.manual_seed(1000 + t)
+        return torch.rand((n, 2), generator=g, device=dev) * 2 - 1
+
+    for contract, n, over, exact in ((A.CONTRACT_X, 4096, dict(autoreset=1, delay_steps=3, thrust_curve=1, seed=9), False),
+                                     (A.CONTRACT_R, 96, dict(autoreset=1), True)):
+        a = _engine(n, contract, **over)
+        a.reset()
+        for t in range(1100):
+            a.step(acts(n, t, a.device), want_final=False)
+        b = _engine(n, contract, **over)
+        b.reset()
+        b.set_state(a.get_state())
+        if exact:
+            assert a.config.diversity_mode == A.DIV_EXACT
+            b.set_reward_history(a.get_reward_history())
+        div_seen = 0.0
+        for t in range(1100, 1250):
+            x = acts(n, t, a.device)
+            oa, ra, ta, tra, ia = a.step_ex(x)
+            ob, rb, tb, trb, ib = b.step_ex(x)
+            assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(ta, tb) and torch.equal(tra, trb), (contract, t)
+            assert torch.equal(ia["reward_components"], ib["reward_components"]), (contract, t)
+            div_seen += float(ia["reward_components"][:, 11].sum())
+        assert div_seen > 0                      # the diversity decision was live in the compared span
+        sa, sb = a.get_state(), b.get_state()
+        for f in ("n_clip", "n_run", "hist_count", "clip_bits", "run_bits", "ring10", "delay_ring"):
+            assert np.array_equal(sa[f], sb[f]), f
+        a.close(); b.close()
+
+
+def test_seed_zero_is_a_seed_and_none_keeps_the_key(lib_built):
+    """tvc_reset: every value but TVC_SEED_KEEP re-keys the Philox streams -- seed 0 included (Gymnasium's reset(seed=0))."""
+    from tvc_ai_b200 import _abi as A
+    n = 256
+    mk = lambda: _engine(n, A.CONTRACT_X, autoreset=1, init_tilt_max=0.2)  # noqa: E731
+    e0, e5, e50, e00 = mk(), mk(), mk(), mk()
+    o0 = e0.reset(seed=0).clone()
+    o5 = e5.reset(seed=5).clone()
+    assert not torch.equal(o0, o5)
+    e50.reset(seed=5); e00.reset(seed=0)
+    a, b = e50.reset(seed=0).clone(), e00.reset(seed=0).clone()      # same key, same episode index -> same draws
+    assert torch.equal(a, b)
+    c = e50.reset(seed=None).clone()                                  # keeps key 0
+    d = e00.reset().clone()
+    assert torch.equal(c, d) and e50.config.seed == 0
+    for e in (e0, e5, e50, e00):
+        e.close()
+
+
+def test_engine_on_a_device_other_than_the_current_one(lib_built):
+    """Every ABI entry point switches to the handle's device and back (several engines in one process)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from tvc_ai_b200 import _abi as A
+    from tvc_ai_b200.engine import BatchedEngine
+    torch.cuda.set_device(0)
+    e1 = BatchedEngine(4096, A.default_config(A.CONTRACT_X, autoreset=1), device=1)
+    e0 = BatchedEngine(4096, A.default_config(A.CONTRACT_X, autoreset=1), device=0)
+    e1.reset(); e0.reset()
+    assert torch.cuda.current_device() == 0
+    for _ in range(40):
+        o1 = e1.step(None)[0]
+        o0 = e0.step(None)[0]
+    assert o1.device.index == 1 and torch.equal(o1.cpu(), o0.cpu())
+    h = e1.step_host(None)
+    assert np.isfinite(h[0]).all() and torch.cuda.current_device() == 0
+    assert e1.stats()[14] == 41 * 4096 and e0.stats()[14] == 40 * 4096
+    assert e1.get_state()["step"].shape == (4096,)
+    e1.close(); e0.close()
+
+
 def test_sharding_invariance_and_determinism(lib_built):
     """Property test at scale (Contract X, 65536 envs): results depend on global env ids only, so two
     half-size engines with env_id_base offsets reproduce one full-size engine bit-for-bit, and a
@@ -564,6 +705,9 @@ def test_step_under_cuda_graph_capture(lib_built):
         oe, re_, te, tre = eager.step(a, want_final=False)
         torch.cuda.synchronize()
         assert torch.equal(graphed.obs, oe) and torch.equal(graphed.reward, re_) and torch.equal(graphed.terminated, te), f"replay {t}"
+    # the step counter of the statistics lives on the device: replays count (3 warm-up steps + 40 replays)
+    np.testing.assert_array_equal(graphed.stats(), eager.stats())
+    assert graphed.stats()[14] == 43 * n
     eager.close(); graphed.close()
 
 

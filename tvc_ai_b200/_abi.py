@@ -12,11 +12,18 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TVC_B200_LIB") or os.path.join(_HERE, "libtvc_b200.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 OBS_DIM, ACT_DIM, NUM_COMPONENTS, NUM_STATS, MAX_DELAY = 10, 2, 12, 16, 4
 CONTRACT_R, CONTRACT_X = 0, 1
 DIV_OFF, DIV_FAST, DIV_EXACT = 0, 1, 2
-Q_DOUBLE_GRAVITY, Q_KEEP_CRITERIA, Q_KEEP_REWARD_HIST, Q_LAGGED_PHASE, Q_ALL_REFERENCE = 1, 2, 4, 8, 0xF
+# quirk switches (include/tvc_b200.h TVC_Q_*): a set bit reproduces the reference, see the header for the cleared meaning
+Q_DOUBLE_GRAVITY, Q_KEEP_CRITERIA, Q_KEEP_REWARD_HIST, Q_LAGGED_PHASE = 1, 2, 4, 8
+Q_THRUST_VECTOR, Q_FROZEN_FORCES, Q_DRAG_CUTOFF, Q_STACKED_DAMPING, Q_EULER_TILT = 1 << 4, 1 << 5, 1 << 6, 1 << 7, 1 << 8
+Q_DIVERSITY_BONUS, Q_VARIANCE_PENALTY, Q_CLIP_BEFORE_CURIOSITY = 1 << 9, 1 << 10, 1 << 11
+Q_SUCCESS_MASKS_TRUNCATION, Q_CRASH_IS_COM_HEIGHT = 1 << 12, 1 << 13
+Q_ALL_REFERENCE = 0x3FFF
+Q_CONTRACT_X = Q_ALL_REFERENCE & ~(Q_KEEP_CRITERIA | Q_KEEP_REWARD_HIST)
+SEED_KEEP = 0xFFFFFFFFFFFFFFFF   # tvc_reset: keep the current Philox key
 
 COMPONENT_NAMES = ("mission_completion", "safety_compliance", "fuel_efficiency", "stability_bonus",
                    "control_smoothness", "altitude_maintenance", "crash_penalty", "excessive_tilt",
@@ -27,7 +34,7 @@ STAT_NAMES = ("episodes", "sum_return", "sum_return_sq", "sum_length", "successe
 
 EXPORTS = ("tvc_abi_version", "tvc_last_error", "tvc_config_default", "tvc_create", "tvc_destroy", "tvc_reset",
            "tvc_step", "tvc_step_ex", "tvc_step_host", "tvc_step_host_async", "tvc_host_sync", "tvc_rollout", "tvc_state_bytes", "tvc_get_state",
-           "tvc_set_state", "tvc_read_info", "tvc_episode_stats", "tvc_episode_stats_dev", "tvc_set_curriculum",
+           "tvc_set_state", "tvc_get_reward_history", "tvc_set_reward_history", "tvc_read_info", "tvc_episode_stats", "tvc_episode_stats_dev", "tvc_set_curriculum",
            "tvc_get_config", "tvc_num_envs", "tvc_lifetime_steps")
 
 
@@ -44,6 +51,9 @@ class TvcConfig(C.Structure):
                 ("thrust_hi", C.c_float), ("cg_offset_max", C.c_float), ("wind_std", C.c_float),
                 ("sensor_noise_std", C.c_float), ("init_tilt_max", C.c_float), ("init_omega_max", C.c_float),
                 ("propellant_fraction", C.c_float), ("cg_burn_shift", C.c_float), ("reserved1", C.c_float),
+                ("contact_mu", C.c_float), ("contact_mu_spin", C.c_float), ("contact_mu_roll", C.c_float),
+                ("contact_restitution", C.c_float), ("contact_rest_threshold", C.c_float), ("contact_erp", C.c_float),
+                ("contact_margin", C.c_float), ("reserved2", C.c_float),
                 ("seed", C.c_uint64), ("env_id_base", C.c_int64)]
 
 
@@ -73,7 +83,8 @@ class TvcEnvState(C.Structure):
                 ("has_prev", C.c_int32), ("consec", C.c_int32), ("hist_count", C.c_int32), ("episode", C.c_int32),
                 ("n_clip", C.c_int32), ("n_run", C.c_int32), ("ring10", C.c_float * 10),
                 ("mass_scale", C.c_float), ("thrust_scale", C.c_float), ("cg_offset", C.c_float),
-                ("wind", C.c_float * 2), ("delay_ring", (C.c_float * 2) * MAX_DELAY)]
+                ("wind", C.c_float * 2), ("delay_ring", (C.c_float * 2) * MAX_DELAY),
+                ("clip_bits", C.c_uint32 * 32), ("run_bits", C.c_uint32 * 32)]
 
 
 class TvcActorWeights(C.Structure):
@@ -119,6 +130,8 @@ def load(path: str | None = None):
     L.tvc_state_bytes.restype = C.c_size_t
     L.tvc_get_state.argtypes = [vp, vp, C.c_size_t, vp]
     L.tvc_set_state.argtypes = [vp, vp, C.c_size_t, vp]
+    L.tvc_get_reward_history.argtypes = [vp, vp, C.c_size_t, vp]
+    L.tvc_set_reward_history.argtypes = [vp, vp, C.c_size_t, vp]
     L.tvc_read_info.argtypes = [vp, C.POINTER(TvcInfoSoa), vp]
     L.tvc_episode_stats.argtypes = [vp, C.POINTER(C.c_double), C.c_int, vp]
     L.tvc_episode_stats_dev.argtypes = [vp, vp, C.c_int, vp]

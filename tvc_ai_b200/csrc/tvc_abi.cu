@@ -4,6 +4,7 @@
 #include "tvc_device.cuh"
 #include "tvc_internal.h"
 
+#include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -175,7 +176,7 @@ classify_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevSta
         }
         if (tid == 0) o[0] = 0;
     }
-    if (tid == 0) { st.counter[0] = 0u; st.counter[1] = 0u; }
+    if (tid == 0) { st.counter[0] = 0u; st.counter[1] = 0u; if (!FROM_STATE) st.counter[2] += 1u; }   // [2]: steps since the statistics were reset
 }
 
 // Position p of the global class-ordered sequence -> env id (binary search over the chunk scans of p's class).
@@ -249,7 +250,7 @@ __device__ __forceinline__ int env_at_group(const DevState &st, int p, int lane,
 // A split into an airborne-part kernel at twice the occupancy (64 registers, solver out of line) followed by a near-ground
 // kernel was measured: 0.150 ms against 0.125 ms for this single kernel -- the FP32-pipe-bound solver warps and the
 // latency-bound airborne warps hide each other only when they share the SM sub-partitions.
-template <bool X, int DIV, bool DEFER>
+template <bool X, int DIV, bool DEFER, bool FOLLOW>
 __global__ void __launch_bounds__(TVC_V2_BLOCK, TVC_MIN_BLOCKS_V2)
 step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevState st, const __grid_constant__ DevIO io) {
     // launched with programmatic stream serialization: everything above this line may overlap classify_kernel's tail
@@ -327,13 +328,13 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
             memset(&e, 0, sizeof(e));
             e.qw = 1.0f; e.pz = 1.0f;
             P = body_params(c, false, 1.0f, 0.0f, 1.0f);
-            f.Fx = f.Fy = f.Fz = f.Tx = f.Ty = f.Tz = f.a0 = f.a1 = 0.0f;
+            f.Fx = f.Fy = f.Fz = f.Tx = f.Ty = f.Tz = f.a0 = f.a1 = f.fl0 = f.fl1 = f.fl2 = f.arm = 0.0f;
         }
         PH2_CLK(pt1);
 #ifdef TVC_V2_LOCKSTEP
-        integrate_thread<true>(c, P, e, f.Fx, f.Fy, f.Fz, f.Tx, f.Ty, f.Tz PH2_PASS);
+        integrate_thread<true, FOLLOW>(c, P, e, f PH2_PASS);
 #else
-        if (live) integrate_thread<false>(c, P, e, f.Fx, f.Fy, f.Fz, f.Tx, f.Ty, f.Tz PH2_PASS);
+        if (live) integrate_thread<false, FOLLOW>(c, P, e, f PH2_PASS);
 #endif
         PH2_CLK(pt2);
         if (live) {
@@ -473,6 +474,7 @@ __global__ void get_state_kernel(const __grid_constant__ DevState st, tvc_env_st
     s.mass_scale = e.mass_scale; s.thrust_scale = e.thrust_scale; s.cg_offset = e.cg_off;
     s.wind[0] = e.wind_x; s.wind[1] = e.wind_y;
     if (X) for (int k = 0; k < delay; k++) { float2 d = st.delay[(long long)k * st.n + i]; s.delay_ring[k][0] = d.x; s.delay_ring[k][1] = d.y; }
+    if (st.clipb) for (int k = 0; k < 32; k++) { s.clip_bits[k] = st.clipb[(long long)k * st.n + i]; s.run_bits[k] = st.runb[(long long)k * st.n + i]; }
     out[i] = s;
 }
 
@@ -494,6 +496,17 @@ __global__ void set_state_kernel(const __grid_constant__ DevState st, const tvc_
     store_env(st, X, i, e);
     for (int k = 0; k < 10; k++) st.ring[12 * i + k] = s.ring10[k];
     if (X) for (int k = 0; k < delay; k++) st.delay[(long long)k * st.n + i] = make_float2(s.delay_ring[k][0], s.delay_ring[k][1]);
+    if (st.clipb) for (int k = 0; k < 32; k++) { st.clipb[(long long)k * st.n + i] = s.clip_bits[k]; st.runb[(long long)k * st.n + i] = s.run_bits[k]; }
+}
+
+// [N][1000] caller layout <-> [1000][N] planes (TVC_DIV_EXACT window)
+__global__ void hist_copy_kernel(float *planes, float *rows, long long n, int to_planes) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int k = 0; k < TVC_HIST; k++) {
+        if (to_planes) planes[(long long)k * n + i] = rows[i * TVC_HIST + k];
+        else rows[i * TVC_HIST + k] = planes[(long long)k * n + i];
+    }
 }
 
 template <bool X>
@@ -519,7 +532,7 @@ __global__ void info_kernel(const __grid_constant__ DevState st, const __grid_co
 // deterministic reduction of the statistics rows: 512 threads = 32 row-lanes x 16 statistics (each row is one
 // coalesced 128-byte read), row-strided partial sums in a fixed order, then a fixed-order fold over the row-lanes
 __global__ void __launch_bounds__(512)
-stats_reduce_kernel(double *partial, int nrows, double *out, double steps, int reset_after) {
+stats_reduce_kernel(double *partial, int nrows, double *out, unsigned *step_counter, double envs, int reset_after) {
     __shared__ double s[32][TVC_NSTAT];
     const int k = threadIdx.x & (TVC_NSTAT - 1), rl = threadIdx.x >> 4;
     double acc = 0.0;
@@ -532,13 +545,25 @@ stats_reduce_kernel(double *partial, int nrows, double *out, double steps, int r
     if (threadIdx.x < TVC_NSTAT) {
         double t = 0.0;
         for (int j = 0; j < 32; j++) t += s[j][threadIdx.x];
-        out[threadIdx.x] = (threadIdx.x == 14) ? steps : t;
+        out[threadIdx.x] = (threadIdx.x == 14) ? envs * (double)step_counter[0] : t;
+        if (threadIdx.x == 14 && reset_after) step_counter[0] = 0u;
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+// Every entry point that touches CUDA runs on the handle's device and restores the caller's current device afterwards
+// (several engines in one process, or an engine on a device other than the current one).
+struct DevGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DevGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DevGuard() { if (switched) cudaSetDevice(prev); }
+};
+
 static thread_local std::string g_err;
 const char *tvc_set_err(const std::string &m) { g_err = m; return g_err.c_str(); }
 
@@ -579,9 +604,8 @@ static void make_devcfg(const tvc_config &c, DevCfg &d) {
     d.mass_var = c.mass_variation; d.thrust_std = c.thrust_std; d.thrust_lo = c.thrust_lo; d.thrust_hi = c.thrust_hi;
     d.cg_max = c.cg_offset_max; d.wind_std = c.wind_std; d.noise_std = c.sensor_noise_std;
     d.tilt_max = c.init_tilt_max; d.omega_max = c.init_omega_max; d.prop_frac = c.propellant_fraction; d.cg_burn = c.cg_burn_shift;
-    // contact material: enhanced_rocket_tvc_env.py:349-352 (plane) x :455-458 (rocket); Bullet combination rules
-    d.mu = 0.3f * 0.8f; d.mu_spin = 0.1f * 0.8f + 0.1f * 0.3f; d.mu_roll = 0.05f * 0.8f + 0.05f * 0.3f;
-    d.restitution = 0.1f; d.rest_thr = 0.2f; d.erp = 0.2f; d.margin = 0.05f;
+    d.mu = c.contact_mu; d.mu_spin = c.contact_mu_spin; d.mu_roll = c.contact_mu_roll;
+    d.restitution = c.contact_restitution; d.rest_thr = c.contact_rest_threshold; d.erp = c.contact_erp; d.margin = c.contact_margin;
     d.seed_lo = (unsigned)c.seed; d.seed_hi = (unsigned)(c.seed >> 32);
     d.env_base = c.env_id_base;
 }
@@ -599,7 +623,7 @@ int tvc_config_default(tvc_config *c, int contract) {
     c->substeps = contract == TVC_CONTRACT_R ? 4 : 10;
     c->max_episode_steps = 1000;
     c->autoreset = 0;
-    c->quirks = contract == TVC_CONTRACT_R ? TVC_Q_ALL_REFERENCE : (TVC_Q_DOUBLE_GRAVITY | TVC_Q_LAGGED_PHASE);
+    c->quirks = contract == TVC_CONTRACT_R ? TVC_Q_ALL_REFERENCE : TVC_Q_CONTRACT_X;
     c->diversity_mode = contract == TVC_CONTRACT_R ? TVC_DIV_EXACT : TVC_DIV_FAST;
     c->contact_iters = 2;
     c->contact_warm_iters = 1;
@@ -610,6 +634,9 @@ int tvc_config_default(tvc_config *c, int contract) {
     c->gimbal_max_rad = (float)(18.0 * (3.14159265358979323846 / 180.0));
     c->lin_damp = 0.01f; c->ang_damp = 0.02f;
     c->thrust_lo = 0.4f; c->thrust_hi = 1.6f;
+    // contact material: enhanced_rocket_tvc_env.py:349-352 (plane) x :455-458 (rocket); Bullet combination rules
+    c->contact_mu = 0.3f * 0.8f; c->contact_mu_spin = 0.1f * 0.8f + 0.1f * 0.3f; c->contact_mu_roll = 0.05f * 0.8f + 0.05f * 0.3f;
+    c->contact_restitution = 0.1f; c->contact_rest_threshold = 0.2f; c->contact_erp = 0.2f; c->contact_margin = 0.05f;
     if (contract == TVC_CONTRACT_X) {
         c->mass_variation = 0.3f; c->thrust_std = 0.2f; c->cg_offset_max = 0.1f; c->wind_std = 3.0f;
         c->sensor_noise_std = 0.02f;
@@ -623,7 +650,7 @@ int tvc_config_default(tvc_config *c, int contract) {
 static int validate(const tvc_config *c, int64_t n) {
     if (!c) { tvc_set_err("config is NULL"); return TVC_E_BADARG; }
     if (c->abi_version != TVC_ABI_VERSION) { tvc_set_err("tvc_config.abi_version mismatch"); return TVC_E_ABI; }
-    if (n <= 0 || n > (1ll << 31)) { tvc_set_err("num_envs out of range"); return TVC_E_BADARG; }
+    if (n <= 0 || n > (long long)INT32_MAX - TVC_CHUNK) { tvc_set_err("num_envs out of range [1, 2^31 - 1 - 1024] (env ids and the work sequence are int32)"); return TVC_E_BADARG; }
     if (c->contract != TVC_CONTRACT_R && c->contract != TVC_CONTRACT_X) { tvc_set_err("bad contract"); return TVC_E_BADARG; }
     if (c->substeps < 1 || c->substeps > 64) { tvc_set_err("substeps out of range [1,64]"); return TVC_E_BADARG; }
     if (c->max_episode_steps < 1) { tvc_set_err("max_episode_steps < 1"); return TVC_E_BADARG; }
@@ -631,6 +658,16 @@ static int validate(const tvc_config *c, int64_t n) {
     if (c->delay_steps < 0 || c->delay_steps > TVC_MAX_DELAY) { tvc_set_err("delay_steps out of range"); return TVC_E_BADARG; }
     if (c->contact_iters < 0 || c->contact_iters > 256 || c->contact_warm_iters < 0 || c->contact_warm_iters > 256) { tvc_set_err("contact_iters out of range"); return TVC_E_BADARG; }
     if (!(c->dt_step > 0) || !(c->mass > 0) || !(c->radius > 0) || !(c->length > 0)) { tvc_set_err("non-positive physical parameter"); return TVC_E_BADARG; }
+    // the thrust-angle sine / cosine are polynomials valid to 0.8 rad (sincos_small)
+    if (!(c->gimbal_max_rad > 0.0f && c->gimbal_max_rad <= 0.8f)) { tvc_set_err("gimbal_max_rad out of range (0, 0.8]"); return TVC_E_BADARG; }
+    if (!(c->mass_variation >= 0.0f && c->mass_variation < 1.0f)) { tvc_set_err("mass_variation out of range [0, 1)"); return TVC_E_BADARG; }
+    if (!(c->thrust_lo <= c->thrust_hi) || !(c->thrust_std >= 0.0f)) { tvc_set_err("thrust_lo > thrust_hi or thrust_std < 0"); return TVC_E_BADARG; }
+    if (!(c->propellant_fraction >= 0.0f && c->propellant_fraction < 1.0f)) { tvc_set_err("propellant_fraction out of range [0, 1)"); return TVC_E_BADARG; }
+    if (!(c->contact_mu >= 0.0f) || !(c->contact_mu_spin >= 0.0f) || !(c->contact_mu_roll >= 0.0f) || !(c->contact_restitution >= 0.0f && c->contact_restitution <= 1.0f) ||
+        !(c->contact_rest_threshold >= 0.0f) || !(c->contact_erp >= 0.0f && c->contact_erp <= 1.0f) || !(c->contact_margin > 0.0f)) {
+        tvc_set_err("contact material parameter out of range"); return TVC_E_BADARG;
+    }
+    if (c->quirks & ~TVC_Q_ALL_REFERENCE) { tvc_set_err("unknown quirk bit"); return TVC_E_BADARG; }
     return TVC_OK;
 }
 
@@ -658,7 +695,7 @@ int tvc_create(const tvc_config *cfg, int device, int64_t num_envs, tvc_handle *
                     "; libtvc_b200 is built for sm_100a only (no fallback path)");
         return TVC_E_DEVICE;
     }
-    CUDA_OK(cudaSetDevice(device));
+    DevGuard _guard(device);
     tvc_handle *h = new (std::nothrow) tvc_handle();
     if (!h) { tvc_set_err("out of host memory"); return TVC_E_NOMEM; }
     h->device = device; h->n = num_envs; h->base = *cfg; h->cur = *cfg; h->num_sms = prop.multiProcessorCount;
@@ -703,7 +740,7 @@ int tvc_create(const tvc_config *cfg, int device, int64_t num_envs, tvc_handle *
 
 int tvc_destroy(tvc_handle *h) {
     if (!h) return TVC_OK;
-    cudaSetDevice(h->device);
+    DevGuard _guard(h->device);
     DevState &s = h->st;
     cudaFree(s.s0); cudaFree(s.s1); cudaFree(s.s2); cudaFree(s.s3); cudaFree(s.s4);
     cudaFree(s.d0); cudaFree(s.d1); cudaFree(s.ring); cudaFree(s.clipb); cudaFree(s.runb); cudaFree(s.hist);
@@ -717,12 +754,12 @@ int tvc_destroy(tvc_handle *h) {
     return TVC_OK;
 }
 
-#define CHECK_H(h) do { if (!(h)) { tvc_set_err("handle is NULL"); return TVC_E_BADARG; } } while (0)
+#define CHECK_H(h) if (!(h)) { tvc_set_err("handle is NULL"); return TVC_E_BADARG; } DevGuard _guard((h)->device)
 #define LAUNCH_OK(what) do { cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { tvc_set_err(std::string(what) + ": " + cudaGetErrorString(_e)); return TVC_E_CUDA; } } while (0)
 
 int tvc_reset(tvc_handle *h, const uint8_t *mask_dev, uint64_t seed, float *obs_out_dev, tvc_stream stream) {
     CHECK_H(h);
-    if (seed != 0) { h->cur.seed = seed; h->base.seed = seed; h->dc.seed_lo = (unsigned)seed; h->dc.seed_hi = (unsigned)(seed >> 32); }
+    if (seed != TVC_SEED_KEEP) { h->cur.seed = seed; h->base.seed = seed; h->dc.seed_lo = (unsigned)seed; h->dc.seed_hi = (unsigned)(seed >> 32); }
     cudaStream_t s = (cudaStream_t)stream;
     if (h->cur.contract == TVC_CONTRACT_X) reset_kernel<true><<<h->grid, TVC_BLOCK, 0, s>>>(h->dc, h->st, mask_dev, obs_out_dev, 0);
     else reset_kernel<false><<<h->grid, TVC_BLOCK, 0, s>>>(h->dc, h->st, mask_dev, obs_out_dev, 0);
@@ -746,8 +783,8 @@ static int launch_step(tvc_handle *h, const DevIO &io, cudaStream_t s) {
         }
         if (h->v2_grid == 0) {   // persistent grid: resident CTAs of the v2 kernel, capped by the number of groups
             int per_sm = 0;
-            cudaError_t e = X ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_v2<true, 1, true>, TVC_V2_BLOCK, 0)
-                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_v2<false, 1, true>, TVC_V2_BLOCK, 0);
+            cudaError_t e = X ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_v2<true, 1, true, false>, TVC_V2_BLOCK, 0)
+                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_v2<false, 1, true, false>, TVC_V2_BLOCK, 0);
             if (e != cudaSuccess || per_sm < 1) per_sm = 1;
             const int cap = per_sm * h->num_sms;
             const int wpb = TVC_V2_BLOCK / 32;
@@ -759,7 +796,9 @@ static int launch_step(tvc_handle *h, const DevIO &io, cudaStream_t s) {
             const int want = h->ngroups <= cap ? h->ngroups : ctas;
             h->v2_grid = want < cap ? want : cap;
         }
-#define GO(XX, DD, FF) (void)launch_dep(step_kernel_v2<XX, DD, FF>, h->v2_grid, TVC_V2_BLOCK, s, h->pdl, h->dc, h->st, io)
+        const bool follow = !(h->cur.quirks & TVC_Q_FROZEN_FORCES);   // quirk Q3 cleared: the thrust follows the body every substep
+#define GO(XX, DD, FF) do { if (follow) (void)launch_dep(step_kernel_v2<XX, DD, FF, true>, h->v2_grid, TVC_V2_BLOCK, s, h->pdl, h->dc, h->st, io); \
+                            else (void)launch_dep(step_kernel_v2<XX, DD, FF, false>, h->v2_grid, TVC_V2_BLOCK, s, h->pdl, h->dc, h->st, io); } while (0)
 #define GO3(FF) do { \
         if (X) { if (dv == 0) GO(true, 0, FF); else if (dv == 1) GO(true, 1, FF); else GO(true, 2, FF); } \
         else   { if (dv == 0) GO(false, 0, FF); else if (dv == 1) GO(false, 1, FF); else GO(false, 2, FF); } } while (0)
@@ -780,7 +819,6 @@ static int launch_step(tvc_handle *h, const DevIO &io, cudaStream_t s) {
 #undef GO
     }
     h->lifetime_steps += 1;
-    h->stat_steps += 1;
     return TVC_OK;
 }
 
@@ -911,6 +949,24 @@ int tvc_set_state(tvc_handle *h, const void *dev_blob, size_t bytes, tvc_stream 
     return TVC_OK;
 }
 
+int tvc_get_reward_history(tvc_handle *h, float *dev_out, size_t bytes, tvc_stream stream) {
+    CHECK_H(h);
+    if (!h->st.hist) { tvc_set_err("tvc_get_reward_history: the handle does not keep the window (diversity_mode != TVC_DIV_EXACT)"); return TVC_E_STATE; }
+    if (!dev_out || bytes < sizeof(float) * TVC_HIST * (size_t)h->n) { tvc_set_err("tvc_get_reward_history: buffer too small"); return TVC_E_BADARG; }
+    hist_copy_kernel<<<(int)((h->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(h->st.hist, dev_out, h->n, 0);
+    LAUNCH_OK("hist_copy_kernel");
+    return TVC_OK;
+}
+
+int tvc_set_reward_history(tvc_handle *h, const float *dev_in, size_t bytes, tvc_stream stream) {
+    CHECK_H(h);
+    if (!h->st.hist) { tvc_set_err("tvc_set_reward_history: the handle does not keep the window (diversity_mode != TVC_DIV_EXACT)"); return TVC_E_STATE; }
+    if (!dev_in || bytes < sizeof(float) * TVC_HIST * (size_t)h->n) { tvc_set_err("tvc_set_reward_history: buffer too small"); return TVC_E_BADARG; }
+    hist_copy_kernel<<<(int)((h->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(h->st.hist, const_cast<float *>(dev_in), h->n, 1);
+    LAUNCH_OK("hist_copy_kernel");
+    return TVC_OK;
+}
+
 int tvc_read_info(tvc_handle *h, const tvc_info_soa *u, tvc_stream stream) {
     CHECK_H(h);
     if (!u) { tvc_set_err("info is NULL"); return TVC_E_BADARG; }
@@ -928,10 +984,9 @@ int tvc_read_info(tvc_handle *h, const tvc_info_soa *u, tvc_stream stream) {
 int tvc_episode_stats_dev(tvc_handle *h, double *dev_out, int reset_after, tvc_stream stream) {
     CHECK_H(h);
     if (!dev_out) { tvc_set_err("dev_out is NULL"); return TVC_E_BADARG; }
-    const double steps = (double)h->stat_steps * (double)h->n;
-    stats_reduce_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(h->st.partial, h->ngroups, dev_out, steps, reset_after);
+    // the step count lives on the device (bumped by the kernel that closes a step), so that CUDA-graph replays count too
+    stats_reduce_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(h->st.partial, h->ngroups, dev_out, h->st.counter + 2, (double)h->n, reset_after);
     LAUNCH_OK("stats_reduce_kernel");
-    if (reset_after) h->stat_steps = 0;
     return TVC_OK;
 }
 
@@ -959,6 +1014,10 @@ int tvc_set_curriculum(tvc_handle *h, const tvc_stage_conditions *c) {
     n.wind_std = c->wind_enabled ? c->wind_force : 0.0f;
     if (c->max_gimbal_angle_deg > 0.0f) n.gimbal_max_rad = c->max_gimbal_angle_deg * (float)(3.14159265358979323846 / 180.0);
     n.seed = h->cur.seed;
+    {   // the same checks as at creation, before the new conditions are committed
+        const int rc = validate(&n, h->n);
+        if (rc) return rc;
+    }
     h->cur = n;
     make_devcfg(h->cur, h->dc);
     h->order_valid = false;

@@ -17,6 +17,12 @@
 
 namespace tvc {
 
+// quirk bits (include/tvc_b200.h TVC_Q_*)
+enum : unsigned { Q_DOUBLE_GRAVITY = 1u << 0, Q_KEEP_CRITERIA = 1u << 1, Q_KEEP_REWARD_HIST = 1u << 2, Q_LAGGED_PHASE = 1u << 3,
+                  Q_THRUST_VECTOR = 1u << 4, Q_FROZEN_FORCES = 1u << 5, Q_DRAG_CUTOFF = 1u << 6, Q_STACKED_DAMPING = 1u << 7,
+                  Q_EULER_TILT = 1u << 8, Q_DIVERSITY_BONUS = 1u << 9, Q_VARIANCE_PENALTY = 1u << 10,
+                  Q_SUCCESS_MASKS_TRUNCATION = 1u << 12, Q_CRASH_IS_COM_HEIGHT = 1u << 13 };
+
 struct DevCfg {
     int contract, K, max_steps, autoreset;
     unsigned quirks;
@@ -214,6 +220,13 @@ __device__ __forceinline__ float thrust_curve(int mode, int burn) {
     if (u < 0.9f) return 1.0f;
     return 1.0f - 5.0f * (u - 0.9f);
 }
+
+// what env_pre hands to the K substeps
+struct Forces {
+    float Fx, Fy, Fz, Tx, Ty, Tz;   // world frame, thrust included (as evaluated from the pre-step state)
+    float a0, a1;   // clipped policy action
+    float fl0, fl1, fl2, arm;   // thrust in the body frame and its lever arm along body z (quirk Q3 cleared: thrust follows the body)
+};
 
 struct BodyP {
     float mass, inv_mass, Ixy, Iz, inv_Ixy, inv_Iz, cg;
@@ -468,11 +481,23 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
 // (Q3): no shared memory, no CTA barriers, the contact solver inline with its 18 carried impulses in registers.  Used by
 // step_kernel_v2 and the rollout kernel, whose warps hold envs of one class (near the ground or not), so the contact
 // branch is nearly warp-uniform.
-template <bool LOCKSTEP>   // LOCKSTEP: the CTA's warps re-align at every substep (every thread of the CTA must call this)
-__device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P, Env &e, float Fx, float Fy, float Fz,
-                                                 float Tx, float Ty, float Tz PH2_ARG) {
+// LOCKSTEP: the CTA's warps re-align at every substep (every thread of the CTA must call this).
+// FOLLOW (quirk Q3 cleared): the thrust force and torque are body-fixed and re-evaluated at every substep's attitude instead
+// of being held constant in the world frame; a separate instantiation, so that the reference path carries none of it.
+template <bool LOCKSTEP, bool FOLLOW>
+__device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P, Env &e, const Forces &f PH2_ARG) {
     const float dt = c.dt;
-    const float ax_ = Fx * P.inv_mass, ay_ = Fy * P.inv_mass, az_ = Fz * P.inv_mass;
+    float Fx = f.Fx, Fy = f.Fy, Fz = f.Fz, Tx = f.Tx, Ty = f.Ty, Tz = f.Tz;
+    float ax_ = Fx * P.inv_mass, ay_ = Fy * P.inv_mass, az_ = Fz * P.inv_mass;
+    float Fox = 0.0f, Foy = 0.0f, Foz = 0.0f, Tox = 0.0f, Toy = 0.0f, Toz = 0.0f;
+    const float tl0 = -f.arm * f.fl1, tl1 = f.arm * f.fl0;   // (0, 0, arm) x thrust, body frame
+    if (FOLLOW) {   // everything but the thrust: subtract the thrust as env_pre evaluated it (same attitude)
+        float R[9];
+        quat_to_mat(e.qx, e.qy, e.qz, e.qw, R);
+        Fox = Fx - (R[0] * f.fl0 + R[1] * f.fl1 + R[2] * f.fl2); Foy = Fy - (R[3] * f.fl0 + R[4] * f.fl1 + R[5] * f.fl2);
+        Foz = Fz - (R[6] * f.fl0 + R[7] * f.fl1 + R[8] * f.fl2);
+        Tox = Tx - (R[0] * tl0 + R[1] * tl1); Toy = Ty - (R[3] * tl0 + R[4] * tl1); Toz = Tz - (R[6] * tl0 + R[7] * tl1);
+    }
     float lam[18];
 #pragma unroll
     for (int j = 0; j < 18; j++) lam[j] = 0.0f;
@@ -486,6 +511,14 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
 #else
         if (LOCKSTEP) __syncthreads();
 #endif
+        if (FOLLOW && k > 0) {
+            float R[9];
+            quat_to_mat(e.qx, e.qy, e.qz, e.qw, R);
+            Fx = Fox + (R[0] * f.fl0 + R[1] * f.fl1 + R[2] * f.fl2); Fy = Foy + (R[3] * f.fl0 + R[4] * f.fl1 + R[5] * f.fl2);
+            Fz = Foz + (R[6] * f.fl0 + R[7] * f.fl1 + R[8] * f.fl2);
+            Tx = Tox + (R[0] * tl0 + R[1] * tl1); Ty = Toy + (R[3] * tl0 + R[4] * tl1); Tz = Toz + (R[6] * tl0 + R[7] * tl1);
+            ax_ = Fx * P.inv_mass; ay_ = Fy * P.inv_mass; az_ = Fz * P.inv_mass;
+        }
         // B5 with I = diag(a, a, b): R diag(1/a,1/a,1/b) R^T tau = tau/a + (1/b - 1/a)(e.tau) e, e = body axis in the
         // world frame (third column of R); the k(1+|w|) damping is isotropic.  Only e and the third row of R are needed
         // outside the contact solver.
@@ -577,8 +610,8 @@ __device__ __forceinline__ void reset_env(const DevCfg &c, bool X, long long gid
     e.vx = e.vy = e.vz = 0.0f; e.step = 0;
     e.wx = e.wy = e.wz = 0.0f;
     e.burn = 0; e.phase = 0; e.success = 0;
-    if (first_time || !(c.quirks & 2u)) e.consec = 0;
-    if (first_time || !(c.quirks & 4u)) { e.has_prev = 0; e.ap0 = 0.0f; e.ap1 = 0.0f; e.hist_count = 0; e.n_clip = 0; e.n_run = 0; }
+    if (first_time || !(c.quirks & Q_KEEP_CRITERIA)) e.consec = 0;
+    if (first_time || !(c.quirks & Q_KEEP_REWARD_HIST)) { e.has_prev = 0; e.ap0 = 0.0f; e.ap1 = 0.0f; e.hist_count = 0; e.n_clip = 0; e.n_run = 0; }
     e.mass_scale = 1.0f; e.thrust_scale = 1.0f; e.cg_off = 0.0f; e.wind_x = 0.0f; e.wind_y = 0.0f;
     if (X) {
         float d[11];
@@ -675,10 +708,6 @@ struct StepResult {
     int viol;
 };
 
-struct Forces {
-    float Fx, Fy, Fz, Tx, Ty, Tz;
-    float a0, a1;   // clipped policy action
-};
 
 // First half of one env step (ref:466-476): S2 action processing, S3 control forces, S5 aerodynamics.
 template <bool X>
@@ -699,7 +728,8 @@ __device__ __forceinline__ void env_pre(const DevCfg &c, const DevState &st, lon
     float fuel_pre = fuel_of(e.burn);
     P = body_params(c, X, e.mass_scale, e.cg_off, fuel_pre);
     float Fx = 0.0f, Fy = 0.0f, Fz = 0.0f, Tx = 0.0f, Ty = 0.0f, Tz = 0.0f;
-    if (c.quirks & 1u) Fz += -9.81f * P.mass;                         // Q1: explicit gravity force
+    if (c.quirks & Q_DOUBLE_GRAVITY) Fz += -9.81f * P.mass;           // Q1: explicit gravity force
+    f.fl0 = 0.0f; f.fl1 = 0.0f; f.fl2 = 0.0f; f.arm = 0.0f;
     if (e.burn < 1000) {                                               // Q4: fuel > 0 on entry
         int burn_before = e.burn;
         e.burn += 1;
@@ -708,6 +738,10 @@ __device__ __forceinline__ void env_pre(const DevCfg &c, const DevState &st, lon
         float sp, cp, sy, cy;
         sincos_small(pitch, sp, cp); sincos_small(yaw, sy, cy);    // |angle| <= gimbal limit (< 0.8 rad)
         float fl0 = T * sy, fl1 = T * sp, fl2 = T * cp * cy;           // Q2 (ref:539-543)
+        if (!(c.quirks & Q_THRUST_VECTOR)) {                           // Q2 cleared: the same direction, |F| = T
+            const float sc = T * rsqrt_normal(fmaxf(fl0 * fl0 + fl1 * fl1 + fl2 * fl2, 1e-30f));
+            fl0 *= sc; fl1 *= sc; fl2 *= sc;
+        }
         float R[9];
         quat_to_mat(e.qx, e.qy, e.qz, e.qw, R);
         float fwx = R[0] * fl0 + R[1] * fl1 + R[2] * fl2;
@@ -717,17 +751,20 @@ __device__ __forceinline__ void env_pre(const DevCfg &c, const DevState &st, lon
         float rx = R[2] * arm, ry = R[5] * arm, rz = R[8] * arm;
         Fx += fwx; Fy += fwy; Fz += fwz;
         Tx += ry * fwz - rz * fwy; Ty += rz * fwx - rx * fwz; Tz += rx * fwy - ry * fwx;
+        f.fl0 = fl0; f.fl1 = fl1; f.fl2 = fl2; f.arm = arm;
     }
     {   // ---- S5 (ref:561-585) aerodynamics ----
         float rho = 1.225f * expf(-e.pz / 8400.0f);
         float vmag = sqrt_fast(e.vx * e.vx + e.vy * e.vy + e.vz * e.vz);
-        if (vmag > 0.1f) {                                             // Q5
+        if (vmag > 0.1f || (!(c.quirks & Q_DRAG_CUTOFF) && vmag > 0.0f)) {   // Q5
             float dm = 0.5f * rho * (vmag * vmag) * 0.47f * (3.14159265358979f * 0.0025f);
             float k = -dm * rcp_fast(vmag);
             Fx += k * e.vx; Fy += k * e.vy; Fz += k * e.vz;
         }
-        float ad = 0.02f * rho;
-        Tx -= ad * e.wx; Ty -= ad * e.wy; Tz -= ad * e.wz;
+        if (c.quirks & Q_STACKED_DAMPING) {                            // Q6
+            float ad = 0.02f * rho;
+            Tx -= ad * e.wx; Ty -= ad * e.wy; Tz -= ad * e.wz;
+        }
     }
     if (X) { Fx += e.wind_x; Fy += e.wind_y; }
     Fz += -9.81f * P.mass;                                             // B4: world gravity (ref:338)
@@ -759,11 +796,21 @@ __device__ __forceinline__ void env_post(const DevCfg &c, const DevState &st, lo
     float ox, oy, oz, ow, epitch, eyaw;
     reported_quat(e.qx, e.qy, e.qz, e.qw, ox, oy, oz, ow);
     euler_pitch_yaw(ox, oy, oz, ow, epitch, eyaw);
-    const float tilt = sqrtf(epitch * epitch + eyaw * eyaw);           // Q7
+    float tilt = sqrtf(epitch * epitch + eyaw * eyaw);                 // Q7
+    if (!(c.quirks & Q_EULER_TILT)) {                                  // Q7 cleared: angle between the body axis and the vertical
+        const float sxy = 2.0f * sqrtf((ox * ox + oy * oy) * (oz * oz + ow * ow));   // |sin|, reported quaternion is unit norm
+        tilt = atan2f(sxy, 1.0f - 2.0f * (ox * ox + oy * oy));
+    }
     const float wmag = sqrtf(e.wx * e.wx + e.wy * e.wy + e.wz * e.wz);
     const float vh = sqrtf(e.vx * e.vx + e.vy * e.vy), vv = fabsf(e.vz);
     const float alt = e.pz;
-    const bool crashed = alt < 0.1f;                                   // Q17
+    bool crashed = alt < 0.1f;                                         // Q17
+    if (!(c.quirks & Q_CRASH_IS_COM_HEIGHT)) {                         // Q17 cleared: a hard or tilted touchdown
+        const float cgx = X ? e.cg_off + c.cg_burn * (1.0f - fuel_of(e.burn)) : 0.0f;
+        const float R31 = 2.0f * (ox * oz - ow * oy), R32 = 2.0f * (oy * oz + ow * ox), R33 = 1.0f - 2.0f * (ox * ox + oy * oy);
+        const float low = alt + fminf(R33 * (-c.half_len - cgx), R33 * (c.half_len - cgx)) - c.radius * sqrtf(R31 * R31 + R32 * R32);
+        crashed = low < 0.01f && (e.vz < -2.0f || tilt > 0.52f);
+    }
     const int phase_pre = e.phase, success_pre = e.success;
     const int burn = e.burn;   // fuel thresholds as integer compares (row S4): <0.8 <=> n>=200, >0.1 <=> n<=899
 
@@ -780,7 +827,7 @@ __device__ __forceinline__ void env_post(const DevCfg &c, const DevState &st, lo
         e.consec = all_met ? min(e.consec + 1, 0x7FF) : 0;
         if (e.consec >= 100) e.success = 1;
     }
-    const bool lag = (c.quirks & 8u) != 0;
+    const bool lag = (c.quirks & Q_LAGGED_PHASE) != 0;
     const int phase_r = lag ? phase_pre : e.phase;
     const int success_r = lag ? success_pre : e.success;
 
@@ -827,14 +874,14 @@ __device__ __forceinline__ void env_post(const DevCfg &c, const DevState &st, lo
 #pragma unroll
             for (int k = 0; k < 10; k++) { float d = rv[k] - mean; q += d * d; }
             float var = q / 10.0f;
-            if (var > 10000.0f) adj -= c.gp * var;
+            if (var > 10000.0f && (c.quirks & Q_VARIANCE_PENALTY)) adj -= c.gp * var;
         }
     }
     // R9 (ref:220-224): diversity bonus, len(set(history)) > 0.8 len  <=>  5 distinct > 4 len
     int distinct = 0;
     if (DIV == 1) distinct = len - e.n_run - e.n_clip + (e.n_clip > 0 ? 1 : 0);
     if (DIV == 2) distinct = e.n_clip;   // exact mode keeps the distinct count in the n_clip field
-    const bool div_flag = (DIV != 0) && (5 * distinct > 4 * len);
+    const bool div_flag = (DIV != 0) && (c.quirks & Q_DIVERSITY_BONUS) && (5 * distinct > 4 * len);
     if (div_flag) adj += c.db;
     float total = comp[0] + comp[1];
     total += comp[2]; total += comp[3]; total += comp[4]; total += comp[5];
@@ -895,8 +942,10 @@ __device__ __forceinline__ void env_post(const DevCfg &c, const DevState &st, lo
 
     // ---- S11 (ref:697-721) ----
     int terminated = 0, truncated = 0, reason = 0;
-    if (e.success) { terminated = 1; reason = 1; }                     // Q16
-    else {
+    if (e.success) {                                                   // Q16
+        terminated = 1; reason = 1;
+        if (!(c.quirks & Q_SUCCESS_MASKS_TRUNCATION) && e.step >= c.max_steps) truncated = 1;
+    } else {
         if (crashed) { terminated = 1; reason = 2; }
         else if (tilt > 0.52f) { terminated = 1; reason = 3; }
         else if (alt > 20.0f) { terminated = 1; reason = 4; }

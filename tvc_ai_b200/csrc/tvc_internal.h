@@ -20,7 +20,6 @@ struct tvc_handle {
     tvc::DevCfg dc;
     tvc::DevState st;
     int64_t lifetime_steps = 0;  // env steps taken by every env of this handle (Philox action counter)
-    int64_t stat_steps = 0;      // steps since the statistics were last reset
     double *stats_dev = nullptr;
     double *stats_host = nullptr;  // pinned
     cudaStream_t own_stream = nullptr;

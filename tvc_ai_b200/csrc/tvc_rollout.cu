@@ -410,14 +410,14 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
         if (live) env_pre<X>(c, st, i, e, a0, a1, P, f);
         else {
             P = body_params(c, false, 1.0f, 0.0f, 1.0f);
-            f.Fx = f.Fy = f.Fz = f.Tx = f.Ty = f.Tz = f.a0 = f.a1 = 0.0f;
+            f.Fx = f.Fy = f.Fz = f.Tx = f.Ty = f.Tz = f.a0 = f.a1 = f.fl0 = f.fl1 = f.fl2 = f.arm = 0.0f;
         }
         // every thread solves its own env's contacts inline (same device code as the step kernel)
 #ifdef TVC_PHASE_PROF2
         Ph2 ph2s = {0u, 0u, 0u};
-        if (live) integrate_thread<false>(c, P, e, f.Fx, f.Fy, f.Fz, f.Tx, f.Ty, f.Tz, &ph2s);
+        if (live) integrate_thread<false, false>(c, P, e, f, &ph2s);
 #else
-        if (live) integrate_thread<false>(c, P, e, f.Fx, f.Fy, f.Fz, f.Tx, f.Ty, f.Tz);
+        if (live) integrate_thread<false, false>(c, P, e, f);
 #endif
         done = 0; viol = 0;
         int ev_len = 0, ev_succ = 0, ev_reason = 0, ev_trunc = 0;
@@ -490,6 +490,7 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
         if (io.reward_sum) io.reward_sum[i] = rsum;
         if (io.actions_last) reinterpret_cast<float2 *>(io.actions_last)[i] = make_float2(a0, a1);
     }
+    if (blockIdx.x == 0 && tid == 0) atomicAdd(&st.counter[2], (unsigned)io.T);   // steps since the statistics were reset
     // ---- teardown: release TMEM ----
     tc_fence_before();
     __syncthreads();
@@ -511,9 +512,13 @@ void tvc_rollout_free(tvc_handle *h) {
 
 extern "C" int tvc_rollout(tvc_handle *h, const tvc_actor_weights *w, int32_t T, const tvc_rollout_io *u, tvc_stream stream) {
     if (!h) { tvc_set_err("handle is NULL"); return TVC_E_BADARG; }
+    int prev_dev = -1;
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{-1};
+    if (cudaGetDevice(&prev_dev) == cudaSuccess && prev_dev != h->device && cudaSetDevice(h->device) == cudaSuccess) restore.d = prev_dev;
     if (!w || !w->w1 || !w->b1 || !w->w2 || !w->b2 || !w->w3 || !w->b3) { tvc_set_err("tvc_rollout: NULL weight pointer"); return TVC_E_BADARG; }
     if (!u || !u->obs) { tvc_set_err("tvc_rollout: io.obs (current observation, [N,10]) must be non-NULL"); return TVC_E_BADARG; }
     if (T < 1 || T > 65536) { tvc_set_err("tvc_rollout: T out of range [1,65536]"); return TVC_E_BADARG; }
+    if (!(h->cur.quirks & TVC_Q_FROZEN_FORCES)) { tvc_set_err("tvc_rollout: built for TVC_Q_FROZEN_FORCES (quirk Q3) only"); return TVC_E_STATE; }
     cudaStream_t s = (cudaStream_t)stream;
     if (!h->rollout_ws) {
         RolloutWs *ws = new (std::nothrow) RolloutWs();
@@ -544,6 +549,5 @@ extern "C" int tvc_rollout(tvc_handle *h, const tvc_actor_weights *w, int32_t T,
     if (e != cudaSuccess) { tvc_set_err(std::string("rollout_kernel: ") + cudaGetErrorString(e)); return TVC_E_CUDA; }
     h->lifetime_steps += T;
     h->order_valid = false;   // the rollout moved the envs behind the step path's sorted sequence
-    h->stat_steps += T;
     return TVC_OK;
 }

@@ -19,7 +19,8 @@ STATE_DTYPE = np.dtype([
     ("step", np.int32), ("burn", np.int32), ("phase", np.int32), ("success", np.int32), ("has_prev", np.int32),
     ("consec", np.int32), ("hist_count", np.int32), ("episode", np.int32), ("n_clip", np.int32), ("n_run", np.int32),
     ("ring10", np.float32, 10), ("mass_scale", np.float32), ("thrust_scale", np.float32), ("cg_offset", np.float32),
-    ("wind", np.float32, 2), ("delay_ring", np.float32, (A.MAX_DELAY, 2))])
+    ("wind", np.float32, 2), ("delay_ring", np.float32, (A.MAX_DELAY, 2)),
+    ("clip_bits", np.uint32, 32), ("run_bits", np.uint32, 32)])
 assert STATE_DTYPE.itemsize == C.sizeof(A.TvcEnvState), (STATE_DTYPE.itemsize, C.sizeof(A.TvcEnvState))
 
 
@@ -88,10 +89,12 @@ class BatchedEngine:
         return actions if actions.is_contiguous() else actions.contiguous()
 
     # ------------------------------------------------------------------ hot path
-    def reset(self, mask: torch.Tensor | None = None, seed: int = 0):
+    def reset(self, mask: torch.Tensor | None = None, seed: int | None = None):
+        """seed=None keeps the current Philox key; any integer (0 included) re-keys the streams."""
         if mask is not None:
             mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
-        A.check(self.L.tvc_reset(self.h, _ptr(mask), int(seed or 0), _ptr(self.obs), self._stream()), "tvc_reset")
+        key = A.SEED_KEEP if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF
+        A.check(self.L.tvc_reset(self.h, _ptr(mask), key, _ptr(self.obs), self._stream()), "tvc_reset")
         return self.obs
 
     def step(self, actions: torch.Tensor | None, want_final: bool = True):
@@ -188,6 +191,19 @@ class BatchedEngine:
             raise ValueError(f"state must have shape ({self.n},)")
         blob = torch.from_numpy(state.view(np.uint8).copy()).to(self.device)
         A.check(self.L.tvc_set_state(self.h, _ptr(blob), blob.numel(), self._stream()), "tvc_set_state")
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def get_reward_history(self) -> torch.Tensor:
+        """TVC_DIV_EXACT only: the [N, 1000] reward window (checkpoints; the rest of the state is in get_state())."""
+        out = torch.empty((self.n, 1000), dtype=torch.float32, device=self.device)
+        A.check(self.L.tvc_get_reward_history(self.h, _ptr(out), out.numel() * 4, self._stream()), "tvc_get_reward_history")
+        return out
+
+    def set_reward_history(self, hist: torch.Tensor):
+        hist = hist.to(device=self.device, dtype=torch.float32).contiguous()
+        if tuple(hist.shape) != (self.n, 1000):
+            raise ValueError(f"history must have shape ({self.n}, 1000)")
+        A.check(self.L.tvc_set_reward_history(self.h, _ptr(hist), hist.numel() * 4, self._stream()), "tvc_set_reward_history")
         torch.cuda.current_stream(self.device).synchronize()
 
     def read_info(self):

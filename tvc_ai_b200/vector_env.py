@@ -63,7 +63,7 @@ class RocketTVCVectorEnv:
         """Resets every env.  `seed` re-keys the Philox streams in Contract X; in Contract R the
         reference's reset is deterministic and ignores it (quirk Q15)."""
         as_torch = bool(options and options.get("return_torch"))
-        obs = self.engine.reset(seed=int(seed) if seed is not None else 0)
+        obs = self.engine.reset(seed=seed)
         if self.enable_curiosity:
             self._has_prev.zero_()          # ref:399-401: reset() clears state_history
         return (obs if as_torch else obs.cpu().numpy().copy()), {}
@@ -202,7 +202,7 @@ class RocketTVCHostPipelineEnv:
     def reset(self, *, seed: Optional[int] = None, options: Optional[dict] = None):
         obs = self._np["obs"]
         for eng, (lo, hi) in zip(self.engines, self._ranges):
-            obs[lo:hi] = eng.reset(seed=int(seed) if seed is not None else 0).cpu().numpy()
+            obs[lo:hi] = eng.reset(seed=seed).cpu().numpy()
         return obs.copy(), {}
 
     def step(self, actions):
