@@ -64,17 +64,32 @@ def _issue_roofline(ms, clocks):
             "warp_instructions_per_step": wi,
             "fp32_ceilings": {"ffma_three_register_sources": 0.65, "ffma_two_shared_sources": 0.93,
                               "source": "tools/micro/fp32_rate.cu on this pool's B200 (profiles/r01_fp32_rate_microbench.txt)"},
-            "note": "with the lazy contact rows the step is a single wave of dependent chains (1,750 near-ground groups of ~45 us, 6,450 "
-                    "airborne groups of ~13 us on 2,368 warp slots): neither more warps (5 CTAs/SM spill-free: no gain) nor a pipe limit "
-                    "bounds it, the instruction count along each warp's chain does; see DESIGN.md section 6"}
+            "note": "the step is a single wave of dependent chains (near-ground groups and airborne groups on 2,368 warp slots): "
+                    "the instruction count and latency along each warp's chain bound it; see DESIGN.md section 6"}
+
+
+def csrc_hash() -> str:
+    """sha256 (first 16 hex digits) over the kernel sources: the committed ncu figures are only quoted for the build they
+    were captured from."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "tvc_ai_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def _traffic(key="dram_bytes_per_launch"):
-    """A per-launch figure of the step path from the committed ncu --set full capture (DRAM bytes, warp-instructions), or None."""
+    """A per-launch figure of the step path from the committed ncu --set full capture (DRAM bytes, warp-instructions), or
+    None -- also None when the capture was taken from other kernel sources than the ones being measured (stale)."""
     p = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(key)
+            d = json.load(open(p))
+            if d.get("csrc_sha16") != csrc_hash():
+                return None
+            return d.get(key)
         except Exception:  # noqa: BLE001
             return None
     return None
@@ -207,7 +222,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     n = args.envs_per_gpu
-    eng = BatchedEngine(n, _workload_cfg(A, env_id_base=rank * n), device=local)
+    cfg_used = _workload_cfg(A, env_id_base=rank * n)
+    eng = BatchedEngine(n, cfg_used, device=local)
     eng.reset()
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
@@ -216,6 +232,10 @@ def run_ours(args):
     side = torch.cuda.Stream(device=dev)
     K, W = args.steps, max(args.warmup, 3)
     launches = 0
+    # episode-statistics reduction (+ NCCL all-reduce over NVLink when N > 1): every 64 steps in production; a
+    # short run still gets at least one inside the timed region
+    stat_every = min(64, max(1, K // 2))
+    stat_events = []
 
     def barrier():
         if world > 1:
@@ -243,14 +263,19 @@ def run_ours(args):
         eng.step(pool[k % 16], want_final=False)
         launches += 2            # step_kernel_v2 + the closing sort kernel (classify_kernel with the deferred resets)
         ends[k].record()
-        if (k + 1) % 64 == 0:   # episode-statistics reduction (+ NCCL all-reduce over NVLink when N>1), side stream
+        if (k + 1) % stat_every == 0:   # side stream: does not delay the next step's launch
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record(side)
                 D.allreduce_stats(eng.stats_device(False))
+                s1.record(side)
+                stat_events.append((s0, s1))
             launches += 1        # stats_reduce_kernel
     barrier()
     wall = time.perf_counter() - wall0
     per = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    stat_us = [1e3 * a.elapsed_time(b) for a, b in stat_events]
     ms = sum(per) / K
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -258,6 +283,21 @@ def run_ours(args):
     ms_max = float(t.item())
     total_envs = n * world
     value = total_envs / (ms_max * 1e-3)
+
+    # the same loop with the kernel's own Philox action stream (actions U(-1,1) from Philox4x32-10, counter =
+    # (env id, step)) instead of the pre-generated torch.rand pool -- reported beside the headline
+    torch.cuda.synchronize(dev)
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ph_ms = 0.0
+    for k in range(min(K, 20)):
+        flush.zero_()
+        pe0.record()
+        eng.step(None, want_final=False)
+        pe1.record()
+        torch.cuda.synchronize(dev)
+        ph_ms += pe0.elapsed_time(pe1)
+    ph_ms /= min(K, 20)
+    launches += 2 * min(K, 20)
 
     # warm-L2 number (no flush, back to back) -- reported beside the headline, not instead of it
     torch.cuda.synchronize(dev)
@@ -368,20 +408,31 @@ def run_ours(args):
             "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"configs[2] per-GPU slab: {n} envs/GPU x {world} GPU, Contract X (mass/thrust/cg/wind DR, "
-                                   "sensor noise), K=10 substeps/step, same-step autoreset, U(-1,1) actions resident in HBM, "
-                                   "episode-stat reduction every 64 steps (NCCL all-reduce when N>1)",
-                       "envs_per_gpu": n, "substeps": 10, "contact_iters": 8, "parallelism": f"env-slab x{world}",
+                                   "sensor noise), K=10 substeps/step, same-step autoreset (final observations not requested in the "
+                                   "device-timed loop), U(-1,1) actions pre-generated with torch.rand and resident in HBM, "
+                                   f"episode-stat reduction every {stat_every} steps on a side stream ({len(stat_events)} inside the timed "
+                                   "region; NCCL all-reduce when N>1)",
+                       "envs_per_gpu": n, "substeps": int(cfg_used.substeps), "contact_iters": [int(cfg_used.contact_iters), int(cfg_used.contact_warm_iters)],
+                       "quirks": hex(int(cfg_used.quirks)), "parallelism": f"env-slab x{world}",
                        "l2": "flushed between timed steps (256 MiB zero-fill, not timed)",
                        "burn_in_steps": args.burn_in, "overrides": dict(OVERRIDES)},
             "env_substeps_per_sec": value * 10,
+            "stats_allreduce": {"count": len(stat_events), "us_mean": (sum(stat_us) / len(stat_us)) if stat_us else None,
+                                "bytes": 128, "every_steps": stat_every,
+                                "what": "stats_reduce_kernel + " + ("ncclAllReduce(16 x f64) over NVLink" if world > 1 else "no collective at N=1")
+                                        + ", CUDA events on the side stream (rank 0)"},
+            "philox_actions": {"ms_per_step": ph_ms, "env_steps_per_sec_per_gpu": n / (ph_ms * 1e-3),
+                               "note": "same workload with actions=NULL: the kernel draws U(-1,1) actions from Philox4x32-10 (rank 0)"},
+            "csrc_sha16": csrc_hash(),
             "warm_l2": {"ms_per_step": warm_ms, "env_steps_per_sec_per_gpu": n / (warm_ms * 1e-3),
                         "note": "back-to-back launches, state L2-resident (62 MB < 126 MB)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": _traffic(), "peak_source": peak_src,
                          "kernel": "step_kernel_v2<X=true,DIV=fast> (+ the closing sort / deferred-reset kernel)",
                          "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP_X,
-                         "note": "not DRAM-bound (ncu: 8 % of DRAM throughput): ~5,000 thread-instructions per env-step in dependent chains "
-                                 "(contact PGS for the in-contact quarter of the envs, ten substeps, Euler angles, reward, Philox noise for all); "
+                         "traffic_note": None if _traffic() is not None else "no ncu capture of this build is committed (profiles/step_kernel_traffic.json csrc_sha16 differs)",
+                         "note": "not DRAM-bound: thousands of thread-instructions per env-step in dependent chains (block contact solve for "
+                                 "the in-contact quarter of the envs, ten substeps, Euler angles, reward, Philox noise for all); "
                                  "see issue_roofline, DESIGN.md section 6 and profiles/"},
             "issue_roofline": _issue_roofline(ms, clocks),
             "gpu_launches": launches,

@@ -206,7 +206,8 @@ static real r_matrix_from_quat(const real q[4], real m[9]) {
  *          (direction -(R31,R32)/max(rho, 1e-3): slides to the cap centre as the axis becomes vertical)
  *      f0,f1,f2  three body-fixed rim points of the bottom cap at 0, 120, 240 degrees
  *  - entered only when the lowest candidate is closer than `margin` AND some row can bind at all:
- *    gap_min - 1e-4 < (1+e) (|vz| + |w| reach) dt  (otherwise the stored impulses are cleared)
+ *    gap_min < g_reach = (1+e) (|vz| + |w| reach) dt + 1e-4  (otherwise the stored impulses are cleared);
+ *    the substep's manifold holds the candidates with gap < g_reach and those that still carry an impulse
  *  - normal target per point: vn >= -gap/dt (gap >= 0, speculative) or vn >= -erp*gap/dt (gap < 0,
  *    Baumgarte), plus restitution e on the approach speed beyond the threshold (continuous at the threshold).
  *    The gap is formed as (pz + cz) + cz (nbz - 1) + cx nbx + cy nby so that the two O(0.5) terms cancel first
@@ -295,11 +296,13 @@ static void solve_contacts(const orc_body_params *p, real dt, const real R[9], r
     const real gb = ((pz + zb) + pzc) + (zb * nz1 + low), gt = ((pz + zt) + pzc) + (zt * nz1 + low);
     const real gmin = gb < gt ? gb : gt;
     int enter = gmin < margin;
+    real gthr = 0;     /* a point further than this from the plane cannot be reached within the substep at the entry speeds */
     if (enter) {
         orc_dbg_entered++;
         real hh = h + (cg < 0 ? -cg : cg), reach = R_SQRT(hh * hh + r * r);
         real vmax = (v[2] < 0 ? -v[2] : v[2]) + R_SQRT(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]) * reach;
-        enter = gmin - (real)1e-4 < ((real)1.0 + (real)p->restitution) * vmax * dt;
+        gthr = ((real)1.0 + (real)p->restitution) * vmax * dt + (real)1e-4;
+        enter = gmin < gthr;
         if (enter) orc_dbg_canbind++;
     }
     if (!enter) { for (int i = 0; i < 18; i++) lam[i] = 0; *have_lam = 0; return; }
@@ -328,10 +331,13 @@ static void solve_contacts(const orc_body_params *p, real dt, const real R[9], r
 
     orc_rows J[5];
     real tgt[5], ln[5], l1[5], l2[5];
+    int active[5];
     for (int i = 0; i < 5; i++) {
         point_rows(c[i], xb, yb, nb, &J[i]);
         /* height of the point above the plane: pz + c.nb = (pz + cz) + cz (nbz - 1) + cx nbx + cy nby */
         real gap = ((pz + c[i][2]) + pzc) + (c[i][2] * nz1 + (nb[0] * c[i][0] + nb[1] * c[i][1]));
+        /* the substep's manifold: points within reach (the entry rule's own bound) or still holding an impulse */
+        active[i] = gap < gthr || lam[i] != 0 || lam[5 + i] != 0 || lam[10 + i] != 0;
         real vn0 = v[2] + (wb0[0] * J[i].Jn[0] + wb0[1] * J[i].Jn[1] + wb0[2] * J[i].Jn[2]);
         real rest = (vn0 < -(real)p->rest_threshold) ? (real)p->restitution * (-vn0 - (real)p->rest_threshold) : (real)0.0;
         tgt[i] = rest + (gap > 0 ? -gap * inv_dt : -(real)p->erp * gap * inv_dt);
@@ -358,7 +364,7 @@ static void solve_contacts(const orc_body_params *p, real dt, const real R[9], r
             for (int k = 0; k < nk; k++) { un += wt[k] * Ji->Jn[k]; ux_ += wt[k] * Ji->Jx[k]; uy_ += wt[k] * Ji->Jy[k]; }
             const real unz = un + (nk == 2 ? wt[2] * Ji->Jn[2] : (real)0.0);      /* true normal velocity */
             /* a point whose normal row cannot bind and that holds no impulse is an exact no-op */
-            if (!(tgt[i] > unz || ln[i] > 0 || l1[i] != 0 || l2[i] != 0)) continue;
+            if (!active[i] || !(tgt[i] > unz || ln[i] > 0 || l1[i] != 0 || l2[i] != 0)) continue;
             if (i) orc_dbg_blocks[3]++;
             /* the point's Delassus matrix (symmetric): A_ab = (1/m) delta_ab + sum_k Ii_k Ja_k Jb_k */
             orc_sym3 A = {im, 0, 0, im, 0, im};
@@ -657,11 +663,15 @@ static void build_obs(const orc_config *c, const orc_env *e, int64_t gid, int ph
                     e->fuel, (double)phase_for_obs / 7.0,
                     fmin(1.0, (double)e->step / (double)c->max_episode_steps)};
     if (c->contract == ORC_CONTRACT_X && c->sensor_noise_std > 0) {
-        uint32_t a[4], b[4]; double n[8];
+        /* eight N(0,1) draws from ONE Philox block: each 32-bit word gives two 16-bit uniforms (k + 0.5) / 2^16 (radius from
+         * the low half, angle from the high half) -> four Box-Muller pairs, |n| <= 4.9 sigma (sensor noise, not a tail study) */
+        uint32_t a[4]; double n[8];
         draw4(c->seed, gid, ST_NOISE_A, (uint32_t)e->episode, (uint32_t)e->step, a);
-        draw4(c->seed, gid, ST_NOISE_B, (uint32_t)e->episode, (uint32_t)e->step, b);
-        box_muller(a[0], a[1], &n[0], &n[1]); box_muller(a[2], a[3], &n[2], &n[3]);
-        box_muller(b[0], b[1], &n[4], &n[5]); box_muller(b[2], b[3], &n[6], &n[7]);
+        for (int k = 0; k < 4; k++) {
+            double u0 = ((double)(a[k] & 0xFFFFu) + 0.5) * (1.0 / 65536.0), u1 = ((double)(a[k] >> 16) + 0.5) * (1.0 / 65536.0);
+            double r = sqrt(-2.0 * log(u0)), th = 2.0 * PI_D * u1;
+            n[2 * k] = r * cos(th); n[2 * k + 1] = r * sin(th);
+        }
         for (int i = 0; i < 7; i++) o[i] += c->sensor_noise_std * n[i];
     }
     for (int i = 0; i < 10; i++) obs[i] = (float)o[i];

@@ -268,6 +268,8 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
 #endif
     bool first_pull = true;
     (void)first_pull;
+    int g_next = 0;
+    (void)g_next;
     for (;;) {
         int g = 0;
 #ifdef TVC_V2_LOCKSTEP
@@ -293,10 +295,7 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
         if (first_pull) {
             g = g_base + (int)(blockIdx.x * (TVC_V2_BLOCK / 32) + (threadIdx.x >> 5));
             first_pull = false;
-        } else {
-            if (lane == 0) g = g_base + (int)(gridDim.x * (TVC_V2_BLOCK / 32)) + (int)atomicAdd(queue, 1u);
-            g = __shfl_sync(full, g, 0);
-        }
+        } else g = __shfl_sync(full, g_next, 0);   // pulled while the previous group was in its second half (below)
         if (g >= ngroups) break;
         const long long slot = (long long)g * 32 + lane;
         const bool live = slot < st.n;
@@ -337,6 +336,11 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
         if (live) integrate_thread<false, FOLLOW>(c, P, e, f PH2_PASS);
 #endif
         PH2_CLK(pt2);
+#ifndef TVC_V2_LOCKSTEP
+        // the next group of the sequence: the atomic's round trip (~1 us with 2,368 warps on one counter) runs under this
+        // group's second half instead of stalling the warp at the top of the loop
+        if (lane == 0) g_next = g_base + (int)(gridDim.x * (TVC_V2_BLOCK / 32)) + (int)atomicAdd(queue, 1u);
+#endif
         if (live) {
             StepResult r;
             env_post<X, DIV>(c, st, i, gid, e, f.a0, f.a1, r);
@@ -403,28 +407,29 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
             pt_prev = clock64();
         }
 #endif
-        // episode statistics: this group owns row g of `partial` for the whole launch (no atomics, deterministic)
-        if (__any_sync(full, done | viol)) {
-            const int n_ep = __reduce_add_sync(full, done), n_len = __reduce_add_sync(full, ev_len);
-            const int n_succ = __reduce_add_sync(full, done ? ev_succ : 0);
-            const int n_cr = __reduce_add_sync(full, ev_reason == 2), n_ti = __reduce_add_sync(full, ev_reason == 3);
-            const int n_al = __reduce_add_sync(full, ev_reason == 4), n_ra = __reduce_add_sync(full, ev_reason == 5);
-            const int n_tr = __reduce_add_sync(full, ev_trunc), n_vi = __reduce_add_sync(full, viol);
-            double d_ret = ev_ret, d_ret2 = (double)ev_ret * (double)ev_ret, d_alt = ev_alt, d_tilt = ev_tilt, d_fuel = ev_fuel;
-            if (n_ep) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    d_ret += __shfl_xor_sync(full, d_ret, o); d_ret2 += __shfl_xor_sync(full, d_ret2, o);
-                    d_alt += __shfl_xor_sync(full, d_alt, o); d_tilt += __shfl_xor_sync(full, d_tilt, o);
-                    d_fuel += __shfl_xor_sync(full, d_fuel, o);
-                }
+        // episode statistics: this group owns row g of `partial` for the whole launch (deterministic).  Counts come from
+        // ballots; the sums walk the (one or two) lanes whose episode ended, in lane order; lane L < 14 then holds statistic L.
+        const unsigned dm = __ballot_sync(full, done), vm = __ballot_sync(full, viol);
+        if (dm | vm) {
+            const int n_succ = __popc(__ballot_sync(full, done && ev_succ)), n_tr = __popc(__ballot_sync(full, ev_trunc));
+            const unsigned r2 = __ballot_sync(full, ev_reason == 2), r3 = __ballot_sync(full, ev_reason == 3);
+            const unsigned r4 = __ballot_sync(full, ev_reason == 4), r5 = __ballot_sync(full, ev_reason == 5);
+            double d_ret = 0.0, d_ret2 = 0.0, d_alt = 0.0, d_tilt = 0.0, d_fuel = 0.0;
+            int n_len = 0;
+            for (unsigned m = dm; m; m &= m - 1u) {
+                const int src = __ffs(m) - 1;
+                const double rt = (double)__shfl_sync(full, ev_ret, src);
+                d_ret += rt; d_ret2 += rt * rt;
+                d_alt += (double)__shfl_sync(full, ev_alt, src); d_tilt += (double)__shfl_sync(full, ev_tilt, src);
+                d_fuel += (double)__shfl_sync(full, ev_fuel, src);
+                n_len += __shfl_sync(full, ev_len, src);
             }
             double v = 0.0;
             switch (lane) {
-                case 0: v = n_ep; break;   case 1: v = d_ret; break;  case 2: v = d_ret2; break; case 3: v = n_len; break;
-                case 4: v = n_succ; break; case 5: v = n_cr; break;   case 6: v = n_ti; break;   case 7: v = n_al; break;
-                case 8: v = n_ra; break;   case 9: v = n_tr; break;   case 10: v = n_vi; break;  case 11: v = d_alt; break;
-                case 12: v = d_tilt; break; case 13: v = d_fuel; break; default: break;
+                case 0: v = __popc(dm); break; case 1: v = d_ret; break;  case 2: v = d_ret2; break; case 3: v = n_len; break;
+                case 4: v = n_succ; break;     case 5: v = __popc(r2); break; case 6: v = __popc(r3); break; case 7: v = __popc(r4); break;
+                case 8: v = __popc(r5); break; case 9: v = n_tr; break;   case 10: v = __popc(vm); break; case 11: v = d_alt; break;
+                case 12: v = d_tilt; break;    case 13: v = d_fuel; break; default: break;
             }
             // the row has exactly one writer per launch (this group), so the order-free reduction is still deterministic; as a
             // reduction it does not make the warp wait for the old value (the read-modify-write stalled on a DRAM round trip)
@@ -486,6 +491,11 @@ __global__ void set_state_kernel(const __grid_constant__ DevState st, const tvc_
     Env e;
     e.px = s.pos[0]; e.py = s.pos[1]; e.pz = s.pos[2]; e.ep_ret = s.ep_return;
     e.qx = s.quat[0]; e.qy = s.quat[1]; e.qz = s.quat[2]; e.qw = s.quat[3];
+    {   // the integrator relies on unit quaternions (it normalises at the end of every substep): a blob that is unit to
+        // rounding is taken bit for bit, anything else is normalised on import
+        const float d = e.qx * e.qx + e.qy * e.qy + e.qz * e.qz + e.qw * e.qw;
+        if (fabsf(d - 1.0f) > 1e-6f && d > 0.0f) { const float sc = rsqrtf(d); e.qx *= sc; e.qy *= sc; e.qz *= sc; e.qw *= sc; }
+    }
     e.vx = s.vel[0]; e.vy = s.vel[1]; e.vz = s.vel[2]; e.step = s.step;
     e.wx = s.omega[0]; e.wy = s.omega[1]; e.wz = s.omega[2];
     e.burn = s.burn; e.phase = s.phase; e.success = s.success; e.has_prev = s.has_prev; e.consec = s.consec;

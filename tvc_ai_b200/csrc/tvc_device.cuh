@@ -146,13 +146,22 @@ __device__ __forceinline__ void box_muller(unsigned x0, unsigned x1, float &n0, 
     sincospif(2.0f * u01(x1), &s, &c);   // exact argument reduction, no Payne-Hanek slow path
     n0 = r * c; n1 = r * s;
 }
-// eight N(0,1) draws for one (env, episode, step) -- one out-of-line copy (sensor noise)
+// Eight N(0,1) draws for one (env, episode, step) from ONE Philox block (sensor noise, Contract X; same bits in the oracle):
+// each 32-bit word gives two 16-bit uniforms (k + 0.5) / 2^16 -- the radius from the low half, the angle from the high half --
+// i.e. four Box-Muller pairs with |n| <= 4.9 sigma.  The noise is scaled by 0.02 before it meets a 1e-5 tolerance, so the
+// logarithm and the sine / cosine are the single-MUFU forms (|error| < 1e-6 on a unit normal); one out-of-line copy.
 static __device__ __noinline__ void noise8(unsigned seed_lo, unsigned seed_hi, long long gid, unsigned episode, unsigned step,
                                     float n[8]) {
     const uint4 a = philox(seed_lo, seed_hi, gid, ST_NOISE_A, episode, step);
-    const uint4 b = philox(seed_lo, seed_hi, gid, ST_NOISE_B, episode, step);
-    box_muller(a.x, a.y, n[0], n[1]); box_muller(a.z, a.w, n[2], n[3]);
-    box_muller(b.x, b.y, n[4], n[5]); box_muller(b.z, b.w, n[6], n[7]);
+    const unsigned w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float u0 = ((float)(w[k] & 0xFFFFu) + 0.5f) * (1.0f / 65536.0f), u1 = ((float)(w[k] >> 16) + 0.5f) * (1.0f / 65536.0f);
+        const float r = sqrt_fast(-2.0f * __logf(u0));
+        float sn, cs;
+        __sincosf(6.283185307179586f * u1, &sn, &cs);
+        n[2 * k] = r * cs; n[2 * k + 1] = r * sn;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -263,28 +272,6 @@ __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fm
 // Bullet's own manifold/solver (row B9) is not reproducible without its source; this model is shared with the oracle
 // (oracle/tvc_oracle.c solve_contacts) by specification only.
 // ------------------------------------------------------------------------------------------
-// Entry rule of the contact model (same in the oracle), evaluated per substep by the env's own thread:
-// the lowest candidate is within `margin` AND some row can bind at all -- a row binds only if
-// (1+e) * approach speed * dt exceeds its gap, and the approach speed of any point is bounded by
-// |vz| + |w| * reach.  When the rule fails the stored impulses are cleared.
-// nz1 = R33 - 1 formed without cancellation, pzc = running compensation of the height update: the gap is assembled as
-// (pz + cz) + cz (R33 - 1) + ..., so that the two O(0.5) terms cancel first (the targets divide the gap by dt).
-__device__ __forceinline__ bool contact_needed_row(const DevCfg &c, const BodyP &P, float R31, float R32, float nz1,
-                                                   float pz, float pzc, float vz, float wx, float wy, float wz) {
-    const float r = c.radius, h = c.half_len;
-    const float rho = sqrt_fast(R31 * R31 + R32 * R32);
-    const float inv = rcp_fast(fmaxf(rho, 1e-3f));
-    const float low = -r * (R31 * R31 + R32 * R32) * inv;
-    const float zb = -h - P.cg, zt = h - P.cg;
-    const float gb = ((pz + zb) + pzc) + (zb * nz1 + low), gt = ((pz + zt) + pzc) + (zt * nz1 + low);
-    const float gmin = fminf(gb, gt);
-    if (!(gmin < c.margin)) return false;
-    const float hh = h + fabsf(P.cg);
-    const float reach = sqrt_fast(hh * hh + r * r);
-    const float vmax = fabsf(vz) + sqrt_fast(wx * wx + wy * wy + wz * wz) * reach;
-    return gmin - 1e-4f < (1.0f + c.restitution) * vmax * c.dt;
-}
-
 #ifdef TVC_PHASE_PROF2
 // diagnostic build only (tools/phase_prof2.py): clock64 cycles per phase of step_kernel_v2, per class of group
 // (0 = in contact / may touch, 1 = airborne), max over the lanes of a warp, summed over the groups:
@@ -324,130 +311,163 @@ __device__ __forceinline__ void point_block(float Axx, float Axy, float Axn, flo
     } else { px = 0.0f; py = 0.0f; pn = 0.0f; }                       // release
 }
 
-// lam: this env's 18 carried impulses, element j at lam[j * LS]: normal(5), tangent-x(5), tangent-y(5), torsional about the
-// body axes z (spin), x, y (roll).  warm: apply them before the passes.
-template <int LS>
-__device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, const float R[9], float nz1, float pz, float pzc,
-                                               float &vx, float &vy, float &vz, float &wx, float &wy, float &wz, float *lam,
-                                               bool warm, int iters PH2_ARG) {
+// What the contact solve carries between the substeps of one control step (cold at every step).  Point 0's impulses and the
+// torsional impulses live in registers; the impulses of points 1-4 -- the top cap's lowest point and the three body-fixed
+// rim points, which carry load in a few per cent of the solves -- live in a small per-thread array that only the threads
+// that visit such a point ever touch.
+struct ContactCarry {
+    float l1, l2, ln;       // point 0: tangent x, tangent y, normal
+    float lt0, lt1, lt2;    // torsional impulses about the body axes x, y (roll) and z (spin)
+    unsigned xmask;         // bit i (1..4): point i holds a stored impulse in lamx[3 (i - 1) ..]
+    bool have;              // the previous substep ran the solve: warm start
+};
+
+// body-frame arm of contact point i (1..4): i == 1 the top cap's lowest rim point, 2..4 the body-fixed rim points of the bottom cap
+__device__ __forceinline__ void extra_point_arm(int i, float cx0, float cy0, float r, float zb, float zt, float &cx, float &cy, float &cz) {
+    cx = i == 1 ? cx0 : (i == 2 ? r : -0.5f * r);
+    cy = i == 1 ? cy0 : (i == 2 ? 0.0f : (i == 3 ? 0.8660254037844386f * r : -0.8660254037844386f * r));
+    cz = i == 1 ? zt : zb;
+}
+
+// The contact solve of one substep (model: DESIGN.md section 4; oracle/tvc_oracle.c solve_contacts is the same algorithm in
+// fp64).  Inputs beyond the state: the rotation matrix R (row-major, body -> world), nz1 = R33 - 1 formed without cancellation,
+// hb = (pz + zb) + pzc and ht = (pz + zt) + pzc (cap-centre heights with the position compensation), u = the direction of the
+// lowest rim point, gthr = the reach bound of the entry rule.  All angular quantities are body-frame inside (w0, w1, w2).
+__device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, const float R[9], float nz1, float hb, float ht,
+                                               float ux, float uy, float gthr, float &vx, float &vy, float &vz, float &wx, float &wy,
+                                               float &wz, ContactCarry &cc, float *lamx PH2_ARG) {
     PH2_CLK(pc0);
-    const float r = c.radius, h = c.half_len;
-    const float R31 = R[6], R32 = R[7];
-    const float rho = sqrt_fast(R31 * R31 + R32 * R32);
-    const float inv = rcp_fast(fmaxf(rho, 1e-3f));
-    const float ux = -R31 * inv, uy = -R32 * inv;
-    const float zb = -h - P.cg, zt = h - P.cg;
+    const float r = c.radius;
+    const float zb = -c.half_len - P.cg, zt = c.half_len - P.cg;
     const float ia = P.inv_Ixy, ib = P.inv_Iz, im = P.inv_mass, mu = c.mu;
-    // body-frame angular velocity wb0 = R^T w; (w0, w1, w2) carries the running value, w += R (wt - wb0) at the end, so that
+    const bool warm = cc.have;
+    const int iters = warm ? c.warm_iters : c.contact_iters;
+    // body-frame angular velocity wb0 = R^T w; (w0, w1, w2) carries the running value and w += R (wt - wb0) at the end, so that
     // a solve in which nothing binds leaves omega bit-identical
     const float wb0x = R[0] * wx + R[3] * wy + R[6] * wz, wb0y = R[1] * wx + R[4] * wy + R[7] * wz;
     const float wb0z = R[2] * wx + R[5] * wy + R[8] * wz;
     float w0 = wb0x, w1 = wb0y, w2 = wb0z;
-
-    const float pcx[5] = {r * ux, r * ux, r, -0.5f * r, -0.5f * r};
-    const float pcy[5] = {r * uy, r * uy, 0.0f, 0.8660254037844386f * r, -0.8660254037844386f * r};
-    // angular Jacobians (body frame) of the world-axis rows at body-frame arm c: c x (row of R).  The normal rows of all
-    // five points stay in registers (every pass tests them); the tangent rows of points 1-4 are formed when such a point
-    // binds, which is rare: the top cap in every upright pose, and a body-fixed rim point only binds within ~0.2 mm.
-    float Jn0[5], Jn1[5], Jn2[5], tgt[5], ln[5], l1[5], l2[5];
-#pragma unroll
-    for (int i = 0; i < 5; i++) {
-        const float cz = i == 1 ? zt : zb;
-        Jn0[i] = pcy[i] * R[8] - cz * R[7]; Jn1[i] = cz * R[6] - pcx[i] * R[8]; Jn2[i] = pcx[i] * R[7] - pcy[i] * R[6];
-        const float gap = ((pz + cz) + pzc) + (cz * nz1 + (R[6] * pcx[i] + R[7] * pcy[i]));
-        const float vn0 = vz + (wb0x * Jn0[i] + wb0y * Jn1[i] + wb0z * Jn2[i]);
+    // ---- point 0: angular Jacobians c x (row of R) of the world-axis rows z (normal), x, y ----
+    const float cx0 = r * ux, cy0 = r * uy;
+    const float Jn0 = cy0 * R[8] - zb * R[7], Jn1 = zb * R[6] - cx0 * R[8], Jn2 = cx0 * R[7] - cy0 * R[6];
+    const float Jx0 = cy0 * R[2] - zb * R[1], Jx1 = zb * R[0] - cx0 * R[2], Jx2 = cx0 * R[1] - cy0 * R[0];
+    const float Jy0 = cy0 * R[5] - zb * R[4], Jy1 = zb * R[3] - cx0 * R[5], Jy2 = cx0 * R[4] - cy0 * R[3];
+    float tgt0;
+    {
+        const float gap = hb + (zb * nz1 + (R[6] * cx0 + R[7] * cy0));
+        const float vn0 = vz + (wb0x * Jn0 + wb0y * Jn1 + wb0z * Jn2);
         const float rest = (vn0 < -c.rest_thr) ? c.restitution * (-vn0 - c.rest_thr) : 0.0f;
-        tgt[i] = rest + (gap > 0.0f ? -gap * c.inv_dt : -c.erp * gap * c.inv_dt);
-        ln[i] = warm ? lam[i * LS] : 0.0f;
-        l1[i] = warm ? lam[(5 + i) * LS] : 0.0f;
-        l2[i] = warm ? lam[(10 + i) * LS] : 0.0f;
+        tgt0 = rest + (gap > 0.0f ? -gap * c.inv_dt : -c.erp * gap * c.inv_dt);
     }
-    float lt0 = warm ? lam[16 * LS] : 0.0f, lt1 = warm ? lam[17 * LS] : 0.0f, lt2 = warm ? lam[15 * LS] : 0.0f;
-    // tangent rows of point 0
-    const float Jx0 = pcy[0] * R[2] - zb * R[1], Jx1 = zb * R[0] - pcx[0] * R[2], Jx2 = pcx[0] * R[1] - pcy[0] * R[0];
-    const float Jy0 = pcy[0] * R[5] - zb * R[4], Jy1 = zb * R[3] - pcx[0] * R[5], Jy2 = pcx[0] * R[4] - pcy[0] * R[3];
-    if (warm) {   // apply the stored impulses at the current contact geometry
+    // ---- points 1-4: the substep's manifold holds those within reach (gap below the entry rule's own bound) or still
+    // holding an impulse; their targets are fixed here, before the warm start (same rule and order in the oracle) ----
+    unsigned amask = 0u;
+    float tgtx[4];
 #pragma unroll
-        for (int i = 0; i < 5; i++) {
-            if (i != 0 && ln[i] == 0.0f && l1[i] == 0.0f && l2[i] == 0.0f) continue;   // adds exact zeros
-            float jx0 = Jx0, jx1 = Jx1, jx2 = Jx2, jy0 = Jy0, jy1 = Jy1, jy2 = Jy2;
-            if (i != 0) {
-                const float cz = i == 1 ? zt : zb;
-                jx0 = pcy[i] * R[2] - cz * R[1]; jx1 = cz * R[0] - pcx[i] * R[2]; jx2 = pcx[i] * R[1] - pcy[i] * R[0];
-                jy0 = pcy[i] * R[5] - cz * R[4]; jy1 = cz * R[3] - pcx[i] * R[5]; jy2 = pcx[i] * R[4] - pcy[i] * R[3];
-            }
-            vx += l1[i] * im; vy += l2[i] * im; vz += ln[i] * im;
-            w0 += ia * (jx0 * l1[i] + jy0 * l2[i] + Jn0[i] * ln[i]);
-            w1 += ia * (jx1 * l1[i] + jy1 * l2[i] + Jn1[i] * ln[i]);
-            w2 += ib * (jx2 * l1[i] + jy2 * l2[i] + Jn2[i] * ln[i]);
+    for (int i = 1; i < 5; i++) {
+        float cx, cy, cz;
+        extra_point_arm(i, cx0, cy0, r, zb, zt, cx, cy, cz);
+        const float gap = (i == 1 ? ht : hb) + (cz * nz1 + (R[6] * cx + R[7] * cy));
+        tgtx[i - 1] = 0.0f;
+        if (gap < gthr || (cc.xmask >> i) & 1u) {
+            const float jn0 = cy * R[8] - cz * R[7], jn1 = cz * R[6] - cx * R[8], jn2 = cx * R[7] - cy * R[6];
+            const float vn0 = vz + (wb0x * jn0 + wb0y * jn1 + wb0z * jn2);
+            const float rest = (vn0 < -c.rest_thr) ? c.restitution * (-vn0 - c.rest_thr) : 0.0f;
+            tgtx[i - 1] = rest + (gap > 0.0f ? -gap * c.inv_dt : -c.erp * gap * c.inv_dt);
+            amask |= 1u << i;
         }
-        w0 += ia * lt0; w1 += ia * lt1; w2 += ib * lt2;
     }
+    float l1 = cc.l1, l2 = cc.l2, ln = cc.ln, lt0 = cc.lt0, lt1 = cc.lt1, lt2 = cc.lt2;
+    float lx_sum = 0.0f;    // normal impulses held by points 1-4
+    if (warm) {   // apply the stored impulses at the current contact geometry
+        vx += l1 * im; vy += l2 * im; vz += ln * im;
+        w0 += ia * (Jx0 * l1 + Jy0 * l2 + Jn0 * ln + lt0);
+        w1 += ia * (Jx1 * l1 + Jy1 * l2 + Jn1 * ln + lt1);
+        w2 += ib * (Jx2 * l1 + Jy2 * l2 + Jn2 * ln + lt2);
+        for (unsigned m = cc.xmask; m; m &= m - 1u) {
+            const int i = __ffs(m) - 1;
+            float cx, cy, cz;
+            extra_point_arm(i, cx0, cy0, r, zb, zt, cx, cy, cz);
+            const float p1 = lamx[3 * (i - 1)], p2 = lamx[3 * (i - 1) + 1], pn = lamx[3 * (i - 1) + 2];
+            vx += p1 * im; vy += p2 * im; vz += pn * im;
+            w0 += ia * ((cy * R[2] - cz * R[1]) * p1 + (cy * R[5] - cz * R[4]) * p2 + (cy * R[8] - cz * R[7]) * pn);
+            w1 += ia * ((cz * R[0] - cx * R[2]) * p1 + (cz * R[3] - cx * R[5]) * p2 + (cz * R[6] - cx * R[8]) * pn);
+            w2 += ib * ((cx * R[1] - cy * R[0]) * p1 + (cx * R[4] - cy * R[3]) * p2 + (cx * R[7] - cy * R[6]) * pn);
+            lx_sum += pn;
+        }
+    }
+    // point 0's Delassus matrix with the axial row folded in: body axis z is left out of the angular dynamics
+    const float Axx = im + ia * (Jx0 * Jx0 + Jx1 * Jx1), Axy = ia * (Jx0 * Jy0 + Jx1 * Jy1), Axn = ia * (Jx0 * Jn0 + Jx1 * Jn1);
+    const float Ayy = im + ia * (Jy0 * Jy0 + Jy1 * Jy1), Ayn = ia * (Jy0 * Jn0 + Jy1 * Jn1);
+    const float Ann = im + ia * (Jn0 * Jn0 + Jn1 * Jn1);
     PH2_CLK(pc1);
     for (int it = 0; it < iters; it++) {
         float lsum = 0.0f;
         bool spin_done = false;
-        {   // ---- point 0, with the axial spin row folded in: body axis z is left out of the angular dynamics ----
-            const float un = vz + (w0 * Jn0[0] + w1 * Jn1[0]);
-            const float unz = un + w2 * Jn2[0];                          // true normal velocity
-            if (tgt[0] > unz || ln[0] > 0.0f || l1[0] != 0.0f || l2[0] != 0.0f) {
+        {   // ---- point 0 (rim friction and axial spin are coupled through 1/Iz: the block is solved with the axial row
+            //      sticking; if the axial impulse that needs exceeds its limit it goes to the limit and the point is solved again
+            //      with the full angular dynamics -- both solutions coincide at the limit) ----
+            const float un = vz + (w0 * Jn0 + w1 * Jn1);
+            const float unz = un + w2 * Jn2;                             // true normal velocity
+            if (tgt0 > unz || ln > 0.0f || l1 != 0.0f || l2 != 0.0f) {
                 const float ux_ = vx + (w0 * Jx0 + w1 * Jx1), uy_ = vy + (w0 * Jy0 + w1 * Jy1);
-                float Axx = im + ia * (Jx0 * Jx0 + Jx1 * Jx1), Axy = ia * (Jx0 * Jy0 + Jx1 * Jy1), Axn = ia * (Jx0 * Jn0[0] + Jx1 * Jn1[0]);
-                float Ayy = im + ia * (Jy0 * Jy0 + Jy1 * Jy1), Ayn = ia * (Jy0 * Jn0[0] + Jy1 * Jn1[0]);
-                float Ann = im + ia * (Jn0[0] * Jn0[0] + Jn1[0] * Jn1[0]);
                 float px, py, pn;
-                point_block(Axx, Axy, Axn, Ayy, Ayn, Ann, -ux_, -uy_, tgt[0] - un, mu, l1[0], l2[0], ln[0], px, py, pn);
-                float dx = px - l1[0], dy = py - l2[0], dn = pn - ln[0];
-                // the axial impulse that keeps w_z at zero through this block, limited by mu_spin * (this point's new normal
-                // impulse + what the other points hold)
-                const float slim = c.mu_spin * (pn + ln[1] + ln[2] + ln[3] + ln[4]);
-                const float cand = lt2 - (w2 * P.Iz + (Jx2 * dx + Jy2 * dy + Jn2[0] * dn));
+                point_block(Axx, Axy, Axn, Ayy, Ayn, Ann, -ux_, -uy_, tgt0 - un, mu, l1, l2, ln, px, py, pn);
+                float dx = px - l1, dy = py - l2, dn = pn - ln;
+                const float slim = c.mu_spin * (pn + lx_sum);
+                const float cand = lt2 - (w2 * P.Iz + (Jx2 * dx + Jy2 * dy + Jn2 * dn));
                 if (cand >= -slim && cand <= slim) { w2 = 0.0f; lt2 = cand; }
                 else {
-                    // the axial row slips: its impulse goes to the limit of the OLD normal impulses and the point is solved
-                    // again with the full angular dynamics (both solutions coincide at the limit)
-                    const float slim0 = c.mu_spin * (ln[0] + ln[1] + ln[2] + ln[3] + ln[4]);
+                    const float slim0 = c.mu_spin * (ln + lx_sum);
                     const float nl = clampf(cand, -slim0, slim0);
                     w2 += ib * (nl - lt2);
                     lt2 = nl;
-                    const float un3 = un + w2 * Jn2[0], ux3 = ux_ + w2 * Jx2, uy3 = uy_ + w2 * Jy2;
-                    Axx += ib * Jx2 * Jx2; Axy += ib * Jx2 * Jy2; Axn += ib * Jx2 * Jn2[0];
-                    Ayy += ib * Jy2 * Jy2; Ayn += ib * Jy2 * Jn2[0]; Ann += ib * Jn2[0] * Jn2[0];
-                    point_block(Axx, Axy, Axn, Ayy, Ayn, Ann, -ux3, -uy3, tgt[0] - un3, mu, l1[0], l2[0], ln[0], px, py, pn);
-                    dx = px - l1[0]; dy = py - l2[0]; dn = pn - ln[0];
-                    w2 += ib * (Jx2 * dx + Jy2 * dy + Jn2[0] * dn);
+                    const float un3 = un + w2 * Jn2, ux3 = ux_ + w2 * Jx2, uy3 = uy_ + w2 * Jy2;
+                    point_block(Axx + ib * Jx2 * Jx2, Axy + ib * Jx2 * Jy2, Axn + ib * Jx2 * Jn2, Ayy + ib * Jy2 * Jy2,
+                                Ayn + ib * Jy2 * Jn2, Ann + ib * Jn2 * Jn2, -ux3, -uy3, tgt0 - un3, mu, l1, l2, ln, px, py, pn);
+                    dx = px - l1; dy = py - l2; dn = pn - ln;
+                    w2 += ib * (Jx2 * dx + Jy2 * dy + Jn2 * dn);
                 }
                 spin_done = true;
                 vx += dx * im; vy += dy * im; vz += dn * im;
-                w0 += ia * (Jx0 * dx + Jy0 * dy + Jn0[0] * dn);
-                w1 += ia * (Jx1 * dx + Jy1 * dy + Jn1[0] * dn);
-                l1[0] = px; l2[0] = py; ln[0] = pn;
+                w0 += ia * (Jx0 * dx + Jy0 * dy + Jn0 * dn);
+                w1 += ia * (Jx1 * dx + Jy1 * dy + Jn1 * dn);
+                l1 = px; l2 = py; ln = pn;
                 lsum += pn;
             }
         }
-#pragma unroll
-        for (int i = 1; i < 5; i++) {   // ---- points 1-4, visited lazily ----
-            const float un = vz + (w0 * Jn0[i] + w1 * Jn1[i] + w2 * Jn2[i]);
-            if (!(tgt[i] > un || ln[i] > 0.0f || l1[i] != 0.0f || l2[i] != 0.0f)) continue;   // exact no-op
-            const float cz = i == 1 ? zt : zb;
-            const float jx0 = pcy[i] * R[2] - cz * R[1], jx1 = cz * R[0] - pcx[i] * R[2], jx2 = pcx[i] * R[1] - pcy[i] * R[0];
-            const float jy0 = pcy[i] * R[5] - cz * R[4], jy1 = cz * R[3] - pcx[i] * R[5], jy2 = pcx[i] * R[4] - pcy[i] * R[3];
+        lx_sum = 0.0f;
+        for (unsigned m = amask; m; m &= m - 1u) {   // ---- points 1-4 of this substep's manifold ----
+            const int i = __ffs(m) - 1;
+            float cx, cy, cz;
+            extra_point_arm(i, cx0, cy0, r, zb, zt, cx, cy, cz);
+            const float jn0 = cy * R[8] - cz * R[7], jn1 = cz * R[6] - cx * R[8], jn2 = cx * R[7] - cy * R[6];
+            const float un = vz + (w0 * jn0 + w1 * jn1 + w2 * jn2);
+            const bool held = (cc.xmask >> i) & 1u;
+            float q1 = 0.0f, q2 = 0.0f, qn = 0.0f;
+            if (held) { q1 = lamx[3 * (i - 1)]; q2 = lamx[3 * (i - 1) + 1]; qn = lamx[3 * (i - 1) + 2]; }
+            const float tg = i == 1 ? tgtx[0] : (i == 2 ? tgtx[1] : (i == 3 ? tgtx[2] : tgtx[3]));
+            if (!(tg > un || qn > 0.0f || q1 != 0.0f || q2 != 0.0f)) continue;   // exact no-op
+            const float jx0 = cy * R[2] - cz * R[1], jx1 = cz * R[0] - cx * R[2], jx2 = cx * R[1] - cy * R[0];
+            const float jy0 = cy * R[5] - cz * R[4], jy1 = cz * R[3] - cx * R[5], jy2 = cx * R[4] - cy * R[3];
             const float ux_ = vx + (w0 * jx0 + w1 * jx1 + w2 * jx2), uy_ = vy + (w0 * jy0 + w1 * jy1 + w2 * jy2);
-            const float Axx = im + (ia * (jx0 * jx0 + jx1 * jx1) + ib * jx2 * jx2);
-            const float Axy = ia * (jx0 * jy0 + jx1 * jy1) + ib * jx2 * jy2;
-            const float Axn = ia * (jx0 * Jn0[i] + jx1 * Jn1[i]) + ib * jx2 * Jn2[i];
-            const float Ayy = im + (ia * (jy0 * jy0 + jy1 * jy1) + ib * jy2 * jy2);
-            const float Ayn = ia * (jy0 * Jn0[i] + jy1 * Jn1[i]) + ib * jy2 * Jn2[i];
-            const float Ann = im + (ia * (Jn0[i] * Jn0[i] + Jn1[i] * Jn1[i]) + ib * Jn2[i] * Jn2[i]);
+            const float Bxx = im + (ia * (jx0 * jx0 + jx1 * jx1) + ib * jx2 * jx2);
+            const float Bxy = ia * (jx0 * jy0 + jx1 * jy1) + ib * jx2 * jy2;
+            const float Bxn = ia * (jx0 * jn0 + jx1 * jn1) + ib * jx2 * jn2;
+            const float Byy = im + (ia * (jy0 * jy0 + jy1 * jy1) + ib * jy2 * jy2);
+            const float Byn = ia * (jy0 * jn0 + jy1 * jn1) + ib * jy2 * jn2;
+            const float Bnn = im + (ia * (jn0 * jn0 + jn1 * jn1) + ib * jn2 * jn2);
             float px, py, pn;
-            point_block(Axx, Axy, Axn, Ayy, Ayn, Ann, -ux_, -uy_, tgt[i] - un, mu, l1[i], l2[i], ln[i], px, py, pn);
-            const float dx = px - l1[i], dy = py - l2[i], dn = pn - ln[i];
+            point_block(Bxx, Bxy, Bxn, Byy, Byn, Bnn, -ux_, -uy_, tg - un, mu, q1, q2, qn, px, py, pn);
+            const float dx = px - q1, dy = py - q2, dn = pn - qn;
             vx += dx * im; vy += dy * im; vz += dn * im;
-            w0 += ia * (jx0 * dx + jy0 * dy + Jn0[i] * dn);
-            w1 += ia * (jx1 * dx + jy1 * dy + Jn1[i] * dn);
-            w2 += ib * (jx2 * dx + jy2 * dy + Jn2[i] * dn);
-            l1[i] = px; l2[i] = py; ln[i] = pn;
+            w0 += ia * (jx0 * dx + jy0 * dy + jn0 * dn);
+            w1 += ia * (jx1 * dx + jy1 * dy + jn1 * dn);
+            w2 += ib * (jx2 * dx + jy2 * dy + jn2 * dn);
+            lamx[3 * (i - 1)] = px; lamx[3 * (i - 1) + 1] = py; lamx[3 * (i - 1) + 2] = pn;
+            cc.xmask = (px != 0.0f || py != 0.0f || pn != 0.0f) ? (cc.xmask | (1u << i)) : (cc.xmask & ~(1u << i));
             lsum += pn;
+            lx_sum += pn;
         }
         {   // torsional rows about the body axes x, y (and z when point 0 did not carry it): the impulse that zeroes the
             // component, limited by mu_k * (total normal impulse)
@@ -463,9 +483,7 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
             }
         }
     }
-#pragma unroll
-    for (int i = 0; i < 5; i++) { lam[i * LS] = ln[i]; lam[(5 + i) * LS] = l1[i]; lam[(10 + i) * LS] = l2[i]; }
-    lam[15 * LS] = lt2; lam[16 * LS] = lt0; lam[17 * LS] = lt1;
+    cc.l1 = l1; cc.l2 = l2; cc.ln = ln; cc.lt0 = lt0; cc.lt1 = lt1; cc.lt2 = lt2; cc.have = true;
     {   // back to the world frame: w += R (wt - wb0)
         const float d0 = w0 - wb0x, d1 = w1 - wb0y, d2 = w2 - wb0z;
         wx += R[0] * d0 + R[1] * d1 + R[2] * d2;
@@ -478,9 +496,8 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
 }
 
 // Rows B2, B4, B5, B6: K substeps for ONE env on its own thread with the world-frame force F and torque T held constant
-// (Q3): no shared memory, no CTA barriers, the contact solver inline with its 18 carried impulses in registers.  Used by
-// step_kernel_v2 and the rollout kernel, whose warps hold envs of one class (near the ground or not), so the contact
-// branch is nearly warp-uniform.
+// (Q3): no shared memory, no CTA barriers, the contact solver inline.  Used by step_kernel_v2 and the rollout kernel, whose
+// warps hold envs of one class (near the ground or not), so the contact branch is nearly warp-uniform.
 // LOCKSTEP: the CTA's warps re-align at every substep (every thread of the CTA must call this).
 // FOLLOW (quirk Q3 cleared): the thrust force and torque are body-fixed and re-evaluated at every substep's attitude instead
 // of being held constant in the world frame; a separate instantiation, so that the reference path carries none of it.
@@ -498,13 +515,15 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
         Foz = Fz - (R[6] * f.fl0 + R[7] * f.fl1 + R[8] * f.fl2);
         Tox = Tx - (R[0] * tl0 + R[1] * tl1); Toy = Ty - (R[3] * tl0 + R[4] * tl1); Toz = Tz - (R[6] * tl0 + R[7] * tl1);
     }
-    float lam[18];
-#pragma unroll
-    for (int j = 0; j < 18; j++) lam[j] = 0.0f;
-    bool have_lam = false;   // cold start at every control step
+    ContactCarry cc;
+    cc.l1 = cc.l2 = cc.ln = cc.lt0 = cc.lt1 = cc.lt2 = 0.0f; cc.xmask = 0u; cc.have = false;   // cold start at every control step
+    float lamx[12];          // impulses of points 1-4, valid where cc.xmask says so
     float pzc = 0.0f;        // running compensation of the height update: true height = e.pz + pzc
     const float dI = P.inv_Iz - P.inv_Ixy;
-    const float far_z = 1.001f * (c.half_len + fabsf(P.cg) + c.radius) + c.margin;
+    const float hh = c.half_len + fabsf(P.cg);
+    const float far_z = 1.001f * (hh + c.radius) + c.margin;
+    const float reach = sqrt_fast(hh * hh + c.radius * c.radius);
+    const float zb = -c.half_len - P.cg, zt = c.half_len - P.cg;
     for (int k = 0; k < c.K; k++) {
 #ifdef TVC_PHASE_PROF2
         { const long long b0 = clock64(); if (LOCKSTEP) __syncthreads(); ph2->bar += (unsigned)(clock64() - b0); }
@@ -521,8 +540,9 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
         }
         // B5 with I = diag(a, a, b): R diag(1/a,1/a,1/b) R^T tau = tau/a + (1/b - 1/a)(e.tau) e, e = body axis in the
         // world frame (third column of R); the k(1+|w|) damping is isotropic.  Only e and the third row of R are needed
-        // outside the contact solver.
-        const float s2 = 2.0f * rcp_fast(e.qx * e.qx + e.qy * e.qy + e.qz * e.qz + e.qw * e.qw);
+        // outside the contact solver.  The quaternion is unit to rounding (normalised at the end of every substep, on
+        // import and at reset), so 2 / |q|^2 is its first-order expansion 2 (2 - |q|^2): exact to 1e-13, no MUFU.
+        const float s2 = 2.0f * (2.0f - (e.qx * e.qx + e.qy * e.qy + e.qz * e.qz + e.qw * e.qw));
         const float xs = e.qx * s2, ys = e.qy * s2, zs = e.qz * s2;
         const float nz1 = -(e.qx * xs + e.qy * ys);          // R33 - 1, without the cancellation
         const float e0 = e.qx * zs + e.qw * ys, e1 = e.qy * zs - e.qw * xs, e2 = 1.0f + nz1;
@@ -542,20 +562,36 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
         e.vx = clampf(e.vx + (ax_ - e.vx * kl) * dt, -100.0f, 100.0f);
         e.vy = clampf(e.vy + (ay_ - e.vy * kl) * dt, -100.0f, 100.0f);
         e.vz = clampf(e.vz + (az_ - e.vz * kl) * dt, -100.0f, 100.0f);
-        // the lowest point of the body is never lower than pz - 1.001 (h + |cg| + r): above `far_z` the entry rule fails
-        // without evaluating it (same decision, one compare for the airborne envs)
+        // B9 (our model): contacts detected at the pre-integration pose, solved on velocities.  Entry rule (same in the
+        // oracle): the lowest candidate is within `margin` AND within reach, gap_min < g_reach = (1+e)(|vz| + |w| reach) dt
+        // + 1e-4 -- a row binds only if (1+e) * approach speed * dt exceeds its gap.  The lowest point of the body is never
+        // lower than pz - 1.001 (h + |cg| + r): above `far_z` the rule fails without evaluating it (one compare for the
+        // airborne envs).  When the rule fails the stored impulses are cleared.
+        bool solved = false;
         if (c.ground && e.pz < far_z) {
             const float R31 = e.qx * zs - e.qw * ys, R32 = e.qy * zs + e.qw * xs;   // third row of R (R33 == e2)
-            if (contact_needed_row(c, P, R31, R32, nz1, e.pz, pzc, e.vz, e.wx, e.wy, e.wz)) {
-                float R[9];
-                quat_to_mat(e.qx, e.qy, e.qz, e.qw, R);
-                solve_contacts<1>(c, P, R, nz1, e.pz, pzc, e.vx, e.vy, e.vz, e.wx, e.wy, e.wz, lam, have_lam,
-                                  have_lam ? c.warm_iters : c.contact_iters PH2_PASS);
-                have_lam = true;
-            } else have_lam = false;
-        } else have_lam = false;
-        // B6: semi-implicit Euler (the height with a running compensation: the contact targets divide the gap by dt, so
-        // the 3e-8 rounding of pz + dt vz per substep would otherwise show up as 1.5e-5 m/s at dt = 0.002)
+            const float rr = R31 * R31 + R32 * R32;
+            const float rho = sqrt_fast(rr);
+            const float inv = rcp_fast(fmaxf(rho, 1e-3f));
+            const float low = -c.radius * rr * inv;
+            const float hb = (e.pz + zb) + pzc, ht = (e.pz + zt) + pzc;
+            const float gmin = fminf(hb + (zb * nz1 + low), ht + (zt * nz1 + low));
+            if (gmin < c.margin) {
+                const float vmax = fabsf(e.vz) + sqrt_fast(e.wx * e.wx + e.wy * e.wy + e.wz * e.wz) * reach;
+                const float gthr = (1.0f + c.restitution) * vmax * dt + 1e-4f;
+                if (gmin < gthr) {
+                    float R[9];
+                    R[0] = 1.0f - (e.qy * ys + e.qz * zs); R[1] = e.qx * ys - e.qw * zs; R[2] = e0;
+                    R[3] = e.qx * ys + e.qw * zs; R[4] = 1.0f - (e.qx * xs + e.qz * zs); R[5] = e1;
+                    R[6] = R31; R[7] = R32; R[8] = e2;
+                    solve_contacts(c, P, R, nz1, hb, ht, -R31 * inv, -R32 * inv, gthr, e.vx, e.vy, e.vz, e.wx, e.wy, e.wz, cc, lamx PH2_PASS);
+                    solved = true;
+                }
+            }
+        }
+        if (!solved) { cc.l1 = cc.l2 = cc.ln = cc.lt0 = cc.lt1 = cc.lt2 = 0.0f; cc.xmask = 0u; cc.have = false; }
+        // B6: semi-implicit Euler; near the ground the height carries a running compensation (the contact targets divide the
+        // gap by dt, so the 3e-8 rounding of pz + dt vz per substep would otherwise show up as 1.5e-5 m/s at dt = 0.002)
         e.px += dt * e.vx; e.py += dt * e.vy;
         {
             const float y = __fadd_rn(__fmul_rn(dt, e.vz), pzc), t = __fadd_rn(e.pz, y);
@@ -573,7 +609,8 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
         float ny = cw * e.qy + by * e.qw + bz * e.qx - bx * e.qz;
         float nz = cw * e.qz + bz * e.qw + bx * e.qy - by * e.qx;
         float nw = cw * e.qw - bx * e.qx - by * e.qy - bz * e.qz;
-        float inv = rsqrt_fast(nx * nx + ny * ny + nz * nz + nw * nw);
+        // |dq (x) q|^2 = 1 + O(1e-7) (both factors are unit to rounding): 1/sqrt by its first-order expansion, exact to 1e-13
+        float inv = 1.5f - 0.5f * (nx * nx + ny * ny + nz * nz + nw * nw);
         e.qx = nx * inv; e.qy = ny * inv; e.qz = nz * inv; e.qw = nw * inv;
     }
 }
