@@ -244,6 +244,28 @@ int tvc_host_sync(tvc_handle *h);
  * (replaces train.py:546-603's get_action -> step loop for the legacy 2x256 actor). */
 int tvc_rollout(tvc_handle *h, const tvc_actor_weights *w, int32_t T, const tvc_rollout_io *io, tvc_stream stream);
 
+/* On-device replay ring (replaces train.py:574-591's batch-of-1 agent.update feed).  The ring
+ * is caller memory; tvc_rollout fills it in place when tvc_rollout_io.obs_all / actions_all / reward_all / next_obs_all /
+ * terminated_all point at its head (T * N consecutive transitions).  tvc_replay_sample draws `batch` uniform indices in
+ * [0, filled) from Philox4x32-10 (key = seed, counter = (sample, draw)) and gathers the transitions into the learner's batch
+ * tensors in one launch: reward * reward_scale, done = terminated as float (agent/multi_algorithm_agent.py:950-1016 inputs). */
+typedef struct tvc_replay_ring {
+    const float *obs;          /* [capacity,10] */
+    const float *actions;      /* [capacity,2] */
+    const float *reward;       /* [capacity] */
+    const float *next_obs;     /* [capacity,10] */
+    const uint8_t *terminated; /* [capacity] */
+    int64_t capacity;
+} tvc_replay_ring;
+typedef struct tvc_replay_batch {
+    float *obs, *actions, *reward, *next_obs, *done; /* [batch,10], [batch,2], [batch], [batch,10], [batch] */
+    int64_t *indices;                                 /* [batch] nullable: the ring indices drawn */
+} tvc_replay_batch;
+/* ctl_dev (nullable): two device words {filled, draw_base}; when given, the kernel reads `filled` from it and adds draw_base to
+ * `draw`, so that a launch captured into a CUDA graph follows the ring as it fills and never repeats a draw. */
+int tvc_replay_sample(const tvc_replay_ring *ring, int64_t filled, int32_t batch, uint64_t seed, uint64_t draw,
+                      const uint64_t *ctl_dev, float reward_scale, const tvc_replay_batch *out, int device, tvc_stream stream);
+
 /* state exchange; dev_blob = N x tvc_env_state on the device */
 size_t tvc_state_bytes(const tvc_handle *h);
 int tvc_get_state(tvc_handle *h, void *dev_blob, size_t bytes, tvc_stream stream);

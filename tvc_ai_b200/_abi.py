@@ -35,7 +35,7 @@ STAT_NAMES = ("episodes", "sum_return", "sum_return_sq", "sum_length", "successe
 EXPORTS = ("tvc_abi_version", "tvc_last_error", "tvc_config_default", "tvc_create", "tvc_destroy", "tvc_reset",
            "tvc_step", "tvc_step_ex", "tvc_step_host", "tvc_step_host_async", "tvc_host_sync", "tvc_rollout", "tvc_state_bytes", "tvc_get_state",
            "tvc_set_state", "tvc_get_reward_history", "tvc_set_reward_history", "tvc_read_info", "tvc_episode_stats", "tvc_episode_stats_dev", "tvc_set_curriculum",
-           "tvc_get_config", "tvc_num_envs", "tvc_lifetime_steps")
+           "tvc_get_config", "tvc_num_envs", "tvc_lifetime_steps", "tvc_replay_sample")
 
 
 class TvcConfig(C.Structure):
@@ -92,6 +92,16 @@ class TvcActorWeights(C.Structure):
                 ("w3", C.c_void_p), ("b3", C.c_void_p)]
 
 
+class TvcReplayRing(C.Structure):
+    _fields_ = [("obs", C.c_void_p), ("actions", C.c_void_p), ("reward", C.c_void_p), ("next_obs", C.c_void_p),
+                ("terminated", C.c_void_p), ("capacity", C.c_int64)]
+
+
+class TvcReplayBatch(C.Structure):
+    _fields_ = [("obs", C.c_void_p), ("actions", C.c_void_p), ("reward", C.c_void_p), ("next_obs", C.c_void_p),
+                ("done", C.c_void_p), ("indices", C.c_void_p)]
+
+
 class TvcRolloutIO(C.Structure):
     _fields_ = [("obs", C.c_void_p), ("reward_sum", C.c_void_p), ("actions_last", C.c_void_p),
                 ("actions_all", C.c_void_p), ("reward_all", C.c_void_p), ("deterministic", C.c_int32),
@@ -141,6 +151,7 @@ def load(path: str | None = None):
     L.tvc_num_envs.restype = i64
     L.tvc_lifetime_steps.argtypes = [vp]
     L.tvc_lifetime_steps.restype = i64
+    L.tvc_replay_sample.argtypes = [C.POINTER(TvcReplayRing), i64, i32, u64, u64, vp, C.c_float, C.POINTER(TvcReplayBatch), C.c_int, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("tvc_abi_version",):

@@ -245,12 +245,13 @@ __device__ __forceinline__ int env_at_group(const DevState &st, int p, int lane,
 // fetches).  That won 7 % while the kernel was 92 KB of code with every contact row always visited (0.1767 -> 0.164 ms); with
 // the class-ordered sequence, the lazy rows and 57 KB of code the barrier costs more than the instruction cache gains:
 // 0.0947 ms with it, 0.0925 ms without.  Default: every warp pulls its own groups and never waits for another warp.
-// DEFER: finished envs are marked for the closing sort kernel (large batches) instead of being reset in place (small batches,
-// where one launch fewer matters more than the idle lanes).
+// Finished envs are never reset here: they are marked for the sort kernel that closes the step (see below).  An in-place
+// reset for small batches existed as a second template instantiation; nvcc contracted the solver's FMAs differently in the
+// two, so the two launch plans differed in the last bit of contact steps -- one instantiation per configuration cannot.
 // A split into an airborne-part kernel at twice the occupancy (64 registers, solver out of line) followed by a near-ground
 // kernel was measured: 0.150 ms against 0.125 ms for this single kernel -- the FP32-pipe-bound solver warps and the
 // latency-bound airborne warps hide each other only when they share the SM sub-partitions.
-template <bool X, int DIV, bool DEFER, bool FOLLOW>
+template <bool X, int DIV, bool FOLLOW>
 __global__ void __launch_bounds__(TVC_V2_BLOCK, TVC_MIN_BLOCKS_V2)
 step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevState st, const __grid_constant__ DevIO io) {
     // launched with programmatic stream serialization: everything above this line may overlap classify_kernel's tail
@@ -370,20 +371,16 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
 #pragma unroll
                     for (int k = 0; k < 5; k++) f2[k] = make_float2(r.obs[2 * k], r.obs[2 * k + 1]);
                 }
-                if (!DEFER && c.autoreset) {   // small batches: reset in place (one launch fewer)
-                    reset_env(c, X, gid, e, false);
-                    build_obs(c, X, gid, e, 0, r.obs);
-                }
             }
             store_env(st, X, i, e);
-            // class byte for the next step's sort; 0xFF = "episode ended, reset me" (DEFER, consumed by the sort kernel)
-            st.cls[i] = (DEFER && done && c.autoreset) ? (uint8_t)0xFF
+            // class byte for the next step's sort; 0xFF = "episode ended, reset me" (consumed by the sort kernel)
+            st.cls[i] = (done && c.autoreset) ? (uint8_t)0xFF
                         : (uint8_t)class_of(c, X, e.pz, e.qx, e.qy, e.qz, e.qw, e.vz, e.wx, e.wy, e.wz, e.cg_off);
             float2 *o2 = reinterpret_cast<float2 *>(io.obs + 10 * i);
 #pragma unroll
             for (int k = 0; k < 5; k++) o2[k] = make_float2(r.obs[2 * k], r.obs[2 * k + 1]);
         }
-        // Same-step autoreset is deferred (DEFER): ~1 env in 38 ends its episode per step, i.e. 1-2 lanes per warp would walk
+        // Same-step autoreset is deferred: ~1 env in 38 ends its episode per step, i.e. 1-2 lanes per warp would walk
         // through the per-episode Philox draws and a second observation here (10 % of this kernel's warp-instructions
         // at 1.7 live lanes).  The terminal state and observation are stored above and the env is marked in its class
         // byte; the sort kernel that closes the step (classify_kernel<X, false, true>) compacts the marked envs of its
@@ -600,26 +597,6 @@ static cudaError_t launch_dep(void (*kernel)(KArgs...), int grid, int block, cud
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
-static void make_devcfg(const tvc_config &c, DevCfg &d) {
-    memset(&d, 0, sizeof(d));
-    d.contract = c.contract; d.K = c.substeps; d.max_steps = c.max_episode_steps; d.autoreset = c.autoreset;
-    d.quirks = c.quirks; d.div_mode = c.diversity_mode; d.contact_iters = c.contact_iters; d.warm_iters = c.contact_warm_iters; d.ground = c.ground;
-    d.delay = c.delay_steps; d.thrust_curve = c.thrust_curve;
-    const double dt = c.dt_step / (double)c.substeps;
-    d.dt = (float)dt; d.inv_dt = (float)(1.0 / dt);
-    d.inv_max_steps = (float)(1.0 / (double)c.max_episode_steps);
-    d.gp = c.gradient_penalty; d.db = c.diversity_bonus;
-    d.mass = c.mass; d.radius = c.radius; d.half_len = 0.5f * c.length; d.thrust = c.thrust; d.gimbal_max = c.gimbal_max_rad;
-    d.lin_damp = c.lin_damp; d.ang_damp = c.ang_damp;
-    d.mass_var = c.mass_variation; d.thrust_std = c.thrust_std; d.thrust_lo = c.thrust_lo; d.thrust_hi = c.thrust_hi;
-    d.cg_max = c.cg_offset_max; d.wind_std = c.wind_std; d.noise_std = c.sensor_noise_std;
-    d.tilt_max = c.init_tilt_max; d.omega_max = c.init_omega_max; d.prop_frac = c.propellant_fraction; d.cg_burn = c.cg_burn_shift;
-    d.mu = c.contact_mu; d.mu_spin = c.contact_mu_spin; d.mu_roll = c.contact_mu_roll;
-    d.restitution = c.contact_restitution; d.rest_thr = c.contact_rest_threshold; d.erp = c.contact_erp; d.margin = c.contact_margin;
-    d.seed_lo = (unsigned)c.seed; d.seed_hi = (unsigned)(c.seed >> 32);
-    d.env_base = c.env_id_base;
-}
-
 extern "C" {
 
 int tvc_abi_version(void) { return TVC_ABI_VERSION; }
@@ -793,27 +770,22 @@ static int launch_step(tvc_handle *h, const DevIO &io, cudaStream_t s) {
         }
         if (h->v2_grid == 0) {   // persistent grid: resident CTAs of the v2 kernel, capped by the number of groups
             int per_sm = 0;
-            cudaError_t e = X ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_v2<true, 1, true, false>, TVC_V2_BLOCK, 0)
-                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_v2<false, 1, true, false>, TVC_V2_BLOCK, 0);
+            cudaError_t e = X ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_v2<true, 1, false>, TVC_V2_BLOCK, 0)
+                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_v2<false, 1, false>, TVC_V2_BLOCK, 0);
             if (e != cudaSuccess || per_sm < 1) per_sm = 1;
             const int cap = per_sm * h->num_sms;
             const int wpb = TVC_V2_BLOCK / 32;
             const int ctas = (h->ngroups + wpb - 1) / wpb;
-            // small batches (every group resident at once): finished envs are reset in place -> two launches per step
             { const char *p = getenv("TVC_PDL"); h->pdl = !(p && p[0] == '0'); }   // diagnostics: TVC_PDL=0 launches plainly
-            const char *force = getenv("TVC_STEP_DEFER");   // tests / diagnostics: 0 or 1 overrides the choice
-            h->v2_defer = force ? (force[0] == '1') : (ctas > cap);
             const int want = h->ngroups <= cap ? h->ngroups : ctas;
             h->v2_grid = want < cap ? want : cap;
         }
         const bool follow = !(h->cur.quirks & TVC_Q_FROZEN_FORCES);   // quirk Q3 cleared: the thrust follows the body every substep
-#define GO(XX, DD, FF) do { if (follow) (void)launch_dep(step_kernel_v2<XX, DD, FF, true>, h->v2_grid, TVC_V2_BLOCK, s, h->pdl, h->dc, h->st, io); \
-                            else (void)launch_dep(step_kernel_v2<XX, DD, FF, false>, h->v2_grid, TVC_V2_BLOCK, s, h->pdl, h->dc, h->st, io); } while (0)
-#define GO3(FF) do { \
-        if (X) { if (dv == 0) GO(true, 0, FF); else if (dv == 1) GO(true, 1, FF); else GO(true, 2, FF); } \
-        else   { if (dv == 0) GO(false, 0, FF); else if (dv == 1) GO(false, 1, FF); else GO(false, 2, FF); } } while (0)
-        const bool defer = h->v2_defer && h->cur.autoreset;
-        if (defer) GO3(true); else GO3(false);
+#define GO(XX, DD) do { if (follow) (void)launch_dep(step_kernel_v2<XX, DD, true>, h->v2_grid, TVC_V2_BLOCK, s, h->pdl, h->dc, h->st, io); \
+                        else (void)launch_dep(step_kernel_v2<XX, DD, false>, h->v2_grid, TVC_V2_BLOCK, s, h->pdl, h->dc, h->st, io); } while (0)
+        if (X) { if (dv == 0) GO(true, 0); else if (dv == 1) GO(true, 1); else GO(true, 2); }
+        else   { if (dv == 0) GO(false, 0); else if (dv == 1) GO(false, 1); else GO(false, 2); }
+        const bool defer = h->cur.autoreset != 0;   // the closing sort kernel re-initialises the envs the step kernel marked
         LAUNCH_OK("step_kernel_v2");
         // close the step: (reset the finished envs of every chunk and) sort for the next step from the class bytes
         if (defer) {
@@ -825,7 +797,6 @@ static int launch_step(tvc_handle *h, const DevIO &io, cudaStream_t s) {
         }
         LAUNCH_OK("classify_kernel (end of step)");
         h->order_valid = true;
-#undef GO3
 #undef GO
     }
     h->lifetime_steps += 1;

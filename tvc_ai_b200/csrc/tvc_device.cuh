@@ -105,14 +105,18 @@ enum { ST_DR_A = 1, ST_DR_B = 2, ST_NOISE_A = 3, ST_NOISE_B = 4, ST_ACTION = 5, 
 // reciprocal of a well-scaled positive number (masses, inertias, squared norms): one MUFU.RCP.  __fdividef(1, x) carries
 // range handling for |x| > 2^126 (two predicated FMULs, two FSELs per call, 42 call sites: 5 % of the step kernel's
 // instructions and 11 % of its stall samples in the ncu source view)
-#ifdef TVC_RCP_FDIVIDEF
+#if defined(TVC_RCP_FDIVIDEF) || defined(TVC_HOST_TWIN)   // (host twin: tests/host_twin, g++ has no PTX)
 __device__ __forceinline__ float rcp_fast(float x) { return __fdividef(1.0f, x); }
 #else
 __device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 #endif
 // operand known to be a normal number (callers clamp it away from the subnormal range): one MUFU.RSQ, without the
 // subnormal pre/post-scaling rsqrtf() carries
+#ifdef TVC_HOST_TWIN
+__device__ __forceinline__ float rsqrt_normal(float x) { return 1.0f / sqrtf(x); }
+#else
 __device__ __forceinline__ float rsqrt_normal(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#endif
 // squared magnitudes below 1e-30 (|.| < 1e-15) count as zero; callers of rsqrt_fast pass (near-)unit quaternion norms.
 // (rsqrtf()'s subnormal pre/post-scaling measured 2.4 % slower end to end with identical trajectories; an L2 prefetch of
 // the reward ring / bit-ring lines right after the state load measured 2.7 % slower.)
@@ -353,8 +357,10 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
     const float Jx0 = cy0 * R[2] - zb * R[1], Jx1 = zb * R[0] - cx0 * R[2], Jx2 = cx0 * R[1] - cy0 * R[0];
     const float Jy0 = cy0 * R[5] - zb * R[4], Jy1 = zb * R[3] - cx0 * R[5], Jy2 = cx0 * R[4] - cy0 * R[3];
     float tgt0;
+    bool act0;   // point 0 is in the substep's manifold: within reach or still holding an impulse (same rule as points 1-4)
     {
         const float gap = hb + (zb * nz1 + (R[6] * cx0 + R[7] * cy0));
+        act0 = gap < gthr || cc.ln != 0.0f || cc.l1 != 0.0f || cc.l2 != 0.0f;
         const float vn0 = vz + (wb0x * Jn0 + wb0y * Jn1 + wb0z * Jn2);
         const float rest = (vn0 < -c.rest_thr) ? c.restitution * (-vn0 - c.rest_thr) : 0.0f;
         tgt0 = rest + (gap > 0.0f ? -gap * c.inv_dt : -c.erp * gap * c.inv_dt);
@@ -409,7 +415,7 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
             //      with the full angular dynamics -- both solutions coincide at the limit) ----
             const float un = vz + (w0 * Jn0 + w1 * Jn1);
             const float unz = un + w2 * Jn2;                             // true normal velocity
-            if (tgt0 > unz || ln > 0.0f || l1 != 0.0f || l2 != 0.0f) {
+            if (act0 && (tgt0 > unz || ln > 0.0f || l1 != 0.0f || l2 != 0.0f)) {
                 const float ux_ = vx + (w0 * Jx0 + w1 * Jx1), uy_ = vy + (w0 * Jy0 + w1 * Jy1);
                 float px, py, pn;
                 point_block(Axx, Axy, Axn, Ayy, Ayn, Ann, -ux_, -uy_, tgt0 - un, mu, l1, l2, ln, px, py, pn);

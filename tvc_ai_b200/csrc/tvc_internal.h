@@ -3,6 +3,7 @@
 #include "../../include/tvc_b200.h"
 #include "tvc_device.cuh"
 
+#include <cstring>
 #include <string>
 
 struct tvc_handle {
@@ -14,7 +15,6 @@ struct tvc_handle {
     int v2_grid = 0;    // persistent grid of step_kernel_v2 (computed on first launch)
     bool order_valid = false;  // the sorted sequence describes the current state (false after reset / set_state / rollout / curriculum)
     bool pdl = true;         // programmatic dependent launch of step_kernel_v2 and of the closing sort kernel
-    bool v2_defer = false;   // large batches: finished envs are reset by the closing sort kernel; small ones in place
     tvc_config base;   // as created
     tvc_config cur;    // after tvc_set_curriculum
     tvc::DevCfg dc;
@@ -33,6 +33,27 @@ struct tvc_handle {
     // fused-rollout workspace (tvc_rollout.cu)
     void *rollout_ws = nullptr;
 };
+
+// tvc_config (ABI) -> the constants the device code reads
+inline void make_devcfg(const tvc_config &c, tvc::DevCfg &d) {
+    memset(&d, 0, sizeof(d));
+    d.contract = c.contract; d.K = c.substeps; d.max_steps = c.max_episode_steps; d.autoreset = c.autoreset;
+    d.quirks = c.quirks; d.div_mode = c.diversity_mode; d.contact_iters = c.contact_iters; d.warm_iters = c.contact_warm_iters; d.ground = c.ground;
+    d.delay = c.delay_steps; d.thrust_curve = c.thrust_curve;
+    const double dt = c.dt_step / (double)c.substeps;
+    d.dt = (float)dt; d.inv_dt = (float)(1.0 / dt);
+    d.inv_max_steps = (float)(1.0 / (double)c.max_episode_steps);
+    d.gp = c.gradient_penalty; d.db = c.diversity_bonus;
+    d.mass = c.mass; d.radius = c.radius; d.half_len = 0.5f * c.length; d.thrust = c.thrust; d.gimbal_max = c.gimbal_max_rad;
+    d.lin_damp = c.lin_damp; d.ang_damp = c.ang_damp;
+    d.mass_var = c.mass_variation; d.thrust_std = c.thrust_std; d.thrust_lo = c.thrust_lo; d.thrust_hi = c.thrust_hi;
+    d.cg_max = c.cg_offset_max; d.wind_std = c.wind_std; d.noise_std = c.sensor_noise_std;
+    d.tilt_max = c.init_tilt_max; d.omega_max = c.init_omega_max; d.prop_frac = c.propellant_fraction; d.cg_burn = c.cg_burn_shift;
+    d.mu = c.contact_mu; d.mu_spin = c.contact_mu_spin; d.mu_roll = c.contact_mu_roll;
+    d.restitution = c.contact_restitution; d.rest_thr = c.contact_rest_threshold; d.erp = c.contact_erp; d.margin = c.contact_margin;
+    d.seed_lo = (unsigned)c.seed; d.seed_hi = (unsigned)(c.seed >> 32);
+    d.env_base = c.env_id_base;
+}
 
 const char *tvc_set_err(const std::string &m);
 void tvc_rollout_free(tvc_handle *h);
