@@ -35,5 +35,6 @@ static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline void sincospif(float x, float *s, float *c) { *s = (float)sin(3.141592653589793 * (double)x); *c = (float)cos(3.141592653589793 * (double)x); }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline void __syncthreads() {}
+template <typename T> static inline T __ldcg(const T *p) { return *p; }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }

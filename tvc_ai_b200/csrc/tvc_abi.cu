@@ -28,211 +28,147 @@ __device__ __forceinline__ void warp_store_obs(float *dst, const float *s_warp, 
 }
 
 // ------------------------------------------------------------------------------------------
-// step path: sort, then one warp per 32-env group, solver inline, no CTA barriers
+// step path: ONE class-ordered work sequence over all envs, one warp per 32-env group, solver inline, no CTA barriers
 // ------------------------------------------------------------------------------------------
 #ifndef TVC_CHUNK
-#define TVC_CHUNK 1024   // envs sorted together (stable partition, near-ground class first)
+#define TVC_CHUNK 1024   // envs whose class counts are kept together (and whose part of the sequence one CTA writes)
 #endif
-#ifndef TVC_CLS_THREADS
-#define TVC_CLS_THREADS 256    // (512 measured equal, 1,024 -- one env per thread -- 3 % slower end to end)
-#endif
-#define TVC_CLS_WARPS (TVC_CLS_THREADS / 32)
-#define TVC_EPT (TVC_CHUNK / TVC_CLS_THREADS)   // envs per classify thread
+#define TVC_SUPER 256    // chunks per super-chunk (second level of the counts: the prefix of a chunk is O(nsuper + TVC_SUPER))
 
-// Heuristic class of an env for the coming step: 0 = its lowest point touches the ground now (measured: such envs need
-// the contact solve in 9.4 of the 10 substeps), 1 = it may come within reach during the step, 2 = airborne.
+// Heuristic class of an env for the coming step (class_of): 0 = its lowest point touches the ground now (measured: such
+// envs need the contact solve in 9.4 of the 10 substeps), 1 = it may come within reach during the step, 2 = airborne.
 // Only the grouping depends on it (every thread carries the solver), never the results.
 //
-// Each 1024-env chunk is sorted by class (stable), its class counts go to goff[c][chunk + 1], and the last CTA to finish
-// turns the counts into exclusive scans over the chunks.  step_kernel_v2 then walks ONE global sequence -- all class-0
-// envs, all class-1 envs, all class-2 envs -- so that a warp's 32 envs are of one class (the solver path is walked by
-// full warps or not at all) and the long class-0 groups start first, with the short airborne groups filling in behind and
-// beside them.  Deterministic: no atomics on data, the sequence depends on the states only.
-// FROM_STATE: compute the classes from the state planes (80 B per env; first step, or after a reset / set_state / rollout
-// touched the state behind the step path's back).  Otherwise read the class byte step_kernel_v2 left for every env
-// (1 B per env) -- this instantiation CLOSES a step and prepares the next one's sequence.
-// RESET (large batches, same-step autoreset): before sorting, the envs the step kernel marked 0xFF are compacted per chunk
-// and re-initialised by as many threads (ref:381-464 reset + the reset observation; their terminal state was stored by
-// the step kernel and every Env field round-trips through store_env / load_env, so this equals resetting in place).
-// One launch does what a separate reset kernel and the next step's classify did (-8 us per step).
-template <bool X, bool FROM_STATE, bool RESET>
-__global__ void __launch_bounds__(TVC_CLS_THREADS)
-classify_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState st, float *obs) {
-    __shared__ int wcnt[3][TVC_EPT][TVC_CLS_WARPS];
-    __shared__ int s_scan[TVC_CLS_WARPS];
-    __shared__ int s_pre[3][32], s_tot[3];
-    __shared__ int s_last;
-    __shared__ uint8_t s_cls[RESET ? TVC_CHUNK : 4];
-    __shared__ unsigned short s_done[RESET ? TVC_CHUNK : 2];
-    __shared__ int s_ndone;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long base = (long long)blockIdx.x * TVC_CHUNK;
-    const int nc = st.nchunks;
-    asm volatile("griddepcontrol.wait;" ::: "memory");   // behind step_kernel_v2 when it closes a step
-    if (RESET) {
-        if (tid == 0) s_ndone = 0;
-        __syncthreads();
+// The sequence step_kernel_v2 walks -- all class-0 envs, then class 1, then class 2, each in env order -- is the flat array
+// st.order.  Its producer is split over the two kernels of a step so that almost nothing of it is on the critical path:
+//   * whoever decides an env's class (step_kernel_v2 at the end of the env's step; classify_state_kernel after a reset /
+//     set_state / rollout) stores the class byte and adds 1 to the (class, chunk) and (class, super-chunk) counters of the
+//     NEXT sequence -- one warp-aggregated integer reduction per distinct (class, chunk) in the warp (deterministic: sums);
+//   * close_kernel, the second and last launch of a step, turns that into the sequence: scatter CTA b sums the counters in
+//     front of chunk b (exclusive prefix, two levels), ranks its chunk's 1,024 class bytes with ballots and writes the env
+//     ids to their global positions.  No sort, no scan pass, no last-CTA tail: ~3 us for 262,144 envs.
+// The counters are double-buffered by a parity P kept ON THE DEVICE (st.counter[CTR_PAR]; a host-side parity would be baked into a
+// captured CUDA graph): the current sequence was built from buffer P, the step kernel adds into P ^ 1, close_kernel reads
+// P ^ 1 and clears P, and the last CTA of close_kernel to finish flips P.
+//
+// An env whose episode ended gets class 2 for the next sequence (a fresh env starts at z = 1 m); it is re-initialised by the
+// reset CTAs of close_kernel.
+__device__ __forceinline__ void count_class(const DevState &st, int buf, bool live, long long env, int cls) {
+    // lanes of the warp with the same (chunk, class) elect a leader, which adds their number to both counter levels
+    const int chunk = (int)(env / TVC_CHUNK);
+    const int key = live ? (chunk * 4 + cls) : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (live && (int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+        const int cnt = __popc(peers);
+        int *cc = st.ccount + (long long)buf * 3 * st.nchunks, *sc = st.scount + buf * 3 * st.nsuper;
+        atomicAdd(cc + (long long)cls * st.nchunks + chunk, cnt);
+        atomicAdd(sc + cls * st.nsuper + chunk / TVC_SUPER, cnt);
+    }
+}
+
+// Classes from the state planes (80 B per env): first step, or a reset / set_state / rollout / curriculum change moved the
+// envs behind the step path's back.  Writes the class bytes and adds to the counters (both buffers zeroed by the host before).
+template <bool X>
+__global__ void __launch_bounds__(256)
+classify_state_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState st) {
+    const long long env = (long long)blockIdx.x * 256 + threadIdx.x;
+    const bool live = env < st.n;
+    int cls = 2;
+    if (live) {
+        const float4 p = st.s0[env], q = st.s1[env], v = st.s2[env], w = st.s3[env];
+        cls = class_of(c, X, p.z, q.x, q.y, q.z, q.w, v.z, w.x, w.y, w.z, X ? st.d0[env].z : 0.0f);
+        st.cls[env] = (uint8_t)cls;
+    }
+    count_class(st, (int)st.counter[CTR_PAR] ^ 1, live, live ? env : 0, cls);   // like a step: the buffer the following close_kernel reads
+}
+
+// One warp writes chunk b's part of the next sequence: the exclusive prefix of the chunk (super-chunks in front, then the
+// chunks of its own super-chunk) and the class totals from the counters of buffer `buf`, then 32 rounds of 32 class bytes
+// ranked with ballots.  Clears the chunk's counters of the other buffer (the next step adds there).
+__device__ __forceinline__ void scatter_chunk(const DevState &st, int b, int buf, int lane) {
+    const unsigned full = 0xffffffffu;
+    const int nc = st.nchunks, ns = st.nsuper, sup = b / TVC_SUPER;
+    const int *cc = st.ccount + (long long)buf * 3 * nc, *sc = st.scount + buf * 3 * ns;
+    long long pos[3];
+    {
+        int pre[3], tot[3];
 #pragma unroll
-        for (int j = 0; j < TVC_EPT; j++) {
-            const int li = j * TVC_CLS_THREADS + tid;
-            const long long env = base + li;
-            const int cl = env < st.n ? (int)st.cls[env] : 3;
-            s_cls[li] = (uint8_t)cl;
-            const unsigned dm = __ballot_sync(0xffffffffu, cl == 0xFF);
-            if (dm) {
-                int pos = 0;
-                if (lane == 0) pos = atomicAdd(&s_ndone, __popc(dm));
-                pos = __shfl_sync(0xffffffffu, pos, 0);
-                if (cl == 0xFF) s_done[pos + __popc(dm & ((1u << lane) - 1u))] = (unsigned short)li;
-            }
+        for (int k = 0; k < 3; k++) {
+            int p = 0, t = 0;
+            for (int s0 = lane; s0 < ns; s0 += 32) { const int v = __ldcg(sc + k * ns + s0); t += v; if (s0 < sup) p += v; }
+            for (int ch = sup * TVC_SUPER + lane; ch < b; ch += 32) p += __ldcg(cc + (long long)k * nc + ch);
+            pre[k] = __reduce_add_sync(full, p); tot[k] = __reduce_add_sync(full, t);
         }
-        __syncthreads();
-        for (int k = tid; k < s_ndone; k += TVC_CLS_THREADS) {   // list order is arbitrary, results are not
-            const int li = s_done[k];
-            const long long i = base + li, gid = c.env_base + i;
+        pos[0] = pre[0]; pos[1] = (long long)tot[0] + pre[1]; pos[2] = (long long)tot[0] + tot[1] + pre[2];
+        if (b == 0 && lane < 3) st.totals[lane] = lane == 0 ? tot[0] : (lane == 1 ? tot[1] : tot[2]);
+    }
+    const long long base = (long long)b * TVC_CHUNK;
+    static_assert(TVC_CHUNK == 1024, "a lane holds the class bytes of 32 envs of the chunk");
+    int cl[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) {      // all 32 byte loads of the lane in flight at once (one round trip)
+        const long long env = base + j * 32 + lane;
+        cl[j] = env < st.n ? (int)__ldcg(st.cls + env) : 3;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        const long long env = base + j * 32 + lane;
+        const unsigned m0 = __ballot_sync(full, cl[j] == 0), m1 = __ballot_sync(full, cl[j] == 1), m2 = __ballot_sync(full, cl[j] == 2);
+        const unsigned mk = cl[j] == 0 ? m0 : (cl[j] == 1 ? m1 : m2);
+        const long long at = (cl[j] == 0 ? pos[0] : (cl[j] == 1 ? pos[1] : pos[2])) + __popc(mk & ((1u << lane) - 1u));
+        if (cl[j] < 3) st.order[at] = (int)env;
+        pos[0] += __popc(m0); pos[1] += __popc(m1); pos[2] += __popc(m2);
+    }
+    if (lane < 3) {
+        st.ccount[(long long)(buf ^ 1) * 3 * nc + (long long)lane * nc + b] = 0;
+        if (b % TVC_SUPER == 0) st.scount[(buf ^ 1) * 3 * ns + lane * ns + sup] = 0;
+    }
+}
+
+// What the last CTA of close_kernel does before it leaves: hand the counters over to the next step.
+__device__ __forceinline__ void hand_over(const DevState &st, int count_step) {
+    st.counter[CTR_TICKET] = 0u;
+    st.counter[CTR_QUEUE] = 0u;                            // work-queue head of the next step kernel
+    st.counter[CTR_DONE] = 0u;                             // the done list is consumed
+    st.counter[CTR_PAR] ^= 1u;                             // the sequence now in st.order was built from the other buffer
+    if (count_step) st.counter[CTR_STEPS] += 1u;           // steps since the statistics were reset
+}
+
+// The second and last launch of a step (also follows classify_state_kernel).  CTAs [0, nreset): same-step autoreset -- one
+// env of st.done_list per thread, full warps (ref:381-464 reset + the reset observation over the terminal one; the terminal
+// state was stored by the step kernel and every Env field round-trips through store_env / load_env, so this equals resetting
+// in place); grid-stride, so any number of episodes may end in one step.  CTAs [nreset, ...): one warp per chunk of the next
+// sequence (scatter_chunk).  The last CTA to finish hands the counters to the next step.
+template <bool X>
+__global__ void __launch_bounds__(128)
+close_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState st, float *obs, int nreset, int count_step) {
+    const int lane = threadIdx.x & 31;
+    asm volatile("griddepcontrol.wait;" ::: "memory");              // behind step_kernel_v2 / classify_state_kernel
+    asm volatile("griddepcontrol.launch_dependents;");              // the next step kernel may be scheduled; it waits for this grid
+    if ((int)blockIdx.x < nreset) {
+        const unsigned ndone = st.counter[CTR_DONE];
+        for (unsigned k = blockIdx.x * 128u + threadIdx.x; k < ndone; k += (unsigned)nreset * 128u) {
+            const long long i = st.done_list[k], gid = c.env_base + i;
             Env e;
             load_env(st, X, i, e);
             reset_env(c, X, gid, e, false);
             store_env(st, X, i, e);
-            const uint8_t nc_ = (uint8_t)class_of(c, X, e.pz, e.qx, e.qy, e.qz, e.qw, e.vz, e.wx, e.wy, e.wz, e.cg_off);
-            s_cls[li] = nc_;
-            st.cls[i] = nc_;   // never leave a stale "reset me" mark behind
             float o[10];
             build_obs(c, X, gid, e, 0, o);
             float2 *o2 = reinterpret_cast<float2 *>(obs + 10 * i);
 #pragma unroll
             for (int q = 0; q < 5; q++) o2[q] = make_float2(o[2 * q], o[2 * q + 1]);
         }
-        __syncthreads();
-    }
-    unsigned mask[3][TVC_EPT];
-#pragma unroll
-    for (int j = 0; j < TVC_EPT; j++) {
-        const long long env = base + j * TVC_CLS_THREADS + tid;
-        int cls = 3;
-        if (env < st.n) {
-            if (FROM_STATE) {
-                const float4 p = st.s0[env], q = st.s1[env], v = st.s2[env], w = st.s3[env];
-                cls = class_of(c, X, p.z, q.x, q.y, q.z, q.w, v.z, w.x, w.y, w.z, X ? st.d0[env].z : 0.0f);
-            } else if (RESET) cls = s_cls[j * TVC_CLS_THREADS + tid];
-            else cls = st.cls[env];
-        }
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            mask[k][j] = __ballot_sync(0xffffffffu, cls == k);
-            if (lane == 0) wcnt[k][j][warp] = __popc(mask[k][j]);
-        }
+    } else {
+        const int b = (int)((blockIdx.x - nreset) * 4 + (threadIdx.x >> 5));
+        const int buf = (int)st.counter[CTR_PAR] ^ 1;      // the buffer the step kernel (or classify_state_kernel) just filled
+        if (b < st.nchunks) scatter_chunk(st, b, buf, lane);
     }
     __syncthreads();
-    // exclusive prefix of the 32 (j, warp) counts of each class: warp k scans class k (TVC_CHUNK / 32 == 32 entries)
-    static_assert(TVC_EPT * TVC_CLS_WARPS == 32, "one warp scans the per-warp counts of a chunk");
-    if (warp < 3) {
-        const int cnt = wcnt[warp][lane / TVC_CLS_WARPS][lane % TVC_CLS_WARPS];
-        int v = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += u; }
-        s_pre[warp][lane] = v - cnt;
-        if (lane == 31) {
-            s_tot[warp] = v;
-            st.goff[warp * (nc + 1) + blockIdx.x + 1] = v;   // per-chunk count; the last CTA to arrive scans them
-            __threadfence();
-        }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&st.counter[CTR_TICKET], 1u) == gridDim.x - 1u) hand_over(st, count_step);
     }
-    __syncthreads();
-    const int t0c = s_tot[0], t1c = s_tot[1];
-#pragma unroll
-    for (int j = 0; j < TVC_EPT; j++) {
-        const long long env = base + j * TVC_CLS_THREADS + tid;
-        if (env < st.n) {
-            const int k = (mask[0][j] >> lane) & 1u ? 0 : ((mask[1][j] >> lane) & 1u ? 1 : 2);
-            const unsigned mk = k == 0 ? mask[0][j] : (k == 1 ? mask[1][j] : mask[2][j]);
-            // envs of the same class ahead of this one in linear order (j, warp, lane)
-            const int rank = s_pre[k][j * TVC_CLS_WARPS + warp] + __popc(mk & ((1u << lane) - 1u));
-            const int start = k == 0 ? 0 : (k == 1 ? t0c : t0c + t1c);
-            st.order[base + start + rank] = (int)env;
-        }
-    }
-    asm volatile("griddepcontrol.launch_dependents;");   // step_kernel_v2 may be scheduled; it waits for this whole grid
-    if (tid == 0) s_last = (atomicAdd(&st.counter[1], 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    for (int k = 0; k < 3; k++) {
-        volatile int *o = st.goff + k * (nc + 1);
-        int carry = 0;
-        for (int t0 = 0; t0 < nc; t0 += TVC_CLS_THREADS) {
-            const int idx = t0 + tid;
-            int v = idx < nc ? o[idx + 1] : 0;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += u; }
-            if (lane == 31) s_scan[warp] = v;
-            __syncthreads();
-            int wbase = 0, tile = 0;
-#pragma unroll
-            for (int w = 0; w < TVC_CLS_WARPS; w++) { const int sv = s_scan[w]; if (w < warp) wbase += sv; tile += sv; }
-            if (idx < nc) o[idx + 1] = carry + wbase + v;
-            carry += tile;
-            __syncthreads();
-        }
-        if (tid == 0) o[0] = 0;
-    }
-    if (tid == 0) { st.counter[0] = 0u; st.counter[1] = 0u; if (!FROM_STATE) st.counter[2] += 1u; }   // [2]: steps since the statistics were reset
-}
-
-// Position p of the global class-ordered sequence -> env id (binary search over the chunk scans of p's class).
-__device__ __forceinline__ int env_at(const DevState &st, int p) {
-    const int nc = st.nchunks;
-    const int *g0 = st.goff, *g1 = st.goff + (nc + 1), *g2 = st.goff + 2 * (nc + 1);
-    const int T0 = g0[nc], T1 = g1[nc];
-    const int k = p < T0 ? 0 : (p < T0 + T1 ? 1 : 2);
-    const int q = p - (k == 0 ? 0 : (k == 1 ? T0 : T0 + T1));
-    const int *o = k == 0 ? g0 : (k == 1 ? g1 : g2);
-    int lo = 0, hi = nc;   // o[lo] <= q < o[hi]
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (o[mid] <= q) lo = mid; else hi = mid;
-    }
-    int intra = q - o[lo];
-    if (k >= 1) intra += g0[lo + 1] - g0[lo];
-    if (k == 2) intra += g1[lo + 1] - g1[lo];
-    return st.order[(long long)lo * TVC_CHUNK + intra];
-}
-
-// The same lookup for the 32 consecutive positions of one group, warp-cooperatively: the lanes probe 32 chunk boundaries
-// per round trip (two rounds for 1,024 chunks instead of ten dependent loads per lane), then every lane walks forward
-// from the chunk of the group's first position.  A group that straddles a class boundary takes the per-lane search.
-__device__ __forceinline__ int env_at_group(const DevState &st, int p, int lane, bool valid) {
-#ifdef TVC_NO_COOP_SEARCH
-    return valid ? env_at(st, p) : 0;
-#else
-    const unsigned full = 0xffffffffu;
-    const int nc = st.nchunks;
-    const int *g0 = st.goff, *g1 = st.goff + (nc + 1), *g2 = st.goff + 2 * (nc + 1);
-    const int T0 = g0[nc], T1 = g1[nc];
-    const int k = p < T0 ? 0 : (p < T0 + T1 ? 1 : 2);
-    const int k0 = __shfl_sync(full, k, 0);
-    if (!__all_sync(full, k == k0 || !valid)) return valid ? env_at(st, p) : 0;
-    const int q = p - (k0 == 0 ? 0 : (k0 == 1 ? T0 : T0 + T1));
-    const int q0 = __shfl_sync(full, q, 0);
-    const int *o = k0 == 0 ? g0 : (k0 == 1 ? g1 : g2);
-    int lo = 0, hi = nc;   // o[lo] <= q0 < o[hi]
-    while (hi - lo > 1) {
-        const int step = (hi - lo + 31) >> 5;
-        int idx = lo + step * (lane + 1);
-        idx = idx > hi ? hi : idx;
-        const int m = __popc(__ballot_sync(full, o[idx] <= q0));   // probes are monotone in the lane index
-        int nlo = lo + step * m, nhi = lo + step * (m + 1);
-        lo = nlo > hi ? hi : nlo;
-        hi = nhi > hi ? hi : nhi;
-    }
-    if (!valid) return 0;
-    int ch = lo, end = o[ch + 1];
-    while (q >= end) { ch++; end = o[ch + 1]; }   // valid positions lie below o[nc]
-    int intra = q - o[ch];
-    if (k0 >= 1) intra += g0[ch + 1] - g0[ch];
-    if (k0 == 2) intra += g1[ch + 1] - g1[ch];
-    return st.order[(long long)ch * TVC_CHUNK + intra];
-#endif
 }
 
 #ifndef TVC_MIN_BLOCKS_V2
@@ -241,66 +177,49 @@ __device__ __forceinline__ int env_at_group(const DevState &st, int p, int lane,
 #ifndef TVC_V2_BLOCK
 #define TVC_V2_BLOCK 128
 #endif
-// -DTVC_V2_LOCKSTEP: a CTA pulls four consecutive groups at once and its warps re-align at every substep (shared instruction
-// fetches).  That won 7 % while the kernel was 92 KB of code with every contact row always visited (0.1767 -> 0.164 ms); with
-// the class-ordered sequence, the lazy rows and 57 KB of code the barrier costs more than the instruction cache gains:
-// 0.0947 ms with it, 0.0925 ms without.  Default: every warp pulls its own groups and never waits for another warp.
-// Finished envs are never reset here: they are marked for the sort kernel that closes the step (see below).  An in-place
-// reset for small batches existed as a second template instantiation; nvcc contracted the solver's FMAs differently in the
-// two, so the two launch plans differed in the last bit of contact steps -- one instantiation per configuration cannot.
-// A split into an airborne-part kernel at twice the occupancy (64 registers, solver out of line) followed by a near-ground
-// kernel was measured: 0.150 ms against 0.125 ms for this single kernel -- the FP32-pipe-bound solver warps and the
-// latency-bound airborne warps hide each other only when they share the SM sub-partitions.
+
+// The hot kernel: a persistent grid (TVC_MIN_BLOCKS_V2 CTAs of TVC_V2_BLOCK threads per SM); every warp pulls 32-env groups
+// of the class-ordered sequence from an atomic queue on its own and never waits for another warp.  One thread = one env for
+// the whole step (K substeps, contact solve inline), state in registers between one load and one store.
+//
+// Same-step autoreset is deferred to close_kernel.  ~1 env in 38 ends its episode per step: resetting it where it ends made
+// 1-2 lanes per warp walk through three Philox blocks, the per-episode draws and a second observation (10 % of the kernel's
+// warp-instructions at 1.7 live lanes).  Instead the warp stores the terminal state and observation and appends the env to
+// st.done_list (one atomic per group that has such lanes, issued under the group's stores).
+// An in-place reset for small batches existed as a second template instantiation; nvcc contracted the solver's FMAs
+// differently in the two, so the two launch plans differed in the last bit of contact steps -- one instantiation per
+// configuration cannot.  Measured and rejected: resets and the next sequence in the kernel's own tail by warps that ran out
+// of work (one launch per step, correct, but 0.21 ms: the last groups in flight took 140 us instead of 14 while idle warps
+// of their CTAs polled the list -- with a poll interval of 128 ns or of 4 us alike, fewer pollers less); a per-substep CTA
+// barrier that keeps a CTA's warps on the same instruction lines (won 7 % when the kernel was 92 KB of code, loses 2 % now);
+// an airborne-part kernel at twice the occupancy followed by a near-ground kernel (0.150 ms against 0.125 ms at the time);
+// 5 or 6 CTAs per SM with spills (0.098 / 0.102 ms against 0.089).
 template <bool X, int DIV, bool FOLLOW>
 __global__ void __launch_bounds__(TVC_V2_BLOCK, TVC_MIN_BLOCKS_V2)
 step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevState st, const __grid_constant__ DevIO io) {
-    // launched with programmatic stream serialization: everything above this line may overlap classify_kernel's tail
+    // launched with programmatic stream serialization: everything above this line may overlap close_kernel's tail
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
     const int ngroups = (int)((st.n + 31) / 32);
-    const int g_base = 0;
-    unsigned *const queue = &st.counter[0];
-#ifdef TVC_V2_LOCKSTEP
-    __shared__ int s_g0;
-#endif
+    unsigned *const queue = &st.counter[CTR_QUEUE];
+    const int par = (int)st.counter[CTR_PAR];    // parity of the counter buffers (device-side: see close_kernel)
 #ifdef TVC_PHASE_PROF2
     long long pt_prev = clock64();
 #endif
     bool first_pull = true;
-    (void)first_pull;
     int g_next = 0;
-    (void)g_next;
     for (;;) {
         int g = 0;
-#ifdef TVC_V2_LOCKSTEP
-        // a CTA pulls its warps' worth of consecutive (same-class) groups and the warps re-align at every substep, so that
-        // they fetch the same instruction lines: ncu shows the GPC instruction cache at 80 % of its request rate and a
-        // 76 % hit rate in the SM instruction cache when 16 warps per SM wander through the ~57 KB kernel on their own
-        __syncthreads();
-        if (threadIdx.x == 0) s_g0 = g_base + (int)atomicAdd(queue, (unsigned)(TVC_V2_BLOCK / 32));
-        __syncthreads();
-        if (s_g0 >= ngroups) break;
-        g = s_g0 + (threadIdx.x >> 5);
-        const long long slot = (long long)g * 32 + lane;
-#ifdef TVC_DBG   // timing experiments only (env TVC_DBG_ONLY): 0 = only the in-contact / may-touch groups, 1 = only the airborne groups
-        const int near_end = st.goff[st.nchunks] + st.goff[2 * st.nchunks + 1];
-        const bool skip = c.dbg_only == 0 ? (slot >= near_end) : (c.dbg_only == 1 ? (slot + 31 < near_end) : false);
-        const bool live = g < ngroups && slot < st.n && !skip;
-#else
-        const bool live = g < ngroups && slot < st.n;
-#endif
-#else
         // every warp's first group is its own index (no atomic: 2,368 warps hitting one counter at t = 0 showed up as 6 % of
-        // the stall samples); after that a dynamic queue over the remaining 32-env groups of the sorted sequence
+        // the stall samples); after that a dynamic queue over the remaining 32-env groups of the sequence
         if (first_pull) {
-            g = g_base + (int)(blockIdx.x * (TVC_V2_BLOCK / 32) + (threadIdx.x >> 5));
+            g = (int)(blockIdx.x * (TVC_V2_BLOCK / 32) + (threadIdx.x >> 5));
             first_pull = false;
         } else g = __shfl_sync(full, g_next, 0);   // pulled while the previous group was in its second half (below)
         if (g >= ngroups) break;
         const long long slot = (long long)g * 32 + lane;
         const bool live = slot < st.n;
-#endif
         int done = 0, viol = 0;
         int ev_len = 0, ev_succ = 0, ev_reason = 0, ev_trunc = 0;
         float ev_ret = 0.0f, ev_alt = 0.0f, ev_tilt = 0.0f, ev_fuel = 0.0f;
@@ -312,10 +231,10 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
         const long long pt0 = clock64();
         Ph2 ph2s = {0u, 0u, 0u}; Ph2 *ph2 = &ph2s;
 #endif
-        i = env_at_group(st, (int)slot, lane, live);
         if (live) {
+            i = st.order[slot];   // the sequence is a flat array: one coalesced load
             gid = c.env_base + i;
-            load_env(st, X, i, e);
+            load_env<false>(st, X, i, e);
             float2 a;
             if (io.actions) a = io.actions[i];
             else {
@@ -324,27 +243,18 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
             }
             if (io.actions_out) io.actions_out[i] = a;
             env_pre<X>(c, st, i, e, a.x, a.y, P, f);
-        } else {
-            memset(&e, 0, sizeof(e));
-            e.qw = 1.0f; e.pz = 1.0f;
-            P = body_params(c, false, 1.0f, 0.0f, 1.0f);
-            f.Fx = f.Fy = f.Fz = f.Tx = f.Ty = f.Tz = f.a0 = f.a1 = f.fl0 = f.fl1 = f.fl2 = f.arm = 0.0f;
         }
         PH2_CLK(pt1);
-#ifdef TVC_V2_LOCKSTEP
-        integrate_thread<true, FOLLOW>(c, P, e, f PH2_PASS);
-#else
         if (live) integrate_thread<false, FOLLOW>(c, P, e, f PH2_PASS);
-#endif
         PH2_CLK(pt2);
-#ifndef TVC_V2_LOCKSTEP
         // the next group of the sequence: the atomic's round trip (~1 us with 2,368 warps on one counter) runs under this
         // group's second half instead of stalling the warp at the top of the loop
-        if (lane == 0) g_next = g_base + (int)(gridDim.x * (TVC_V2_BLOCK / 32)) + (int)atomicAdd(queue, 1u);
-#endif
+        if (lane == 0) g_next = (int)(gridDim.x * (TVC_V2_BLOCK / 32)) + (int)atomicAdd(queue, 1u);
         if (live) {
             StepResult r;
             env_post<X, DIV>(c, st, i, gid, e, f.a0, f.a1, r);
+            viol = r.viol;
+            done = r.terminated | r.truncated;
             io.reward[i] = r.reward;
             io.term[i] = (uint8_t)r.terminated;
             io.trunc[i] = (uint8_t)r.truncated;
@@ -361,8 +271,6 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
 #pragma unroll
                 for (int k = 0; k < 12; k++) io.comp[12 * i + k] = r.comp[k];
             }
-            viol = r.viol;
-            done = r.terminated | r.truncated;
             if (done) {
                 ev_len = e.step; ev_succ = e.success; ev_reason = r.reason; ev_trunc = r.truncated;
                 ev_ret = e.ep_ret; ev_alt = r.alt; ev_tilt = r.tilt; ev_fuel = r.fuel;
@@ -373,22 +281,29 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
                 }
             }
             store_env(st, X, i, e);
-            // class byte for the next step's sort; 0xFF = "episode ended, reset me" (consumed by the sort kernel)
-            st.cls[i] = (done && c.autoreset) ? (uint8_t)0xFF
-                        : (uint8_t)class_of(c, X, e.pz, e.qx, e.qy, e.qz, e.qw, e.vz, e.wx, e.wy, e.wz, e.cg_off);
             float2 *o2 = reinterpret_cast<float2 *>(io.obs + 10 * i);
 #pragma unroll
             for (int k = 0; k < 5; k++) o2[k] = make_float2(r.obs[2 * k], r.obs[2 * k + 1]);
         }
-        // Same-step autoreset is deferred: ~1 env in 38 ends its episode per step, i.e. 1-2 lanes per warp would walk
-        // through the per-episode Philox draws and a second observation here (10 % of this kernel's warp-instructions
-        // at 1.7 live lanes).  The terminal state and observation are stored above and the env is marked in its class
-        // byte; the sort kernel that closes the step (classify_kernel<X, false, true>) compacts the marked envs of its
-        // chunk, re-initialises them and overwrites their observation rows before it sorts.
+        {   // the env's place in the NEXT sequence: class byte + (class, chunk) counters; an env whose episode ended goes to the
+            // done list (close_kernel re-initialises it) and is airborne in the next sequence (a fresh env starts at z = 1 m)
+            const bool relist = live && done && c.autoreset;
+            const unsigned rm = __ballot_sync(full, relist);
+            int rbase = 0;
+            if (rm && lane == 0) rbase = (int)atomicAdd(&st.counter[CTR_DONE], (unsigned)__popc(rm));
+            int cl = 2;
+            if (live && !relist) cl = class_of(c, X, e.pz, e.qx, e.qy, e.qz, e.qw, e.vz, e.wx, e.wy, e.wz, e.cg_off);
+            if (live) st.cls[i] = (uint8_t)cl;
+            count_class(st, par ^ 1, live, i, cl);   // the buffer the close_kernel of THIS step reads
+            if (rm) {
+                rbase = __shfl_sync(full, rbase, 0);
+                if (relist) st.done_list[rbase + __popc(rm & ((1u << lane) - 1u))] = (int)i;
+            }
+        }
 #ifdef TVC_PHASE_PROF2
         {
             const long long pt3 = clock64();
-            const int cls = ((long long)g * 32 < (long long)st.goff[st.nchunks] + st.goff[2 * st.nchunks + 1]) ? 0 : 1;   // by position, any MODE
+            const int cls = ((long long)g * 32 < (long long)st.totals[0] + st.totals[1]) ? 0 : 1;   // by position
             const unsigned tot = (unsigned)(pt2 - pt1);
             const unsigned v1 = __reduce_max_sync(full, (unsigned)(pt1 - pt0)), v3 = __reduce_max_sync(full, ph2s.setup);
             const unsigned v4 = __reduce_max_sync(full, ph2s.sweeps), v5 = __reduce_max_sync(full, (unsigned)(pt3 - pt2));
@@ -430,7 +345,7 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
             }
             // the row has exactly one writer per launch (this group), so the order-free reduction is still deterministic; as a
             // reduction it does not make the warp wait for the old value (the read-modify-write stalled on a DRAM round trip)
-            if (lane < 14 && v != 0.0 && g < ngroups) atomicAdd(&st.partial[(long long)g * TVC_NSTAT + lane], v);
+            if (lane < 14 && v != 0.0) atomicAdd(&st.partial[(long long)g * TVC_NSTAT + lane], v);
         }
     }
 }
@@ -705,8 +620,13 @@ int tvc_create(const tvc_config *cfg, int device, int64_t num_envs, tvc_handle *
     TRY(dalloc(&s.partial, (size_t)h->ngroups * TVC_NSTAT));
     TRY(dalloc(&s.order, n));
     s.nchunks = (int)((num_envs + TVC_CHUNK - 1) / TVC_CHUNK);
-    TRY(dalloc(&s.goff, (size_t)3 * (s.nchunks + 1)));
-    TRY(dalloc(&s.counter, (size_t)4));
+    s.nsuper = (s.nchunks + TVC_SUPER - 1) / TVC_SUPER;
+    TRY(dalloc(&s.ccount, (size_t)2 * 3 * s.nchunks));
+    TRY(dalloc(&s.scount, (size_t)2 * 3 * s.nsuper));
+    TRY(dalloc(&s.done_list, n));
+    { cudaError_t e_ = cudaMemset(s.done_list, 0xFF, n * sizeof(int)); if (e_ != cudaSuccess) { tvc_set_err(cudaGetErrorString(e_)); tvc_destroy(h); return TVC_E_CUDA; } }   // -1 = empty slot
+    TRY(dalloc(&s.totals, (size_t)4));
+    TRY(dalloc(&s.counter, (size_t)CTR_WORDS));
     TRY(dalloc(&s.cls, n));
     TRY(dalloc(&h->stats_dev, (size_t)TVC_NSTAT));
     {
@@ -731,7 +651,7 @@ int tvc_destroy(tvc_handle *h) {
     DevState &s = h->st;
     cudaFree(s.s0); cudaFree(s.s1); cudaFree(s.s2); cudaFree(s.s3); cudaFree(s.s4);
     cudaFree(s.d0); cudaFree(s.d1); cudaFree(s.ring); cudaFree(s.clipb); cudaFree(s.runb); cudaFree(s.hist);
-    cudaFree(s.delay); cudaFree(s.partial); cudaFree(s.order); cudaFree(s.goff); cudaFree(s.counter); cudaFree(s.cls); cudaFree(h->stats_dev);
+    cudaFree(s.delay); cudaFree(s.partial); cudaFree(s.order); cudaFree(s.ccount); cudaFree(s.scount); cudaFree(s.done_list); cudaFree(s.totals); cudaFree(s.counter); cudaFree(s.cls); cudaFree(h->stats_dev);
     cudaFree(h->io_act); cudaFree(h->io_obs) /* the obs|reward|flags slab */; cudaFree(h->io_final);
     tvc_rollout_free(h);
     if (h->stats_host) cudaFreeHost(h->stats_host);
@@ -763,10 +683,16 @@ static int launch_step(tvc_handle *h, const DevIO &io, cudaStream_t s) {
     const int dv = h->cur.diversity_mode;
     {
         const int cgrid = h->st.nchunks;
-        if (!h->order_valid) {   // first step, or the state was changed behind the step path's back: sort from the state planes
-            if (X) classify_kernel<true, true, false><<<cgrid, TVC_CLS_THREADS, 0, s>>>(h->dc, h->st, nullptr);
-            else classify_kernel<false, true, false><<<cgrid, TVC_CLS_THREADS, 0, s>>>(h->dc, h->st, nullptr);
-            LAUNCH_OK("classify_kernel");
+        if (!h->order_valid) {   // first step, or the state was changed behind the step path's back: classes from the state planes
+            CUDA_OK(cudaMemsetAsync(h->st.ccount, 0, sizeof(int) * 2 * 3 * (size_t)h->st.nchunks, s));
+            CUDA_OK(cudaMemsetAsync(h->st.scount, 0, sizeof(int) * 2 * 3 * (size_t)h->st.nsuper, s));
+            const int g256 = (int)((h->n + 255) / 256);
+            if (X) classify_state_kernel<true><<<g256, 256, 0, s>>>(h->dc, h->st);
+            else classify_state_kernel<false><<<g256, 256, 0, s>>>(h->dc, h->st);
+            LAUNCH_OK("classify_state_kernel");
+            if (X) close_kernel<true><<<(cgrid + 3) / 4, 128, 0, s>>>(h->dc, h->st, nullptr, 0, 0);
+            else close_kernel<false><<<(cgrid + 3) / 4, 128, 0, s>>>(h->dc, h->st, nullptr, 0, 0);
+            LAUNCH_OK("close_kernel (from state)");
         }
         if (h->v2_grid == 0) {   // persistent grid: resident CTAs of the v2 kernel, capped by the number of groups
             int per_sm = 0;
@@ -785,17 +711,14 @@ static int launch_step(tvc_handle *h, const DevIO &io, cudaStream_t s) {
                         else (void)launch_dep(step_kernel_v2<XX, DD, false>, h->v2_grid, TVC_V2_BLOCK, s, h->pdl, h->dc, h->st, io); } while (0)
         if (X) { if (dv == 0) GO(true, 0); else if (dv == 1) GO(true, 1); else GO(true, 2); }
         else   { if (dv == 0) GO(false, 0); else if (dv == 1) GO(false, 1); else GO(false, 2); }
-        const bool defer = h->cur.autoreset != 0;   // the closing sort kernel re-initialises the envs the step kernel marked
-        LAUNCH_OK("step_kernel_v2");
-        // close the step: (reset the finished envs of every chunk and) sort for the next step from the class bytes
-        if (defer) {
-            if (X) (void)launch_dep(classify_kernel<true, false, true>, cgrid, TVC_CLS_THREADS, s, h->pdl, h->dc, h->st, io.obs);
-            else (void)launch_dep(classify_kernel<false, false, true>, cgrid, TVC_CLS_THREADS, s, h->pdl, h->dc, h->st, io.obs);
-        } else {
-            if (X) (void)launch_dep(classify_kernel<true, false, false>, cgrid, TVC_CLS_THREADS, s, h->pdl, h->dc, h->st, io.obs);
-            else (void)launch_dep(classify_kernel<false, false, false>, cgrid, TVC_CLS_THREADS, s, h->pdl, h->dc, h->st, io.obs);
+        {   // close the step: reset CTAs (one env of the done list per thread for twice the expected n / 38 finished episodes; more
+            // are walked grid-stride) + one warp per chunk of the next sequence, one launch
+            int nreset = 0;
+            if (h->cur.autoreset) { nreset = (int)((h->n + 16 * 128 - 1) / (16 * 128)); if (nreset > 4 * h->num_sms) nreset = 4 * h->num_sms; }
+            if (X) (void)launch_dep(close_kernel<true>, nreset + (cgrid + 3) / 4, 128, s, h->pdl, h->dc, h->st, io.obs, nreset, 1);
+            else (void)launch_dep(close_kernel<false>, nreset + (cgrid + 3) / 4, 128, s, h->pdl, h->dc, h->st, io.obs, nreset, 1);
+            LAUNCH_OK("close_kernel (end of step)");
         }
-        LAUNCH_OK("classify_kernel (end of step)");
         h->order_valid = true;
 #undef GO
     }
@@ -966,7 +889,7 @@ int tvc_episode_stats_dev(tvc_handle *h, double *dev_out, int reset_after, tvc_s
     CHECK_H(h);
     if (!dev_out) { tvc_set_err("dev_out is NULL"); return TVC_E_BADARG; }
     // the step count lives on the device (bumped by the kernel that closes a step), so that CUDA-graph replays count too
-    stats_reduce_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(h->st.partial, h->ngroups, dev_out, h->st.counter + 2, (double)h->n, reset_after);
+    stats_reduce_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(h->st.partial, h->ngroups, dev_out, h->st.counter + CTR_STEPS, (double)h->n, reset_after);
     LAUNCH_OK("stats_reduce_kernel");
     return TVC_OK;
 }

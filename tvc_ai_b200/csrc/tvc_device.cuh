@@ -55,13 +55,24 @@ struct DevState {
     float *hist;      // [1000][N] exact diversity only
     float2 *delay;    // [TVC_MAX_DELAY][N] X: actuator delay ring, slot = step % delay
     double *partial;  // [ceil(N/32)][16] episode statistics rows: one owner (CTA or 32-env group) per row per launch
-    int *order;       // [N] env ids sorted per 1024-env chunk by class: in contact, may touch, airborne (classify_kernel)
-    int *goff;        // [3][nchunks + 1] exclusive scans over the chunks of the per-chunk class counts (goff[c][0] = 0)
-    unsigned *counter;  // [0] work-queue head of step_kernel_v2 (zeroed by classify_kernel), [1] classify_kernel's ticket
-    uint8_t *cls;       // [N] class of every env for the next step's sort (written by step_kernel_v2; 0xFF = reset me)
-    int nchunks;
+    int *order;       // [N] the class-ordered work sequence: env ids, all of class 0 (in contact), then 1 (may touch), then 2 (airborne)
+    int *ccount;      // [2][3][nchunks] envs of each class per 1,024-env chunk in the NEXT sequence (double-buffered by the parity counter[5])
+    int *scount;      // [2][3][nsuper]  the same per super-chunk (256 chunks)
+    int *done_list;   // [N] envs whose episode ended in this step (re-initialised by close_kernel's reset CTAs)
+    int *totals;      // [3] class totals of the current sequence (diagnostics)
+    unsigned *counter;  // CTR_* words (below), one cache line each
+    uint8_t *cls;       // [N] class of every env in the next sequence (written by whoever moved the env last)
+    int nchunks, nsuper;
     long long n;
 };
+
+// words of DevState::counter, one 128-byte line each (the queue pulls of the step kernel do not share a line with anything)
+enum { CTR_QUEUE = 0,      // work-queue head of step_kernel_v2
+       CTR_TICKET = 32,    // close_kernel: CTAs that have finished
+       CTR_STEPS = 64,     // steps since the statistics were reset
+       CTR_DONE = 96,      // length of done_list
+       CTR_PAR = 128,      // parity of ccount / scount
+       CTR_WORDS = 160 };
 
 struct DevIO {
     const float2 *actions;
@@ -685,8 +696,12 @@ __device__ __forceinline__ void build_obs(const DevCfg &c, bool X, long long gid
     }
 }
 
+// CG: L1-bypassing loads (ld.global.cg) for an env another SM stored during the same launch (reset workers of step_kernel_v2)
+template <bool CG = false>
 __device__ __forceinline__ void load_env(const DevState &st, bool X, long long i, Env &e) {
-    float4 a = st.s0[i], b = st.s1[i], c = st.s2[i], d = st.s3[i], f = st.s4[i];
+    float4 a, b, c, d, f;
+    if (CG) { a = __ldcg(st.s0 + i); b = __ldcg(st.s1 + i); c = __ldcg(st.s2 + i); d = __ldcg(st.s3 + i); f = __ldcg(st.s4 + i); }
+    else { a = st.s0[i]; b = st.s1[i]; c = st.s2[i]; d = st.s3[i]; f = st.s4[i]; }
     e.px = a.x; e.py = a.y; e.pz = a.z; e.ep_ret = a.w;
     e.qx = b.x; e.qy = b.y; e.qz = b.z; e.qw = b.w;
     e.vx = c.x; e.vy = c.y; e.vz = c.z; e.step = __float_as_int(c.w);
@@ -698,7 +713,8 @@ __device__ __forceinline__ void load_env(const DevState &st, bool X, long long i
     int dv = __float_as_int(f.w);
     e.n_clip = dv & 0x3FF; e.n_run = (dv >> 10) & 0x3FF;
     if (X) {
-        float4 g = st.d0[i], h = st.d1[i];
+        float4 g, h;
+        if (CG) { g = __ldcg(st.d0 + i); h = __ldcg(st.d1 + i); } else { g = st.d0[i]; h = st.d1[i]; }
         e.mass_scale = g.x; e.thrust_scale = g.y; e.cg_off = g.z; e.wind_x = g.w;
         e.wind_y = h.x; e.episode = __float_as_int(h.y);
     } else {

@@ -490,7 +490,7 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
         if (io.reward_sum) io.reward_sum[i] = rsum;
         if (io.actions_last) reinterpret_cast<float2 *>(io.actions_last)[i] = make_float2(a0, a1);
     }
-    if (blockIdx.x == 0 && tid == 0) atomicAdd(&st.counter[2], (unsigned)io.T);   // steps since the statistics were reset
+    if (blockIdx.x == 0 && tid == 0) atomicAdd(&st.counter[CTR_STEPS], (unsigned)io.T);   // steps since the statistics were reset
     // ---- teardown: release TMEM ----
     tc_fence_before();
     __syncthreads();
