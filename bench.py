@@ -220,6 +220,8 @@ def run_ours(args):
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
+    all_cpus = os.sched_getaffinity(0)
+    affinity = D.bind_to_gpu_cpus(local)     # before any pinned allocation (first touch decides the NUMA node of the slabs)
     dev = torch.device("cuda", local)
     n = args.envs_per_gpu
     cfg_used = _workload_cfg(A, env_id_base=rank * n)
@@ -313,7 +315,45 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     eng.close()
 
-    extra = {}
+    # end-to-end through the public VectorEnv API with HOST (numpy) buffers, every rank (its own env slab): the
+    # timed region contains, per step, the H2D copy of the actions and the D2H copies of obs / reward / flags /
+    # final observations (tvc_step_host: pinned host buffers, stream sync inside the call)
+    import numpy as np
+    venv = RocketTVCVectorEnv(n, config={}, contract="X", device=local, final_info=False, copy_outputs=False,
+                              env_id_base=rank * n, **OVERRIDES)
+    venv.reset(seed=42)
+    for b in range(args.burn_in):          # same steady-state mix as the device-timed region (device-resident actions, untimed)
+        venv.engine.step(pool[b % 16], want_final=False)
+    torch.cuda.synchronize(dev)            # tvc_step_host runs on the handle's own stream: drain the burn-in first
+    # the step's inputs live in pinned host memory (what a host-side policy would write into `venv.pinned_actions()`)
+    host_actions = [torch.from_numpy(np.random.default_rng(100 * rank + i).uniform(-1, 1, (n, 2)).astype(np.float32)).pin_memory().numpy()
+                    for i in range(4)]
+    for w in range(3):
+        venv.step(host_actions[w % 4])
+    ke = max(5, min(K, 30))
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(ke):
+        o_h, r_h, te_h, tr_h, _ = venv.step(host_actions[k % 4])
+    torch.cuda.synchronize(dev)
+    e2e_dt = (time.perf_counter() - t0) / ke
+    e2e_check = float(r_h[:16].sum())      # touch the result on the host
+    done_rows = int((te_h | tr_h).sum())   # final-observation rows the last step wrote into the pinned host buffer
+    venv.close()
+    te = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_dt = float(te.item())
+    launches += 2 * ke
+    e2e_rec = {"value": total_envs / e2e_dt, "unit": "env-steps/s", "h2d_bytes_per_step": n * 8,
+                    "d2h_bytes_per_step": n * (40 + 4 + 1 + 1) + done_rows * 40, "ms_per_step": 1e3 * e2e_dt, "n_gpus_measured": world,
+                    "bytes_are": "per GPU", "result_checksum": e2e_check, "cpu_affinity": affinity,
+                    "d2h_note": f"obs 40 B + reward 4 B + 2 flag bytes per env by copy engine; the final observations of the {done_rows} "
+                                "envs that ended an episode in the (last) step are stored by the kernel straight into the pinned host buffer",
+                    "api": "RocketTVCVectorEnv.step(pinned numpy actions, copy_outputs=False) -> tvc_step_host (H2D from the pinned actions, one 46 B/env D2H into the pinned result slab, stream sync inside)"}
+
+    clocks = sampler.stop()   # sampled from the start of the timed region to the end of the e2e measurement (all under load)
+    extra = {"e2e": e2e_rec}
     if rank == 0:
         # configs[1]: 4,096 envs on one GPU (latency-bound), same Contract X settings
         small = BatchedEngine(4096, _workload_cfg(A), device=local)
@@ -359,46 +399,66 @@ def run_ours(args):
                                       "actor_tflops": flops / (rms * 1e-3) / 1e12,
                                       "tensor_peak_tflops": _bf16_peak(), "note": "physics-bound: the MLP is a small share"}
             launches += 2 * (reps + 4)   # pack_actor_kernel + rollout_kernel per call
+            # the same T steps UNFUSED, at its best: step path + one batched bf16 actor forward (cuBLAS) + the sampling
+            # elementwise kernels per step, captured into ONE CUDA graph (no launch gaps) -- what the fusion has to beat
+            try:
+                netb = net.to(torch.bfloat16)
+                act_buf = torch.zeros((nr, 2), device=dev)
+
+                def unfused_step():
+                    out4 = netb(ro.obs.to(torch.bfloat16)).float()
+                    act_buf.copy_(torch.tanh(out4[:, :2] + out4[:, 2:].clamp(-20, 2).exp() * torch.randn((nr, 2), device=dev)))
+                    ro.step(act_buf, want_final=False)
+                cs = torch.cuda.Stream(device=dev)
+                cs.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(cs), torch.no_grad():
+                    for wu in range(4):
+                        unfused_step()
+                torch.cuda.current_stream(dev).wait_stream(cs)
+                torch.cuda.synchronize(dev)
+                ug = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(ug), torch.no_grad():
+                    unfused_step()
+                for wu in range(8):
+                    ug.replay()
+                torch.cuda.synchronize(dev)
+                e0.record()
+                for k in range(T):
+                    ug.replay()
+                e1.record()
+                torch.cuda.synchronize(dev)
+                ums = e0.elapsed_time(e1)
+                extra["fused_rollout"]["unfused_ms_per_T_steps"] = ums
+                extra["fused_rollout"]["unfused_env_steps_per_sec"] = nr * T / (ums * 1e-3)
+                extra["fused_rollout"]["unfused_what"] = ("per step, replayed as one CUDA graph: torch bf16 nn.Sequential forward (cuBLAS) + tanh / exp / randn "
+                                                          "elementwise kernels + tvc_step (step_kernel_v2 + close_kernel)")
+            except Exception as exc:  # noqa: BLE001
+                extra["fused_rollout"]["unfused_error"] = f"{type(exc).__name__}: {exc}"
+            launches += 2 * (T + 8)
             ro.close()
 
-    # end-to-end through the public VectorEnv API with HOST (numpy) buffers, every rank (its own env slab): the
-    # timed region contains, per step, the H2D copy of the actions and the D2H copies of obs / reward / flags /
-    # final observations (tvc_step_host: pinned host buffers, stream sync inside the call)
-    import numpy as np
-    venv = RocketTVCVectorEnv(n, config={}, contract="X", device=local, final_info=False, copy_outputs=False,
-                              env_id_base=rank * n, **OVERRIDES)
-    venv.reset(seed=42)
-    for b in range(args.burn_in):          # same steady-state mix as the device-timed region (device-resident actions, untimed)
-        venv.engine.step(pool[b % 16], want_final=False)
-    torch.cuda.synchronize(dev)            # tvc_step_host runs on the handle's own stream: drain the burn-in first
-    # the step's inputs live in pinned host memory (what a host-side policy would write into `venv.pinned_actions()`)
-    host_actions = [torch.from_numpy(np.random.default_rng(100 * rank + i).uniform(-1, 1, (n, 2)).astype(np.float32)).pin_memory().numpy()
-                    for i in range(4)]
-    for w in range(3):
-        venv.step(host_actions[w % 4])
-    ke = max(5, min(K, 30))
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(ke):
-        o_h, r_h, te_h, tr_h, _ = venv.step(host_actions[k % 4])
-    torch.cuda.synchronize(dev)
-    e2e_dt = (time.perf_counter() - t0) / ke
-    e2e_check = float(r_h[:16].sum())      # touch the result on the host
-    done_rows = int((te_h | tr_h).sum())   # final-observation rows the last step wrote into the pinned host buffer
-    venv.close()
-    te = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_dt = float(te.item())
-    launches += 2 * ke
-    extra["e2e"] = {"value": total_envs / e2e_dt, "unit": "env-steps/s", "h2d_bytes_per_step": n * 8,
-                    "d2h_bytes_per_step": n * (40 + 4 + 1 + 1) + done_rows * 40, "ms_per_step": 1e3 * e2e_dt, "n_gpus_measured": world,
-                    "bytes_are": "per GPU", "result_checksum": e2e_check,
-                    "d2h_note": f"obs 40 B + reward 4 B + 2 flag bytes per env by copy engine; the final observations of the {done_rows} "
-                                "envs that ended an episode in the (last) step are stored by the kernel straight into the pinned host buffer",
-                    "api": "RocketTVCVectorEnv.step(pinned numpy actions, copy_outputs=False) -> tvc_step_host (H2D from the pinned actions, one 46 B/env D2H into the pinned result slab, stream sync inside)"}
+            # configs[4]: curriculum stage 6 with the end-to-end SAC loop -- fused rollout -> on-device replay ring ->
+            # graph-replayed batched SAC updates (tvc_ai_b200/replay.py, sac.py), 4,096 envs, one GPU
+            try:
+                from tvc_ai_b200.curriculum import stage6_conditions
+                from tvc_ai_b200.sac import SACConfig, train_sac
+                e5 = BatchedEngine(4096, A.default_config(A.CONTRACT_X, autoreset=1, delay_steps=3, thrust_curve=1, propellant_fraction=0.2,
+                                                          cg_burn_shift=0.05), device=local)
+                e5.set_curriculum(stage6_conditions())
+                e5.reset()
+                scfg = SACConfig(batch_size=4096, learning_starts=4096 * 8, lr_actor=3e-4, lr_critic=3e-4)
+                _, rp5, tm5 = train_sac(e5, 24, rollout_steps=8, config=scfg, seed=0)
+                extra["config5"] = {"workload": "configs[4]: stage 6 (wind 3 N, mass +-30 %, tilt 0.7 rad, sensor noise, actuator delay 3, thrust curve), "
+                                                "4096 envs, per iteration: tvc_rollout T=8 (transitions stored into the replay ring by the kernel) + 8 SAC "
+                                                "updates of batch 4096 (tvc_replay_sample gather + PyTorch SAC update, one CUDA-graph replay)",
+                                    "env_steps_per_sec_e2e": tm5["env_steps_per_sec_e2e"], "learner_share": tm5["learner_share"],
+                                    "env_ms_per_iter": tm5["env_ms_per_iter"], "learner_ms_per_iter": tm5["learner_ms_per_iter"],
+                                    "updates": tm5["updates"], "replay_filled": rp5.filled}
+                launches += 24 * (2 + 8)     # pack + rollout + 8 gather kernels per iteration
+                e5.close()
+            except Exception as exc:  # noqa: BLE001 -- the learner is adjacent to the hot path: never lose the headline line over it
+                extra["config5"] = {"error": f"{type(exc).__name__}: {exc}"}
 
-    clocks = sampler.stop()   # sampled from the start of the timed region to the end of the e2e measurement (all under load)
     if rank == 0:
         peak, peak_src = _peaks()
         per_launch_bytes = ALGO_BYTES_PER_ENV_STEP_X * n
@@ -444,6 +504,7 @@ def run_ours(args):
         if "e2e" not in line:
             line["e2e"] = None
         if world == 1 or True:
+            os.sched_setaffinity(0, all_cpus)      # the CPU baseline uses every host core
             line["cpu_baseline"] = cpu_baseline() if world == 1 else None
         print(json.dumps(line), flush=True)
     if world > 1:

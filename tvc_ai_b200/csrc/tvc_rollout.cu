@@ -158,6 +158,7 @@ struct RolloutIO {
     float *obs_all, *next_obs_all;
     uint8_t *term_all, *trunc_all;
     int T, deterministic;
+    int per;             // envs per CTA (<= RB): the batch is spread over all SMs when it is large enough (148 CTAs of 443 envs, not 128 of 512)
     unsigned long long t0;   // lifetime step of the first rollout step (Philox counters)
 };
 
@@ -169,8 +170,9 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = tid / TM, row = tid % TM;          // this thread's MMA tile and accumulator row
     // env held by this thread: fixed at first, re-assigned within the CTA every step (class sort, below)
-    long long i = (long long)blockIdx.x * RB + tid;
-    bool live = i < st.n;
+    const long long cta_base = (long long)blockIdx.x * io.per;
+    long long i = cta_base + tid;
+    bool live = tid < io.per && i < st.n;
     long long gid = c.env_base + i;
 
     const uint32_t s_base = smem_u32(smem);
@@ -384,7 +386,7 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
                             e.wx, e.wy, e.wz, __int_as_float(e.burn), __int_as_float(e.phase), __int_as_float(e.success),
                             __int_as_float(e.has_prev), __int_as_float(e.consec), e.ap0, e.ap1, __int_as_float(e.hist_count),
                             __int_as_float(e.n_clip), __int_as_float(e.n_run), e.mass_scale, e.thrust_scale, e.cg_off,
-                            e.wind_x, e.wind_y, __int_as_float(e.episode), a0, a1, rsum, __int_as_float((int)(i - (long long)blockIdx.x * RB))};
+                            e.wind_x, e.wind_y, __int_as_float(e.episode), a0, a1, rsum, __int_as_float((int)(i - cta_base))};
 #pragma unroll
             for (int k = 0; k < 35; k++) s_x[k * RB + pos] = w_[k];
             __syncthreads();
@@ -398,8 +400,8 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
             e.n_run = __float_as_int(w_[24]); e.mass_scale = w_[25]; e.thrust_scale = w_[26]; e.cg_off = w_[27];
             e.wind_x = w_[28]; e.wind_y = w_[29]; e.episode = __float_as_int(w_[30]);
             a0 = w_[31]; a1 = w_[32]; rsum = w_[33];
-            i = (long long)blockIdx.x * RB + __float_as_int(w_[34]);
-            live = i < st.n;
+            i = cta_base + __float_as_int(w_[34]);
+            live = __float_as_int(w_[34]) < io.per && i < st.n;
             gid = c.env_base + i;
             __syncthreads();   // the exchange area is the MLP's operand / hidden-tile area again from the next step on
         }
@@ -534,13 +536,20 @@ extern "C" int tvc_rollout(tvc_handle *h, const tvc_actor_weights *w, int32_t T,
     io.reward_all = u->reward_all; io.T = T; io.deterministic = u->deterministic;
     io.obs_all = u->obs_all; io.next_obs_all = u->next_obs_all; io.term_all = u->terminated_all; io.trunc_all = u->truncated_all;
     io.t0 = (unsigned long long)h->lifetime_steps;
+    // one CTA per SM (222 KB of shared memory): a batch of more than 256 envs per SM is cut into a whole number of waves over
+    // every SM (65,536 envs: 148 CTAs of 443 envs instead of 128 CTAs of 512 on 148 SMs; 262,144: 592 of 443 instead of 512 of
+    // 512 = three and a half waves); smaller batches keep full CTAs.  One statistics row per CTA.
+    int ctas = (int)((h->n + RB - 1) / RB);
+    if (h->n > (int64_t)h->num_sms * 256) ctas = (ctas + h->num_sms - 1) / h->num_sms * h->num_sms;
+    io.per = (int)((h->n + ctas - 1) / ctas);
+    ctas = (int)((h->n + io.per - 1) / io.per);
     const bool X = h->cur.contract == TVC_CONTRACT_X;
     const int dv = h->cur.diversity_mode;
     cudaError_t e = cudaSuccess;
 #define GO(XX, DD)                                                                                                   \
     do {                                                                                                             \
         e = cudaFuncSetAttribute(rollout_kernel<XX, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL); \
-        if (e == cudaSuccess) rollout_kernel<XX, DD><<<(int)((h->n + RB - 1) / RB), RB, SMEM_TOTAL, s>>>(h->dc, h->st, ws->img, io); \
+        if (e == cudaSuccess) rollout_kernel<XX, DD><<<ctas, RB, SMEM_TOTAL, s>>>(h->dc, h->st, ws->img, io); \
     } while (0)
     if (X) { if (dv == 0) GO(true, 0); else if (dv == 1) GO(true, 1); else GO(true, 2); }
     else   { if (dv == 0) GO(false, 0); else if (dv == 1) GO(false, 1); else GO(false, 2); }

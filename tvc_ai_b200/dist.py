@@ -32,6 +32,42 @@ def init_from_env(backend: str | None = None):
     return rank, world, local
 
 
+def bind_to_gpu_cpus(device_index: int) -> dict:
+    """Pin this process to the CPU cores next to GPU `device_index` (its PCIe root's NUMA node) BEFORE any pinned host
+    buffer is allocated, so that the first-touch policy places the e2e result slabs (46 B per env and step over PCIe) in
+    that node's memory and the copies do not cross the socket interconnect.  Reads the GPU's PCI address from torch and
+    /sys/bus/pci/devices/<addr>/local_cpulist; a box that reports one node for every GPU (or hides sysfs) is left alone.
+    Returns what was found / done (for the bench line)."""
+    info = {"bound": False}
+    try:
+        prop = torch.cuda.get_device_properties(device_index)
+        addr = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{addr}"
+        with open(f"{base}/local_cpulist") as f:
+            cpulist = f.read().strip()
+        try:
+            with open(f"{base}/numa_node") as f:
+                info["numa_node"] = int(f.read().strip())
+        except OSError:
+            pass
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        want = cpus & allowed
+        info.update(pci=addr, local_cpus=len(cpus), allowed_cpus=len(allowed))
+        if want and want != allowed:
+            os.sched_setaffinity(0, want)
+            info["bound"] = True
+    except (OSError, AttributeError, ValueError, RuntimeError) as exc:
+        info["error"] = type(exc).__name__
+    return info
+
+
 def slab(total_envs: int, rank: int, world: int):
     """Contiguous env slab [base, base + count) owned by `rank`; global ids feed the Philox
     counters so trajectories do not depend on the GPU count."""
