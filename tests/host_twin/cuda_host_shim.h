@@ -17,6 +17,7 @@
 #endif
 // glibc declares __logf / __sincosf (internal aliases, not exported): route the CUDA fast intrinsics to the libm functions
 #define __logf(x) logf(x)
+#define __expf(x) expf(x)
 #define __sincosf(x, s, c) sincosf((x), (s), (c))
 
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }

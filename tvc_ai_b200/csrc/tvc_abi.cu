@@ -47,9 +47,12 @@ __device__ __forceinline__ void warp_store_obs(float *dst, const float *s_warp, 
 //   * close_kernel, the second and last launch of a step, turns that into the sequence: scatter CTA b sums the counters in
 //     front of chunk b (exclusive prefix, two levels), ranks its chunk's 1,024 class bytes with ballots and writes the env
 //     ids to their global positions.  No sort, no scan pass, no last-CTA tail: ~3 us for 262,144 envs.
-// The counters are double-buffered by a parity P kept ON THE DEVICE (st.counter[CTR_PAR]; a host-side parity would be baked into a
-// captured CUDA graph): the current sequence was built from buffer P, the step kernel adds into P ^ 1, close_kernel reads
-// P ^ 1 and clears P, and the last CTA of close_kernel to finish flips P.
+// The counters (and the done-list length) are double-buffered by the parity of a sequence number S kept ON THE DEVICE
+// (a host-side parity would be baked into a captured CUDA graph).  No kernel reads a word that the same launch writes, so the
+// hand-over needs no ticket, fence or last-CTA tail: the step kernel reads S (CTR_SEQ) and leaves a copy (CTR_SEQ2); it adds
+// into count buffer (S & 1) ^ 1 and appends to the done list of length CTR_DONE + (S & 1); close_kernel reads the copy, builds
+// the sequence from buffer (S & 1) ^ 1, clears buffer S & 1, and one of its threads writes S + 1, zeroes the queue head and
+// the other done-list length.
 //
 // An env whose episode ended gets class 2 for the next sequence (a fresh env starts at z = 1 m); it is re-initialised by the
 // reset CTAs of close_kernel.
@@ -79,7 +82,9 @@ classify_state_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ 
         cls = class_of(c, X, p.z, q.x, q.y, q.z, q.w, v.z, w.x, w.y, w.z, X ? st.d0[env].z : 0.0f);
         st.cls[env] = (uint8_t)cls;
     }
-    count_class(st, (int)st.counter[CTR_PAR] ^ 1, live, live ? env : 0, cls);   // like a step: the buffer the following close_kernel reads
+    const unsigned seq = st.counter[CTR_SEQ];
+    if (env == 0) st.counter[CTR_SEQ2] = seq;
+    count_class(st, (int)(seq & 1u) ^ 1, live, live ? env : 0, cls);   // like a step: the buffer the following close_kernel reads
 }
 
 // One warp writes chunk b's part of the next sequence: the exclusive prefix of the chunk (super-chunks in front, then the
@@ -125,15 +130,6 @@ __device__ __forceinline__ void scatter_chunk(const DevState &st, int b, int buf
     }
 }
 
-// What the last CTA of close_kernel does before it leaves: hand the counters over to the next step.
-__device__ __forceinline__ void hand_over(const DevState &st, int count_step) {
-    st.counter[CTR_TICKET] = 0u;
-    st.counter[CTR_QUEUE] = 0u;                            // work-queue head of the next step kernel
-    st.counter[CTR_DONE] = 0u;                             // the done list is consumed
-    st.counter[CTR_PAR] ^= 1u;                             // the sequence now in st.order was built from the other buffer
-    if (count_step) st.counter[CTR_STEPS] += 1u;           // steps since the statistics were reset
-}
-
 // The second and last launch of a step (also follows classify_state_kernel).  CTAs [0, nreset): same-step autoreset -- one
 // env of st.done_list per thread, full warps (ref:381-464 reset + the reset observation over the terminal one; the terminal
 // state was stored by the step kernel and every Env field round-trips through store_env / load_env, so this equals resetting
@@ -145,10 +141,13 @@ close_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState 
     const int lane = threadIdx.x & 31;
     asm volatile("griddepcontrol.wait;" ::: "memory");              // behind step_kernel_v2 / classify_state_kernel
     asm volatile("griddepcontrol.launch_dependents;");              // the next step kernel may be scheduled; it waits for this grid
+    const unsigned seq = st.counter[CTR_SEQ2];                      // the sequence number the kernel before this one ran with
     if ((int)blockIdx.x < nreset) {
-        const unsigned ndone = st.counter[CTR_DONE];
-        for (unsigned k = blockIdx.x * 128u + threadIdx.x; k < ndone; k += (unsigned)nreset * 128u) {
-            const long long i = st.done_list[k], gid = c.env_base + i;
+        unsigned k = blockIdx.x * 128u + threadIdx.x;
+        long long i = st.done_list[k < (unsigned)st.n ? k : 0u];   // issued beside the length, not behind it
+        const unsigned ndone = st.counter[CTR_DONE + (seq & 1u)];
+        while (k < ndone) {
+            const long long gid = c.env_base + i;
             Env e;
             load_env(st, X, i, e);
             reset_env(c, X, gid, e, false);
@@ -158,16 +157,18 @@ close_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevState 
             float2 *o2 = reinterpret_cast<float2 *>(obs + 10 * i);
 #pragma unroll
             for (int q = 0; q < 5; q++) o2[q] = make_float2(o[2 * q], o[2 * q + 1]);
+            k += (unsigned)nreset * 128u;
+            if (k < ndone) i = st.done_list[k];
         }
     } else {
         const int b = (int)((blockIdx.x - nreset) * 4 + (threadIdx.x >> 5));
-        const int buf = (int)st.counter[CTR_PAR] ^ 1;      // the buffer the step kernel (or classify_state_kernel) just filled
-        if (b < st.nchunks) scatter_chunk(st, b, buf, lane);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(&st.counter[CTR_TICKET], 1u) == gridDim.x - 1u) hand_over(st, count_step);
+        if (b < st.nchunks) scatter_chunk(st, b, (int)(seq & 1u) ^ 1, lane);     // the buffer the kernel before this one filled
+        if (b == 0 && lane == 0) {   // hand over to the next step: nobody in this launch reads these words
+            st.counter[CTR_SEQ] = seq + 1u;
+            st.counter[CTR_QUEUE] = 0u;                              // work-queue head of the next step kernel
+            st.counter[CTR_DONE + ((seq + 1u) & 1u)] = 0u;           // the next step's done list is empty
+            if (count_step) st.counter[CTR_STEPS] += 1u;             // steps since the statistics were reset
+        }
     }
 }
 
@@ -203,7 +204,9 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
     const unsigned full = 0xffffffffu;
     const int ngroups = (int)((st.n + 31) / 32);
     unsigned *const queue = &st.counter[CTR_QUEUE];
-    const int par = (int)st.counter[CTR_PAR];    // parity of the counter buffers (device-side: see close_kernel)
+    const unsigned seq = st.counter[CTR_SEQ];    // sequence number (device-side: see close_kernel); its parity picks the buffers
+    const int par = (int)(seq & 1u);
+    if (blockIdx.x == 0 && threadIdx.x == 0) st.counter[CTR_SEQ2] = seq;
 #ifdef TVC_PHASE_PROF2
     long long pt_prev = clock64();
 #endif
@@ -290,7 +293,7 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
             const bool relist = live && done && c.autoreset;
             const unsigned rm = __ballot_sync(full, relist);
             int rbase = 0;
-            if (rm && lane == 0) rbase = (int)atomicAdd(&st.counter[CTR_DONE], (unsigned)__popc(rm));
+            if (rm && lane == 0) rbase = (int)atomicAdd(&st.counter[CTR_DONE + par], (unsigned)__popc(rm));
             int cl = 2;
             if (live && !relist) cl = class_of(c, X, e.pz, e.qx, e.qy, e.qz, e.qw, e.vz, e.wx, e.wy, e.wz, e.cg_off);
             if (live) st.cls[i] = (uint8_t)cl;

@@ -68,10 +68,10 @@ struct DevState {
 
 // words of DevState::counter, one 128-byte line each (the queue pulls of the step kernel do not share a line with anything)
 enum { CTR_QUEUE = 0,      // work-queue head of step_kernel_v2
-       CTR_TICKET = 32,    // close_kernel: CTAs that have finished
-       CTR_STEPS = 64,     // steps since the statistics were reset
-       CTR_DONE = 96,      // length of done_list
-       CTR_PAR = 128,      // parity of ccount / scount
+       CTR_SEQ = 32,       // sequence number S: written by close_kernel, read by the kernel that follows it
+       CTR_SEQ2 = 64,      // the S the last step_kernel_v2 / classify_state_kernel ran with: read by close_kernel
+       CTR_STEPS = 96,     // steps since the statistics were reset
+       CTR_DONE = 128,     // [2] length of done_list, double-buffered by S & 1
        CTR_WORDS = 160 };
 
 struct DevIO {
@@ -133,6 +133,9 @@ __device__ __forceinline__ float rsqrt_normal(float x) { float y; asm("rsqrt.app
 // the reward ring / bit-ring lines right after the state load measured 2.7 % slower.)
 __device__ __forceinline__ float sqrt_fast(float x) { return x > 1e-30f ? x * rsqrt_normal(x) : 0.0f; }
 __device__ __forceinline__ float rsqrt_fast(float x) { return rsqrt_normal(x); }
+// e^x for the reward terms and the air density (x <= 0, |x| < 100): ex2.approx of x log2(e), relative error < 3e-7 there --
+// expf() adds a range reduction worth five more instructions and the same MUFU
+__device__ __forceinline__ float exp_fast(float x) { return __expf(x); }
 __device__ __forceinline__ void sincos_small(float x, float &s, float &c) {
     const float x2 = x * x;
     s = x * (1.0f + x2 * (-1.6666667e-1f + x2 * (8.3333333e-3f + x2 * (-1.9841270e-4f + x2 * 2.7557319e-6f))));
@@ -752,9 +755,9 @@ __device__ __forceinline__ int class_of(const DevCfg &c, bool X, float pz, float
     const float R31 = 2.0f * (qx * qz - qw * qy), R32 = 2.0f * (qy * qz + qw * qx);
     const float R33 = 1.0f - 2.0f * (qx * qx + qy * qy);
     const float hh = c.half_len + cg;
-    const float gmin = pz - fabsf(R33) * hh - c.radius * sqrtf(R31 * R31 + R32 * R32);
-    const float reach = sqrtf(hh * hh + c.radius * c.radius);
-    const float travel = (fabsf(vz) + sqrtf(wx * wx + wy * wy + wz * wz) * reach) * (c.dt * (float)c.K);
+    const float gmin = pz - fabsf(R33) * hh - c.radius * sqrt_fast(R31 * R31 + R32 * R32);
+    const float reach = sqrt_fast(hh * hh + c.radius * c.radius);
+    const float travel = (fabsf(vz) + sqrt_fast(wx * wx + wy * wy + wz * wz) * reach) * (c.dt * (float)c.K);
     return gmin < TVC_NOW_GAP ? 0 : (gmin - travel < TVC_MAYBE_GAP ? 1 : 2);
 }
 
@@ -813,7 +816,7 @@ __device__ __forceinline__ void env_pre(const DevCfg &c, const DevState &st, lon
         f.fl0 = fl0; f.fl1 = fl1; f.fl2 = fl2; f.arm = arm;
     }
     {   // ---- S5 (ref:561-585) aerodynamics ----
-        float rho = 1.225f * expf(-e.pz / 8400.0f);
+        float rho = 1.225f * exp_fast(e.pz * (-1.0f / 8400.0f));
         float vmag = sqrt_fast(e.vx * e.vx + e.vy * e.vy + e.vz * e.vz);
         if (vmag > 0.1f || (!(c.quirks & Q_DRAG_CUTOFF) && vmag > 0.0f)) {   // Q5
             float dm = 0.5f * rho * (vmag * vmag) * 0.47f * (3.14159265358979f * 0.0025f);
@@ -855,13 +858,13 @@ __device__ __forceinline__ void env_post(const DevCfg &c, const DevState &st, lo
     float ox, oy, oz, ow, epitch, eyaw;
     reported_quat(e.qx, e.qy, e.qz, e.qw, ox, oy, oz, ow);
     euler_pitch_yaw(ox, oy, oz, ow, epitch, eyaw);
-    float tilt = sqrtf(epitch * epitch + eyaw * eyaw);                 // Q7
+    float tilt = sqrt_fast(epitch * epitch + eyaw * eyaw);             // Q7
     if (!(c.quirks & Q_EULER_TILT)) {                                  // Q7 cleared: angle between the body axis and the vertical
         const float sxy = 2.0f * sqrtf((ox * ox + oy * oy) * (oz * oz + ow * ow));   // |sin|, reported quaternion is unit norm
         tilt = atan2f(sxy, 1.0f - 2.0f * (ox * ox + oy * oy));
     }
-    const float wmag = sqrtf(e.wx * e.wx + e.wy * e.wy + e.wz * e.wz);
-    const float vh = sqrtf(e.vx * e.vx + e.vy * e.vy), vv = fabsf(e.vz);
+    const float wmag = sqrt_fast(e.wx * e.wx + e.wy * e.wy + e.wz * e.wz);
+    const float vh = sqrt_fast(e.vx * e.vx + e.vy * e.vy), vv = fabsf(e.vz);
     const float alt = e.pz;
     bool crashed = alt < 0.1f;                                         // Q17
     if (!(c.quirks & Q_CRASH_IS_COM_HEIGHT)) {                         // Q17 cleared: a hard or tilted touchdown
@@ -900,20 +903,20 @@ __device__ __forceinline__ void env_post(const DevCfg &c, const DevState &st, lo
     for (int k = 0; k < 12; k++) comp[k] = 0.0f;
     comp[0] = success_r ? 100.0f : (phase_r == 2 ? 10.0f : 0.0f);
     {
-        float tp = expf(-10.0f * fmaxf(0.0f, tilt - 0.087f));
-        float apn = expf(-5.0f * fmaxf(0.0f, wmag - 0.1f));
+        float tp = exp_fast(-10.0f * fmaxf(0.0f, tilt - 0.087f));
+        float apn = exp_fast(-5.0f * fmaxf(0.0f, wmag - 0.1f));
         float alp = (0.2f <= alt && alt <= 20.0f) ? 1.0f : 0.5f;
-        comp[1] = ((tp + apn + alp) / 3.0f) * 50.0f;
+        comp[1] = ((tp + apn + alp) * (1.0f / 3.0f)) * 50.0f;
     }
-    const float ce = sqrtf(a0 * a0 + a1 * a1);
+    const float ce = sqrt_fast(a0 * a0 + a1 * a1);
     if (burn <= 899 && ce < 0.5f) comp[2] = (fuel * (1.0f - ce)) * 20.0f;
     comp[3] = (tilt < 0.05f && wmag < 0.1f) ? 10.0f : ((tilt < 0.1f && wmag < 0.2f) ? 5.0f : 0.0f);
     if (e.has_prev) {                                                   // Q11
         float d0 = a0 - e.ap0, d1 = a1 - e.ap1;
-        comp[4] = expf(-5.0f * sqrtf(d0 * d0 + d1 * d1)) * 5.0f;
+        comp[4] = exp_fast(-5.0f * sqrt_fast(d0 * d0 + d1 * d1)) * 5.0f;
     } else comp[4] = 5.0f;
     e.ap0 = a0; e.ap1 = a1; e.has_prev = 1;
-    comp[5] = expf(-2.0f * fabsf(alt - 3.0f)) * 5.0f;
+    comp[5] = exp_fast(-2.0f * fabsf(alt - 3.0f)) * 5.0f;
     if (crashed) comp[6] = -1000.0f;
     if (tilt > 0.52f) comp[7] = -500.0f * (tilt - 0.52f);
     if (ce > 0.9f) comp[8] = -50.0f * (ce - 0.9f);
@@ -929,10 +932,10 @@ __device__ __forceinline__ void env_post(const DevCfg &c, const DevState &st, lo
         for (int k = 0; k < 10; k++) if (k == ls) last_pushed = rv[k];
         if (len > 10) {
             float s = ((rv[0] + rv[1]) + (rv[2] + rv[3])) + ((rv[4] + rv[5]) + (rv[6] + rv[7])) + rv[8] + rv[9];
-            float mean = s / 10.0f, q = 0.0f;
+            float mean = s * 0.1f, q = 0.0f;
 #pragma unroll
             for (int k = 0; k < 10; k++) { float d = rv[k] - mean; q += d * d; }
-            float var = q / 10.0f;
+            float var = q * 0.1f;
             if (var > 10000.0f && (c.quirks & Q_VARIANCE_PENALTY)) adj -= c.gp * var;
         }
     }
