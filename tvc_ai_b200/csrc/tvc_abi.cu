@@ -339,13 +339,11 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
                 d_fuel += (double)__shfl_sync(full, ev_fuel, src);
                 n_len += __shfl_sync(full, ev_len, src);
             }
-            double v = 0.0;
-            switch (lane) {
-                case 0: v = __popc(dm); break; case 1: v = d_ret; break;  case 2: v = d_ret2; break; case 3: v = n_len; break;
-                case 4: v = n_succ; break;     case 5: v = __popc(r2); break; case 6: v = __popc(r3); break; case 7: v = __popc(r4); break;
-                case 8: v = __popc(r5); break; case 9: v = n_tr; break;   case 10: v = __popc(vm); break; case 11: v = d_alt; break;
-                case 12: v = d_tilt; break;    case 13: v = d_fuel; break; default: break;
-            }
+            // lane L < 14 picks statistic L with selects (a switch compiled to a 14-way divergent jump table)
+            const int iv = lane == 0 ? __popc(dm) : lane == 3 ? n_len : lane == 4 ? n_succ : lane == 5 ? __popc(r2) : lane == 6 ? __popc(r3)
+                         : lane == 7 ? __popc(r4) : lane == 8 ? __popc(r5) : lane == 9 ? n_tr : lane == 10 ? __popc(vm) : 0;
+            const double dv = lane == 1 ? d_ret : lane == 2 ? d_ret2 : lane == 11 ? d_alt : lane == 12 ? d_tilt : lane == 13 ? d_fuel : 0.0;
+            const double v = (lane == 1 || lane == 2 || lane >= 11) ? dv : (double)iv;
             // the row has exactly one writer per launch (this group), so the order-free reduction is still deterministic; as a
             // reduction it does not make the warp wait for the old value (the read-modify-write stalled on a DRAM round trip)
             if (lane < 14 && v != 0.0) atomicAdd(&st.partial[(long long)g * TVC_NSTAT + lane], v);
@@ -702,6 +700,7 @@ static int launch_step(tvc_handle *h, const DevIO &io, cudaStream_t s) {
             cudaError_t e = X ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_v2<true, 1, false>, TVC_V2_BLOCK, 0)
                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_v2<false, 1, false>, TVC_V2_BLOCK, 0);
             if (e != cudaSuccess || per_sm < 1) per_sm = 1;
+            { const char *p = getenv("TVC_V2_CTAS_PER_SM"); if (p && atoi(p) >= 1 && atoi(p) < per_sm) per_sm = atoi(p); }   // diagnostics: fewer resident warps
             const int cap = per_sm * h->num_sms;
             const int wpb = TVC_V2_BLOCK / 32;
             const int ctas = (h->ngroups + wpb - 1) / wpb;

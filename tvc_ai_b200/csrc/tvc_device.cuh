@@ -544,6 +544,7 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
     const float far_z = 1.001f * (hh + c.radius) + c.margin;
     const float reach = sqrt_fast(hh * hh + c.radius * c.radius);
     const float zb = -c.half_len - P.cg, zt = c.half_len - P.cg;
+    float wmag = sqrt_fast(e.wx * e.wx + e.wy * e.wy + e.wz * e.wz);   // carried from substep to substep
     for (int k = 0; k < c.K; k++) {
 #ifdef TVC_PHASE_PROF2
         { const long long b0 = clock64(); if (LOCKSTEP) __syncthreads(); ph2->bar += (unsigned)(clock64() - b0); }
@@ -561,15 +562,13 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
         // B5 with I = diag(a, a, b): R diag(1/a,1/a,1/b) R^T tau = tau/a + (1/b - 1/a)(e.tau) e, e = body axis in the
         // world frame (third column of R); the k(1+|w|) damping is isotropic.  Only e and the third row of R are needed
         // outside the contact solver.  The quaternion is unit to rounding (normalised at the end of every substep, on
-        // import and at reset), so 2 / |q|^2 is its first-order expansion 2 (2 - |q|^2): exact to 1e-13, no MUFU.
-        const float s2 = 2.0f * (2.0f - (e.qx * e.qx + e.qy * e.qy + e.qz * e.qz + e.qw * e.qw));
-        const float xs = e.qx * s2, ys = e.qy * s2, zs = e.qz * s2;
+        // import and at reset: | |q|^2 - 1 | < 2e-7), so btMatrix3x3::setRotation's 2 / |q|^2 is 2 to the last bit or two.
+        const float xs = e.qx + e.qx, ys = e.qy + e.qy, zs = e.qz + e.qz;
         const float nz1 = -(e.qx * xs + e.qy * ys);          // R33 - 1, without the cancellation
         const float e0 = e.qx * zs + e.qw * ys, e1 = e.qy * zs - e.qw * xs, e2 = 1.0f + nz1;
         const float et = (e0 * Tx + e1 * Ty + e2 * Tz) * dI;
-        float wn2 = e.wx * e.wx + e.wy * e.wy + e.wz * e.wz;
-        float wn = wn2 > 2.220446049250313e-16f ? sqrt_fast(wn2) : 0.0f;
-        float kd = c.ang_damp + c.ang_damp * wn;
+        // |w|: the value the previous substep left (btVector3::safeNorm's cut-off at 1.5e-8 is below an ulp of k (1 + |w|))
+        float kd = c.ang_damp + c.ang_damp * wmag;
         float dwx = Tx * P.inv_Ixy + et * e0 - e.wx * kd;
         float dwy = Ty * P.inv_Ixy + et * e1 - e.wy * kd;
         float dwz = Tz * P.inv_Ixy + et * e2 - e.wz * kd;
@@ -609,7 +608,7 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
                 }
             }
         }
-        if (!solved) { cc.l1 = cc.l2 = cc.ln = cc.lt0 = cc.lt1 = cc.lt2 = 0.0f; cc.xmask = 0u; cc.have = false; }
+        if (!solved && cc.have) { cc.l1 = cc.l2 = cc.ln = cc.lt0 = cc.lt1 = cc.lt2 = 0.0f; cc.xmask = 0u; cc.have = false; }
         // B6: semi-implicit Euler; near the ground the height carries a running compensation (the contact targets divide the
         // gap by dt, so the 3e-8 rounding of pz + dt vz per substep would otherwise show up as 1.5e-5 m/s at dt = 0.002)
         e.px += dt * e.vx; e.py += dt * e.vy;
@@ -619,11 +618,13 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
             e.pz = t;
         }
         float ang = sqrt_fast(e.wx * e.wx + e.wy * e.wy + e.wz * e.wz);
+        wmag = ang;
         if (ang * dt > 0.7853981633974483f) ang = 0.7853981633974483f * c.inv_dt;
         // sin(x)/ang and cos(x) with x = ang*dt/2 <= pi/8: polynomials (Bullet switches to its own Taylor form below 1e-3)
         const float hx = 0.5f * ang * dt, hx2 = hx * hx;
-        const float sc = 0.5f * dt * (1.0f + hx2 * (-1.6666667e-1f + hx2 * (8.3333333e-3f + hx2 * (-1.9841270e-4f + hx2 * 2.7557319e-6f))));
-        const float cw = 1.0f + hx2 * (-0.5f + hx2 * (4.1666667e-2f + hx2 * (-1.3888889e-3f + hx2 * 2.4801587e-5f)));
+        // (hx <= pi/8: the x^8 terms are 1.5e-9 and 1.4e-8, below half an ulp)
+        const float sc = 0.5f * dt * (1.0f + hx2 * (-1.6666667e-1f + hx2 * (8.3333333e-3f + hx2 * -1.9841270e-4f)));
+        const float cw = 1.0f + hx2 * (-0.5f + hx2 * (4.1666667e-2f + hx2 * -1.3888889e-3f));
         float bx = e.wx * sc, by = e.wy * sc, bz = e.wz * sc;
         float nx = cw * e.qx + bx * e.qw + by * e.qz - bz * e.qy;
         float ny = cw * e.qy + by * e.qw + bz * e.qx - bx * e.qz;
