@@ -106,9 +106,9 @@ struct Env {
 // ------------------------------------------------------------------------------------------
 enum { ST_DR_A = 1, ST_DR_B = 2, ST_NOISE_A = 3, ST_NOISE_B = 4, ST_ACTION = 5, ST_ACTOR = 6, ST_DR_C = 7 };
 
-// Code size matters here: the step kernels run many desynchronised warps through ~90 KB of straight-line code,
-// and ncu shows instruction-fetch stalls (no_instruction) dominating once the CTA barriers are gone.  So the
-// generators are single out-of-line copies and the hot path uses short, slow-path-free math:
+// Code size matters here: the step kernels run many desynchronised warps through straight-line code, and ncu showed
+// instruction-fetch stalls (no_instruction) dominating at 90 KB.  So the per-episode draws and the gimbal-lock branch
+// are single out-of-line copies and the hot path uses short, slow-path-free math:
 //   rcp_fast / sqrt_fast : MUFU.RCP / MUFU.RSQ based, <= 2 ulp, operands are well-scaled positive numbers
 //   sincos_small         : degree-9/8 Taylor polynomials, |x| <= 0.8 rad, error < 4e-8
 // (an earlier build, then bound by instruction fetch, measured raw `asm volatile` rcp/sqrt/rsqrt.approx.ftz 10 % slower;
@@ -142,7 +142,10 @@ __device__ __forceinline__ void sincos_small(float x, float &s, float &c) {
     c = 1.0f + x2 * (-0.5f + x2 * (4.1666667e-2f + x2 * (-1.3888889e-3f + x2 * (2.4801587e-5f - x2 * 2.7557319e-7f))));
 }
 
-static __device__ __noinline__ uint4 philox(unsigned seed_lo, unsigned seed_hi, long long gid, unsigned stream,
+// (inlined since the step kernel shrank to ~55 KB of code: as out-of-line copies the generator and the sensor-noise draw
+//  were two serialised calls in the middle of env_post; inlined, their integer rounds interleave with the Euler-angle and
+//  reward chains: 0.0821 -> 0.0789 ms per step.  Prefetching the next group's env ids under the statistics: no change.)
+static __device__ __forceinline__ uint4 philox(unsigned seed_lo, unsigned seed_hi, long long gid, unsigned stream,
                                      unsigned a, unsigned b) {
     unsigned c0 = (unsigned)gid, c1 = (unsigned)(((unsigned long long)gid >> 32) & 0xFFFFu) | (stream << 16);
     unsigned c2 = a, c3 = b, k0 = seed_lo, k1 = seed_hi;
@@ -167,8 +170,8 @@ __device__ __forceinline__ void box_muller(unsigned x0, unsigned x1, float &n0, 
 // Eight N(0,1) draws for one (env, episode, step) from ONE Philox block (sensor noise, Contract X; same bits in the oracle):
 // each 32-bit word gives two 16-bit uniforms (k + 0.5) / 2^16 -- the radius from the low half, the angle from the high half --
 // i.e. four Box-Muller pairs with |n| <= 4.9 sigma.  The noise is scaled by 0.02 before it meets a 1e-5 tolerance, so the
-// logarithm and the sine / cosine are the single-MUFU forms (|error| < 1e-6 on a unit normal); one out-of-line copy.
-static __device__ __noinline__ void noise8(unsigned seed_lo, unsigned seed_hi, long long gid, unsigned episode, unsigned step,
+// logarithm and the sine / cosine are the single-MUFU forms (|error| < 1e-6 on a unit normal).
+static __device__ __forceinline__ void noise8(unsigned seed_lo, unsigned seed_hi, long long gid, unsigned episode, unsigned step,
                                     float n[8]) {
     const uint4 a = philox(seed_lo, seed_hi, gid, ST_NOISE_A, episode, step);
     const unsigned w[4] = {a.x, a.y, a.z, a.w};
