@@ -372,6 +372,53 @@ def run_ours(args):
                                 "us_per_step": us, "env_steps_per_sec": 4096 / (us * 1e-6)}
         small.close()
 
+        # row S14 (reference training default enable_curiosity=True): the batch's curiosity term on the tensor cores, timed
+        # alone on a slab of the headline size in its steady mix (cold L2) next to the fp32 torch path it replaces
+        try:
+            from tvc_ai_b200.env import CuriosityModule
+            torch.manual_seed(0)
+            fm = CuriosityModule(obs_dim=8, action_dim=2, device=dev).forward_model
+            ce = BatchedEngine(n, _workload_cfg(A), device=local)
+            ce.reset()
+            cact = pool[0]
+            for w in range(100):
+                ce.step(pool[w % 16], want_final=True)
+            ce.step(cact, want_final=True)
+            prev_s8 = ce.obs[:, :8].clone()
+            hasp = torch.ones(n, dtype=torch.uint8, device=dev)
+            rew_c, intr_c = torch.empty(n, device=dev), torch.empty(n, device=dev)
+            ce.curiosity(cact, prev_s8, hasp, rew_c, intrinsic=intr_c, forward_model=fm)
+            cms, tms = [], []
+            hb = hasp.bool()
+            for k in range(20):
+                flush.zero_()
+                e0.record()
+                ce.curiosity(cact, prev_s8, hasp, rew_c, intrinsic=intr_c)
+                e1.record()
+                torch.cuda.synchronize(dev)
+                cms.append(e0.elapsed_time(e1))
+                flush.zero_()
+                e0.record()
+                with torch.no_grad():
+                    dn = (ce.terminated | ce.truncated).bool()
+                    nx8 = torch.where(dn[:, None], ce.final_obs[:, :8], ce.obs[:, :8])
+                    ii = 0.01 * ((fm(torch.cat([prev_s8, cact.clamp(-1.0, 1.0)], dim=1)) - nx8) ** 2).mean(dim=1)
+                    _ = ce.reward + torch.where(hb, ii, torch.zeros_like(ii))
+                    prev_s8.copy_(ce.obs[:, :8]); hb.copy_(~dn)
+                e1.record()
+                torch.cuda.synchronize(dev)
+                tms.append(e0.elapsed_time(e1))
+            cms.sort(); tms.sort()
+            cflops = 2.0 * n * (16 * 256 + 256 * 256 + 256 * 16)
+            extra["curiosity"] = {"workload": f"row S14 for {n} envs: forward model 10-256-256-8 (bf16 tcgen05.mma, fp32 accumulate in TMEM) + MSE + "
+                                              "reward add + history update in one launch (tvc_curiosity), after the step",
+                                  "ms_per_step": cms[len(cms) // 2], "mma_tflops": cflops / (cms[len(cms) // 2] * 1e-3) / 1e12,
+                                  "torch_fp32_ms_per_step": tms[len(tms) // 2],
+                                  "torch_what": "eager fp32 nn.Sequential forward (cuBLAS) + the elementwise kernels around it"}
+            ce.close()
+        except Exception as exc:  # noqa: BLE001
+            extra["curiosity"] = {"error": f"{type(exc).__name__}: {exc}"}
+
         # configs[3]: fused rollout, 65,536 envs, SAC actor MLP 2x256 (bf16 tcgen05) inside the step loop, T=64
         if not args.no_rollout:
             nr, T = 65536, 64

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TVC_ABI_VERSION 7
+#define TVC_ABI_VERSION 8
 
 #define TVC_OBS_DIM 10
 #define TVC_ACT_DIM 2
@@ -243,6 +243,35 @@ int tvc_host_sync(tvc_handle *h);
 /* Fused rollout: T env steps per launch with the SAC actor MLP evaluated inside the loop
  * (replaces train.py:546-603's get_action -> step loop for the legacy 2x256 actor). */
 int tvc_rollout(tvc_handle *h, const tvc_actor_weights *w, int32_t T, const tvc_rollout_io *io, tvc_stream stream);
+
+/* Row S14 for the whole batch: the intrinsic-curiosity term of enhanced_rocket_tvc_env.py:494-506 with the forward model of
+ * :226-269 (Linear(10,256)-ReLU-Linear(256,256)-ReLU-Linear(256,8) over [state8, action2]; never trained -- quirk Q19) on the
+ * tensor cores (bf16 operands, fp32 accumulation; csrc/tvc_curiosity.cu).  Call it after tvc_step with that step's actions
+ * and results.  Per env: intrinsic = has_prev ? 0.01 * mean((forward([prev_state, clip(action)]) - next8)^2) : 0 with
+ * next8 = the step's own successor state (final_obs[:8] where the episode ended, else obs[:8]); reward_out = reward_in +
+ * intrinsic (quirk Q14: after the env's clip; clip_sum = 1 clips the sum instead); then prev_state <- obs[:8] and
+ * has_prev <- !done (reset() clears state_history, :399-401).  w == NULL reuses the weights packed by an earlier call. */
+typedef struct tvc_forward_model {
+    const float *w1, *b1; /* [256,10], [256]   (torch nn.Linear layout [out,in]) */
+    const float *w2, *b2; /* [256,256], [256] */
+    const float *w3, *b3; /* [8,256], [8] */
+} tvc_forward_model;
+
+typedef struct tvc_curiosity_io {
+    const float *actions;      /* [N,2] REQUIRED */
+    const float *obs;          /* [N,10] REQUIRED: what tvc_step returned */
+    const float *final_obs;    /* [N,10] nullable (same-step autoreset: terminal observations) */
+    const uint8_t *terminated; /* [N] nullable */
+    const uint8_t *truncated;  /* [N] nullable */
+    float *prev_state;         /* [N,8] REQUIRED, in/out: state_history[-1] */
+    uint8_t *has_prev;         /* [N] REQUIRED, in/out: len(state_history) > 0 */
+    const float *reward_in;    /* [N] nullable */
+    float *reward_out;         /* [N] nullable; may alias reward_in */
+    float *intrinsic;          /* [N] nullable: reward_components['curiosity'] */
+    int32_t clip_sum;          /* 0: quirk Q14 (reference) */
+    int32_t reserved;
+} tvc_curiosity_io;
+int tvc_curiosity(tvc_handle *h, const tvc_forward_model *w, const tvc_curiosity_io *io, tvc_stream stream);
 
 /* On-device replay ring (replaces train.py:574-591's batch-of-1 agent.update feed).  The ring
  * is caller memory; tvc_rollout fills it in place when tvc_rollout_io.obs_all / actions_all / reward_all / next_obs_all /

@@ -68,10 +68,14 @@ def test_facade_and_vector_env_match_the_reference_curiosity(lib_built, golden_d
     n = 3
     cm = CuriosityModule(obs_dim=8, action_dim=2, device="cuda")
     _load_weights(cm, g)
-    venv = RocketTVCVectorEnv(n, config={}, contract="R", enable_curiosity=True, curiosity_module=cm, final_info=False)
+    venv = RocketTVCVectorEnv(n, config={}, contract="R", enable_curiosity=True, curiosity_module=cm, final_info=False,
+                              curiosity_impl="torch")
+    tenv = RocketTVCVectorEnv(n, config={}, contract="R", enable_curiosity=True, curiosity_module=cm, final_info=False,
+                              curiosity_impl="tcgen05")      # the batch default: forward model on the tensor cores (bf16)
     env.reset(seed=42)
     venv.reset(seed=42)
-    worst_c, worst_r, worst_v = 0.0, 0.0, 0.0
+    tenv.reset(seed=42)
+    worst_c, worst_r, worst_v, worst_tc, worst_tr = 0.0, 0.0, 0.0, 0.0, 0.0
     for t in range(T):
         a = g["actions"][t]
         obs, r, term, trunc, info = env.step(a)
@@ -83,9 +87,14 @@ def test_facade_and_vector_env_match_the_reference_curiosity(lib_built, golden_d
         _, rv, tv, _, _ = venv.step(torch.from_numpy(np.tile(a, (n, 1))).cuda())
         worst_v = max(worst_v, float((rv - float(r)).abs().max()) / max(1.0, abs(float(r))))
         assert bool(tv[0]) == term
+        _, rt, _, _, _ = tenv.step(torch.from_numpy(np.tile(a, (n, 1))).cuda())
+        worst_tc = max(worst_tc, abs(float(tenv.intrinsic[0]) - g["curiosity"][t]) / max(1e-3, abs(g["curiosity"][t])))
+        worst_tr = max(worst_tr, abs(float(rt[0]) - g["reward"][t]) / max(1.0, abs(g["reward"][t])))
         if g["was_reset"][t]:
             env.reset()          # the VectorEnv reset itself in the same step
     parity_record["curiosity_vs_reference"] = dict(steps=T, intrinsic_rel_max=worst_c, reward_rel_max=worst_r,
-                                                   batched_vs_facade_rel_max=worst_v)
+                                                   batched_vs_facade_rel_max=worst_v, tcgen05_intrinsic_rel_max=worst_tc,
+                                                   tcgen05_reward_rel_max=worst_tr)
     assert worst_c <= 2e-3 and worst_r <= 2e-4 and worst_v <= 1e-5, parity_record["curiosity_vs_reference"]
-    env.close(); venv.close()
+    assert worst_tc <= 3e-2 and worst_tr <= 2e-4, parity_record["curiosity_vs_reference"]     # bf16 bar on the term, the same reward bar
+    env.close(); venv.close(); tenv.close()

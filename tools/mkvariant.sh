@@ -5,5 +5,5 @@ cd "$(dirname "$0")/.."
 name=$1; shift
 SRC=${SRC_ROOT:-.}
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC -cudart shared --threads 2 "$@" \
-  -o variants/$name.so $SRC/tvc_ai_b200/csrc/tvc_abi.cu $SRC/tvc_ai_b200/csrc/tvc_rollout.cu $SRC/tvc_ai_b200/csrc/tvc_replay.cu
+  -o variants/$name.so $SRC/tvc_ai_b200/csrc/tvc_abi.cu $SRC/tvc_ai_b200/csrc/tvc_rollout.cu $SRC/tvc_ai_b200/csrc/tvc_replay.cu $SRC/tvc_ai_b200/csrc/tvc_curiosity.cu
 echo built variants/$name.so

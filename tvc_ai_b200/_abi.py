@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TVC_B200_LIB") or os.path.join(_HERE, "libtvc_b200.so")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 OBS_DIM, ACT_DIM, NUM_COMPONENTS, NUM_STATS, MAX_DELAY = 10, 2, 12, 16, 4
 CONTRACT_R, CONTRACT_X = 0, 1
 DIV_OFF, DIV_FAST, DIV_EXACT = 0, 1, 2
@@ -35,7 +35,7 @@ STAT_NAMES = ("episodes", "sum_return", "sum_return_sq", "sum_length", "successe
 EXPORTS = ("tvc_abi_version", "tvc_last_error", "tvc_config_default", "tvc_create", "tvc_destroy", "tvc_reset",
            "tvc_step", "tvc_step_ex", "tvc_step_host", "tvc_step_host_async", "tvc_host_sync", "tvc_rollout", "tvc_state_bytes", "tvc_get_state",
            "tvc_set_state", "tvc_get_reward_history", "tvc_set_reward_history", "tvc_read_info", "tvc_episode_stats", "tvc_episode_stats_dev", "tvc_set_curriculum",
-           "tvc_get_config", "tvc_num_envs", "tvc_lifetime_steps", "tvc_replay_sample")
+           "tvc_get_config", "tvc_num_envs", "tvc_lifetime_steps", "tvc_replay_sample", "tvc_curiosity")
 
 
 class TvcConfig(C.Structure):
@@ -90,6 +90,17 @@ class TvcEnvState(C.Structure):
 class TvcActorWeights(C.Structure):
     _fields_ = [("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
                 ("w3", C.c_void_p), ("b3", C.c_void_p)]
+
+
+class TvcForwardModel(C.Structure):
+    _fields_ = [("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+                ("w3", C.c_void_p), ("b3", C.c_void_p)]
+
+
+class TvcCuriosityIO(C.Structure):
+    _fields_ = [("actions", C.c_void_p), ("obs", C.c_void_p), ("final_obs", C.c_void_p), ("terminated", C.c_void_p),
+                ("truncated", C.c_void_p), ("prev_state", C.c_void_p), ("has_prev", C.c_void_p), ("reward_in", C.c_void_p),
+                ("reward_out", C.c_void_p), ("intrinsic", C.c_void_p), ("clip_sum", C.c_int32), ("reserved", C.c_int32)]
 
 
 class TvcReplayRing(C.Structure):
@@ -151,6 +162,7 @@ def load(path: str | None = None):
     L.tvc_num_envs.restype = i64
     L.tvc_lifetime_steps.argtypes = [vp]
     L.tvc_lifetime_steps.restype = i64
+    L.tvc_curiosity.argtypes = [vp, C.POINTER(TvcForwardModel), C.POINTER(TvcCuriosityIO), vp]
     L.tvc_replay_sample.argtypes = [C.POINTER(TvcReplayRing), i64, i32, u64, u64, vp, C.c_float, C.POINTER(TvcReplayBatch), C.c_int, vp]
     for name in EXPORTS:
         fn = getattr(L, name)

@@ -8,12 +8,12 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libtvc_b200.so")
-SOURCES = ("tvc_abi.cu", "tvc_rollout.cu", "tvc_replay.cu")
-HEADERS = ("tvc_device.cuh", "tvc_internal.h", os.path.join("..", "..", "include", "tvc_b200.h"))
+SOURCES = ("tvc_abi.cu", "tvc_rollout.cu", "tvc_replay.cu", "tvc_curiosity.cu")
+HEADERS = ("tvc_device.cuh", "tvc_internal.h", "tvc_umma.cuh", os.path.join("..", "..", "include", "tvc_b200.h"))
 # -cudart shared: the library imports only the runtime symbols it uses (libcudart.so.12, the same SONAME torch loads)
 # instead of embedding the whole static runtime; --threads 2: the two translation units compile side by side
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC", "-cudart", "shared", "--threads", "3"]
+              "-shared", "-Xcompiler", "-fPIC", "-cudart", "shared", "--threads", "4"]
 
 
 def _nvcc() -> str:

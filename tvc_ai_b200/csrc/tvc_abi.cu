@@ -655,6 +655,7 @@ int tvc_destroy(tvc_handle *h) {
     cudaFree(s.delay); cudaFree(s.partial); cudaFree(s.order); cudaFree(s.ccount); cudaFree(s.scount); cudaFree(s.done_list); cudaFree(s.totals); cudaFree(s.counter); cudaFree(s.cls); cudaFree(h->stats_dev);
     cudaFree(h->io_act); cudaFree(h->io_obs) /* the obs|reward|flags slab */; cudaFree(h->io_final);
     tvc_rollout_free(h);
+    tvc_curiosity_free(h);
     if (h->stats_host) cudaFreeHost(h->stats_host);
     if (h->act_pinned) cudaFreeHost(h->act_pinned);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);

@@ -32,6 +32,8 @@ struct tvc_handle {
     float *final_host_dev = nullptr;          // its device alias when it is pinned (mapped) host memory, else NULL
     // fused-rollout workspace (tvc_rollout.cu)
     void *rollout_ws = nullptr;
+    // packed forward-model weights of tvc_curiosity (tvc_curiosity.cu)
+    void *curiosity_ws = nullptr;
 };
 
 // tvc_config (ABI) -> the constants the device code reads
@@ -57,3 +59,4 @@ inline void make_devcfg(const tvc_config &c, tvc::DevCfg &d) {
 
 const char *tvc_set_err(const std::string &m);
 void tvc_rollout_free(tvc_handle *h);
+void tvc_curiosity_free(tvc_handle *h);

@@ -14,12 +14,14 @@
 //   Philox eps, tanh -> action -> env_pre / integrate / env_post (same device code as step_kernel).
 // One elected thread issues the MMAs; completion is signalled through tcgen05.commit -> mbarrier.
 #include "tvc_internal.h"
+#include "tvc_umma.cuh"
 
 #include <cuda_bf16.h>
 #include <cstring>
 #include <string>
 
 using namespace tvc;
+using namespace tvc_umma;
 
 namespace {
 
@@ -51,74 +53,11 @@ static_assert(NT >= 2 && NT % 2 == 0, "tiles alternate between two TMEM column s
 static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 
 // UMMA instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=128 (cute::UMMA::InstrDescriptor)
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC = idesc_bf16(128, 256);
 
 struct RolloutWs {
     uint8_t *img = nullptr;   // [W2 image][W1 image][vec] in the shared-memory layout
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-// core matrix = 8 rows x 16 bytes; SBO = stride between 8-row groups, LBO = stride between the two
-// 16-byte K chunks of one K=16 step.  Images are laid out [K/8][rows/8][8 rows][8 elems].
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t lo = (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16);
-    uint64_t hi = (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) | (1ull << 14);   // version = 1 (Blackwell)
-    return lo | (hi << 32);
-}
-
-__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-        :: "r"(tmem_d), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}\n"
-        :: "r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// 32 consecutive accumulator columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr) : "memory");
-}
-
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t *>(&h);
-}
 
 // fp32 [out,in] torch weights -> bf16 UMMA images + fp32 vectors, in the shared-memory layout
 __global__ void pack_actor_kernel(tvc_actor_weights w, uint8_t *img) {
@@ -256,7 +195,7 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
 #pragma unroll
                 for (int j = 0; j < NSET; j++) {
                     mma_bf16(tmem_base + j * HID, umma_desc(s_base + OFF_A1 + j * A1_BYTES, TM * 16, 128),
-                             umma_desc(s_base + OFF_W1, HID * 16, 128), 0u);
+                             umma_desc(s_base + OFF_W1, HID * 16, 128), IDESC, 0u);
                     mma_commit(s_base + OFF_BAR + 8 + 8 * j);
                 }
             }
@@ -294,7 +233,7 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
 #pragma unroll
                         for (int kk = 0; kk < HID / 16; kk++)
                             mma_bf16(tmem_base + sj * HID, umma_desc(s_base + OFF_H1 + kk * 2 * (TM * 16), TM * 16, 128),
-                                     umma_desc(s_base + OFF_W2 + kk * 2 * (HID * 16), HID * 16, 128), kk > 0 ? 1u : 0u);
+                                     umma_desc(s_base + OFF_W2 + kk * 2 * (HID * 16), HID * 16, 128), IDESC, kk > 0 ? 1u : 0u);
                         mma_commit(s_base + OFF_BAR + 8 + 8 * sj);
                     }
                 }
@@ -326,7 +265,7 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
                 if (tid == 0 && j > 0 && j + 1 < NT) {   // layer 1 of tile j + 1 into the set tile j - 1 just left
                     tc_fence_after();
                     mma_bf16(tmem_base + ((j + 1) % NSET) * HID, umma_desc(s_base + OFF_A1 + (j + 1) * A1_BYTES, TM * 16, 128),
-                             umma_desc(s_base + OFF_W1, HID * 16, 128), 0u);
+                             umma_desc(s_base + OFF_W1, HID * 16, 128), IDESC, 0u);
                     mma_commit(s_base + OFF_BAR + 8 + 8 * ((j + 1) % NSET));
                 }
             }

@@ -239,6 +239,38 @@ class BatchedEngine:
         return int(self.L.tvc_lifetime_steps(self.h))
 
     # ------------------------------------------------------------------ fused rollout
+    def curiosity(self, actions: torch.Tensor, prev_state: torch.Tensor, has_prev: torch.Tensor, reward_out: torch.Tensor,
+                  intrinsic: torch.Tensor | None = None, forward_model=None, clip_sum: bool = False):
+        """Row S14 for the batch on the tensor cores (tvc_curiosity): call after `step` with that step's actions.
+
+        prev_state [N,8] f32 and has_prev [N] u8 are the kernel's in/out history; reward_out [N] receives reward + intrinsic
+        (the engine's own reward buffer keeps the extrinsic value).  forward_model: a torch nn.Sequential
+        Linear(10,256)-ReLU-Linear(256,256)-ReLU-Linear(256,8) to (re)pack, or None to reuse the packed weights."""
+        w = None
+        keep = []
+        if forward_model is not None:
+            w = A.TvcForwardModel()
+            lin = [m for m in forward_model if isinstance(m, torch.nn.Linear)]
+            if [tuple(m.weight.shape) for m in lin] != [(256, 10), (256, 256), (8, 256)]:
+                raise ValueError("tvc_curiosity is built for the reference's forward model 10-256-256-8")
+            for k, m in zip(("1", "2", "3"), lin):
+                wt = m.weight.detach().to(device=self.device, dtype=torch.float32).contiguous()
+                bt = m.bias.detach().to(device=self.device, dtype=torch.float32).contiguous()
+                keep += [wt, bt]
+                setattr(w, "w" + k, wt.data_ptr()), setattr(w, "b" + k, bt.data_ptr())
+        a = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        io = A.TvcCuriosityIO()
+        io.actions, io.obs, io.final_obs = a.data_ptr(), self.obs.data_ptr(), self.final_obs.data_ptr()
+        io.terminated, io.truncated = self.terminated.data_ptr(), self.truncated.data_ptr()
+        io.prev_state, io.has_prev = prev_state.data_ptr(), has_prev.data_ptr()
+        io.reward_in, io.reward_out = self.reward.data_ptr(), reward_out.data_ptr()
+        io.intrinsic = intrinsic.data_ptr() if intrinsic is not None else None
+        io.clip_sum = int(clip_sum)
+        A.check(self.L.tvc_curiosity(self.h, C.byref(w) if w is not None else None, C.byref(io), self._stream()), "tvc_curiosity")
+        if keep:
+            torch.cuda.current_stream(self.device).synchronize()   # the pack kernel read the temporaries
+        return reward_out
+
     def rollout(self, weights: dict, T: int, deterministic: bool = False, record: bool = False, transitions: dict | None = None):
         """T env steps per launch with the 2x256 SAC actor evaluated in-kernel (tvc_rollout).
 

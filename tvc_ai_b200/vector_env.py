@@ -28,7 +28,7 @@ class RocketTVCVectorEnv:
     def __init__(self, num_envs: int, config: Optional[dict] = None, max_episode_steps: int = 1000,
                  contract: str | int = "R", device: Optional[int] = None, env_id_base: int = 0,
                  final_info: bool = True, copy_outputs: bool = True, enable_curiosity: bool = False,
-                 curiosity_module=None, **engine_over):
+                 curiosity_module=None, curiosity_impl: str = "tcgen05", **engine_over):
         if isinstance(contract, str):
             contract = {"R": A.CONTRACT_R, "X": A.CONTRACT_X}[contract.upper()]
         self.num_envs = int(num_envs)
@@ -50,13 +50,22 @@ class RocketTVCVectorEnv:
         # Row S14 / quirks Q14, Q19 for the batch (torch path): the reference's never-trained forward model adds
         # 0.01 * mean((f([s8, a]) - s8')^2) to the clipped reward, skipped on the first step of every episode
         # (ref:257-269, :496-502).  Off by default, as in the reference's evaluation env (scripts/train.py:329).
+        # curiosity_impl: "tcgen05" = the batched tensor-core kernel tvc_curiosity (bf16 operands, fp32 accumulation: the
+        # term agrees with the fp32 module to ~3e-3 relative, the reward to < 1e-6); "torch" = the fp32 torch module.
         self.enable_curiosity = bool(enable_curiosity)
         self.curiosity_module = None
+        if curiosity_impl not in ("tcgen05", "torch"):
+            raise ValueError("curiosity_impl must be 'tcgen05' or 'torch'")
+        self.curiosity_impl = curiosity_impl
         if self.enable_curiosity:
             from .env import CuriosityModule
             self.curiosity_module = curiosity_module or CuriosityModule(obs_dim=8, action_dim=2, device=self.engine.device)
             self._prev_s8 = torch.zeros((self.num_envs, 8), device=self.engine.device)
             self._has_prev = torch.zeros(self.num_envs, dtype=torch.bool, device=self.engine.device)
+            self._has_prev_u8 = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.engine.device)
+            self._rew_total = torch.zeros(self.num_envs, dtype=torch.float32, device=self.engine.device)
+            self.intrinsic = torch.zeros(self.num_envs, dtype=torch.float32, device=self.engine.device)
+            self._fm_packed = False
 
     # ------------------------------------------------------------------
     def reset(self, *, seed: Optional[int] = None, options: Optional[dict] = None):
@@ -66,6 +75,7 @@ class RocketTVCVectorEnv:
         obs = self.engine.reset(seed=seed)
         if self.enable_curiosity:
             self._has_prev.zero_()          # ref:399-401: reset() clears state_history
+            self._has_prev_u8.zero_()
         return (obs if as_torch else obs.cpu().numpy().copy()), {}
 
     def step(self, actions):
@@ -90,14 +100,22 @@ class RocketTVCVectorEnv:
         if self.enable_curiosity:
             if actions is None:
                 raise ValueError("enable_curiosity needs the actions (in-kernel random actions are not visible to the forward model)")
-            with torch.no_grad():
-                a = actions.reshape(self.num_envs, 2).clamp(-1.0, 1.0)
-                s8_next = torch.where(done[:, None], self.engine.final_obs[:, :8], obs[:, :8])   # the env's own next state
-                pred = self.curiosity_module.forward_model(torch.cat([self._prev_s8, a], dim=1))
-                intrinsic = 0.01 * ((pred - s8_next) ** 2).mean(dim=1)
-                rew = rew + torch.where(self._has_prev, intrinsic, torch.zeros_like(intrinsic))   # a new tensor: the engine's buffer keeps the extrinsic reward
-                self._prev_s8.copy_(obs[:, :8])
-                self._has_prev.copy_(~done)
+            if self.curiosity_impl == "tcgen05":
+                # one launch: forward model on the tensor cores + MSE + reward add + history update (csrc/tvc_curiosity.cu)
+                rew = self.engine.curiosity(actions.reshape(self.num_envs, 2), self._prev_s8, self._has_prev_u8, self._rew_total,
+                                            intrinsic=self.intrinsic,
+                                            forward_model=None if self._fm_packed else self.curiosity_module.forward_model)
+                self._fm_packed = True
+            else:
+                with torch.no_grad():
+                    a = actions.reshape(self.num_envs, 2).clamp(-1.0, 1.0)
+                    s8_next = torch.where(done[:, None], self.engine.final_obs[:, :8], obs[:, :8])   # the env's own next state
+                    pred = self.curiosity_module.forward_model(torch.cat([self._prev_s8, a], dim=1))
+                    intrinsic = 0.01 * ((pred - s8_next) ** 2).mean(dim=1)
+                    self.intrinsic = torch.where(self._has_prev, intrinsic, torch.zeros_like(intrinsic))
+                    rew = rew + self.intrinsic   # a new tensor: the engine's buffer keeps the extrinsic reward
+                    self._prev_s8.copy_(obs[:, :8])
+                    self._has_prev.copy_(~done)
         infos = {"final_observation": self.engine.final_obs, "_final_observation": done}
         if info is not None:
             infos["final_info"] = {k: info[k] for k in ("altitude", "tilt_deg", "omega_mag", "fuel", "phase", "step",
