@@ -38,7 +38,7 @@ timeit("engine.step(device actions) + sync", dev_step)
 # slab-pipelined host env
 from tvc_ai_b200.vector_env import RocketTVCHostPipelineEnv
 venv.close()
-for slabs in (1, 2, 3, 4):
+for slabs in ((1, 2) if os.environ.get('E2E_PROBE_SHORT') else (1, 2, 3, 4)):
     env = RocketTVCHostPipelineEnv(n, config={}, contract="X", device=0, slabs=slabs)
     env.reset(seed=42)
     for e_, (lo, hi) in zip(env.engines, env._ranges):

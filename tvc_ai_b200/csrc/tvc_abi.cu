@@ -789,7 +789,10 @@ int tvc_step_host_async(tvc_handle *h, const float *actions_host, float *obs_hos
     cudaStream_t s = h->own_stream;
     if (actions_host) {
         // pinned caller memory goes to the copy engine as it is; pageable memory is staged through the handle's own
-        // pinned buffer first (an asynchronous copy from pageable memory would stage inside the driver anyway)
+        // pinned buffer first (an asynchronous copy from pageable memory would stage inside the driver anyway).
+        // Measured and rejected: the step kernel reading pinned actions in place over PCIe (8 B per env beside the state
+        // loads, no host-to-device copy): 0.474 ms per end-to-end step against 0.370 with the copy -- 2,368 warps' 256-byte
+        // reads arrive far below the copy engine's 56 GB/s and sit at the head of every env's dependent chain.
         const float *src = actions_host;
         cudaPointerAttributes at;
         const bool pinned = cudaPointerGetAttributes(&at, actions_host) == cudaSuccess && at.type == cudaMemoryTypeHost;

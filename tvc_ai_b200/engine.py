@@ -159,19 +159,23 @@ class BatchedEngine:
                               rew=slab[40 * n:44 * n].view(torch.float32),
                               term=slab[44 * n:45 * n], trunc=slab[45 * n:46 * n],
                               final=pin((n, 10), torch.float32))
+            h_ = self._host
+            # numpy views and raw pointers are made once: the step path does no per-call tensor bookkeeping
+            h_["views"] = (h_["obs"].numpy(), h_["rew"].numpy(), h_["term"].numpy().view(np.bool_), h_["trunc"].numpy().view(np.bool_),
+                           h_["final"].numpy())
+            h_["ptrs"] = tuple(C.c_void_p(h_[k].data_ptr()) for k in ("obs", "rew", "term", "trunc", "final"))
         hb = self._host
         ap = None
         if actions_np is not None:
-            # the library copies straight from pinned memory (e.g. `pinned_actions()`) and stages pageable arrays itself
-            act = np.ascontiguousarray(actions_np, np.float32)
+            # the library reads pinned memory (e.g. `pinned_actions()`) in place and stages pageable arrays itself
+            act = actions_np if (actions_np.dtype == np.float32 and actions_np.flags.c_contiguous) else np.ascontiguousarray(actions_np, np.float32)
             if act.size != 2 * self.n:
                 raise ValueError(f"actions must have shape ({self.n}, 2)")
-            ap = C.c_void_p(act.ctypes.data)
-        A.check(self.L.tvc_step_host(self.h, ap, C.c_void_p(hb["obs"].data_ptr()), C.c_void_p(hb["rew"].data_ptr()),
-                                     C.c_void_p(hb["term"].data_ptr()), C.c_void_p(hb["trunc"].data_ptr()),
-                                     C.c_void_p(hb["final"].data_ptr()) if want_final else None), "tvc_step_host")
-        return (hb["obs"].numpy(), hb["rew"].numpy(), hb["term"].numpy().view(np.bool_),
-                hb["trunc"].numpy().view(np.bool_), hb["final"].numpy() if want_final else None)
+            ap = act.ctypes.data
+        p = hb["ptrs"]
+        A.check(self.L.tvc_step_host(self.h, ap, p[0], p[1], p[2], p[3], p[4] if want_final else None), "tvc_step_host")
+        v = hb["views"]
+        return v[0], v[1], v[2], v[3], (v[4] if want_final else None)
 
     def pinned_actions(self) -> np.ndarray:
         """A pinned (page-locked) [N,2] float32 array: actions written here go to the device without a staging copy."""

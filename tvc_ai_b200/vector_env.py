@@ -47,6 +47,7 @@ class RocketTVCVectorEnv:
         # numpy path: True returns fresh arrays every step (Gymnasium semantics); False returns views of the pinned
         # host buffers tvc_step_host writes into (valid until the next step) and float32 rewards -- no host copies
         self._copy_outputs = bool(copy_outputs)
+        self._done_buf = None
         # Row S14 / quirks Q14, Q19 for the batch (torch path): the reference's never-trained forward model adds
         # 0.01 * mean((f([s8, a]) - s8')^2) to the clipped reward, skipped on the first step of every episode
         # (ref:257-269, :496-502).  Off by default, as in the reference's evaluation env (scripts/train.py:329).
@@ -134,7 +135,12 @@ class RocketTVCVectorEnv:
         obs, rew, term, trunc, final = self.engine.step_host(actions, want_final=True)
         if self._copy_outputs:
             obs, rew, term, trunc = obs.copy(), rew.astype(np.float64), term.copy(), trunc.copy()
-        done = term | trunc
+        if self._copy_outputs:
+            done = term | trunc
+        else:       # views path: the mask lives in a reused buffer as well
+            if self._done_buf is None:
+                self._done_buf = np.empty(self.num_envs, np.bool_)
+            done = np.bitwise_or(term, trunc, out=self._done_buf)
         infos = {}
         if done.any():
             if self.num_envs <= self.OBJECT_INFO_MAX:
