@@ -68,15 +68,17 @@ def _issue_roofline(ms, clocks):
                     "the instruction count and latency along each warp's chain bound it; see DESIGN.md section 6"}
 
 
+STEP_PATH_SOURCES = ("tvc_abi.cu", "tvc_device.cuh", "tvc_internal.h")   # what step_kernel_v2 / close_kernel are compiled from
+
+
 def csrc_hash() -> str:
-    """sha256 (first 16 hex digits) over the kernel sources: the committed ncu figures are only quoted for the build they
-    were captured from."""
+    """sha256 (first 16 hex digits) over the step path's kernel sources: the committed ncu figures of the step kernel are only
+    quoted for the build they were captured from."""
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, "tvc_ai_b200", "csrc")
-    for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh", ".h")):
-            h.update(open(os.path.join(d, f), "rb").read())
+    for f in STEP_PATH_SOURCES:
+        h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]
 
 
