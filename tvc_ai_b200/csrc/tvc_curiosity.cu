@@ -54,7 +54,7 @@ static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 static_assert(OFF_A1 % 1024 == 0 && OFF_H % 1024 == 0, "operand tiles stay 1 KB aligned");
 constexpr uint32_t IDESC_WIDE = idesc_bf16(128, 256), IDESC_OUT = idesc_bf16(128, NOUT);
 constexpr uint32_t TMEM_COLS = 512;                      // 256 (layers 1 / 2) + 16 (layer 3), power of two
-constexpr uint32_t COL_OUT = 256;
+constexpr uint32_t COL_L2 = 256;                         // layer-2 accumulators; layer 3 reuses the first 16 of them
 
 struct CuriosityWs { uint8_t *img = nullptr; bool packed = false; };
 
@@ -187,83 +187,102 @@ curiosity_kernel(const uint8_t *__restrict__ img, const __grid_constant__ CurIO 
     const bool closer = tid >= TM && tid < 2 * TM;       // warps 4-7: row = tid - 128 (TMEM lane quarter = warp - 4), narrow epilogue
     const int crow = tid - TM;
 
+    // One wide epilogue pass: this thread's 32 accumulator columns `col0 .. col0 + 31` of row r -> bias + ReLU -> bf16 -> the
+    // hidden tile's K chunks col0 / 8 .. + 3 (thread-contiguous 16-byte stores = the UMMA layout, conflict-free).
+    auto wide_pass = [&](uint32_t tcol, int col0, const float *bias) {
+        uint32_t v[32];
+        tmem_ld32(tq + tcol, v);
+#pragma unroll
+        for (int qq = 0; qq < 4; qq++) {
+            float h[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) h[jj] = fmaxf(__uint_as_float(v[8 * qq + jj]) + bias[col0 + 8 * qq + jj], 0.0f);
+            *reinterpret_cast<uint4 *>(smem + OFF_H + ((col0 >> 3) + qq) * (TM * 16) + r * 16) =
+                make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+        }
+    };
+    // eight K steps (hidden columns 128 half .. + 127) of a 256-deep layer: A = the hidden tile, B = a weight image of `rows` rows
+    auto mma_half = [&](uint32_t d_tmem, uint32_t w_off, uint32_t rows, uint32_t idesc, int half) {
+#pragma unroll
+        for (int kk = 8 * half; kk < 8 * half + 8; kk++)
+            mma_bf16(d_tmem, umma_desc(s_base + OFF_H + kk * 2 * (TM * 16), TM * 16, 128),
+                     umma_desc(s_base + w_off + kk * 2 * (rows * 16), rows * 16, 128), idesc, kk > 0 ? 1u : 0u);
+    };
+    auto write_operand = [&](const RowA &x) {   // layer-1 operand [2][128][8] bf16: chunk 0 = the eight state inputs, chunk 1 = the two actions + zero padding
+        *reinterpret_cast<uint4 *>(smem + OFF_A1 + tid * 16) =
+            make_uint4(pack_bf16(x.s[0], x.s[1]), pack_bf16(x.s[2], x.s[3]), pack_bf16(x.s[4], x.s[5]), pack_bf16(x.s[6], x.s[7]));
+        *reinterpret_cast<uint4 *>(smem + OFF_A1 + TM * 16 + tid * 16) = make_uint4(pack_bf16(x.a0, x.a1), 0u, 0u, 0u);
+    };
+
+    // TMEM columns: [0, 256) layer-1 accumulators, [256, 512) layer-2 accumulators, [256, 272) layer-3 accumulators (written
+    // once the first pass of the second epilogue has read them).  The wide epilogues run in two passes of 128 hidden columns
+    // (32 per thread); the next layer's first eight K steps are issued after pass 0 and run on the tensor pipe under pass 1,
+    // and layer 1 of the NEXT tile is issued as soon as this tile's first epilogue has left its accumulators.
     RowA ca;
     RowB cb_;
-    if (feeder) load_row_a(io, (long long)blockIdx.x * TM + tid, ca);
+    if (feeder) { load_row_a(io, (long long)blockIdx.x * TM + tid, ca); write_operand(ca); }
     if (closer) load_row_b(io, (long long)blockIdx.x * TM + crow, cb_);
     mbar_wait(bar_w, 0);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+        tc_fence_after();
+        mma_bf16(tmem_base, umma_desc(s_base + OFF_A1, TM * 16, 128), umma_desc(s_base + OFF_W1, HID * 16, 128), IDESC_WIDE, 0u);
+        mma_commit(bar1);
+    }
+    const int c32 = m * 32;                              // this thread's 32 columns within a 128-column pass
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1u) {
         RowA na;
         RowB nb;
         const bool more = tile + (int)gridDim.x < ntiles;
-        if (closer && more) load_row_b(io, (long long)(tile + gridDim.x) * TM + crow, nb);
-        if (feeder) {
-            // layer-1 operand [2][128][8] bf16: chunk 0 = the eight state inputs, chunk 1 = the two actions + zero padding
-            *reinterpret_cast<uint4 *>(smem + OFF_A1 + tid * 16) =
-                make_uint4(pack_bf16(ca.s[0], ca.s[1]), pack_bf16(ca.s[2], ca.s[3]), pack_bf16(ca.s[4], ca.s[5]), pack_bf16(ca.s[6], ca.s[7]));
-            *reinterpret_cast<uint4 *>(smem + OFF_A1 + TM * 16 + tid * 16) = make_uint4(pack_bf16(ca.a0, ca.a1), 0u, 0u, 0u);
-            // the next tile's rows: their round trip runs under this tile's three layers
-            if (more) load_row_a(io, (long long)(tile + gridDim.x) * TM + tid, na);
-            ca = na;
+        if (more) {     // the next tile's rows: their round trip runs under this tile's first epilogue / its three layers
+            if (feeder) load_row_a(io, (long long)(tile + gridDim.x) * TM + tid, na);
+            if (closer) load_row_b(io, (long long)(tile + gridDim.x) * TM + crow, nb);
         }
+        mbar_wait(bar1, ph);                             // layer 1 of this tile (issued during the previous tile)
+        if (tile != (int)blockIdx.x) mbar_wait(bar3, ph ^ 1u);   // layer 3 of the previous tile has left the hidden tile
+        tc_fence_after();
+        // ---- epilogue 1 (layer-1 accumulators -> hidden 1), layer 2 issued in halves behind it ----
+        wide_pass(0u + c32, c32, b1);
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();                                 // (also: every warp is done with the previous tile's TMEM and hidden tile)
+        __syncthreads();
+        if (tid == 0) { tc_fence_after(); mma_half(tmem_base + COL_L2, OFF_W2, HID, IDESC_WIDE, 0); }
+        wide_pass(128u + c32, 128 + c32, b1);
+        if (feeder && more) write_operand(na);           // the operand buffer is free: layer 1 of this tile completed above
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();                                 // every warp has read the layer-1 accumulators
         if (tid == 0) {
             tc_fence_after();
-            mma_bf16(tmem_base, umma_desc(s_base + OFF_A1, TM * 16, 128), umma_desc(s_base + OFF_W1, HID * 16, 128), IDESC_WIDE, 0u);
-            mma_commit(bar1);
-        }
-        // ---- the two wide epilogues: bias + ReLU -> bf16 hidden tile; then the next layer's MMAs ----
-#pragma unroll
-        for (int layer = 0; layer < 2; layer++) {
-            mbar_wait(layer == 0 ? bar1 : bar2, ph);
-            tc_fence_after();
-            const float *bias = layer == 0 ? b1 : b2;
-            uint32_t v0[32], v1[32];                     // this thread's 64 accumulator columns: both loads in flight, one wait
-            tmem_ld32_nowait(tq + (uint32_t)(m * 64), v0);
-            tmem_ld32_nowait(tq + (uint32_t)(m * 64 + 32), v1);
-            tmem_ld_wait();
-#pragma unroll
-            for (int hh = 0; hh < 2; hh++) {
-                const int cb = m * 64 + hh * 32;
-#pragma unroll
-                for (int qq = 0; qq < 4; qq++) {
-                    float h[8];
-#pragma unroll
-                    for (int jj = 0; jj < 8; jj++)
-                        h[jj] = fmaxf(__uint_as_float(hh == 0 ? v0[8 * qq + jj] : v1[8 * qq + jj]) + bias[cb + 8 * qq + jj], 0.0f);
-                    *reinterpret_cast<uint4 *>(smem + OFF_H + ((cb >> 3) + qq) * (TM * 16) + r * 16) =
-                        make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
-                }
-            }
-            fence_async_smem();
-            tc_fence_before();
-            __syncthreads();                             // hidden tile complete, accumulators read out by every warp
-            if (tid == 0) {
-                tc_fence_after();
-                if (layer == 0) {
-#pragma unroll
-                    for (int kk = 0; kk < HID / 16; kk++)
-                        mma_bf16(tmem_base, umma_desc(s_base + OFF_H + kk * 2 * (TM * 16), TM * 16, 128),
-                                 umma_desc(s_base + OFF_W2 + kk * 2 * (HID * 16), HID * 16, 128), IDESC_WIDE, kk > 0 ? 1u : 0u);
-                    mma_commit(bar2);
-                } else {
-#pragma unroll
-                    for (int kk = 0; kk < HID / 16; kk++)
-                        mma_bf16(tmem_base + COL_OUT, umma_desc(s_base + OFF_H + kk * 2 * (TM * 16), TM * 16, 128),
-                                 umma_desc(s_base + OFF_W3 + kk * 2 * (NOUT * 16), NOUT * 16, 128), IDESC_OUT, kk > 0 ? 1u : 0u);
-                    mma_commit(bar3);
-                }
+            mma_half(tmem_base + COL_L2, OFF_W2, HID, IDESC_WIDE, 1);
+            mma_commit(bar2);
+            if (more) {                                  // layer 1 of the next tile, under this tile's second epilogue
+                mma_bf16(tmem_base, umma_desc(s_base + OFF_A1, TM * 16, 128), umma_desc(s_base + OFF_W1, HID * 16, 128), IDESC_WIDE, 0u);
+                mma_commit(bar1);
             }
         }
+        // ---- epilogue 2 (layer-2 accumulators -> hidden 2), layer 3 issued in halves behind it ----
+        mbar_wait(bar2, ph);
+        tc_fence_after();
+        wide_pass(COL_L2 + c32, c32, b2);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();                                 // columns [256, 384) have been read: layer 3 may write [256, 272)
+        if (tid == 0) { tc_fence_after(); mma_half(tmem_base + COL_L2, OFF_W3, NOUT, IDESC_OUT, 0); }
+        wide_pass(COL_L2 + 128u + c32, 128 + c32, b2);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) { tc_fence_after(); mma_half(tmem_base + COL_L2, OFF_W3, NOUT, IDESC_OUT, 1); mma_commit(bar3); }
         // ---- the narrow epilogue: one env per thread of warps 4-7 ----
         if (closer) {
             mbar_wait(bar3, ph);
             tc_fence_after();
             uint32_t v[16];
-            tmem_ld16(tmem_base + ((uint32_t)((warp - 4) * 32) << 16) + COL_OUT, v);
+            tmem_ld16(tmem_base + ((uint32_t)((warp - 4) * 32) << 16) + COL_L2, v);
             const long long env = (long long)tile * TM + crow;
             if (env < io.n) {
                 float sq = 0.0f;
