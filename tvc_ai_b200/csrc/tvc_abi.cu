@@ -207,6 +207,8 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
     const unsigned seq = st.counter[CTR_SEQ];    // sequence number (device-side: see close_kernel); its parity picks the buffers
     const int par = (int)(seq & 1u);
     if (blockIdx.x == 0 && threadIdx.x == 0) st.counter[CTR_SEQ2] = seq;
+    const bool any_info = io.altitude || io.tilt_deg || io.omega_mag || io.fuel || io.position || io.phase || io.step || io.success ||
+                          io.criteria_met || io.comp;
 #ifdef TVC_PHASE_PROF2
     long long pt_prev = clock64();
 #endif
@@ -261,18 +263,20 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
             io.reward[i] = r.reward;
             io.term[i] = (uint8_t)r.terminated;
             io.trunc[i] = (uint8_t)r.truncated;
-            if (io.altitude) io.altitude[i] = r.alt;
-            if (io.tilt_deg) io.tilt_deg[i] = r.tilt * 57.29577951308232f;
-            if (io.omega_mag) io.omega_mag[i] = r.wmag;
-            if (io.fuel) io.fuel[i] = r.fuel;
-            if (io.position) { io.position[3 * i] = e.px; io.position[3 * i + 1] = e.py; io.position[3 * i + 2] = e.pz; }
-            if (io.phase) io.phase[i] = e.phase;
-            if (io.step) io.step[i] = e.step;
-            if (io.success) io.success[i] = (uint8_t)e.success;
-            if (io.criteria_met) io.criteria_met[i] = (uint8_t)(e.consec >= 10);
-            if (io.comp) {
+            if (any_info) {     // tvc_step_ex's optional per-env info planes: one uniform test on the plain step path
+                if (io.altitude) io.altitude[i] = r.alt;
+                if (io.tilt_deg) io.tilt_deg[i] = r.tilt * 57.29577951308232f;
+                if (io.omega_mag) io.omega_mag[i] = r.wmag;
+                if (io.fuel) io.fuel[i] = r.fuel;
+                if (io.position) { io.position[3 * i] = e.px; io.position[3 * i + 1] = e.py; io.position[3 * i + 2] = e.pz; }
+                if (io.phase) io.phase[i] = e.phase;
+                if (io.step) io.step[i] = e.step;
+                if (io.success) io.success[i] = (uint8_t)e.success;
+                if (io.criteria_met) io.criteria_met[i] = (uint8_t)(e.consec >= 10);
+                if (io.comp) {
 #pragma unroll
-                for (int k = 0; k < 12; k++) io.comp[12 * i + k] = r.comp[k];
+                    for (int k = 0; k < 12; k++) io.comp[12 * i + k] = r.comp[k];
+                }
             }
             if (done) {
                 ev_len = e.step; ev_succ = e.success; ev_reason = r.reason; ev_trunc = r.truncated;
@@ -339,14 +343,27 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
                 d_fuel += (double)__shfl_sync(full, ev_fuel, src);
                 n_len += __shfl_sync(full, ev_len, src);
             }
-            // lane L < 14 picks statistic L with selects (a switch compiled to a 14-way divergent jump table)
-            const int iv = lane == 0 ? __popc(dm) : lane == 3 ? n_len : lane == 4 ? n_succ : lane == 5 ? __popc(r2) : lane == 6 ? __popc(r3)
-                         : lane == 7 ? __popc(r4) : lane == 8 ? __popc(r5) : lane == 9 ? n_tr : lane == 10 ? __popc(vm) : 0;
-            const double dv = lane == 1 ? d_ret : lane == 2 ? d_ret2 : lane == 11 ? d_alt : lane == 12 ? d_tilt : lane == 13 ? d_fuel : 0.0;
-            const double v = (lane == 1 || lane == 2 || lane >= 11) ? dv : (double)iv;
-            // the row has exactly one writer per launch (this group), so the order-free reduction is still deterministic; as a
-            // reduction it does not make the warp wait for the old value (the read-modify-write stalled on a DRAM round trip)
-            if (lane < 14 && v != 0.0) atomicAdd(&st.partial[(long long)g * TVC_NSTAT + lane], v);
+            // The row has exactly one writer per launch (this group) and every slot gets at most one add, so the order-free
+            // reductions are still deterministic; as reductions they do not make the warp wait for the old value.  Every lane
+            // holds every statistic (ballots and fixed-order shuffle sums), so lane 0 issues the adds one after the other behind
+            // warp-uniform tests: ~10 instructions for the usual episode end (an earlier form let lane L < 14 pick statistic L with
+            // a select chain over 64-bit values -- 140 instructions and 8 % of the kernel's stall samples; a switch before that
+            // compiled to a 14-way divergent jump table).
+            double *row = &st.partial[(long long)g * TVC_NSTAT];
+            const int n_ep = __popc(dm), n_r2 = __popc(r2), n_r3 = __popc(r3), n_r4 = __popc(r4), n_r5 = __popc(r5), n_v = __popc(vm);
+            if (lane == 0) {
+                if (n_ep) {
+                    atomicAdd(row + 0, (double)n_ep); atomicAdd(row + 1, d_ret); atomicAdd(row + 2, d_ret2); atomicAdd(row + 3, (double)n_len);
+                    atomicAdd(row + 11, d_alt); atomicAdd(row + 12, d_tilt); atomicAdd(row + 13, d_fuel);
+                }
+                if (n_succ) atomicAdd(row + 4, (double)n_succ);
+                if (n_r2) atomicAdd(row + 5, (double)n_r2);
+                if (n_r3) atomicAdd(row + 6, (double)n_r3);
+                if (n_r4) atomicAdd(row + 7, (double)n_r4);
+                if (n_r5) atomicAdd(row + 8, (double)n_r5);
+                if (n_tr) atomicAdd(row + 9, (double)n_tr);
+                if (n_v) atomicAdd(row + 10, (double)n_v);
+            }
         }
     }
 }
