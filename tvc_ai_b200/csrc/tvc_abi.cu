@@ -221,7 +221,7 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
         if (first_pull) {
             g = (int)(blockIdx.x * (TVC_V2_BLOCK / 32) + (threadIdx.x >> 5));
             first_pull = false;
-        } else g = __shfl_sync(full, g_next, 0);   // pulled while the previous group was in its second half (below)
+        } else g = (int)(gridDim.x * (TVC_V2_BLOCK / 32)) + __shfl_sync(full, g_next, 0);   // pulled while the previous group was in its second half (below)
         if (g >= ngroups) break;
         const long long slot = (long long)g * 32 + lane;
         const bool live = slot < st.n;
@@ -254,7 +254,14 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
         PH2_CLK(pt2);
         // the next group of the sequence: the atomic's round trip (~1 us with 2,368 warps on one counter) runs under this
         // group's second half instead of stalling the warp at the top of the loop
-        if (lane == 0) g_next = (int)(gridDim.x * (TVC_V2_BLOCK / 32)) + (int)atomicAdd(queue, 1u);
+        // (ptxas turns an atomic on a warp-uniform address into its warp-aggregated form -- vote, one ATOMG, SHFL of the returned
+        //  value -- and that SHFL waits for the round trip on the spot: 2 % of the kernel's stall samples sat there.  The address
+        //  below is not provably uniform (threadIdx.y is 0 in this 1-D launch), so the value is first touched at the loop top.)
+        if (lane == 0) {
+            unsigned old;
+            asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(queue + threadIdx.y));
+            g_next = (int)old;      // (untouched until the loop top: any arithmetic here would wait for the round trip)
+        }
         if (live) {
             StepResult r;
             env_post<X, DIV>(c, st, i, gid, e, f.a0, f.a1, r);
@@ -292,20 +299,21 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
 #pragma unroll
             for (int k = 0; k < 5; k++) o2[k] = make_float2(r.obs[2 * k], r.obs[2 * k + 1]);
         }
-        {   // the env's place in the NEXT sequence: class byte + (class, chunk) counters; an env whose episode ended goes to the
-            // done list (close_kernel re-initialises it) and is airborne in the next sequence (a fresh env starts at z = 1 m)
-            const bool relist = live && done && c.autoreset;
-            const unsigned rm = __ballot_sync(full, relist);
-            int rbase = 0;
-            if (rm && lane == 0) rbase = (int)atomicAdd(&st.counter[CTR_DONE + par], (unsigned)__popc(rm));
+        // the env's place in the NEXT sequence: class byte + (class, chunk) counters; an env whose episode ended goes to the
+        // done list (close_kernel re-initialises it) and is airborne in the next sequence (a fresh env starts at z = 1 m)
+        const bool relist = live && done && c.autoreset;
+        const unsigned rm = __ballot_sync(full, relist);
+        int rbase = 0;
+        {
+            if (rm && lane == 0) {      // (plain PTX for the same reason: the base is first needed after the class counters below)
+                unsigned old;
+                asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(&st.counter[CTR_DONE + par] + threadIdx.y), "r"((unsigned)__popc(rm)));
+                rbase = (int)old;
+            }
             int cl = 2;
             if (live && !relist) cl = class_of(c, X, e.pz, e.qx, e.qy, e.qz, e.qw, e.vz, e.wx, e.wy, e.wz, e.cg_off);
             if (live) st.cls[i] = (uint8_t)cl;
             count_class(st, par ^ 1, live, i, cl);   // the buffer the close_kernel of THIS step reads
-            if (rm) {
-                rbase = __shfl_sync(full, rbase, 0);
-                if (relist) st.done_list[rbase + __popc(rm & ((1u << lane) - 1u))] = (int)i;
-            }
         }
 #ifdef TVC_PHASE_PROF2
         {
@@ -364,6 +372,10 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
                 if (n_tr) atomicAdd(row + 9, (double)n_tr);
                 if (n_v) atomicAdd(row + 10, (double)n_v);
             }
+        }
+        if (rm) {   // the done-list slots: the base's round trip ran under the class counters and the statistics
+            rbase = __shfl_sync(full, rbase, 0);
+            if (relist) st.done_list[rbase + __popc(rm & ((1u << lane) - 1u))] = (int)i;
         }
     }
 }
