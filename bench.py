@@ -504,6 +504,12 @@ def run_ours(args):
                                     "env_ms_per_iter": tm5["env_ms_per_iter"], "learner_ms_per_iter": tm5["learner_ms_per_iter"],
                                     "updates": tm5["updates"], "replay_filled": rp5.filled}
                 launches += 24 * (2 + 8)     # pack + rollout + 8 gather kernels per iteration
+                # the same loop with the reference's own update arithmetic (sac.reference_update: agent/multi_algorithm_agent.py:950-1016)
+                e5.reset()
+                _, rp5r, tm5r = train_sac(e5, 12, rollout_steps=8, config=SACConfig.reference_rule(batch_size=4096, learning_starts=4096 * 8), seed=0)
+                extra["config5"]["reference_rule"] = {"env_steps_per_sec_e2e": tm5r["env_steps_per_sec_e2e"], "learner_share": tm5r["learner_share"],
+                                                      "learner_ms_per_iter": tm5r["learner_ms_per_iter"], "updates": tm5r["updates"]}
+                launches += 12 * (2 + 8)
                 e5.close()
             except Exception as exc:  # noqa: BLE001 -- the learner is adjacent to the hot path: never lose the headline line over it
                 extra["config5"] = {"error": f"{type(exc).__name__}: {exc}"}

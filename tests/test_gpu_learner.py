@@ -116,6 +116,34 @@ def test_sac_graph_update_equals_eager_update(lib_built):
         assert float((a - b).abs().max()) < 5e-2
 
 
+def test_reference_rule_learner_runs_graph_captured(lib_built, parity_record):
+    """`SACConfig.reference_rule()` (the reference's `_update_sac` arithmetic, pinned on the CPU by tests/test_host.py against the
+    reference function itself) inside the graph-captured learner: the captured update runs, the parameters move by Adam(3e-4)
+    steps, the targets follow by Polyak 0.005, everything stays finite."""
+    from tvc_ai_b200.replay import DeviceReplay
+    from tvc_ai_b200.sac import SACConfig, SACLearner
+    n, T = 512, 4
+    cfg = SACConfig.reference_rule(batch_size=512, learning_starts=1)
+    eng = _stage6_engine(n)
+    rp = DeviceReplay(n, T, capacity=8 * n * T, device=0, seed=11, reward_scale=cfg.reward_scale)
+    ln = SACLearner(rp, cfg, updates_per_replay=2, use_cuda_graph=True, seed=5)
+    assert not ln.auto_alpha and ln.opt_alpha is None and ln._alpha_const == 0.2
+    w0 = [p.detach().clone() for p in list(ln.actor.parameters()) + list(ln.q1.parameters())]
+    t0 = [p.detach().clone() for p in ln.q1t.parameters()]
+    for it in range(4):
+        rp.collect(eng, ln.weights())
+        ln.update()
+    torch.cuda.synchronize()
+    assert ln._graph is not None and ln.updates == 6 + 4 * 2
+    moved = max(float((a - b.detach()).abs().max()) for a, b in zip(w0, list(ln.actor.parameters()) + list(ln.q1.parameters())))
+    lag = max(float((a - b.detach()).abs().max()) for a, b in zip(t0, ln.q1t.parameters()))
+    assert all(bool(torch.isfinite(p).all()) for p in list(ln.actor.parameters()) + list(ln.q1.parameters()) + list(ln.q1t.parameters()))
+    assert 1e-3 < moved < 0.1 and 0.0 < lag < moved, (moved, lag)
+    parity_record["sac_reference_rule"] = dict(updates=ln.updates, batch=cfg.batch_size, moved=moved, target_lag=lag,
+                                               q_loss=float(ln.losses["q"]), actor_loss=float(ln.losses["actor"]))
+    eng.close()
+
+
 def test_sac_training_improves_the_deterministic_policy(lib_built, parity_record):
     """BASELINE config 5 end to end on one GPU: 4,096 stage-6 envs, fused rollout -> replay ring -> graph-replayed SAC updates.
     The deterministic policy after 60 iterations (504 updates) must beat the random policy (uniform actions) on episode return by

@@ -103,3 +103,42 @@ def test_stats_allreduce_gloo_world2(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "stage 1" in o
+
+
+def test_reference_sac_rule_matches_the_reference_function():
+    """sac.reference_update against the reference's own `_update_sac` (agent/multi_algorithm_agent.py:950-1016), which
+    tests/golden/make_sac_update_golden.py executed unmodified on networks of this package's shapes: from the same initial
+    parameters, batch and generator state, three consecutive updates give the same losses and the same parameters."""
+    import torch
+
+    from tvc_ai_b200.sac import Actor, SACConfig, _mlp, reference_update
+    z = np.load(os.path.join(ROOT, "tests", "golden", "sac_update.npz"))
+    hidden = z["init/actor/net.0.weight"].shape[0]
+    actor = Actor(hidden=hidden)
+    q1, q2, q1t, q2t = (_mlp(12, 1, hidden) for _ in range(4))
+    nets = dict(actor=actor, q1=q1, q2=q2, q1t=q1t, q2t=q2t)
+    for n, net in nets.items():
+        net.load_state_dict({k: torch.from_numpy(z[f"init/{n}/{k}"]) for k in net.state_dict()})
+    cfg = SACConfig.reference_rule()
+    assert (cfg.lr_actor, cfg.lr_critic, cfg.gamma, cfg.tau, cfg.ent_coef, cfg.grad_clip_norm, cfg.reward_scale) == \
+        (3e-4, 3e-4, 0.99, 0.005, 0.2, 0.0, 1.0)
+    opt_a = torch.optim.Adam(actor.parameters(), lr=cfg.lr_actor)
+    opt_c = torch.optim.Adam(list(q1.parameters()) + list(q2.parameters()), lr=cfg.lr_critic)
+    batch = dict(obs=torch.from_numpy(z["batch/states"]), actions=torch.from_numpy(z["batch/actions"]),
+                 reward=torch.from_numpy(z["batch/rewards"]), next_obs=torch.from_numpy(z["batch/next_states"]),
+                 done=torch.from_numpy(z["batch/dones"]))
+    worst = 0.0
+    for u in range(3):
+        torch.manual_seed(1000 + u)
+        l1, l2, la = reference_update(actor, q1, q2, q1t, q2t, opt_a, opt_c, batch, gamma=cfg.gamma, alpha=float(cfg.ent_coef),
+                                      tau=cfg.tau)
+        np.testing.assert_allclose([float(l1), float(l2), float(la)], z[f"loss/{u}"], rtol=2e-6, atol=1e-7)
+        for n, net in nets.items():
+            for k, v in net.state_dict().items():
+                want = z[f"after{u}/{n}/{k}"]
+                worst = max(worst, float(np.abs(v.numpy() - want).max()))
+                np.testing.assert_allclose(v.numpy(), want, rtol=1e-5, atol=2e-7, err_msg=f"update {u} {n}/{k}")
+    # the parameters moved (three Adam steps of 3e-4) and the targets lag behind the critics
+    assert float(np.abs(q1.state_dict()["0.weight"].numpy() - z["init/q1/0.weight"]).max()) > 5e-4
+    assert float(np.abs(q1t.state_dict()["0.weight"].numpy() - z["init/q1t/0.weight"]).max()) < 2e-5
+    print(f"reference SAC rule: worst parameter difference after 3 updates {worst:.2e}")

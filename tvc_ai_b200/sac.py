@@ -39,6 +39,20 @@ class SACConfig:
     reward_scale: float = 0.01       # rewards span [-1000, 200] (ref env :121): brought to O(1) for the critics
     tf32: bool = True                # the learner's GEMMs on the tensor cores in TF32 (fp32 accumulate); scoped to the update
     fused_adam: bool = True          # one fused multi-tensor Adam kernel per optimiser step (capturable)
+    rule: str = "sac"                # "sac": squashed-Gaussian SAC (entropy term in the target, learned temperature);
+                                     # "reference": `_update_sac` as the reference wrote it (see reference_update)
+
+    @classmethod
+    def reference_rule(cls, **over) -> "SACConfig":
+        """The constants agent/multi_algorithm_agent.py hard-codes: Adam(3e-4) for policy and critics (:623-625), gamma 0.99
+        (:970), entropy weight 0.2 (:996), tau 0.005 (:1002), no gradient clipping, rewards as the env returns them."""
+        c = cls(lr_actor=3e-4, lr_critic=3e-4, lr_alpha=3e-4, tau=0.005, gamma=0.99, grad_clip_norm=0.0, ent_coef=0.2,
+                reward_scale=1.0, rule="reference")
+        for k, v in over.items():
+            if not hasattr(c, k):
+                raise AttributeError(f"SACConfig has no field {k!r}")
+            setattr(c, k, v)
+        return c
 
     @classmethod
     def from_yaml(cls, config: dict | None) -> "SACConfig":
@@ -65,17 +79,22 @@ class SACConfig:
         return c
 
 
-def _mlp(i: int, o: int) -> nn.Sequential:
-    return nn.Sequential(nn.Linear(i, 256), nn.ReLU(), nn.Linear(256, 256), nn.ReLU(), nn.Linear(256, o))
+def _mlp(i: int, o: int, hidden: int = 256) -> nn.Sequential:
+    return nn.Sequential(nn.Linear(i, hidden), nn.ReLU(), nn.Linear(hidden, hidden), nn.ReLU(), nn.Linear(hidden, o))
 
 
 class Actor(nn.Module):
     """10-256-256-4 -> (mean, log_std): the network `tvc_rollout` evaluates in-kernel (include/tvc_b200.h tvc_actor_weights)."""
 
-    def __init__(self, obs_dim: int = 10, action_dim: int = 2):
+    def __init__(self, obs_dim: int = 10, action_dim: int = 2, hidden: int = 256):
         super().__init__()
         self.action_dim = action_dim
-        self.net = _mlp(obs_dim, 2 * action_dim)
+        self.net = _mlp(obs_dim, 2 * action_dim, hidden)   # (tvc_rollout is built for hidden = 256)
+
+    def mean_log_std(self, obs):
+        """(mean, log_std clamp [-20, 2]): what the reference's policy networks return (multi_algorithm_agent.py:223-227)."""
+        out = self.net(obs)
+        return out[:, :self.action_dim], out[:, self.action_dim:].clamp(-20.0, 2.0)
 
     def forward(self, obs, deterministic: bool = False, eps: torch.Tensor | None = None):
         out = self.net(obs)
@@ -89,6 +108,53 @@ class Actor(nn.Module):
         a = torch.tanh(u)
         logp = (-0.5 * eps * eps - log_std - 0.5 * math.log(2.0 * math.pi)).sum(-1) - torch.log(1.0 - a * a + 1e-6).sum(-1)
         return a, logp
+
+
+def reference_update(actor: Actor, q1, q2, q1t, q2t, opt_actor, opt_critic, batch: dict, gamma: float = 0.99,
+                     alpha: float = 0.2, tau: float = 0.005, losses: dict | None = None):
+    """One update by the reference's own rule, agent/multi_algorithm_agent.py:950-1016 `_update_sac`, on a batch:
+
+    * target (:962-970): next action = a SAMPLE of the unsquashed Gaussian N(mean, exp(log_std)) of the policy, target
+      `r + gamma (1 - done) min(Q1t, Q2t)(s', a')` -- no entropy term, no tanh;
+    * critics (:972-984): MSE of each critic against that target (the reference steps two Adam optimisers; one Adam over both
+      parameter sets is the same arithmetic, Adam being per-parameter);
+    * policy (:988-1000): reparameterised sample a = mean + std eps, loss `-(min(Q1, Q2)(s, a) - alpha log N(a)).mean()` with the
+      constant alpha = 0.2;
+    * targets (:1002-1008): Polyak tau = 0.005.
+    The random draws are made in the reference's order with the same torch calls (Normal.sample, then Normal.rsample), so that
+    from one generator state both produce the same numbers (tests/golden/make_sac_update_golden.py runs the reference's
+    function itself on these networks; tests/test_host.py compares)."""
+    from torch.distributions import Normal
+    s, a, r, sn, d = batch["obs"], batch["actions"], batch["reward"], batch["next_obs"], batch["done"]
+    with torch.no_grad():
+        mn, lsn = actor.mean_log_std(sn)
+        # Normal(mean, std).sample() is torch.normal(mean, std) = eps * std + mean with eps from normal_(0, 1); written out,
+        # because torch.normal(tensor, tensor) checks std >= 0 on the host (a sync: illegal inside a CUDA-graph capture)
+        an = torch.randn_like(mn) * lsn.exp() + mn
+        san = torch.cat([sn, an], -1)
+        y = r + gamma * (1.0 - d) * torch.min(q1t(san), q2t(san)).squeeze(-1)
+    sa = torch.cat([s, a], -1)
+    lq1, lq2 = F.mse_loss(q1(sa).squeeze(-1), y), F.mse_loss(q2(sa).squeeze(-1), y)
+    opt_critic.zero_grad(set_to_none=False)
+    (lq1 + lq2).backward()
+    opt_critic.step()
+    m, ls = actor.mean_log_std(s)
+    dist = Normal(m, ls.exp(), validate_args=False)
+    ap = dist.rsample()
+    sap = torch.cat([s, ap], -1)
+    la = -(torch.min(q1(sap), q2(sap)) - alpha * dist.log_prob(ap).sum(-1, keepdim=True)).mean()
+    opt_actor.zero_grad(set_to_none=False)
+    la.backward()
+    opt_actor.step()
+    with torch.no_grad():
+        src = list(q1.parameters()) + list(q2.parameters())
+        dst = list(q1t.parameters()) + list(q2t.parameters())
+        torch._foreach_mul_(dst, 1.0 - tau)
+        torch._foreach_add_(dst, src, alpha=tau)
+    if losses is not None:
+        losses["q"].copy_((lq1 + lq2).detach())
+        losses["actor"].copy_(la.detach())
+    return lq1.detach(), lq2.detach(), la.detach()
 
 
 class SACLearner:
@@ -106,8 +172,11 @@ class SACLearner:
         self.q1t.load_state_dict(self.q1.state_dict()), self.q2t.load_state_dict(self.q2.state_dict())
         for p in list(self.q1t.parameters()) + list(self.q2t.parameters()):
             p.requires_grad_(False)
-        self.auto_alpha = isinstance(self.cfg.ent_coef, str)
-        a0 = self.cfg.init_alpha if self.auto_alpha else float(self.cfg.ent_coef)
+        if self.cfg.rule not in ("sac", "reference"):
+            raise ValueError(f"SACConfig.rule must be 'sac' or 'reference', got {self.cfg.rule!r}")
+        self.auto_alpha = isinstance(self.cfg.ent_coef, str) and self.cfg.rule == "sac"
+        a0 = self.cfg.init_alpha if isinstance(self.cfg.ent_coef, str) else float(self.cfg.ent_coef)
+        self._alpha_const = float(a0)     # the reference rule's constant entropy weight (a Python float: graph-safe)
         self.log_alpha = torch.full((), math.log(a0), device=dev, requires_grad=self.auto_alpha)
         self.target_entropy = -float(self.actor.action_dim)
         cap = dict(capturable=True, fused=True) if self.cfg.fused_adam else dict(capturable=True)
@@ -138,6 +207,10 @@ class SACLearner:
             torch.nn.utils.clip_grad_norm_(params, self.cfg.grad_clip_norm, foreach=True)
 
     def _one_update(self):
+        if self.cfg.rule == "reference":
+            reference_update(self.actor, self.q1, self.q2, self.q1t, self.q2t, self.opt_actor, self.opt_critic, self.batch,
+                             gamma=self.cfg.gamma, alpha=self._alpha_const, tau=self.cfg.tau, losses=self.losses)
+            return
         b, g, tau = self.batch, self.cfg.gamma, self.cfg.tau
         s, a, r, sn, d = b["obs"], b["actions"], b["reward"], b["next_obs"], b["done"]
         alpha = self.log_alpha.exp().detach()
