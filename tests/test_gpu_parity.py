@@ -279,6 +279,113 @@ def test_contract_x_reset_draws_and_steps(lib_built, oracle_mod, parity_record):
     eng.close()
 
 
+def _oracle_from_device(sim, st, base, delay, fuel_tab):
+    """Load the device's state blob rows [base, base + sim.n) into the oracle's envs (every field of orc_env): the device is
+    the master here, the oracle then steps from the identical (float32) state."""
+    for j in range(sim.n):
+        s, e = st[base + j], sim.env(j)
+        b = e.body
+        for k in range(3):
+            b.pos[k], b.vel[k], b.omega[k] = float(s["pos"][k]), float(s["vel"][k]), float(s["omega"][k])
+        for k in range(4):
+            b.quat[k] = float(s["quat"][k])
+        step, burn, hc = int(s["step"]), int(s["burn"]), int(s["hist_count"])
+        e.burn, e.fuel, e.step, e.phase, e.success = burn, fuel_tab[burn], step, int(s["phase"]), int(s["success"])
+        e.has_prev, e.consec, e.crit_pushes = int(s["has_prev"]), int(s["consec"]), step
+        e.prev_action[0], e.prev_action[1] = float(s["prev_action"][0]), float(s["prev_action"][1])
+        e.hist_count, e.ep_return, e.episode = hc, float(s["ep_return"]), int(s["episode"])
+        for q in range(max(0, hc - 10), hc):            # the last ten totals (R8 variance, run detection)
+            e.hist[q % 1000] = float(s["ring10"][q % 10])
+        for w in range(32):
+            e.clip_bits[w], e.run_bits[w] = int(s["clip_bits"][w]), int(s["run_bits"][w])
+        e.n_clip, e.n_run = int(s["n_clip"]), int(s["n_run"])
+        e.mass_scale, e.thrust_scale, e.cg_offset = float(s["mass_scale"]), float(s["thrust_scale"]), float(s["cg_offset"])
+        e.wind[0], e.wind[1] = float(s["wind"][0]), float(s["wind"][1])
+        # the device keeps the delayed commands in a slot ring (slot = step % delay), the oracle in a shift register
+        # (entry 0 = the command issued `delay` steps ago); commands from before the episode are zero on both sides
+        for q in range(delay):
+            issued = step - delay + q
+            src = s["delay_ring"][(step + q) % delay] if issued >= 0 else (0.0, 0.0)
+            e.delay_ring[q][0], e.delay_ring[q][1] = float(src[0]), float(src[1])
+
+
+def test_full_size_steady_state_sampled_parity(lib_built, oracle_mod, parity_record):
+    """BASELINE's full per-GPU size (262,144 envs, Contract X with delay ring, thrust curve, variable mass / CG, sensor noise,
+    same-step autoreset), in the steady-state mix the bench times (1,100 burn-in steps: about a fifth of the envs near the
+    ground, episodes of every age; the record counts the phases seen and the envs whose diversity window is full).  The device free-runs; at each of 5 further steps the state
+    of four 512-env blocks (first, last and two odd offsets) is loaded into the fp64 oracle (identical float32 inputs, global
+    env ids, episode and step counters -> identical Philox noise and reset draws), both take the step with the same actions,
+    and observations (terminal ones where the episode ended), rewards and flags are compared with the bars of the 512-env
+    test.  A size-independent property: an env's result depends on its own state and global id only."""
+    O = oracle_mod
+    from tvc_ai_b200 import _abi as A
+    n, K, delay, blk = 262144, 10, 3, 512
+    over = dict(delay_steps=delay, thrust_curve=1, propellant_fraction=0.2, cg_burn_shift=0.05, autoreset=1)
+    eng = _engine(n, A.CONTRACT_X, **over)
+    eng.reset(seed=2026)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(77)
+    pool = [torch.rand((n, 2), generator=gen, device="cuda") * 2 - 1 for _ in range(8)]
+    for t in range(1100):
+        eng.step(pool[t % 8], want_final=False)
+    bases = [0, 87381, 174763, n - blk]
+    sims = [_oracle(O, blk, O.CONTRACT_X, env_id_base=b, seed=2026, **over) for b in bases]
+    fuel_tab = [1.0]
+    for _ in range(1001):
+        fuel_tab.append(fuel_tab[-1] - 0.001)
+    free_errs, contact_errs, rew_errs = [], [], []
+    bad = near = done_total = full_windows = 0
+    phases = set()
+    for t in range(5):
+        st = eng.get_state()
+        acts = pool[(3 * t + 1) % 8]
+        acts_h = acts.cpu().numpy()
+        obs_d, rew_d, term_d, trunc_d = (x.cpu().numpy() for x in eng.step(acts, want_final=True))
+        fin_d = eng.final_obs.cpu().numpy()
+        for b, sim in zip(bases, sims):
+            _oracle_from_device(sim, st, b, delay, fuel_tab)
+            pre = np.array([_body13(sim.env(i)) for i in range(blk)])
+            obs_o, rew_o, term_o, trunc_o, outs = sim.step(acts_h[b:b + blk], threads=4)
+            fin_o = np.stack([np.frombuffer(o.final_obs, np.float32) for o in outs])
+            sl = slice(b, b + blk)
+            td, ud = term_d[sl].astype(bool), trunc_d[sl].astype(bool)
+            mism = (td != term_o) | (ud != trunc_o)
+            for i in np.flatnonzero(mism):
+                if _near_threshold(outs[i]):
+                    near += 1
+                else:
+                    bad += 1
+            ok = ~mism
+            done_o = term_o | trunc_o
+            done_total += int(done_o.sum())
+            cmp_d = np.where(done_o[:, None], fin_d[sl], obs_d[sl])
+            cmp_o = np.where(done_o[:, None], fin_o, obs_o)
+            err = (np.abs(cmp_d - cmp_o) / np.maximum(1.0, np.abs(cmp_o))).max(axis=1)
+            contact = np.array([min(_lowest_gap(pre[i][:3], pre[i][3:7], h=0.6), outs[i].position[2] - 0.65) < 0.06 for i in range(blk)])
+            free_errs.append(err[ok & ~contact])
+            contact_errs.append(err[ok & contact])
+            rew_errs.append((np.abs(rew_d[sl] - rew_o) / np.maximum(1.0, np.abs(rew_o)))[ok])
+            full_windows += int((st["hist_count"][sl] >= 1000).sum())
+            phases |= set(int(x) for x in st["phase"][sl])
+    fe, ce, re_ = np.concatenate(free_errs), np.concatenate(contact_errs), np.concatenate(rew_errs)
+    rec = dict(contract="X", K=K, envs=n, sampled_env_steps=5 * len(bases) * blk, burn_in_steps=1100, free_env_steps=len(fe),
+               contact_env_steps=len(ce), episodes_ended=done_total, envs_with_full_diversity_window=full_windows,
+               phases_seen=sorted(phases), free_flight_max=float(fe.max()), free_flight_bar=K * 1e-5,
+               contact_median=float(np.median(ce)), contact_q99=float(np.quantile(ce, 0.99)), contact_max=float(ce.max()),
+               contact_q99_bar=K * 1e-5, contact_max_bar=CONTACT_MAX_X, reward_max=float(re_.max()),
+               reward_q99=float(np.quantile(re_, 0.99)), flag_mismatches=bad, near_threshold_events=near)
+    parity_record["contract_x_full_size_steady_state"] = rec
+    print(f"\n[contract X, 262,144 envs, steady state] {rec}")
+    assert len(ce) > 500 and done_total > 50, rec
+    assert rec["free_flight_max"] <= K * 1e-5, rec
+    assert rec["contact_q99"] <= K * 1e-5 and rec["contact_max"] <= CONTACT_MAX_X, rec
+    assert bad == 0 and near <= 4, rec
+    assert rec["reward_max"] <= 1e-3, rec
+    for sim in sims:
+        sim.close()
+    eng.close()
+
+
 def test_episode_statistics_match_oracle(lib_built, oracle_mod, parity_record):
     """Warp-shuffle episode statistics vs the oracle's, Contract R with autoreset, golden random actions scaled per env,
     300 envs (non-multiple of the warp / block size), teacher-forced from identical float32 states so that the two sides
