@@ -250,8 +250,24 @@ step_kernel_v2(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
             env_pre<X>(c, st, i, e, a.x, a.y, P, f);
         }
         PH2_CLK(pt1);
-        if (live) integrate_thread<false, FOLLOW>(c, P, e, f PH2_PASS);
+#ifdef TVC_SOLVE_STATS
+        unsigned ss_mask = 0u;
+#endif
+        if (live) integrate_thread<false, FOLLOW>(c, P, e, f PH2_PASS SS_PASS);
         PH2_CLK(pt2);
+#ifdef TVC_SOLVE_STATS
+        {
+            const long long p0 = (long long)g * 32;
+            const int scls = p0 < (long long)st.totals[0] ? 0 : (p0 < (long long)st.totals[0] + st.totals[1] ? 1 : 2);
+            for (int k = 0; k < c.K && k < 16; k++) {
+                const unsigned m = __ballot_sync(full, live && ((ss_mask >> k) & 1u));
+                if (lane == 0) {
+                    atomicAdd(&g_ss[scls][k][0], 1ull);
+                    if (m) { atomicAdd(&g_ss[scls][k][1], 1ull); atomicAdd(&g_ss[scls][k][2], (unsigned long long)__popc(m)); }
+                }
+            }
+        }
+#endif
         // the next group of the sequence: the atomic's round trip (~1 us with 2,368 warps on one counter) runs under this
         // group's second half instead of stalling the warp at the top of the loop
         // (ptxas turns an atomic on a warp-uniform address into its warp-aggregated form -- vote, one ATOMG, SHFL of the returned
@@ -969,6 +985,14 @@ int tvc_get_config(const tvc_handle *h, tvc_config *out) {
     *out = h->cur;
     return TVC_OK;
 }
+#ifdef TVC_SOLVE_STATS
+int tvc_debug_solve_stats(unsigned long long *out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, tvc::g_ss, sizeof(unsigned long long) * 3 * 16 * 3);
+    if (reset) { unsigned long long z[3 * 16 * 3] = {0}; cudaMemcpyToSymbol(tvc::g_ss, z, sizeof(z)); }
+    return 0;
+}
+#endif
 #ifdef TVC_PHASE_PROF2
 int tvc_debug_phase2(unsigned long long *out, int reset) {
     cudaDeviceSynchronize();

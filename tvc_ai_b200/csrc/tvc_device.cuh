@@ -308,6 +308,16 @@ struct Ph2 { unsigned setup, sweeps, bar; };
 #define PH2_PASS
 #define PH2_CLK(x)
 #endif
+#ifdef TVC_SOLVE_STATS
+// diagnostic build only (tools/solve_stats.py): which substeps of a step ran the contact solve, per lane
+// g_ss[class by position][substep][0 = warps with a live lane, 1 = warps in which a lane solved, 2 = lanes that solved]
+__device__ unsigned long long g_ss[3][16][3];
+#define SS_ARG , unsigned &ss_mask
+#define SS_PASS , ss_mask
+#else
+#define SS_ARG
+#define SS_PASS
+#endif
 
 // One point block: the point's Delassus matrix A (symmetric), the wanted change of the contact velocity (ex, ey, en) and
 // the old impulses -> new impulses.  Stick solution p* = p + A^-1 e, accepted when p*_n > 0 and |p*_t| <= mu p*_n;
@@ -525,7 +535,7 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
 // FOLLOW (quirk Q3 cleared): the thrust force and torque are body-fixed and re-evaluated at every substep's attitude instead
 // of being held constant in the world frame; a separate instantiation, so that the reference path carries none of it.
 template <bool LOCKSTEP, bool FOLLOW>
-__device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P, Env &e, const Forces &f PH2_ARG) {
+__device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P, Env &e, const Forces &f PH2_ARG SS_ARG) {
     const float dt = c.dt;
     float Fx = f.Fx, Fy = f.Fy, Fz = f.Fz, Tx = f.Tx, Ty = f.Ty, Tz = f.Tz;
     float ax_ = Fx * P.inv_mass, ay_ = Fy * P.inv_mass, az_ = Fz * P.inv_mass;
@@ -612,6 +622,9 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
             }
         }
         if (!solved && cc.have) { cc.l1 = cc.l2 = cc.ln = cc.lt0 = cc.lt1 = cc.lt2 = 0.0f; cc.xmask = 0u; cc.have = false; }
+#ifdef TVC_SOLVE_STATS
+        if (solved) ss_mask |= 1u << k;
+#endif
         // B6: semi-implicit Euler; near the ground the height carries a running compensation (the contact targets divide the
         // gap by dt, so the 3e-8 rounding of pz + dt vz per substep would otherwise show up as 1.5e-5 m/s at dt = 0.002)
         e.px += dt * e.vx; e.py += dt * e.vy;

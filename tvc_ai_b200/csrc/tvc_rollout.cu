@@ -357,6 +357,9 @@ rollout_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevStat
 #ifdef TVC_PHASE_PROF2
         Ph2 ph2s = {0u, 0u, 0u};
         if (live) integrate_thread<false, false>(c, P, e, f, &ph2s);
+#elif defined(TVC_SOLVE_STATS)
+        unsigned ss_mask = 0u;
+        if (live) integrate_thread<false, false>(c, P, e, f, ss_mask);
 #else
         if (live) integrate_thread<false, false>(c, P, e, f);
 #endif
