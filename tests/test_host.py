@@ -142,3 +142,22 @@ def test_reference_sac_rule_matches_the_reference_function():
     assert float(np.abs(q1.state_dict()["0.weight"].numpy() - z["init/q1/0.weight"]).max()) > 5e-4
     assert float(np.abs(q1t.state_dict()["0.weight"].numpy() - z["init/q1t/0.weight"]).max()) < 2e-5
     print(f"reference SAC rule: worst parameter difference after 3 updates {worst:.2e}")
+
+
+def test_reference_arm_line_and_evidence_hash():
+    """`bench.py --impl reference` (the oracle port on the host cores) prints the contract's JSON line without a GPU, and the
+    committed ncu figures of the step path (profiles/step_kernel_traffic.json) were captured from the kernel sources in the tree
+    (otherwise bench.py drops `roofline.traffic` / `issue_roofline`: re-capture with tools/capture_step.sh)."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "3"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["metric"] == "env_steps_per_sec" and line["unit"] == "env-steps/s"
+    assert line["higher_is_better"] is True and line["steps"] == 2 and line["warmup"] == 3 and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0 and "workload" in line["config"]
+    import bench
+    rec = json.load(open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")))
+    assert rec["csrc_sha16"] == bench.csrc_hash(), "profiles/step_kernel_traffic.json is stale against tvc_ai_b200/csrc"
+    assert bench._traffic() == rec["dram_bytes_per_launch"] and bench._traffic("warp_instructions_per_step") > 1e7
