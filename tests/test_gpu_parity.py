@@ -179,7 +179,7 @@ def test_golden_trajectories_teacher_forced(lib_built, oracle_mod, golden_dir, p
 
 
 @pytest.mark.parametrize("name", ["zero_120", "random_raw", "random_autoreset", "burnout_1100"])
-def test_golden_trajectories_free_running(lib_built, golden_dir, name):
+def test_golden_trajectories_free_running(lib_built, golden_dir, parity_record, name):
     """Contract R, N=1, no teacher forcing: the drift of the fp32 device trajectory from the fp64
     golden trajectory over the whole run (1000 steps for the random scenarios) is reported; events
     (termination step, success step) must agree."""
@@ -201,6 +201,11 @@ def test_golden_trajectories_free_running(lib_built, golden_dir, name):
     first = lambda x: int(np.flatnonzero(x)[0]) if x.any() else -1  # noqa: E731
     print(f"\n[{name}] free-running obs drift: step10={drift[min(9, T - 1)]:.2e} step100={drift[min(99, T - 1)]:.2e} "
           f"max={drift.max():.2e} at step {int(drift.argmax())}; first termination dev/gold = {first(term)}/{first(g['terminated'])}")
+    q = lambda k: float(drift[min(k, T) - 1])  # noqa: E731
+    parity_record[f"golden_free_running/{name}"] = dict(
+        contract="R", steps=T, obs_drift_step10=q(10), obs_drift_step100=q(100), obs_drift_step500=q(500), obs_drift_step1000=q(1000),
+        obs_drift_max=float(drift.max()), obs_drift_max_at_step=int(drift.argmax()), first_termination_device=first(term),
+        first_termination_golden=first(g["terminated"]), what="max |obs_device - obs_fp64_golden| per step, no teacher forcing")
     assert first(term) == first(g["terminated"])
     if name in ("zero_120", "burnout_1100"):
         np.testing.assert_array_equal(term, g["terminated"])
