@@ -314,3 +314,63 @@ def test_fp32_sensitivity_contract_x_batch(oracle_mod):
           f"{np.median(contact):.2e} q99 {np.quantile(contact, 0.99):.2e} max {contact.max():.2e} ({len(contact)} env-steps)")
     assert len(contact) > 2000 and free.max() <= K * 1e-5
     assert np.quantile(contact, 0.99) <= K * 1e-5 and contact.max() <= 2e-2
+
+
+def test_free_flight_converges_to_the_continuous_rigid_body_equations(oracle_mod):
+    """Rows B3-B6 against an INDEPENDENT formulation: the Newton-Euler equations of the same body (world-frame force and torque
+    held constant, inverse inertia R diag(1/I) R^T, k (1 + |.|) damping, quaternion kinematics q' = (w, 0) (x) q / 2, with and
+    without the gyroscopic term) integrated by scipy's adaptive Runge-Kutta to 1e-12.  The oracle's semi-implicit substeps must
+    approach that solution at first order (error ratio ~4 for substeps 4x smaller) from a general 3-D state: tilted attitude,
+    spin about all three axes, off-axis torque -- a wrong frame, sign or inertia axis anywhere does not converge."""
+    import ctypes as C
+    from scipy.integrate import solve_ivp
+    O = oracle_mod
+    F, T = np.array([3.0, -2.0, 25.0]), np.array([0.02, -0.015, 0.004])
+    q0 = np.array([0.15, -0.1, 0.2, 0.0])
+    q0[3] = math.sqrt(1.0 - float(q0[:3] @ q0[:3]))
+    v0, w0 = np.array([1.0, -0.5, 2.0]), np.array([0.8, -1.1, 2.5])
+
+    def rot(q):
+        x, y, z, w = q
+        return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                         [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                         [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+    for gyro in (0, 1):
+        p, _ = _free_body(O)
+        m, I = p.mass, np.array(list(p.inertia))
+        g, kl, ka = np.array(list(p.gravity)), p.lin_damp, p.ang_damp
+        assert abs(I[0] - I[2]) > 0.1 * I[0]          # an axisymmetric but not spherical body: the frames matter
+
+        def rhs(t, y):
+            q, v, w = y[3:7], y[7:10], y[10:13]
+            R = rot(q / np.linalg.norm(q))
+            wl, tl = R.T @ w, R.T @ T
+            wdl = tl / I - wl * (ka + ka * np.linalg.norm(wl))
+            if gyro:
+                wdl = wdl - np.cross(wl, I * wl) / I
+            qd = 0.5 * np.array([w[0] * q[3] + w[1] * q[2] - w[2] * q[1], w[1] * q[3] + w[2] * q[0] - w[0] * q[2],
+                                 w[2] * q[3] + w[0] * q[1] - w[1] * q[0], -w[0] * q[0] - w[1] * q[1] - w[2] * q[2]])
+            return np.concatenate([v, qd, F / m + g - v * (kl + kl * np.linalg.norm(v)), R @ wdl])
+
+        y0 = np.concatenate([[0, 0, 100.0], q0, v0, w0])
+        ref = solve_ivp(rhs, (0.0, 0.2), y0, method="DOP853", rtol=1e-12, atol=1e-14).y[:, -1]
+        ref[3:7] /= np.linalg.norm(ref[3:7])
+        errs = []
+        for sub in (4, 16, 64):
+            p, b = _free_body(O, use_gyro=gyro, substeps=sub)
+            for k in range(3):
+                b.vel[k], b.omega[k] = v0[k], w0[k]
+            for k in range(4):
+                b.quat[k] = q0[k]
+            for _ in range(10):                       # ten control steps of 0.02 s
+                for k in range(3):
+                    b.force[k], b.torque[k] = F[k], T[k]
+                O.lib().orc_step_simulation(C.byref(p), C.byref(b), None)
+            got = np.array(list(b.pos) + list(b.quat) + list(b.vel) + list(b.omega))
+            if got[3:7] @ ref[3:7] < 0:
+                got[3:7] = -got[3:7]
+            errs.append(float(np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref)))))
+        print(f"[free flight vs continuous equations] gyro={gyro}: max rel. error {errs[0]:.2e} / {errs[1]:.2e} / {errs[2]:.2e} at 4 / 16 / 64 substeps")
+        assert errs[0] < 5e-2 and errs[2] < 1e-3, (gyro, errs)
+        assert 3.0 < errs[0] / errs[1] < 5.0 and 3.0 < errs[1] / errs[2] < 5.0, (gyro, errs)     # first order in the substep
