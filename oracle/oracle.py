@@ -94,7 +94,8 @@ class StepOut(C.Structure):
                 ("altitude", C.c_double), ("tilt", C.c_double), ("omega_mag", C.c_double),
                 ("fuel", C.c_double), ("vh", C.c_double), ("vv", C.c_double),
                 ("position", C.c_double * 3), ("phase", C.c_int32), ("success", C.c_int32),
-                ("step", C.c_int32), ("criteria_met", C.c_int32), ("term_reason", C.c_int32)]
+                ("step", C.c_int32), ("criteria_met", C.c_int32), ("term_reason", C.c_int32),
+                ("contact_margin", C.c_double)]
 
 
 def build(force: bool = False, f32: bool = False) -> str:

@@ -242,6 +242,14 @@ static real r_matrix_from_quat(const real q[4], real m[9]) {
 long long orc_dbg_substeps = 0, orc_dbg_entered = 0, orc_dbg_canbind = 0;
 long long orc_dbg_blocks[4] = {0, 0, 0, 0};   /* release, stick, slide, points 1-4 visited */
 
+/* Diagnostic for the parity reports (orc_step_out.contact_margin): the manifold has DISCRETE decisions -- the entry rule
+ * (gmin < margin, gmin < gthr) and each point's reach rule (gap < gthr).  An evaluation in another arithmetic that lands on
+ * the other side of one of them solves a different manifold in that substep (an impact a substep earlier or later).  This is
+ * the distance in metres between the deciding quantity and its threshold, smallest over the decisions of the current step;
+ * 1e30 when the step made none.  Thread-local: orc_step runs envs on OpenMP threads. */
+static _Thread_local double orc_tl_margin = 1e30;
+static inline void note_margin(double d) { if (d < 0) d = -d; if (d < orc_tl_margin) orc_tl_margin = d; }
+
 typedef struct { real Jx[3], Jy[3], Jn[3]; } orc_rows;
 
 /* angular Jacobians (body frame) of the three world-axis rows at body-frame arm c: c x d_b */
@@ -296,6 +304,7 @@ static void solve_contacts(const orc_body_params *p, real dt, const real R[9], r
     const real gb = ((pz + zb) + pzc) + (zb * nz1 + low), gt = ((pz + zt) + pzc) + (zt * nz1 + low);
     const real gmin = gb < gt ? gb : gt;
     int enter = gmin < margin;
+    if (gmin < (real)4.0 * margin) note_margin((double)gmin - (double)margin);
     real gthr = 0;     /* a point further than this from the plane cannot be reached within the substep at the entry speeds */
     if (enter) {
         orc_dbg_entered++;
@@ -303,6 +312,7 @@ static void solve_contacts(const orc_body_params *p, real dt, const real R[9], r
         real vmax = (v[2] < 0 ? -v[2] : v[2]) + R_SQRT(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]) * reach;
         gthr = ((real)1.0 + (real)p->restitution) * vmax * dt + (real)1e-4;
         enter = gmin < gthr;
+        note_margin((double)gmin - (double)gthr);
         if (enter) orc_dbg_canbind++;
     }
     if (!enter) { for (int i = 0; i < 18; i++) lam[i] = 0; *have_lam = 0; return; }
@@ -338,6 +348,7 @@ static void solve_contacts(const orc_body_params *p, real dt, const real R[9], r
         real gap = ((pz + c[i][2]) + pzc) + (c[i][2] * nz1 + (nb[0] * c[i][0] + nb[1] * c[i][1]));
         /* the substep's manifold: points within reach (the entry rule's own bound) or still holding an impulse */
         active[i] = gap < gthr || lam[i] != 0 || lam[5 + i] != 0 || lam[10 + i] != 0;
+        if (lam[i] == 0 && lam[5 + i] == 0 && lam[10 + i] == 0) note_margin((double)gap - (double)gthr);
         real vn0 = v[2] + (wb0[0] * J[i].Jn[0] + wb0[1] * J[i].Jn[1] + wb0[2] * J[i].Jn[2]);
         real rest = (vn0 < -(real)p->rest_threshold) ? (real)p->restitution * (-vn0 - (real)p->rest_threshold) : (real)0.0;
         tgt[i] = rest + (gap > 0 ? -gap * inv_dt : -(real)p->erp * gap * inv_dt);
@@ -845,7 +856,9 @@ static void env_step(orc_sim *s, orc_env *e, int64_t gid, const float *act, orc_
     }
 
     /* ---- S6 (ref:477) ---- */
+    orc_tl_margin = 1e30;
     orc_step_simulation(&P, b, trace);
+    o->contact_margin = orc_tl_margin;
     e->step += 1;                                  /* ref:478 */
 
     /* ---- S7 (ref:608-633) _get_state_dict ---- */

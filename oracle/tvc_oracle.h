@@ -170,6 +170,9 @@ typedef struct orc_step_out {
     double altitude, tilt, omega_mag, fuel, vh, vv;
     double position[3];
     int32_t phase, success, step, criteria_met, term_reason;
+    /* diagnostic: distance (m) of the step's closest DISCRETE contact-manifold decision (entry rule, per-point reach rule)
+     * from its threshold, 1e30 if the step made none -- the parity reports count steps that sit on such a threshold */
+    double contact_margin;
 } orc_step_out;
 
 typedef struct orc_sim orc_sim;

@@ -118,6 +118,8 @@ enum { ST_DR_A = 1, ST_DR_B = 2, ST_NOISE_A = 3, ST_NOISE_B = 4, ST_ACTION = 5, 
 // instructions and 11 % of its stall samples in the ncu source view)
 #if defined(TVC_RCP_FDIVIDEF) || defined(TVC_HOST_TWIN)   // (host twin: tests/host_twin, g++ has no PTX)
 __device__ __forceinline__ float rcp_fast(float x) { return __fdividef(1.0f, x); }
+#elif defined(TVC_ACCURATE_MATH)   // diagnostic build: correctly rounded reciprocal / square root instead of the MUFU approximations
+__device__ __forceinline__ float rcp_fast(float x) { return __frcp_rn(x); }
 #else
 __device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 #endif
@@ -125,6 +127,8 @@ __device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ft
 // subnormal pre/post-scaling rsqrtf() carries
 #ifdef TVC_HOST_TWIN
 __device__ __forceinline__ float rsqrt_normal(float x) { return 1.0f / sqrtf(x); }
+#elif defined(TVC_ACCURATE_MATH)
+__device__ __forceinline__ float rsqrt_normal(float x) { return __frcp_rn(__fsqrt_rn(x)); }
 #else
 __device__ __forceinline__ float rsqrt_normal(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 #endif
@@ -319,6 +323,40 @@ __device__ unsigned long long g_ss[3][16][3];
 #define SS_PASS
 #endif
 
+// The attitude in double, carried INSIDE a step by the envs that are within `margin` of the ground.  The normal targets divide a
+// candidate's gap by dt (x500 at K = 10), and the gap sees the attitude through an arm of 0.5-0.6 m along the body axis: the 1e-7
+// a float quaternion drifts by over the substeps of a step and the 6e-8 rounding of R33 - 1 are each 1e-5..1e-4 m/s in a target
+// and, through rim friction and 1 / I, most of the tail an fp32 evaluation of this model shows against the fp64 oracle (the
+// oracle's own gain on such steps is up to 2e4 rad/s per metre of height).  So near the ground the
+// quaternion product ALSO runs in double, and the two O(0.5 m) terms of a cap centre's height, (pz + z_cap) + z_cap (R33 - 1),
+// are combined in double before the result (a few cm) is rounded.  Everything else is computed from the float quaternion, and
+// the state a step stores is float (the double attitude rounded once).
+// Cost on B200 (tools/micro/fp64_rate.cu): DFMA at half the FFMA rate with a 10-cycle dependent latency; the float <-> double
+// conversions are the expensive part (15 lanes/clk/SM), hence 8 of them per substep.  A/B of the step path: 0.0789 vs 0.0733 ms
+// (DESIGN.md section 6 lists the cheaper-looking forms that measured worse: out of line in local memory, heights formed a
+// substep ahead, tracking from far_z on).
+struct HpAtt { double x, y, z, w; };
+__device__ __forceinline__ void hp_start(HpAtt &a, float qx, float qy, float qz, float qw) {
+    a.x = (double)qx; a.y = (double)qy; a.z = (double)qz; a.w = (double)qw;
+}
+// heights of the bottom / top cap centre above the plane: (pz + z_cap) + pzc + z_cap (R33 - 1), rounded once
+__device__ __forceinline__ void hp_heights(const HpAtt &a, float pz, float pzc, double zbd, double ztd, float &Hb, float &Ht) {
+    const double nz1 = -2.0 * (a.x * a.x + a.y * a.y);
+    const double pzd = (double)pz, pcd = (double)pzc;
+    Hb = (float)(((pzd + zbd) + pcd) + zbd * nz1); Ht = (float)(((pzd + ztd) + pcd) + ztd * nz1);
+}
+// q <- dq (x) q with the substep's float increment dq = (bx, by, bz, cw): its relative rounding scales a rotation of <= 0.01 rad,
+// and a common factor leaves with the normalisation (first-order 1/sqrt, exact to 1e-13 for |n|^2 = 1 + O(1e-7))
+__device__ __forceinline__ void hp_rotate(HpAtt &a, float cw, float bx, float by, float bz) {
+    const double cb = (double)cw, b0 = (double)bx, b1 = (double)by, b2 = (double)bz;
+    const double nx = cb * a.x + b0 * a.w + b1 * a.z - b2 * a.y;
+    const double ny = cb * a.y + b1 * a.w + b2 * a.x - b0 * a.z;
+    const double nz = cb * a.z + b2 * a.w + b0 * a.y - b1 * a.x;
+    const double nw = cb * a.w - b0 * a.x - b1 * a.y - b2 * a.z;
+    const double inv = 1.5 - 0.5 * (nx * nx + ny * ny + nz * nz + nw * nw);
+    a.x = nx * inv; a.y = ny * inv; a.z = nz * inv; a.w = nw * inv;
+}
+
 // One point block: the point's Delassus matrix A (symmetric), the wanted change of the contact velocity (ex, ey, en) and
 // the old impulses -> new impulses.  Stick solution p* = p + A^-1 e, accepted when p*_n > 0 and |p*_t| <= mu p*_n;
 // otherwise the friction impulse keeps the direction of p*_t at magnitude mu p_n and the normal row is re-solved with
@@ -361,10 +399,11 @@ __device__ __forceinline__ void extra_point_arm(int i, float cx0, float cy0, flo
 }
 
 // The contact solve of one substep (model: DESIGN.md section 4; oracle/tvc_oracle.c solve_contacts is the same algorithm in
-// fp64).  Inputs beyond the state: the rotation matrix R (row-major, body -> world), nz1 = R33 - 1 formed without cancellation,
-// hb = (pz + zb) + pzc and ht = (pz + zt) + pzc (cap-centre heights with the position compensation), u = the direction of the
-// lowest rim point, gthr = the reach bound of the entry rule.  All angular quantities are body-frame inside (w0, w1, w2).
-__device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, const float R[9], float nz1, float hb, float ht,
+// fp64).  Inputs beyond the state: the rotation matrix R (row-major, body -> world), Hb / Ht = the heights of the two cap
+// centres above the plane, (pz + z_cap) + pzc + z_cap (R33 - 1), formed in double by integrate_thread (a candidate's gap is that
+// plus its radial part, arm r = 0.05 m), u = the direction of the lowest rim point, gthr = the reach bound of the entry rule.
+// All angular quantities are body-frame inside (w0, w1, w2).
+__device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, const float R[9], float Hb, float Ht,
                                                float ux, float uy, float gthr, float &vx, float &vy, float &vz, float &wx, float &wy,
                                                float &wz, ContactCarry &cc, float *lamx PH2_ARG) {
     PH2_CLK(pc0);
@@ -386,7 +425,7 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
     float tgt0;
     bool act0;   // point 0 is in the substep's manifold: within reach or still holding an impulse (same rule as points 1-4)
     {
-        const float gap = hb + (zb * nz1 + (R[6] * cx0 + R[7] * cy0));
+        const float gap = Hb + (R[6] * cx0 + R[7] * cy0);
         act0 = gap < gthr || cc.ln != 0.0f || cc.l1 != 0.0f || cc.l2 != 0.0f;
         const float vn0 = vz + (wb0x * Jn0 + wb0y * Jn1 + wb0z * Jn2);
         const float rest = (vn0 < -c.rest_thr) ? c.restitution * (-vn0 - c.rest_thr) : 0.0f;
@@ -400,7 +439,7 @@ __device__ __forceinline__ void solve_contacts(const DevCfg &c, const BodyP &P, 
     for (int i = 1; i < 5; i++) {
         float cx, cy, cz;
         extra_point_arm(i, cx0, cy0, r, zb, zt, cx, cy, cz);
-        const float gap = (i == 1 ? ht : hb) + (cz * nz1 + (R[6] * cx + R[7] * cy));
+        const float gap = (i == 1 ? Ht : Hb) + (R[6] * cx + R[7] * cy);
         tgtx[i - 1] = 0.0f;
         if (gap < gthr || (cc.xmask >> i) & 1u) {
             const float jn0 = cy * R[8] - cz * R[7], jn1 = cz * R[6] - cx * R[8], jn2 = cx * R[7] - cy * R[6];
@@ -552,6 +591,10 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
     cc.l1 = cc.l2 = cc.ln = cc.lt0 = cc.lt1 = cc.lt2 = 0.0f; cc.xmask = 0u; cc.have = false;   // cold start at every control step
     float lamx[12];          // impulses of points 1-4, valid where cc.xmask says so
     float pzc = 0.0f;        // running compensation of the height update: true height = e.pz + pzc
+    // Within `margin` of the ground the attitude is also carried in double INSIDE the step (HpAtt, above), valid while hp
+    HpAtt att;
+    att.x = att.y = att.z = att.w = 0.0;
+    bool hp = false;
     const float dI = P.inv_Iz - P.inv_Ixy;
     const float hh = c.half_len + fabsf(P.cg);
     const float far_z = 1.001f * (hh + c.radius) + c.margin;
@@ -600,15 +643,20 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
         // lower than pz - 1.001 (h + |cg| + r): above `far_z` the rule fails without evaluating it (one compare for the
         // airborne envs).  When the rule fails the stored impulses are cleared.
         bool solved = false;
+        bool nearg = false;      // this substep sees the ground within `margin`: it works on the double attitude
         if (c.ground && e.pz < far_z) {
             const float R31 = e.qx * zs - e.qw * ys, R32 = e.qy * zs + e.qw * xs;   // third row of R (R33 == e2)
             const float rr = R31 * R31 + R32 * R32;
             const float rho = sqrt_fast(rr);
             const float inv = rcp_fast(fmaxf(rho, 1e-3f));
             const float low = -c.radius * rr * inv;
-            const float hb = (e.pz + zb) + pzc, ht = (e.pz + zt) + pzc;
-            const float gmin = fminf(hb + (zb * nz1 + low), ht + (zt * nz1 + low));
-            if (gmin < c.margin) {
+            const float hbf = (e.pz + zb) + pzc, htf = (e.pz + zt) + pzc;
+            if (fminf(hbf + (zb * nz1 + low), htf + (zt * nz1 + low)) < c.margin) {
+                nearg = true;
+                if (!hp) { hp_start(att, e.qx, e.qy, e.qz, e.qw); hp = true; }
+                float Hb, Ht;
+                hp_heights(att, e.pz, pzc, (double)zb, (double)zt, Hb, Ht);
+                const float gmin = fminf(Hb + low, Ht + low);
                 const float vmax = fabsf(e.vz) + sqrt_fast(e.wx * e.wx + e.wy * e.wy + e.wz * e.wz) * reach;
                 const float gthr = (1.0f + c.restitution) * vmax * dt + 1e-4f;
                 if (gmin < gthr) {
@@ -616,7 +664,7 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
                     R[0] = 1.0f - (e.qy * ys + e.qz * zs); R[1] = e.qx * ys - e.qw * zs; R[2] = e0;
                     R[3] = e.qx * ys + e.qw * zs; R[4] = 1.0f - (e.qx * xs + e.qz * zs); R[5] = e1;
                     R[6] = R31; R[7] = R32; R[8] = e2;
-                    solve_contacts(c, P, R, nz1, hb, ht, -R31 * inv, -R32 * inv, gthr, e.vx, e.vy, e.vz, e.wx, e.wy, e.wz, cc, lamx PH2_PASS);
+                    solve_contacts(c, P, R, Hb, Ht, -R31 * inv, -R32 * inv, gthr, e.vx, e.vy, e.vz, e.wx, e.wy, e.wz, cc, lamx PH2_PASS);
                     solved = true;
                 }
             }
@@ -642,14 +690,22 @@ __device__ __forceinline__ void integrate_thread(const DevCfg &c, const BodyP &P
         const float sc = 0.5f * dt * (1.0f + hx2 * (-1.6666667e-1f + hx2 * (8.3333333e-3f + hx2 * -1.9841270e-4f)));
         const float cw = 1.0f + hx2 * (-0.5f + hx2 * (4.1666667e-2f + hx2 * -1.3888889e-3f));
         float bx = e.wx * sc, by = e.wy * sc, bz = e.wz * sc;
-        float nx = cw * e.qx + bx * e.qw + by * e.qz - bz * e.qy;
-        float ny = cw * e.qy + by * e.qw + bz * e.qx - bx * e.qz;
-        float nz = cw * e.qz + bz * e.qw + bx * e.qy - by * e.qx;
-        float nw = cw * e.qw - bx * e.qx - by * e.qy - bz * e.qz;
-        // |dq (x) q|^2 = 1 + O(1e-7) (both factors are unit to rounding): 1/sqrt by its first-order expansion, exact to 1e-13
-        float inv = 1.5f - 0.5f * (nx * nx + ny * ny + nz * nz + nw * nw);
-        e.qx = nx * inv; e.qy = ny * inv; e.qz = nz * inv; e.qw = nw * inv;
+        {
+            float nx = cw * e.qx + bx * e.qw + by * e.qz - bz * e.qy;
+            float ny = cw * e.qy + by * e.qw + bz * e.qx - bx * e.qz;
+            float nz = cw * e.qz + bz * e.qw + bx * e.qy - by * e.qx;
+            float nw = cw * e.qw - bx * e.qx - by * e.qy - bz * e.qz;
+            // |dq (x) q|^2 = 1 + O(1e-7) (both factors are unit to rounding): 1/sqrt by its first-order expansion, exact to 1e-13
+            float inv = 1.5f - 0.5f * (nx * nx + ny * ny + nz * nz + nw * nw);
+            e.qx = nx * inv; e.qy = ny * inv; e.qz = nz * inv; e.qw = nw * inv;
+        }
+        // the same rotation on the double attitude, BESIDE the float one: the next substep's dynamics start from the float
+        // quaternion (short chain); the double one is only read for the cap heights at the solver entry
+        if (nearg) hp_rotate(att, cw, bx, by, bz);
+        else hp = false;
     }
+    // a tracked attitude is what the step hands on (rounded once); the float one beside it has drifted by a few 1e-8
+    if (hp) { e.qx = (float)att.x; e.qy = (float)att.y; e.qz = (float)att.z; e.qw = (float)att.w; }
 }
 
 // Contract X per-episode draws (one out-of-line copy): mass scale, thrust scale, wind x/y, cg offset, initial
