@@ -16,6 +16,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libtvc_oracle.so")
 _LIB_F32_PATH = os.path.join(_HERE, "libtvc_oracle_f32.so")   # physics layer in float32 (sensitivity probe)
+_LIB_F32G_PATH = os.path.join(_HERE, "libtvc_oracle_f32g.so")  # ... with the kernel's precision split (-DORC_GEO_DOUBLE)
 
 MAX_DELAY = 4
 HIST = 1000
@@ -98,18 +99,19 @@ class StepOut(C.Structure):
                 ("contact_margin", C.c_double)]
 
 
-def build(force: bool = False, f32: bool = False) -> str:
+def build(force: bool = False, f32: bool = False, geo_double: bool = False) -> str:
     """Compile oracle/libtvc_oracle.so (building the checker is not using it).  f32=True builds the
-    variant whose physics layer evaluates in float32 (-DORC_PHYS_FLOAT)."""
+    variant whose physics layer evaluates in float32 (-DORC_PHYS_FLOAT); with geo_double=True that variant keeps
+    the attitude and the cap-centre heights in double (-DORC_GEO_DOUBLE: the CUDA kernel's precision split)."""
     src = os.path.join(_HERE, "tvc_oracle.c")
     hdr = os.path.join(_HERE, "tvc_oracle.h")
-    out = _LIB_F32_PATH if f32 else _LIB_PATH
+    out = (_LIB_F32G_PATH if geo_double else _LIB_F32_PATH) if f32 else _LIB_PATH
     if (not force and os.path.exists(out)
             and os.path.getmtime(out) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
         return out
     base = ["-O2", "-fPIC", "-std=c11", "-ffp-contract=off", "-fno-fast-math", "-shared", "-o", out, src, "-lm"]
     if f32:
-        base = ["-DORC_PHYS_FLOAT"] + base
+        base = ["-DORC_PHYS_FLOAT"] + (["-DORC_GEO_DOUBLE"] if geo_double else []) + base
     last = None
     for cc in ("/usr/bin/gcc", "gcc", "cc"):
         for omp in (["-fopenmp"], []):
@@ -123,10 +125,15 @@ def build(force: bool = False, f32: bool = False) -> str:
 
 _lib = None
 _lib_f32 = None
+_lib_f32g = None
 
 
-def lib(f32: bool = False):
-    global _lib, _lib_f32
+def lib(f32: bool = False, geo_double: bool = False):
+    global _lib, _lib_f32, _lib_f32g
+    if f32 and geo_double:
+        if _lib_f32g is None:
+            _lib_f32g = _declare(C.CDLL(build(f32=True, geo_double=True)))
+        return _lib_f32g
     if f32:
         if _lib_f32 is None:
             _lib_f32 = _declare(C.CDLL(build(f32=True)))
@@ -215,8 +222,8 @@ def matrix_from_quat(q):
 class OracleSim:
     """Batch of oracle envs (fp64).  Mirrors the device engine's reset/step surface."""
 
-    def __init__(self, cfg: Config | None = None, num_envs: int = 1, f32_physics: bool = False, **over):
-        self.L = lib(f32_physics)
+    def __init__(self, cfg: Config | None = None, num_envs: int = 1, f32_physics: bool = False, geo_double: bool = False, **over):
+        self.L = lib(f32_physics, geo_double)
         self.cfg = cfg if cfg is not None else default_config(**over)
         self.n = int(num_envs)
         self.h = self.L.orc_create(C.byref(self.cfg), self.n)

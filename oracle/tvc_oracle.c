@@ -179,9 +179,20 @@ typedef double real;
 #define R_EPS2 2.220446049250313e-16
 #endif
 
+/* -DORC_GEO_DOUBLE (with -DORC_PHYS_FLOAT only): the float build with the CUDA kernel's precision split (tvc_device.cuh
+ * HpAtt) -- the attitude and the two O(0.5 m) terms of a contact candidate's height stay double, everything else is float.
+ * tests/test_oracle.py uses it to show on the CPU which part of an fp32 evaluation makes the contact tail. */
+#if defined(ORC_GEO_DOUBLE) && defined(ORC_PHYS_FLOAT)
+typedef double greal;
+#define ORC_SPLIT 1
+#else
+typedef real greal;
+#define ORC_SPLIT 0
+#endif
 static inline real r_clamp(real x, real lo, real hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
-static real r_matrix_from_quat(const real q[4], real m[9]) {
+static greal r_matrix_from_quat(const greal qg[4], real m[9]) {
+    const real q[4] = {(real)qg[0], (real)qg[1], (real)qg[2], (real)qg[3]};   /* (the matrix itself is `real` in every build) */
     real d = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
     real s = (real)2.0 / d;
     real xs = q[0] * s, ys = q[1] * s, zs = q[2] * s;
@@ -191,7 +202,11 @@ static real r_matrix_from_quat(const real q[4], real m[9]) {
     m[0] = (real)1.0 - (yy + zz); m[1] = xy - wz;                 m[2] = xz + wy;
     m[3] = xy + wz;               m[4] = (real)1.0 - (xx + zz);   m[5] = yz - wx;
     m[6] = xz - wy;               m[7] = yz + wx;                 m[8] = (real)1.0 - (xx + yy);
+#if ORC_SPLIT
+    return -2.0 * (qg[0] * qg[0] + qg[1] * qg[1]) / (qg[0] * qg[0] + qg[1] * qg[1] + qg[2] * qg[2] + qg[3] * qg[3]);
+#else
     return -(xx + yy);   /* R33 - 1 without the cancellation */
+#endif
 }
 
 /*
@@ -291,7 +306,7 @@ static inline void point_block(const orc_sym3 *A, real ex, real ey, real en, rea
 
 /* lam[18]: impulses carried between the substeps of a step: normal(5), tangent-x(5), tangent-y(5), torsional about the
  * body axes z (spin), x, y (roll) */
-static void solve_contacts(const orc_body_params *p, real dt, const real R[9], real nz1, real pz, real pzc, real v[3], real w[3],
+static void solve_contacts(const orc_body_params *p, real dt, const real R[9], greal nz1, greal pz, greal pzc, real v[3], real w[3],
                            real lam[18], int *have_lam) {
     const real r = (real)p->radius, h = (real)p->half_len, cg = (real)p->cg, margin = (real)p->margin;
     orc_dbg_substeps++;
@@ -301,7 +316,12 @@ static void solve_contacts(const orc_body_params *p, real dt, const real R[9], r
     const real ux = -R31 * inv, uy = -R32 * inv;
     const real zb = -h - cg, zt = h - cg;
     const real low = r * (R31 * ux + R32 * uy);          /* = -r*rho outside the regularised zone */
+#if ORC_SPLIT   /* the kernel's association: cap-centre height in double, rounded, plus the float radial part */
+    const real Hb = (real)(((pz + (greal)zb) + pzc) + (greal)zb * nz1), Ht = (real)(((pz + (greal)zt) + pzc) + (greal)zt * nz1);
+    const real gb = Hb + low, gt = Ht + low;
+#else
     const real gb = ((pz + zb) + pzc) + (zb * nz1 + low), gt = ((pz + zt) + pzc) + (zt * nz1 + low);
+#endif
     const real gmin = gb < gt ? gb : gt;
     int enter = gmin < margin;
     if (gmin < (real)4.0 * margin) note_margin((double)gmin - (double)margin);
@@ -345,7 +365,11 @@ static void solve_contacts(const orc_body_params *p, real dt, const real R[9], r
     for (int i = 0; i < 5; i++) {
         point_rows(c[i], xb, yb, nb, &J[i]);
         /* height of the point above the plane: pz + c.nb = (pz + cz) + cz (nbz - 1) + cx nbx + cy nby */
+#if ORC_SPLIT
+        real gap = (i == 1 ? Ht : Hb) + (nb[0] * c[i][0] + nb[1] * c[i][1]);
+#else
         real gap = ((pz + c[i][2]) + pzc) + (c[i][2] * nz1 + (nb[0] * c[i][0] + nb[1] * c[i][1]));
+#endif
         /* the substep's manifold: points within reach (the entry rule's own bound) or still holding an impulse */
         active[i] = gap < gthr || lam[i] != 0 || lam[5 + i] != 0 || lam[10 + i] != 0;
         if (lam[i] == 0 && lam[5 + i] == 0 && lam[10 + i] == 0) note_margin((double)gap - (double)gthr);
@@ -442,22 +466,23 @@ void orc_step_simulation(const orc_body_params *p, orc_body *b, double *trace) {
     const real maxv = (real)p->max_vel;
     const real Ia = (real)p->inertia[0], Ib = (real)p->inertia[1], Ic = (real)p->inertia[2];
     /* B4: applyGravity() once before the substep loop; forces constant over the K substeps */
-    real F[3], T[3], pos[3], q[4], v[3], w[3];
+    real F[3], T[3], pos[3], v[3], w[3];
+    greal q[4], pzg = (greal)b->pos[2];       /* (pzg is pos[2] itself unless ORC_SPLIT) */
     for (int i = 0; i < 3; i++) {
         F[i] = (real)(b->force[i] + p->gravity[i] * p->mass); T[i] = (real)b->torque[i];
         pos[i] = (real)b->pos[i]; v[i] = (real)b->vel[i]; w[i] = (real)b->omega[i];
     }
-    for (int i = 0; i < 4; i++) q[i] = (real)b->quat[i];
+    for (int i = 0; i < 4; i++) q[i] = (greal)b->quat[i];
     real lam[18];
     for (int i = 0; i < 18; i++) lam[i] = 0;   /* cold start at every control step */
     int have_lam = 0;                          /* the previous substep ran the solve (warm start) */
-    real pzc = 0;                              /* compensation of the height update, true height = pos[2] + pzc */
+    greal pzc = 0;                             /* compensation of the height update, true height = pos[2] + pzc */
 
     const int follow = b->thrust_local[0] != 0 || b->thrust_local[1] != 0 || b->thrust_local[2] != 0;
     const real F0[3] = {F[0], F[1], F[2]}, T0[3] = {T[0], T[1], T[2]};
     for (int k = 0; k < K; k++) {
         real R[9];
-        const real nz1 = r_matrix_from_quat(q, R);
+        const greal nz1 = r_matrix_from_quat(q, R);
         if (follow) {   /* quirk Q3 cleared: the body-fixed thrust and its torque at this substep's attitude */
             const real fl[3] = {(real)b->thrust_local[0], (real)b->thrust_local[1], (real)b->thrust_local[2]};
             const real tl[3] = {-(real)b->thrust_arm * fl[1], (real)b->thrust_arm * fl[0], (real)0.0};
@@ -498,15 +523,21 @@ void orc_step_simulation(const orc_body_params *p, orc_body *b, double *trace) {
             v[i] = r_clamp(v[i] + vd * dt, -maxv, maxv);
         }
         /* B9 (our model): contacts detected at the pre-integration pose, solved on velocities */
-        if (p->ground) solve_contacts(p, dt, R, nz1, pos[2], pzc, v, w, lam, &have_lam);
+        if (p->ground) solve_contacts(p, dt, R, nz1, pzg, pzc, v, w, lam, &have_lam);
 
         /* B6: stepPositionsMultiDof -- semi-implicit Euler, exponential map */
         pos[0] += dt * v[0]; pos[1] += dt * v[1];
         {   /* height with a running compensation (Kahan): the contact targets divide the gap by dt, so the 3e-8
              * rounding of pz + dt vz per substep would otherwise show up as 1.5e-5 m/s in fp32 at dt = 0.002 */
+#if ORC_SPLIT   /* (the kernel keeps the float height + float compensation and adds them in double: same value) */
+            const real pc = (real)pzc, y = dt * v[2] + pc, t = pos[2] + y;
+            pzc = (greal)(real)(y - (t - pos[2]));
+            pos[2] = t; pzg = (greal)t;
+#else
             const real y = dt * v[2] + pzc, t = pos[2] + y;
             pzc = y - (t - pos[2]);
-            pos[2] = t;
+            pos[2] = t; pzg = t;
+#endif
         }
         real ang = R_SQRT(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
         if (ang * dt > (real)(0.25 * PI_D)) ang = (real)(0.5 * (0.5 * PI_D)) / dt;   /* ANGULAR_MOTION_THRESHOLD */
@@ -516,11 +547,16 @@ void orc_step_simulation(const orc_body_params *p, orc_body *b, double *trace) {
         real ax0 = w[0] * sc, ax1 = w[1] * sc, ax2 = w[2] * sc;
         real cw = R_COS(ang * dt * (real)0.5);
         /* q <- dq (x) q  with dq = (ax, cw) */
-        real nx = cw * q[0] + ax0 * q[3] + ax1 * q[2] - ax2 * q[1];
-        real ny = cw * q[1] + ax1 * q[3] + ax2 * q[0] - ax0 * q[2];
-        real nz = cw * q[2] + ax2 * q[3] + ax0 * q[1] - ax1 * q[0];
-        real nw = cw * q[3] - ax0 * q[0] - ax1 * q[1] - ax2 * q[2];
+        /* (greal == real unless ORC_SPLIT: then the product runs in double on the float increment, as in the kernel) */
+        greal nx = (greal)cw * q[0] + (greal)ax0 * q[3] + (greal)ax1 * q[2] - (greal)ax2 * q[1];
+        greal ny = (greal)cw * q[1] + (greal)ax1 * q[3] + (greal)ax2 * q[0] - (greal)ax0 * q[2];
+        greal nz = (greal)cw * q[2] + (greal)ax2 * q[3] + (greal)ax0 * q[1] - (greal)ax1 * q[0];
+        greal nw = (greal)cw * q[3] - (greal)ax0 * q[0] - (greal)ax1 * q[1] - (greal)ax2 * q[2];
+#if ORC_SPLIT
+        greal inv = 1.0 / sqrt(nx * nx + ny * ny + nz * nz + nw * nw);
+#else
         real inv = (real)1.0 / R_SQRT(nx * nx + ny * ny + nz * nz + nw * nw);
+#endif
         q[0] = nx * inv; q[1] = ny * inv; q[2] = nz * inv; q[3] = nw * inv;
 
         if (trace) {

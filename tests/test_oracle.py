@@ -285,8 +285,9 @@ def test_fp32_sensitivity_contract_x_batch(oracle_mod):
     millimetres from their thresholds (orc_step_out.contact_margin), and both builds take the same solver branches -- but
     gain: the normal targets divide the gap by dt (x500), the gap sees the attitude through the 0.5-0.6 m arm along the body
     axis, and rim friction turns the target into spin through 1 / I.  The fp64 oracle itself answers a 1e-10 m change of the
-    input height with up to 2e-6 rad/s on such steps (second half of this test).  That is why the kernel carries the attitude
-    and the two cap-centre heights in double near the ground (tvc_device.cuh HpAtt)."""
+    input height with up to 2e-6 rad/s on such steps (last part of this test).  That is why the kernel carries the attitude
+    and the two cap-centre heights in double near the ground (tvc_device.cuh HpAtt): the THIRD build of the oracle
+    (-DORC_PHYS_FLOAT -DORC_GEO_DOUBLE: float everywhere except exactly those quantities) loses most of the tail."""
     import ctypes as C
     O = oracle_mod
     n, K = 512, 10
@@ -294,8 +295,9 @@ def test_fp32_sensitivity_contract_x_batch(oracle_mod):
                 autoreset=1, env_id_base=1000)
     a = O.OracleSim(O.default_config(O.CONTRACT_X, **over), n)
     b = O.OracleSim(O.default_config(O.CONTRACT_X, **over), n, f32_physics=True)
-    a.reset(), b.reset()
-    free, contact, margin = [], [], []
+    g = O.OracleSim(O.default_config(O.CONTRACT_X, **over), n, f32_physics=True, geo_double=True)
+    a.reset(), b.reset(), g.reset()
+    free, contact, margin, split = [], [], [], []
     worst = (0.0, None, None, None)
     for t in range(40):
         for i in range(n):
@@ -305,30 +307,38 @@ def test_fp32_sensitivity_contract_x_batch(oracle_mod):
                 for k in range(len(arr)):
                     arr[k] = float(np.float32(arr[k]))
             C.memmove(C.addressof(b.env(i)), C.addressof(ea), C.sizeof(O.Env))
+            C.memmove(C.addressof(g.env(i)), C.addressof(ea), C.sizeof(O.Env))
         pre_z = np.array([a.env(i).body.pos[2] for i in range(n)])
         blobs = [C.string_at(C.addressof(a.env(i)), C.sizeof(O.Env)) for i in range(n)]
         acts = a.random_actions(t)
         _, _, ta, tra, outs = a.step(acts, threads=4)
         _, _, tb, trb, _ = b.step(acts, threads=4)
-        for i in np.flatnonzero(~(ta | tra | tb | trb)):
-            ea, eb = a.env(i).body, b.env(i).body
+        _, _, tg, trg, _ = g.step(acts, threads=4)
+        for i in np.flatnonzero(~(ta | tra | tb | trb | tg | trg)):
+            ea, eb, eg = a.env(i).body, b.env(i).body, g.env(i).body
             sa = np.array(list(ea.pos) + list(ea.quat) + list(ea.vel) + list(ea.omega))
             sb = np.array(list(eb.pos) + list(eb.quat) + list(eb.vel) + list(eb.omega))
+            sg = np.array(list(eg.pos) + list(eg.quat) + list(eg.vel) + list(eg.omega))
             err = float((np.abs(sa - sb) / np.maximum(1, np.abs(sa))).max())
             if min(pre_z[i], ea.pos[2]) > 0.75:
                 free.append(err)
             else:
                 contact.append(err), margin.append(outs[i].contact_margin)
+                split.append(float((np.abs(sa - sg) / np.maximum(1, np.abs(sa))).max()))
                 if err > worst[0]:
                     worst = (err, int(i), blobs[i], acts[i].copy())
-    free, contact, margin = np.array(free), np.array(contact), np.array(margin)
+    free, contact, margin, split = np.array(free), np.array(contact), np.array(margin), np.array(split)
     tail = contact > 1e-4
     print(f"\n[fp32 oracle vs fp64 oracle, Contract X] free-flight max {free.max():.2e} ({len(free)} env-steps); near-ground median "
           f"{np.median(contact):.2e} q99 {np.quantile(contact, 0.99):.2e} max {contact.max():.2e} ({len(contact)} env-steps); "
           f"{int(tail.sum())} steps above 1e-4, their manifold margins {margin[tail].min():.1e} .. {margin[tail].max():.1e} m "
           f"(median {np.median(margin[tail]):.1e})")
+    print(f"[fp32 oracle with the attitude and the cap heights in double vs fp64 oracle] near-ground median {np.median(split):.2e} "
+          f"q99 {np.quantile(split, 0.99):.2e} max {split.max():.2e}; {int((split > 1e-4).sum())} steps above 1e-4")
     assert len(contact) > 2000 and free.max() <= K * 1e-5
     assert np.quantile(contact, 0.99) <= K * 1e-5 and contact.max() <= 2e-2
+    # the kernel's precision split: q99 at 1e-5 per STEP, the maximum several times lower, a third of the steps above 1e-4
+    assert np.quantile(split, 0.99) <= 1e-5 and split.max() <= 0.3 * contact.max() and (split > 1e-4).sum() * 2 < tail.sum()
     # the tail does not sit on a manifold threshold: a float evaluation moves a gap by ~1e-7 m at most
     assert tail.sum() >= 5 and margin[tail].min() > 1e-6 and np.median(margin[tail]) > 1e-3
     # ... it is gain: the fp64 model's own response of omega to 1e-10 m of input height on the worst step
