@@ -530,6 +530,8 @@ def run_ours(args):
                        "envs_per_gpu": n, "substeps": int(cfg_used.substeps), "contact_iters": [int(cfg_used.contact_iters), int(cfg_used.contact_warm_iters)],
                        "quirks": hex(int(cfg_used.quirks)), "parallelism": f"env-slab x{world}",
                        "l2": "flushed between timed steps (256 MiB zero-fill, not timed)",
+                       "arithmetic": "f32; envs within the contact margin of the ground also carry the attitude and the two "
+                                     "cap-centre heights in f64 inside a step (DESIGN.md section 3), state in HBM is f32",
                        "burn_in_steps": args.burn_in, "overrides": dict(OVERRIDES)},
             "env_substeps_per_sec": value * 10,
             "stats_allreduce": {"count": len(stat_events), "us_mean": (sum(stat_us) / len(stat_us)) if stat_us else None,
