@@ -374,6 +374,33 @@ def run_ours(args):
                                 "us_per_step": us, "env_steps_per_sec": 4096 / (us * 1e-6)}
         small.close()
 
+        # the reference's own constants (Contract R: every quirk, K = 4 substeps of 0.005 s, no DR) on a slab of the headline
+        # size, bit-ring diversity window, cold L2 -- what the path costs when it reproduces the shipped env instead of the
+        # north_star's extension; 294 algorithmic bytes per env-step
+        try:
+            cr = BatchedEngine(n, A.default_config(A.CONTRACT_R, autoreset=1, diversity_mode=A.DIV_FAST), device=local)
+            cr.reset()
+            for w in range(1100):                      # past 1,000 pushes: the reward window is full
+                cr.step(pool[w % len(pool)], want_final=False)
+            torch.cuda.synchronize(dev)
+            cr_ms = 0.0
+            for k in range(30):
+                flush.zero_()
+                e0.record()
+                cr.step(pool[k % len(pool)], want_final=False)
+                e1.record()
+                torch.cuda.synchronize(dev)
+                cr_ms += e0.elapsed_time(e1) / 30
+            peak_cr, _ = _peaks()
+            extra["contract_r"] = {"workload": f"Contract R (reference constants, all quirks, K=4, no DR), {n} envs, same-step autoreset, "
+                                               "bit-ring diversity window, L2 flushed between steps",
+                                   "ms_per_step": cr_ms, "env_steps_per_sec": n / (cr_ms * 1e-3),
+                                   "algorithmic_bytes_per_env_step": 294,
+                                   "hbm_frac": 294 * n / (cr_ms * 1e-3) / 1e9 / peak_cr}
+            cr.close()
+        except Exception as exc:  # noqa: BLE001 -- an extra leg must not take the headline line down
+            extra["contract_r"] = {"error": repr(exc)}
+
         # row S14 (reference training default enable_curiosity=True): the batch's curiosity term on the tensor cores, timed
         # alone on a slab of the headline size in its steady mix (cold L2) next to the fp32 torch path it replaces
         try:
